@@ -1,0 +1,156 @@
+/*
+ * promptcache_b200 -- C ABI of the B200 (sm_100a) prompt-cache prefill hot path.
+ *
+ * The reference (yale-sys/prompt-cache) has no FFI layer: its hot path is eager PyTorch.  This
+ * header is the boundary a maintainer would bind (ctypes / cffi / pybind) to replace the torch
+ * call sites cited on each entry point.  All `*_dev` / `void*` tensor arguments are DEVICE
+ * pointers unless a comment says HOST; the caller owns every buffer and keeps it alive until the
+ * stream has drained.  Every call is asynchronous on `stream` (a `cudaStream_t` passed as
+ * `void*`; NULL = legacy default stream), re-entrant, keeps no state between calls other than
+ * internal caches (TMA descriptors, a pinned staging ring) and never throws.
+ *
+ * Return value: 0 on success, a negative `PC_ERR_*` otherwise; `pc_last_error()` returns the
+ * thread-local message of the last failure.
+ *
+ * Element type of K/V/Q/out is IEEE fp16 (`elem_bytes == 2`) everywhere except `pc_splice_*`,
+ * which moves opaque rows and accepts any `elem_bytes` whose row size is a multiple of 16 B.
+ */
+#ifndef PROMPTCACHE_B200_H_
+#define PROMPTCACHE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PC_ABI_VERSION 1
+
+enum {
+  PC_OK = 0,
+  PC_ERR_INVALID = -1,     /* bad argument (shape, alignment, null pointer)            */
+  PC_ERR_UNSUPPORTED = -2, /* valid request this build has no kernel for               */
+  PC_ERR_CUDA = -3,        /* a CUDA runtime / driver call failed (message has detail) */
+  PC_ERR_WORKSPACE = -4    /* caller-provided workspace too small                      */
+};
+
+/* Rounding points of the reference attention that the kernels reproduce:
+ *   PC_ROUND_QK     : Q.K^T is rounded to fp16 before scaling   (llama2.py:371, mpt.py:156 -- fp16 matmul output)
+ *   PC_ROUND_SCALED : the scaled score is rounded to fp16       (llama2.py:371 "/ sqrt(d)", mpt.py:156 "* scale")
+ * P is always rounded to fp16 before P.V (llama2.py:387, mpt.py:181) and the context to fp16 at the end.
+ * Falcon goes through SDPA with fp32 scores (falcon.py:476-478): pass 0. */
+#define PC_ROUND_QK 1
+#define PC_ROUND_SCALED 2
+#define PC_ROUND_LLAMA (PC_ROUND_QK | PC_ROUND_SCALED)
+#define PC_ROUND_MPT (PC_ROUND_QK | PC_ROUND_SCALED)
+#define PC_ROUND_FALCON 0
+
+/* Which attention kernel runs.  AUTO = the tcgen05/TMEM kernel; SIMT = the plain CUDA-core
+ * two-pass kernel kept as an on-device cross-check (never selected implicitly). */
+#define PC_ATTN_AUTO 0
+#define PC_ATTN_SIMT 1
+#define PC_ATTN_TCGEN05 2
+
+int pc_version(void);
+const char* pc_last_error(void);
+
+/* Number of SMs / compute capability of the current device (diagnostics for the host side). */
+int pc_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * Splice: PromptCache.update  (promptcache/cache_engine.py:116-156, the copy loop :135-151)
+ *
+ * Native layout.  One cached segment (= one TokenSequenceCache, cache_engine.py:50-83) is a single
+ * allocation   seg[L][2][Hkv][len][D]   (2 = K then V); the contiguous prompt cache
+ * (PromptCache.device_cache, cache_engine.py:104-107) is   cache[L][2][Hkv][max_ctx][D].
+ * For every segment, layer, K/V and head the kernel copies the run  seg[l][kv][h][0:len][:]  to
+ * cache[l][kv][h][dst_row : dst_row+len][:]  -- bit-exact, TMA bulk load -> smem -> TMA bulk store.
+ * `segs` is a HOST array (it travels as a kernel parameter; no H2D copy); n_segs is unbounded
+ * (launches are chunked internally). */
+typedef struct pc_segment {
+  const void* base; /* device: seg[L][2][Hkv][len][D]                         */
+  int32_t len;      /* tokens in the segment (>0)                             */
+  int32_t dst_row;  /* first row of the segment in the contiguous cache       */
+} pc_segment;
+
+int pc_splice_kv(const pc_segment* segs /*HOST*/, int n_segs, void* cache_dev, int n_layers,
+                 int n_kv_heads, int head_dim, int max_ctx, int elem_bytes, void* stream);
+
+/* Reference layout.  The reference keeps one tensor per (segment, layer, K|V), each [Hkv][len][D]
+ * contiguous, and one target per (layer, K|V), each [Hkv][max_ctx][D] (cache_engine.py:139-149).
+ * One descriptor = one `tgt[:, st:ed, :].copy_(src)`:  n_runs (=Hkv) runs of run_bytes each. */
+typedef struct pc_copy2d {
+  const void* src;        /* device */
+  void* dst;              /* device, already offset to row `st` */
+  int64_t src_run_stride; /* bytes between runs in src (len*D*elem)     */
+  int64_t dst_run_stride; /* bytes between runs in dst (max_ctx*D*elem) */
+  int64_t run_bytes;      /* bytes per run (len*D*elem), multiple of 16 */
+  int32_t n_runs;         /* Hkv */
+  int32_t reserved;
+} pc_copy2d;
+
+int pc_splice_kv_tensors(const pc_copy2d* copies /*HOST*/, int n_copies, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * RoPE at explicit position ids + in-place KV append
+ *   apply_rotary_pos_emb + rotate_half   (promptcache/model/llama2.py:195-210, call :357-359)
+ *   FalconRotaryEmbedding.forward        (promptcache/model/falcon.py:120-154)
+ *   torch.cat([past, new], dim=2)        (llama2.py:361-364, falcon.py:446-452, mpt.py:148-151)
+ *
+ * q_in/k_in/v_in are the projection outputs, token-major: row t of q_in holds H heads of D halfs,
+ * rows `*_stride` ELEMENTS apart (so a fused QKV buffer works).  cos/sin are the [table_rows][D]
+ * fp16 tables the reference model built (llama2.py:128-137); rows are gathered at position_ids[t]
+ * (int64, device).  The rotation is evaluated as half(half(x*cos) + half(rot(x)*sin)) -- the three
+ * fp16 roundings of the reference -- so Q and the new K are bit-exact.  cos == NULL skips the
+ * rotation (MPT).  Rotated Q goes to q_out[H][q_len][D]; rotated K and V go straight into rows
+ * [dst_row0, dst_row0+q_len) of k_cache/v_cache[Hkv][max_ctx][D] (no concatenation). */
+int pc_rope_append(const void* q_in, const void* k_in, const void* v_in, int64_t q_stride,
+                   int64_t k_stride, int64_t v_stride, const int64_t* position_ids_dev,
+                   const void* cos_dev, const void* sin_dev, int table_rows, void* q_out,
+                   void* k_cache, void* v_cache, int max_ctx, int dst_row0, int n_heads,
+                   int n_kv_heads, int head_dim, int q_len, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Attention of the uncached suffix over the spliced cache (prefill) and of one token (decode)
+ *   mask construction   llama2.py:62-76,882-884 ; falcon.py:217-245 ; mpt.py:59-75
+ *   repeat_kv           llama2.py:247-256,368-369
+ *   scores/softmax/PV   llama2.py:371-398 ; falcon.py:460-491 ; mpt.py:156-185
+ *
+ * Keys [0, n_cached) are visible to every query row; key n_cached+t is visible to query row r iff
+ * t <= r (sequence order, not position order).  With alibi_slopes != NULL the fp32 bias
+ * slope[h] * (key_pos[j] - alibi_max_pos) is added after scaling (mpt.py:97-110,172-175).
+ * The kernels never materialise the mask or the score matrix. */
+typedef struct pc_attn_params {
+  const void* q;             /* [H][q_len][D] fp16, rotated (q_out of pc_rope_append)        */
+  const void* k;             /* [Hkv][max_ctx][D] fp16; rows [0, n_cached+q_len) are read    */
+  const void* v;             /* same shape                                                   */
+  void* out;                 /* [q_len][H*D] fp16, token-major (input of o_proj)             */
+  int32_t n_heads;           /* H                                                            */
+  int32_t n_kv_heads;        /* Hkv (H % Hkv == 0)                                           */
+  int32_t head_dim;          /* D: 64 or 128                                                 */
+  int32_t n_cached;          /* N                                                            */
+  int32_t q_len;             /* q                                                            */
+  int32_t max_ctx;           /* row stride of k/v heads                                      */
+  float scale;               /* multiplies the raw score (1/sqrt(D))                         */
+  int32_t rounding;          /* PC_ROUND_* flags                                             */
+  const float* alibi_slopes; /* [H] or NULL                                                  */
+  const int32_t* key_pos;    /* [n_cached+q_len] or NULL (required with alibi_slopes)        */
+  int32_t alibi_max_pos;     /* max(position_ids) (mpt.py:522)                               */
+  int32_t impl;              /* PC_ATTN_*                                                    */
+  void* workspace;           /* split-KV partials, >= pc_attn_workspace_bytes(...) or NULL   */
+  size_t workspace_bytes;
+} pc_attn_params;
+
+size_t pc_attn_workspace_bytes(int n_heads, int q_len, int head_dim);
+int pc_prefill_attn(const pc_attn_params* p, void* stream);
+/* Same contract with q_len == 1 (generation_engine.py:123-147 -> llama2.py:353-398). */
+int pc_decode_attn(const pc_attn_params* p, void* stream);
+
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+int64_t pc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROMPTCACHE_B200_H_ */
