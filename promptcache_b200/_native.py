@@ -1,0 +1,226 @@
+"""ctypes binding of libpromptcache_b200.so (the C ABI in include/promptcache_b200.h).
+
+This is the ONLY way the Python host reaches the kernels; there is no CPU or eager-PyTorch fallback.
+If the shared library is missing or a call fails, a `NativeError` is raised -- loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpromptcache_b200.so")
+
+PC_ROUND_QK = 1
+PC_ROUND_SCALED = 2
+PC_ROUND_LLAMA = 3
+PC_ROUND_MPT = 3
+PC_ROUND_FALCON = 0
+PC_ATTN_AUTO = 0
+PC_ATTN_SIMT = 1
+PC_ATTN_TCGEN05 = 2
+
+EXPORTS = ("pc_version", "pc_last_error", "pc_device_info", "pc_splice_kv", "pc_splice_kv_tensors",
+           "pc_rope_append", "pc_attn_workspace_bytes", "pc_prefill_attn", "pc_decode_attn", "pc_launch_count")
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class pc_segment(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("len", C.c_int32), ("dst_row", C.c_int32)]
+
+
+class pc_copy2d(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("src_run_stride", C.c_int64),
+                ("dst_run_stride", C.c_int64), ("run_bytes", C.c_int64), ("n_runs", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class pc_attn_params(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p),
+                ("n_heads", C.c_int32), ("n_kv_heads", C.c_int32), ("head_dim", C.c_int32),
+                ("n_cached", C.c_int32), ("q_len", C.c_int32), ("max_ctx", C.c_int32),
+                ("scale", C.c_float), ("rounding", C.c_int32),
+                ("alibi_slopes", C.c_void_p), ("key_pos", C.c_void_p),
+                ("alibi_max_pos", C.c_int32), ("impl", C.c_int32),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library (built by promptcache_b200.build) and declare the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(
+            f"{LIB_PATH} is missing: build it with `python -m promptcache_b200.build` "
+            "(promptcache_b200 has no fallback path; the CUDA extension is the product)")
+    # make sure the CUDA runtime torch uses is initialised first so both share the primary context
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_LOCAL)
+    lib.pc_version.restype = C.c_int
+    lib.pc_last_error.restype = C.c_char_p
+    lib.pc_device_info.argtypes = [C.POINTER(C.c_int)] * 3
+    lib.pc_device_info.restype = C.c_int
+    lib.pc_splice_kv.argtypes = [C.POINTER(pc_segment), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_void_p]
+    lib.pc_splice_kv.restype = C.c_int
+    lib.pc_splice_kv_tensors.argtypes = [C.POINTER(pc_copy2d), C.c_int, C.c_void_p]
+    lib.pc_splice_kv_tensors.restype = C.c_int
+    lib.pc_rope_append.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.pc_rope_append.restype = C.c_int
+    lib.pc_attn_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.pc_attn_workspace_bytes.restype = C.c_size_t
+    lib.pc_prefill_attn.argtypes = [C.POINTER(pc_attn_params), C.c_void_p]
+    lib.pc_prefill_attn.restype = C.c_int
+    lib.pc_decode_attn.argtypes = [C.POINTER(pc_attn_params), C.c_void_p]
+    lib.pc_decode_attn.restype = C.c_int
+    lib.pc_launch_count.restype = C.c_int64
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().pc_last_error().decode("utf-8", "replace")
+        raise NativeError(f"{what} failed ({rc}): {msg}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise NativeError("promptcache_b200 kernels take CUDA tensors only (no CPU path exists)")
+
+
+def launch_count() -> int:
+    return int(load().pc_launch_count())
+
+
+def splice_kv(segments: Sequence[tuple], cache: torch.Tensor) -> None:
+    """segments: (packed_segment_tensor[L,2,Hkv,len,D], dst_row) pairs; cache: [L,2,Hkv,max_ctx,D]."""
+    lib = load()
+    _require_cuda(cache)
+    if cache.dim() != 5 or cache.shape[1] != 2 or not cache.is_contiguous():
+        raise NativeError("splice_kv: cache must be a contiguous [L,2,Hkv,max_ctx,D] tensor")
+    L, _, Hkv, max_ctx, D = cache.shape
+    n = len(segments)
+    arr = (pc_segment * max(n, 1))()
+    for i, (seg, row) in enumerate(segments):
+        _require_cuda(seg)
+        if seg.dim() != 5 or tuple(seg.shape[:3]) != (L, 2, Hkv) or seg.shape[4] != D or not seg.is_contiguous() \
+                or seg.dtype != cache.dtype:
+            raise NativeError(f"splice_kv: segment {i} has shape {tuple(seg.shape)}/{seg.dtype}, "
+                              f"expected [{L},2,{Hkv},len,{D}] {cache.dtype} contiguous")
+        arr[i].base = seg.data_ptr()
+        arr[i].len = int(seg.shape[3])
+        arr[i].dst_row = int(row)
+    _check(lib.pc_splice_kv(arr, n, cache.data_ptr(), L, Hkv, D, max_ctx, cache.element_size(), _stream()),
+           "pc_splice_kv")
+
+
+def splice_kv_tensors(copies: Sequence[tuple]) -> None:
+    """copies: (src[Hkv,len,D] contiguous, dst_view[Hkv,len,D] = tgt[:, st:ed, :]) pairs -- the reference layout."""
+    lib = load()
+    n = len(copies)
+    arr = (pc_copy2d * max(n, 1))()
+    for i, (src, dst) in enumerate(copies):
+        _require_cuda(src, dst)
+        if src.shape != dst.shape or src.dtype != dst.dtype or src.dim() != 3 or not src.is_contiguous():
+            raise NativeError(f"splice_kv_tensors: copy {i}: src {tuple(src.shape)} vs dst {tuple(dst.shape)}")
+        Hkv, ln, D = src.shape
+        es = src.element_size()
+        if dst.stride(2) != 1 or dst.stride(1) != D:
+            raise NativeError(f"splice_kv_tensors: copy {i}: dst rows must be contiguous")
+        arr[i].src = src.data_ptr()
+        arr[i].dst = dst.data_ptr()
+        arr[i].src_run_stride = ln * D * es
+        arr[i].dst_run_stride = dst.stride(0) * es
+        arr[i].run_bytes = ln * D * es
+        arr[i].n_runs = Hkv
+    _check(lib.pc_splice_kv_tensors(arr, n, _stream()), "pc_splice_kv_tensors")
+
+
+def rope_append(q_in: torch.Tensor, k_in: torch.Tensor, v_in: torch.Tensor, position_ids: Optional[torch.Tensor],
+                cos: Optional[torch.Tensor], sin: Optional[torch.Tensor], q_out: torch.Tensor,
+                k_cache: torch.Tensor, v_cache: torch.Tensor, dst_row0: int, n_heads: int, n_kv_heads: int,
+                head_dim: int) -> None:
+    """q_in/k_in/v_in: [q, H*D]-like 2-D views (row stride arbitrary, inner contiguous); caches [Hkv,max_ctx,D]."""
+    lib = load()
+    _require_cuda(q_in, k_in, v_in, q_out, k_cache, v_cache)
+    q_len = q_in.shape[0]
+    for t in (q_in, k_in, v_in):
+        if t.dim() != 2 or t.stride(1) != 1 or t.dtype != torch.float16:
+            raise NativeError("rope_append: inputs must be fp16 2-D with a contiguous inner dimension")
+    if k_cache.stride(2) != 1 or k_cache.stride(1) != head_dim or k_cache.stride(0) != v_cache.stride(0):
+        raise NativeError("rope_append: caches must be [Hkv,max_ctx,D] with contiguous rows")
+    max_ctx = k_cache.stride(0) // head_dim
+    if not q_out.is_contiguous():
+        raise NativeError("rope_append: q_out must be contiguous")
+    table_rows = 0
+    if cos is not None:
+        if cos.dtype != torch.float16 or sin.dtype != torch.float16 or not cos.is_contiguous() or not sin.is_contiguous():
+            raise NativeError("rope_append: cos/sin must be contiguous fp16 [T,D] tables")
+        table_rows = cos.shape[0]
+        if position_ids.dtype != torch.int64 or not position_ids.is_contiguous():
+            raise NativeError("rope_append: position_ids must be a contiguous int64 tensor")
+    _check(lib.pc_rope_append(q_in.data_ptr(), k_in.data_ptr(), v_in.data_ptr(), q_in.stride(0), k_in.stride(0),
+                              v_in.stride(0), position_ids.data_ptr() if position_ids is not None else None,
+                              cos.data_ptr() if cos is not None else None,
+                              sin.data_ptr() if sin is not None else None, table_rows, q_out.data_ptr(),
+                              k_cache.data_ptr(), v_cache.data_ptr(), max_ctx, int(dst_row0), n_heads, n_kv_heads,
+                              head_dim, q_len, _stream()), "pc_rope_append")
+
+
+def attn_workspace_bytes(n_heads: int, q_len: int, head_dim: int) -> int:
+    return int(load().pc_attn_workspace_bytes(n_heads, q_len, head_dim))
+
+
+def softmax_scale(head_dim: int) -> float:
+    """fp32 reciprocal of sqrt(D): torch's CUDA `tensor / python_scalar` multiplies by the fp32 reciprocal."""
+    return float(np.float32(1.0) / np.float32(math.sqrt(head_dim)))
+
+
+def attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, out: torch.Tensor, n_cached: int,
+              q_len: int, n_heads: int, n_kv_heads: int, head_dim: int, scale: float, rounding: int,
+              workspace: Optional[torch.Tensor] = None, alibi_slopes: Optional[torch.Tensor] = None,
+              key_pos: Optional[torch.Tensor] = None, alibi_max_pos: int = 0, impl: int = PC_ATTN_AUTO,
+              decode: bool = False) -> None:
+    """q: [H,q,D] fp16; caches [Hkv,max_ctx,D] (row-contiguous views allowed); out: [q,H*D] fp16."""
+    lib = load()
+    _require_cuda(q, k_cache, v_cache, out)
+    if k_cache.stride(2) != 1 or k_cache.stride(1) != head_dim or k_cache.stride(0) != v_cache.stride(0):
+        raise NativeError("attention: caches must be [Hkv,max_ctx,D] with contiguous rows")
+    if not q.is_contiguous() or not out.is_contiguous() or q.dtype != torch.float16 or out.dtype != torch.float16:
+        raise NativeError("attention: q/out must be contiguous fp16")
+    p = pc_attn_params()
+    p.q, p.k, p.v, p.out = q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr()
+    p.n_heads, p.n_kv_heads, p.head_dim = n_heads, n_kv_heads, head_dim
+    p.n_cached, p.q_len = int(n_cached), int(q_len)
+    p.max_ctx = k_cache.stride(0) // head_dim
+    p.scale = scale
+    p.rounding = rounding
+    if alibi_slopes is not None:
+        if alibi_slopes.dtype != torch.float32 or key_pos is None or key_pos.dtype != torch.int32:
+            raise NativeError("attention: alibi needs fp32 slopes and int32 key positions")
+        p.alibi_slopes, p.key_pos = alibi_slopes.data_ptr(), key_pos.data_ptr()
+    p.alibi_max_pos = int(alibi_max_pos)
+    p.impl = impl
+    if workspace is not None:
+        p.workspace, p.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    fn = lib.pc_decode_attn if decode else lib.pc_prefill_attn
+    _check(fn(C.byref(p), _stream()), "pc_decode_attn" if decode else "pc_prefill_attn")

@@ -1,0 +1,321 @@
+"""B200 prompt-cache engine behind the reference's API (promptcache/cache_engine.py).
+
+  TokenSequenceCache   one cached segment; its K/V for ALL layers is ONE HBM allocation
+                       [L, 2, Hkv, len, D] fp16 (reference :50-83 keeps L*2 host tensors and re-uploads them
+                       on every request, :290-292)
+  PromptCache          the contiguous cache, ONE allocation [L, 2, Hkv, max_ctx, D]; `update()` is the splice
+                       (reference :116-156: 2*L*M Python-driven slice copies) = one pc_splice_kv launch
+  SchemaCache          encodes a schema's scaffolds and slices per-TokenSequence segments (reference :186-307)
+  CacheEngine          add_schema / process / remove_schema with the reference's signatures and ValueErrors
+                       (reference :331-522)
+
+Deliberate deviations from the reference, both called out in SURVEY.md section 7:
+  * `PromptCache.staged` records the layout actually written (the usage-ordered list), so the retained-prefix
+    shortcut can never hand back stale rows (the reference stores the unsorted list, :155);
+  * zero-length token sequences are skipped instead of raising in `list.index` (:278).
+"""
+from __future__ import annotations
+
+import gc
+import itertools
+from typing import Dict, List, Optional, Tuple, Union
+
+import torch
+
+from . import _native as nat
+from .prompt import ModuleRef, Prompt
+from .schema import Module, Path, Schema, TokenSequence, UnionModule
+
+KVCache = List[Tuple[torch.Tensor, torch.Tensor]]
+
+
+def pad_batch(batch_list: List[List[int]], pad_id: int) -> Tuple[List[List[int]], List[List[int]]]:
+    """Right-pad id lists to a rectangle and return the matching 0/1 mask (cache_engine.py:38-47)."""
+    width = max(map(len, batch_list))
+    padded = [row + [pad_id] * (width - len(row)) for row in batch_list]
+    mask = [[1] * len(row) + [0] * (width - len(row)) for row in batch_list]
+    return padded, mask
+
+
+class TokenSequenceCache:
+    """KV of one TokenSequence, resident in HBM as a single packed allocation."""
+
+    def __init__(self, seq: TokenSequence, packed: torch.Tensor):
+        if packed.dim() != 5 or packed.shape[1] != 2 or not packed.is_contiguous():
+            raise ValueError("packed segment must be a contiguous [L,2,Hkv,len,D] tensor")
+        self.token_sequence = seq
+        self.packed = packed
+        self.usage_counter = 0
+
+    def inc_usage_counter(self) -> None:
+        self.usage_counter += 1
+
+    # kept for API compatibility: segments are always device-resident here
+    def upload(self, device=None) -> None:
+        return None
+
+    def free(self) -> None:
+        return None
+
+    @property
+    def cache(self) -> KVCache:
+        """Per-layer (K, V) views [Hkv, len, D], the shape the reference stores (:287-288)."""
+        return [(self.packed[l, 0], self.packed[l, 1]) for l in range(self.packed.shape[0])]
+
+    host_cache = cache
+    device_cache = cache
+
+    def __len__(self) -> int:
+        return int(self.packed.shape[3])
+
+
+class PromptCache:
+    """Contiguous per-layer KV buffers + the splice."""
+
+    def __init__(self, max_ctx_length: int, num_layers: int, num_head: int, head_dim: int, target_device):
+        device = torch.device(target_device)
+        if device.type != "cuda":
+            raise nat.NativeError("promptcache_b200.PromptCache lives in B200 HBM; target_device must be CUDA "
+                                  "(there is no CPU path)")
+        self.max_ctx_length = max_ctx_length
+        self.num_layers = num_layers
+        self.num_head = num_head
+        self.head_dim = head_dim
+        # zero-initialised: rows past `length` are read (and masked) by whole-tile attention loads
+        self.buffer = torch.zeros(num_layers, 2, num_head, max_ctx_length, head_dim, dtype=torch.half, device=device)
+        self.staged: List[TokenSequenceCache] = []
+        self.length = 0
+        self.retain_prefix = True
+        self.last_spliced_rows = 0
+
+    @property
+    def device_cache(self) -> KVCache:
+        return [(self.buffer[l, 0], self.buffer[l, 1]) for l in range(self.num_layers)]
+
+    def invalidate(self) -> None:
+        """Forget the staged layout so the next update() moves every segment."""
+        self.staged = []
+        self.length = 0
+
+    @torch.inference_mode()
+    def update(self, modules: List[TokenSequenceCache]) -> None:
+        # most-used segments first (stable), as the reference lays them out (:121)
+        ordered = sorted(modules, key=lambda e: e.usage_counter, reverse=True)
+        kept = 0
+        if self.retain_prefix:
+            for cur, prev in zip(ordered, self.staged):
+                if cur is not prev:
+                    break
+                kept += 1
+        row = sum(len(m) for m in ordered[:kept])
+        plan = []
+        for m in ordered[kept:]:
+            plan.append((m.packed, row))
+            row += len(m)
+        if row > self.max_ctx_length:
+            raise ValueError(f"spliced prompt needs {row} rows but max_ctx_length is {self.max_ctx_length}")
+        nat.splice_kv(plan, self.buffer)
+        self.last_spliced_rows = sum(int(p.shape[3]) for p, _ in plan)
+        self.staged = ordered
+        self.length = row
+
+    def __len__(self) -> int:
+        return self.length
+
+    @property
+    def cache(self) -> KVCache:
+        n = self.length
+        return [(self.buffer[l, 0, :, :n, :], self.buffer[l, 1, :, :n, :]) for l in range(self.num_layers)]
+
+
+class SchemaCache:
+    """Encoded schema: id(TokenSequence) -> TokenSequenceCache."""
+
+    def __init__(self, schema: Schema, lm, batch_size: int = 1, target_device=None, no_cache: bool = False):
+        self.schema = schema
+        self.lm = lm
+        self.cache_l1: Dict[int, TokenSequenceCache] = {}
+        self.cache_l2: Dict[Tuple[int, int], Tuple[TokenSequenceCache, TokenSequenceCache]] = {}
+        self.target_device = lm.device if target_device is None else target_device
+        if not no_cache:
+            self._process(batch_size)
+
+    def scaffold_paths(self) -> List[Path]:
+        """Default scaffold + one path per non-default union member, in the reference's order (:188-210)."""
+        paths = [Path()]
+        pending = [([], True, self.schema)] if self.schema.contains_union() else []
+        while pending:
+            prefix, parent_default, node = pending.pop()
+            here = prefix + [node.name]
+            for child in node.children:
+                if type(child) is Module and child.contains_union():
+                    pending.append((here, parent_default, child))
+                elif type(child) is UnionModule:
+                    for member in child.modules:
+                        is_default = child.scaffold_name == member.name and parent_default
+                        if member.contains_union():
+                            pending.append((here, is_default, member))
+                        if not is_default:
+                            paths.append(Path(here + [member.name]).next)
+        return paths
+
+    @torch.inference_mode()
+    def _process(self, batch_size: int = 1) -> None:
+        # One forward per scaffold path.  `batch_size` is accepted for API compatibility; right-padded batching
+        # gives the same per-path KV, so paths are encoded one at a time and sliced on the device.
+        device = self.lm.device
+        for path in self.scaffold_paths():
+            scaffold = self.schema.get_scaffold(path)
+            token_ids = scaffold.token_ids()
+            position_ids = scaffold.position_ids()
+            if len(token_ids) == 0:
+                continue
+            extra = {"max_position": max(position_ids)} if getattr(self.lm.hf_model, "accepts_max_position", False) else {}
+            out = self.lm(input_ids=torch.tensor([token_ids], device=device, dtype=torch.long),
+                          position_ids=torch.tensor([position_ids], device=device, dtype=torch.long),
+                          attention_mask=torch.ones(1, len(token_ids), device=device, dtype=torch.float16),
+                          use_cache=True, **extra)
+            kv = out.past_key_values
+            target = scaffold.select(path)
+            for seq in target.all_token_sequences():
+                if len(seq) == 0:
+                    continue
+                st = position_ids.index(seq.offset)  # offsets and row order can differ (:275-279)
+                ed = st + len(seq)
+                ks = torch.stack([self.lm.store_k_hook(kv[l][0])[0, :, st:ed, :] for l in range(len(kv))])
+                vs = torch.stack([self.lm.store_v_hook(kv[l][1])[0, :, st:ed, :] for l in range(len(kv))])
+                packed = torch.stack([ks, vs], dim=1).to(device=self.target_device, dtype=torch.half).contiguous()
+                self.cache_l1[id(seq)] = TokenSequenceCache(seq, packed)
+            del out, kv
+        gc.collect()
+
+    def get_cache_l1(self, seq: TokenSequence) -> Optional[TokenSequenceCache]:
+        return self.cache_l1.get(id(seq))
+
+    def get_cache_l2(self, seq1: TokenSequence, seq2: TokenSequence):
+        key = (max(id(seq1), id(seq2)), min(id(seq1), id(seq2)))
+        return self.cache_l2.get(key)
+
+
+class CacheEngine:
+    def __init__(self, max_ctx_length: int, lm, target_device=None):
+        self.lm = lm
+        self.schemas: Dict[str, SchemaCache] = {}
+        self.target_device = lm.device if target_device is None else target_device
+        num_layers, num_head, head_dim = lm.get_cache_shape()
+        self.prompt_cache = PromptCache(max_ctx_length=max_ctx_length, num_layers=num_layers, num_head=num_head,
+                                        head_dim=head_dim, target_device=self.target_device)
+        if hasattr(lm.hf_model, "ensure_rope"):
+            lm.hf_model.ensure_rope(max_ctx_length)
+
+    def add_schema(self, schema: Union[str, Schema], batch_size: int = 1, max_tokens: Optional[int] = None,
+                   no_cache: bool = False) -> None:
+        if isinstance(schema, str):
+            schema = Schema(schema, self.lm, max_tokens=max_tokens)
+        if schema.name in self.schemas:
+            raise ValueError(f"There is already a schema named {schema.name} in the cache")
+        self.schemas[schema.name] = SchemaCache(schema, self.lm, batch_size, target_device=self.target_device,
+                                                no_cache=no_cache)
+
+    def get_schema(self, name: str) -> Optional[Schema]:
+        entry = self.schemas.get(name)
+        return None if entry is None else entry.schema
+
+    def remove_schema(self, name: str) -> None:
+        if name not in self.schemas:
+            raise ValueError(f"There is no such schema named {name} in the cache")
+        del self.schemas[name]
+        self.prompt_cache.invalidate()
+        gc.collect()
+        torch.cuda.empty_cache()
+
+    def remove_all_schemas(self) -> None:
+        self.schemas = {}
+        self.prompt_cache.invalidate()
+        gc.collect()
+        torch.cuda.empty_cache()
+
+    def plan(self, prompt: Prompt, collect_original: bool):
+        """Host-side request plan (reference :396-474): which cached sequences are used, in visit order, and
+        the uncached suffix (parameter arguments at their slots, then trailing text after the schema)."""
+        if prompt.schema not in self.schemas:
+            raise ValueError(f"There is no such layout named {prompt.schema} in the cache")
+        cached = self.schemas[prompt.schema]
+        schema = cached.schema
+        used: List[TokenSequence] = []
+        orig_ids: List[List[int]] = []
+        orig_pos: List[List[int]] = []
+        arg_ids: List[List[int]] = []
+        arg_pos: List[List[int]] = []
+        # explicit LIFO stack => sibling modules are visited in reverse document order (:411-455)
+        todo: List[Tuple[ModuleRef, Module]] = [(prompt, schema)]
+        while todo:
+            ref, module = todo.pop()
+            for seq in module.token_sequences():
+                used.append(seq)
+                if collect_original:
+                    orig_ids.append(seq.token_ids())
+                    orig_pos.append(seq.position_ids())
+            params = module.parameters()
+            for arg in ref.args:
+                param = next((p for p in params if p.name == arg.name), None)
+                if param is None:
+                    raise ValueError(f"There is no such parameter named {arg.name} in the module {module.name}")
+                ids = self.lm.encode(arg.value)
+                if len(ids) > param.length:
+                    raise ValueError(f"The argument {arg.name} is too long. It should be at most {param.length} "
+                                     f"characters long")
+                arg_ids.append(ids)
+                arg_pos.append(param.position_ids()[:len(ids)])
+            for sub in ref.modules:
+                target = module.select(sub.name)
+                if target is None:
+                    raise ValueError(f"There is no such module named @{sub.name} in the module @{module.name}")
+                todo.append((sub, target))
+        if len(prompt.text) > 0:
+            text_ids = self.lm.encode(prompt.text)
+            arg_ids.append(text_ids)
+            arg_pos.append(list(range(len(schema), len(schema) + len(text_ids))))
+        input_ids = list(itertools.chain(*arg_ids))
+        position_ids = list(itertools.chain(*arg_pos))
+        return cached, used, orig_ids, orig_pos, input_ids, position_ids
+
+    def process(self, prompt: Prompt, no_cache: bool = False, return_full_position_ids: bool = False) -> Tuple[
+            List[int], List[int], float, Optional[KVCache]]:
+        start = torch.cuda.Event(enable_timing=True)
+        end = torch.cuda.Event(enable_timing=True)
+        start.record()
+        cached, used, orig_ids, orig_pos, input_ids, position_ids = self.plan(
+            prompt, collect_original=no_cache or return_full_position_ids)
+
+        if no_cache:
+            all_pos = list(itertools.chain(*orig_pos)) + position_ids
+            all_ids = list(itertools.chain(*orig_ids)) + input_ids
+            pairs = sorted(zip(all_pos, all_ids))
+            sorted_ids = tuple(tok for _, tok in pairs)
+            end.record()
+            torch.cuda.synchronize()
+            # positions are renumbered 0..n-1 (reference :491-493)
+            return sorted_ids, list(range(len(pairs))), start.elapsed_time(end), None
+
+        seq_caches: List[TokenSequenceCache] = []
+        for seq in used:
+            entry = cached.get_cache_l1(seq)
+            if entry is None:
+                if len(seq) == 0:
+                    continue
+                raise ValueError(f"token sequence at offset {seq.offset} of schema {prompt.schema} is not cached")
+            entry.inc_usage_counter()
+            seq_caches.append(entry)
+        self.prompt_cache.update(seq_caches)
+        cache = self.prompt_cache.cache
+        end.record()
+        torch.cuda.synchronize()
+        cache_time = start.elapsed_time(end)
+        cache = [(self.lm.read_k_hook(k), self.lm.read_v_hook(v)) for k, v in cache]
+        if return_full_position_ids:
+            # ids of the cached rows IN BUFFER ORDER (equal to the reference's visit order, :517-519, whenever
+            # the usage counters do not reorder the layout; the reference is wrong when they do)
+            laid_out = [m.token_sequence.position_ids() for m in self.prompt_cache.staged]
+            position_ids = list(itertools.chain(*laid_out)) + position_ids
+        return input_ids, position_ids, cache_time, cache

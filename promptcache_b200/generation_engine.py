@@ -1,0 +1,146 @@
+"""Prefill + decode loop with the reference's interface (promptcache/generation_engine.py:21-209).
+
+`GenerationEngine(lm).generate(token_ids, position_ids, params, cache, stream_interval,
+use_full_position_ids)` yields `Output`s exactly like the reference, including its quirks:
+  * decode positions start at max(position_ids)+1+i with i >= 1, i.e. one position is skipped (:82,132);
+  * `Output` is built positionally as (output, new_output, inference_time, response_time), so
+    `.response_time` is the cumulative model time and `.elapsed_time` the prefill time (:53-58,201).
+What changes is underneath: the KV is appended in place (no torch.cat per step) and every forward runs
+pc_rope_append + pc_prefill_attn / pc_decode_attn.
+"""
+from __future__ import annotations
+
+import gc
+from dataclasses import dataclass, field
+from typing import Generator, List, Optional
+
+import torch
+
+from .cache_engine import KVCache
+
+
+@dataclass
+class GenerationParameters:
+    temperature: float = 1.0
+    repetition_penalty: float = 1.0
+    top_p: float = 1.0
+    top_k: int = -1
+    max_new_tokens: int = 256
+    stop_token_ids: List[int] = field(default_factory=lambda: [])
+    stop_str: List[str] = field(default_factory=lambda: [])
+    echo: bool = True
+
+    def get_logits_processor(self):
+        from transformers.generation.logits_process import (LogitsProcessorList, RepetitionPenaltyLogitsProcessor,
+                                                            TemperatureLogitsWarper, TopKLogitsWarper,
+                                                            TopPLogitsWarper)
+        procs = LogitsProcessorList()
+        if self.temperature >= 1e-5 and self.temperature != 1.0:
+            procs.append(TemperatureLogitsWarper(self.temperature))
+        if self.repetition_penalty > 1.0:
+            procs.append(RepetitionPenaltyLogitsProcessor(self.repetition_penalty))
+        if 1e-8 <= self.top_p < 1.0:
+            procs.append(TopPLogitsWarper(self.top_p))
+        if self.top_k > 0:
+            procs.append(TopKLogitsWarper(self.top_k))
+        return procs
+
+
+def is_partial_stop(output: str, stop_str: str) -> bool:
+    """True when the tail of `output` could still grow into `stop_str` (generation_engine.py:45-50)."""
+    for i in range(0, min(len(output), len(stop_str))):
+        if stop_str.startswith(output[-i:]):
+            return True
+    return False
+
+
+@dataclass
+class Output:
+    text: str
+    new_text: str
+    response_time: float = 0.0
+    elapsed_time: float = 0.0
+
+
+class GenerationEngine:
+    def __init__(self, lm):
+        self.lm = lm
+        self.verbose = False
+
+    def _forward(self, ids: List[List[int]], pos: List[List[int]], past, device):
+        extra = {"max_position": max(pos[0])} if getattr(self.lm.hf_model, "accepts_max_position", False) else {}
+        input_ids = torch.tensor(ids, device=device, dtype=torch.long)
+        position_ids = torch.tensor(pos, device=device, dtype=torch.long)
+        start = torch.cuda.Event(enable_timing=True)
+        end = torch.cuda.Event(enable_timing=True)
+        start.record()
+        out = self.lm(input_ids=input_ids, position_ids=position_ids, past_key_values=past, use_cache=True, **extra)
+        end.record()
+        torch.cuda.synchronize()
+        return out, start.elapsed_time(end)
+
+    @torch.inference_mode()
+    def generate(self, token_ids: List[int], position_ids: List[int], params: GenerationParameters,
+                 cache: Optional[KVCache] = None, stream_interval: int = 2,
+                 use_full_position_ids: bool = False) -> Generator[Output, None, None]:
+        logits_processor = params.get_logits_processor()
+        output_ids = list(token_ids)
+        new_output_ids: List[int] = []
+        device = self.lm.device
+        position_offset = max(position_ids) + 1
+        position_ids_og = list(position_ids)
+        past_key_values = None
+        new_token_id = 0
+        inference_time = 0.0
+        response_time = 0.0
+
+        for i in range(params.max_new_tokens):
+            if past_key_values is None:  # prefill of the uncached suffix over the spliced cache
+                if cache is not None:
+                    cache = [(k.unsqueeze(0), v.unsqueeze(0)) for k, v in cache]
+                out, ms = self._forward([list(token_ids)], [position_ids_og], cache, device)
+                inference_time += ms
+                response_time = inference_time
+                if self.verbose:
+                    print(f"Prefill latency: {inference_time:.2f} ms")
+            else:  # one-token decode
+                if use_full_position_ids:
+                    pos = position_ids_og + list(range(position_offset, position_offset + i))
+                else:
+                    pos = [position_offset + i]
+                out, ms = self._forward([[new_token_id]], [pos], past_key_values, device)
+                inference_time += ms
+            logits = out.logits
+            past_key_values = out.past_key_values
+
+            tmp_output_ids = torch.as_tensor([output_ids], device=device) if params.repetition_penalty > 1.0 else None
+            last_token_logits = logits_processor(tmp_output_ids, logits[:, -1, :])[0]
+            if params.temperature < 1e-5 or params.top_p < 1e-8:  # greedy
+                new_token_id = int(torch.argmax(last_token_logits))
+            else:
+                probs = torch.softmax(last_token_logits, dim=-1)
+                new_token_id = int(torch.multinomial(probs, num_samples=1))
+            output_ids.append(new_token_id)
+            new_output_ids.append(new_token_id)
+
+            stopped = new_token_id in params.stop_token_ids
+            if i % stream_interval == 0 or i == params.max_new_tokens - 1 or stopped:
+                output = self.lm.decode(output_ids)
+                new_output = self.lm.decode(new_output_ids)
+                partially_stopped = False
+                for each_stop in params.stop_str:
+                    pos_found = new_output.rfind(each_stop, 0)
+                    if pos_found != -1:
+                        new_output = new_output[:pos_found]
+                        stopped = True
+                        break
+                    partially_stopped = is_partial_stop(output, each_stop)
+                    if partially_stopped:
+                        break
+                if not partially_stopped:
+                    yield Output(output, new_output, inference_time, response_time)
+            if stopped:
+                break
+
+        del past_key_values
+        gc.collect()

@@ -1,0 +1,225 @@
+"""GPU parity of the three kernels (through the C ABI) against the oracle on the same seeded inputs."""
+import math
+
+import pytest
+import torch
+
+from oracle import pc_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-12))
+
+
+# ------------------------------------------------------------------ splice
+def _make_segments(L, Hkv, D, lens, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return [torch.randn(L, 2, Hkv, n, D, generator=g).half().to(DEV) for n in lens]
+
+
+@pytest.mark.parametrize("L,Hkv,D,lens,max_ctx", [
+    (2, 4, 64, [3, 1, 4, 2], 16),                 # tiny, ragged (golden-sized)
+    (3, 1, 64, [5, 130, 1], 200),                 # Falcon MQA rows of 128 B, > 1 tile
+    (4, 8, 128, [24, 400, 400, 7, 129], 1100),    # partial tiles
+    (32, 32, 128, [24, 400, 400, 400, 400, 400, 24], 2304),  # C2 full size
+])
+def test_splice_bit_exact(native, L, Hkv, D, lens, max_ctx):
+    segs = _make_segments(L, Hkv, D, lens, seed=2000 + L)
+    cache = torch.zeros(L, 2, Hkv, max_ctx, D, dtype=torch.half, device=DEV)
+    rows, plan = 0, []
+    for s in segs:
+        plan.append((s, rows))
+        rows += s.shape[3]
+    native.splice_kv(plan, cache)
+    torch.cuda.synchronize()
+    ref, n = O.splice([[(s[l, 0], s[l, 1]) for l in range(L)] for s in segs], [0] * len(segs), max_ctx)
+    assert n == rows
+    for l in range(L):
+        assert torch.equal(cache[l, 0, :, :n], ref[l][0])
+        assert torch.equal(cache[l, 1, :, :n], ref[l][1])
+    assert int(cache[:, :, :, n:].abs().max()) == 0  # nothing written past the spliced rows
+
+
+def test_splice_usage_order_and_offsets(native):
+    L, Hkv, D = 2, 2, 64
+    segs = _make_segments(L, Hkv, D, [4, 2, 3], seed=7)
+    usage = [1, 5, 1]
+    order = O.splice_order(usage)
+    assert order == [1, 0, 2]
+    cache = torch.zeros(L, 2, Hkv, 32, D, dtype=torch.half, device=DEV)
+    rows, plan = 0, []
+    for i in order:
+        plan.append((segs[i], rows))
+        rows += segs[i].shape[3]
+    native.splice_kv(plan, cache)
+    ref, n = O.splice([[(s[l, 0], s[l, 1]) for l in range(L)] for s in segs], usage, 32)
+    for l in range(L):
+        assert torch.equal(cache[l, 0, :, :n], ref[l][0]) and torch.equal(cache[l, 1, :, :n], ref[l][1])
+
+
+def test_splice_reference_layout(native):
+    """pc_splice_kv_tensors: one descriptor per `tgt[:, st:ed, :].copy_(src)` of the reference."""
+    L, Hkv, D, max_ctx = 3, 4, 128, 300
+    g = torch.Generator(device="cpu").manual_seed(11)
+    lens = [17, 130, 64]
+    segs = [[(torch.randn(Hkv, n, D, generator=g).half().to(DEV), torch.randn(Hkv, n, D, generator=g).half().to(DEV))
+             for _ in range(L)] for n in lens]
+    tgt = [(torch.zeros(Hkv, max_ctx, D, dtype=torch.half, device=DEV), torch.zeros(Hkv, max_ctx, D, dtype=torch.half, device=DEV))
+           for _ in range(L)]
+    copies, st = [], 0
+    for m, n in enumerate(lens):
+        for l in range(L):
+            copies.append((segs[m][l][0], tgt[l][0][:, st:st + n, :]))
+            copies.append((segs[m][l][1], tgt[l][1][:, st:st + n, :]))
+        st += n
+    native.splice_kv_tensors(copies)
+    torch.cuda.synchronize()
+    ref, n = O.splice(segs, [0, 0, 0], max_ctx)
+    for l in range(L):
+        assert torch.equal(tgt[l][0][:, :n], ref[l][0]) and torch.equal(tgt[l][1][:, :n], ref[l][1])
+
+
+def test_splice_empty_and_errors(native):
+    cache = torch.zeros(1, 2, 1, 8, 64, dtype=torch.half, device=DEV)
+    native.splice_kv([], cache)  # no-op
+    seg = torch.zeros(1, 2, 1, 9, 64, dtype=torch.half, device=DEV)
+    with pytest.raises(native.NativeError):
+        native.splice_kv([(seg, 0)], cache)  # does not fit
+
+
+# ------------------------------------------------------------------ rope + append
+@pytest.mark.parametrize("H,Hkv,D,q,N,max_ctx", [(4, 4, 64, 5, 10, 32), (32, 32, 128, 16, 2048, 2304),
+                                                  (71, 1, 64, 21, 256, 512), (8, 2, 128, 1, 77, 128)])
+def test_rope_append_bit_exact(native, H, Hkv, D, q, N, max_ctx):
+    g = torch.Generator(device="cpu").manual_seed(100 + H)
+    qkv = (torch.randn(q, (H + 2 * Hkv) * D, generator=g) * 1.3).half().to(DEV)
+    # discontiguous, non-monotone ids (parameter slots + trailing text)
+    pos = torch.randperm(4000, generator=g)[:q].to(DEV)
+    cos, sin = O.rope_tables(D, 4096, 10000.0, DEV, torch.float16)
+    cos, sin = cos.contiguous(), sin.contiguous()
+    kc = torch.zeros(Hkv, max_ctx, D, dtype=torch.half, device=DEV)
+    vc = torch.zeros(Hkv, max_ctx, D, dtype=torch.half, device=DEV)
+    q_out = torch.empty(H, q, D, dtype=torch.half, device=DEV)
+    native.rope_append(qkv[:, :H * D], qkv[:, H * D:(H + Hkv) * D], qkv[:, (H + Hkv) * D:], pos, cos, sin, q_out,
+                       kc, vc, N, H, Hkv, D)
+    torch.cuda.synchronize()
+    qs = qkv[:, :H * D].view(1, q, H, D).transpose(1, 2)
+    ks = qkv[:, H * D:(H + Hkv) * D].view(1, q, Hkv, D).transpose(1, 2)
+    vs = qkv[:, (H + Hkv) * D:].view(1, q, Hkv, D).transpose(1, 2)
+    q_ref, k_ref = O.apply_rotary_pos_emb(qs, ks, cos, sin, pos.view(1, q))
+    assert torch.equal(q_out, q_ref[0])
+    assert torch.equal(kc[:, N:N + q], k_ref[0])
+    assert torch.equal(vc[:, N:N + q], vs[0])
+    assert int(kc[:, :N].abs().max()) == 0 and int(kc[:, N + q:].abs().max()) == 0
+
+
+def test_rope_append_no_rotary(native):
+    H = Hkv = 4
+    D, q, N = 64, 3, 2
+    qkv = torch.randn(q, 3 * H * D, device=DEV).half()
+    kc = torch.zeros(Hkv, 16, D, dtype=torch.half, device=DEV)
+    vc = torch.zeros_like(kc)
+    q_out = torch.empty(H, q, D, dtype=torch.half, device=DEV)
+    native.rope_append(qkv[:, :H * D], qkv[:, H * D:2 * H * D], qkv[:, 2 * H * D:], None, None, None, q_out, kc, vc, N,
+                       H, Hkv, D)
+    assert torch.equal(q_out, qkv[:, :H * D].view(q, H, D).transpose(0, 1))
+    assert torch.equal(kc[:, N:N + q], qkv[:, H * D:2 * H * D].view(q, H, D).transpose(0, 1))
+
+
+# ------------------------------------------------------------------ attention
+def _attn_case(H, Hkv, D, q, N, seed, std=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    max_ctx = ((N + q + 127) // 128) * 128 + 64
+    Q = (torch.randn(H, q, D, generator=g) * std).half().to(DEV)
+    K = torch.zeros(Hkv, max_ctx, D, dtype=torch.half, device=DEV)
+    V = torch.zeros(Hkv, max_ctx, D, dtype=torch.half, device=DEV)
+    K[:, :N + q] = (torch.randn(Hkv, N + q, D, generator=g) * std).half().to(DEV)
+    V[:, :N + q] = torch.randn(Hkv, N + q, D, generator=g).half().to(DEV)
+    return Q, K, V
+
+
+def _oracle_llama(Q, K, V, N, q):
+    """Reference eager attention (llama2.py:368-398) on already-rotated Q / K."""
+    H, _, D = Q.shape
+    k = K[:, :N + q].unsqueeze(0)
+    v = V[:, :N + q].unsqueeze(0)
+    n_rep = H // k.shape[1]
+    kr, vr = O.repeat_kv(k, n_rep), O.repeat_kv(v, n_rep)
+    attn = torch.matmul(Q.unsqueeze(0), kr.transpose(2, 3)) / math.sqrt(D)
+    attn = attn + O.llama_causal_mask(q, N, Q.dtype, Q.device)
+    attn = torch.softmax(attn, dim=-1, dtype=torch.float32).to(Q.dtype)
+    out = torch.matmul(attn, vr)
+    return out.transpose(1, 2).reshape(q, H * D)
+
+
+def _oracle_fp32(Q, K, V, N, q):
+    H, _, D = Q.shape
+    k = O.repeat_kv(K[:, :N + q].unsqueeze(0).float(), H // K.shape[0])
+    v = O.repeat_kv(V[:, :N + q].unsqueeze(0).float(), H // K.shape[0])
+    s = torch.matmul(Q.unsqueeze(0).float(), k.transpose(2, 3)) / math.sqrt(D)
+    s = s.masked_fill(O.bool_causal_mask(q, N, Q.device), float("-inf"))
+    out = torch.matmul(torch.softmax(s, -1), v)
+    return out.transpose(1, 2).reshape(q, H * D)
+
+
+CASES = [
+    (4, 4, 64, 5, 10),        # golden-sized
+    (4, 4, 128, 16, 300),     # 3 tiles, suffix crosses a tile boundary
+    (32, 32, 128, 16, 2048),  # C2
+    (8, 8, 128, 1, 1000),     # decode
+    (8, 8, 128, 200, 0),      # no-cache prefill, 2 row blocks, causal only
+    (71, 1, 64, 21, 256),     # Falcon MQA fold (71*21 rows)
+    (8, 2, 128, 40, 500),     # GQA fold
+]
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("H,Hkv,D,q,N", CASES)
+def test_attention_llama_rounding(native, impl, H, Hkv, D, q, N):
+    Q, K, V = _attn_case(H, Hkv, D, q, N, seed=H * 1000 + q, std=1.28)
+    out = torch.empty(q, H * D, dtype=torch.half, device=DEV)
+    ws_bytes = native.attn_workspace_bytes(H, q, D)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=DEV)
+    native.attention(Q, K, V, out, N, q, H, Hkv, D, native.softmax_scale(D), native.PC_ROUND_LLAMA, workspace=ws,
+                     impl=native.PC_ATTN_SIMT if impl == "simt" else native.PC_ATTN_TCGEN05, decode=(q == 1))
+    torch.cuda.synchronize()
+    ref = _oracle_llama(Q, K, V, N, q)
+    # north_star tolerance: 1e-3 fp16-relative against the reference's own (rounding) attention path
+    assert _rel(out, ref) <= 1e-3, _rel(out, ref)
+    assert torch.allclose(out.float(), ref.float(), rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("H,Hkv,D,q,N", CASES)
+def test_attention_exact_mode(native, impl, H, Hkv, D, q, N):
+    Q, K, V = _attn_case(H, Hkv, D, q, N, seed=H * 77 + q)
+    out = torch.empty(q, H * D, dtype=torch.half, device=DEV)
+    ws = torch.empty(max(native.attn_workspace_bytes(H, q, D), 1), dtype=torch.uint8, device=DEV)
+    native.attention(Q, K, V, out, N, q, H, Hkv, D, 1.0 / math.sqrt(D), 0, workspace=ws,
+                     impl=native.PC_ATTN_SIMT if impl == "simt" else native.PC_ATTN_TCGEN05, decode=(q == 1))
+    torch.cuda.synchronize()
+    ref = _oracle_fp32(Q, K, V, N, q)
+    assert _rel(out, ref) <= 2e-3, _rel(out, ref)  # fp16 P and fp16 output rounding only
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_attention_alibi(native, impl):
+    H = Hkv = 8
+    D, q, N = 128, 9, 300
+    Q, K, V = _attn_case(H, Hkv, D, q, N, seed=5)
+    g = torch.Generator(device="cpu").manual_seed(6)
+    key_pos = torch.cat([torch.randperm(400, generator=g)[:N], torch.arange(400, 400 + q)]).to(torch.int32).to(DEV)
+    slopes = O.mpt_alibi_slopes(H, 8, DEV)
+    scale = 1.0 / math.sqrt(D)
+    out = torch.empty(q, H * D, dtype=torch.half, device=DEV)
+    ws = torch.empty(max(native.attn_workspace_bytes(H, q, D), 1), dtype=torch.uint8, device=DEV)
+    native.attention(Q, K, V, out, N, q, H, Hkv, D, scale, native.PC_ROUND_MPT, workspace=ws, alibi_slopes=slopes,
+                     key_pos=key_pos, alibi_max_pos=int(key_pos.max()),
+                     impl=native.PC_ATTN_SIMT if impl == "simt" else native.PC_ATTN_TCGEN05)
+    torch.cuda.synchronize()
+    ctx, _, _ = O.mpt_attention_core(Q.unsqueeze(0), K[:, N:N + q].unsqueeze(0), V[:, N:N + q].unsqueeze(0),
+                                     K[:, :N].unsqueeze(0), V[:, :N].unsqueeze(0), key_pos.long().view(1, -1), scale)
+    assert _rel(out, ctx[0]) <= 1e-3, _rel(out, ctx[0])

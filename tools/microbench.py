@@ -1,0 +1,102 @@
+"""Kernel micro-benchmarks (CUDA events, inputs larger than L2).  Usage: python tools/microbench.py [splice|attn|all]"""
+import json
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from promptcache_b200 import _native as nat  # noqa: E402
+
+DEV = "cuda"
+PEAK = 6538.3
+try:
+    PEAK = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+
+
+def timeit(fn, iters=20, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def bench_splice():
+    for name, L, Hkv, D, lens in [("C2", 32, 32, 128, [24] + [400] * 5 + [24]), ("C5", 32, 32, 128, [256] * 32),
+                                  ("C3", 40, 40, 128, [512] * 8), ("C4-falcon", 32, 1, 64, [40, 60, 70, 50, 36])]:
+        segs = [torch.randn(L, 2, Hkv, n, D, device=DEV).half() for n in lens]
+        N = sum(lens)
+        cache = torch.zeros(L, 2, Hkv, N + 256, D, dtype=torch.half, device=DEV)
+        plan, r = [], 0
+        for s in segs:
+            plan.append((s, r))
+            r += s.shape[3]
+        ms = timeit(lambda: nat.splice_kv(plan, cache))
+        byts = 2 * sum(s.numel() * 2 for s in segs)
+        # torch baseline: the reference's copy loop on device-resident segments
+        def ref():
+            r0 = 0
+            for s in segs:
+                n = s.shape[3]
+                for l in range(L):
+                    cache[l, 0, :, r0:r0 + n].copy_(s[l, 0])
+                    cache[l, 1, :, r0:r0 + n].copy_(s[l, 1])
+                r0 += n
+        ms_ref = timeit(ref, iters=5, warmup=1)
+        big = torch.empty(byts // 4, dtype=torch.half, device=DEV)
+        big2 = torch.empty_like(big)
+        ms_cp = timeit(lambda: big2.copy_(big))
+        print(f"splice {name}: N={N} {byts/2**30:.2f} GiB r+w  kernel {ms:.3f} ms = {byts/ms/1e6:.0f} GB/s "
+              f"({byts/ms/1e6/PEAK:.2f} of measured {PEAK:.0f})  torch-loop {ms_ref:.3f} ms  torch.copy_ same bytes {ms_cp:.3f} ms",
+              flush=True)
+        del segs, cache, big, big2
+
+
+def bench_attn():
+    for name, H, Hkv, D, q, N in [("C2 q16", 32, 32, 128, 16, 2048), ("C2 q64", 32, 32, 128, 64, 2048),
+                                  ("C2 q256", 32, 32, 128, 256, 2048), ("C2 q1024", 32, 32, 128, 1024, 2048),
+                                  ("full prefill 2K", 32, 32, 128, 2048, 0), ("decode N=2064", 32, 32, 128, 1, 2064),
+                                  ("C5 q32", 32, 32, 128, 32, 8192), ("falcon C4", 71, 1, 64, 21, 256),
+                                  ("falcon q256 N2K", 71, 1, 64, 256, 2048)]:
+        L = 8  # rotate over several layers' KV so the stream does not sit in L2
+        max_ctx = ((N + q + 127) // 128) * 128
+        K = (torch.randn(L, Hkv, max_ctx, D, device=DEV)).half()
+        V = torch.randn(L, Hkv, max_ctx, D, device=DEV).half()
+        Q = torch.randn(H, q, D, device=DEV).half()
+        out = torch.empty(q, H * D, dtype=torch.half, device=DEV)
+        ws = torch.empty(max(nat.attn_workspace_bytes(H, q, D), 1), dtype=torch.uint8, device=DEV)
+        state = {"i": 0}
+        for impl, nm in [(nat.PC_ATTN_TCGEN05, "tcgen05"), (nat.PC_ATTN_SIMT, "simt")]:
+            if impl == nat.PC_ATTN_SIMT and q > 64:
+                continue
+            def run():
+                l = state["i"] % L
+                state["i"] += 1
+                nat.attention(Q, K[l], V[l], out, N, q, H, Hkv, D, nat.softmax_scale(D), nat.PC_ROUND_LLAMA, workspace=ws,
+                              impl=impl, decode=(q == 1))
+            ms = timeit(run, iters=16, warmup=3)
+            G = H // Hkv
+            # causal-aware flop count: key j>=N visible to rows r>=j-N
+            vis = q * N + q * (q + 1) // 2
+            flops = 4.0 * H * vis * D
+            byts = 4.0 * Hkv * (N + q) * D + 4.0 * H * q * D
+            print(f"attn {name} [{nm}]: {ms*1e3:.1f} us  {flops/ms/1e9:.1f} TFLOP/s  {byts/ms/1e6:.0f} GB/s "
+                  f"({byts/ms/1e6/PEAK:.2f} of HBM peak)", flush=True)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    print("device:", torch.cuda.get_device_name(0), flush=True)
+    if what in ("splice", "all"):
+        bench_splice()
+    if what in ("attn", "all"):
+        bench_attn()
