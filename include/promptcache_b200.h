@@ -138,7 +138,9 @@ typedef struct pc_attn_params {
   const int32_t* key_pos;    /* [n_cached+q_len] or NULL (required with alibi_slopes)        */
   int32_t alibi_max_pos;     /* max(position_ids) (mpt.py:522)                               */
   int32_t impl;              /* PC_ATTN_*                                                    */
-  void* workspace;           /* split-KV partials, >= pc_attn_workspace_bytes(...) or NULL   */
+  void* workspace;           /* split-KV scratch, >= pc_attn_workspace_bytes(...) or NULL;   *
+                              * ZERO it once before first use (arrival counters; kernels     *
+                              * leave them zeroed); one workspace per concurrent stream      */
   size_t workspace_bytes;
 } pc_attn_params;
 
@@ -146,6 +148,16 @@ size_t pc_attn_workspace_bytes(int n_heads, int q_len, int head_dim);
 int pc_prefill_attn(const pc_attn_params* p, void* stream);
 /* Same contract with q_len == 1 (generation_engine.py:123-147 -> llama2.py:353-398). */
 int pc_decode_attn(const pc_attn_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Support kernels (not part of the parity scope; they replace ~25 eager
+ * launches per layer so that the TTFT step is not launch-bound).  fp16 tensors, rounding as the reference:
+ *   pc_add_rmsnorm: x[rows][hidden] += delta (fp16 add, written back; delta may be NULL), then
+ *                   h_out = weight * half(x_f32 * rsqrt(mean(x_f32^2) + eps))   (llama2.py:104-109,636,644)
+ *   pc_silu_mul   : out[r][i] = half(silu_f32(gate_up[r][i])) * gate_up[r][inter+i]   (llama2.py:241) */
+int pc_add_rmsnorm(void* x, const void* delta, const void* weight, void* h_out, int rows, int hidden,
+                   float eps, void* stream);
+int pc_silu_mul(const void* gate_up, void* out, int rows, int inter, int64_t row_stride, void* stream);
 
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 int64_t pc_launch_count(void);

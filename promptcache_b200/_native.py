@@ -26,7 +26,8 @@ PC_ATTN_SIMT = 1
 PC_ATTN_TCGEN05 = 2
 
 EXPORTS = ("pc_version", "pc_last_error", "pc_device_info", "pc_splice_kv", "pc_splice_kv_tensors",
-           "pc_rope_append", "pc_attn_workspace_bytes", "pc_prefill_attn", "pc_decode_attn", "pc_launch_count")
+           "pc_rope_append", "pc_attn_workspace_bytes", "pc_prefill_attn", "pc_decode_attn", "pc_launch_count",
+           "pc_add_rmsnorm", "pc_silu_mul")
 
 
 class NativeError(RuntimeError):
@@ -87,6 +88,10 @@ def load() -> C.CDLL:
     lib.pc_decode_attn.argtypes = [C.POINTER(pc_attn_params), C.c_void_p]
     lib.pc_decode_attn.restype = C.c_int
     lib.pc_launch_count.restype = C.c_int64
+    lib.pc_add_rmsnorm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]
+    lib.pc_add_rmsnorm.restype = C.c_int
+    lib.pc_silu_mul.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]
+    lib.pc_silu_mul.restype = C.c_int
     _lib = lib
     return lib
 
@@ -224,3 +229,23 @@ def attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, out
         p.workspace, p.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
     fn = lib.pc_decode_attn if decode else lib.pc_prefill_attn
     _check(fn(C.byref(p), _stream()), "pc_decode_attn" if decode else "pc_prefill_attn")
+
+
+def add_rmsnorm(x: torch.Tensor, delta: Optional[torch.Tensor], weight: torch.Tensor, h_out: torch.Tensor,
+                eps: float) -> None:
+    """x[rows,hidden] += delta (in place, fp16), h_out = RMSNorm(x) * weight."""
+    _require_cuda(x, weight, h_out)
+    if not (x.is_contiguous() and h_out.is_contiguous() and (delta is None or delta.is_contiguous())) or x.dtype != torch.float16:
+        raise NativeError("add_rmsnorm: tensors must be contiguous fp16")
+    rows, hidden = x.shape
+    _check(load().pc_add_rmsnorm(x.data_ptr(), delta.data_ptr() if delta is not None else None, weight.data_ptr(),
+                                 h_out.data_ptr(), rows, hidden, float(eps), _stream()), "pc_add_rmsnorm")
+
+
+def silu_mul(gate_up: torch.Tensor, out: torch.Tensor, inter: int) -> None:
+    """out[rows,inter] = silu(gate_up[:, :inter]) * gate_up[:, inter:]."""
+    _require_cuda(gate_up, out)
+    if gate_up.stride(1) != 1 or not out.is_contiguous() or gate_up.dtype != torch.float16:
+        raise NativeError("silu_mul: tensors must be fp16 with contiguous rows")
+    _check(load().pc_silu_mul(gate_up.data_ptr(), out.data_ptr(), gate_up.shape[0], inter, gate_up.stride(0), _stream()),
+           "pc_silu_mul")

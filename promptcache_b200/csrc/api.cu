@@ -38,6 +38,9 @@ int sm_count() {
 int launch_attn_simt(const pc_attn_params& p, cudaStream_t st);
 int launch_attn_tc(const pc_attn_params& p, cudaStream_t st);
 size_t attn_tc_workspace_bytes(int n_heads, int q_len, int head_dim);
+int launch_attn_small(const pc_attn_params& p, cudaStream_t st);
+bool attn_small_supported(const pc_attn_params& p);
+size_t attn_small_partial_bytes(int n_heads, int q_len, int head_dim);
 
 static int check_sm100() {
   static int ok = -1;
@@ -74,7 +77,11 @@ static int attn_dispatch(const pc_attn_params* p, void* stream, const char* who)
     else impl = PC_ATTN_TCGEN05;
   }
   if (impl == PC_ATTN_SIMT) return launch_attn_simt(*p, st);
-  if (impl == PC_ATTN_TCGEN05) return launch_attn_tc(*p, st);
+  if (impl == PC_ATTN_TCGEN05) {
+    const char* e = getenv("PC_ATTN_SMALL");
+    if (attn_small_supported(*p) && !(e && e[0] == '0')) return launch_attn_small(*p, st);
+    return launch_attn_tc(*p, st);
+  }
   return set_error(PC_ERR_INVALID, "%s: unknown impl %d", who, p->impl);
 }
 
@@ -105,7 +112,9 @@ PC_API int pc_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 
 PC_API size_t pc_attn_workspace_bytes(int n_heads, int q_len, int head_dim) {
   if (n_heads <= 0 || q_len <= 0 || head_dim <= 0) return 0;
-  return pc::attn_tc_workspace_bytes(n_heads, q_len, head_dim);
+  const size_t a = pc::attn_tc_workspace_bytes(n_heads, q_len, head_dim);
+  const size_t b = pc::attn_small_partial_bytes(n_heads, q_len, head_dim);
+  return pc::kAttnCounterBytes + (a > b ? a : b);
 }
 
 PC_API int pc_prefill_attn(const pc_attn_params* p, void* stream) {

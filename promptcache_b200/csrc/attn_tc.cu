@@ -377,19 +377,29 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 3-D fp16 tensor [heads][rows][D] (row stride D, head stride head_stride elements), box 64 x 128 x 1.
-int make_map(CUtensorMap* map, const void* base, int D, long long rows, int heads, long long head_stride) {
+}  // namespace
+
+// 3-D fp16 tensor [heads][rows][D] (row stride D, head stride head_stride elements), box 64 x box_rows x 1,
+// 128B swizzle, out-of-bounds rows read as zeros.
+int make_tensor_map_3d(CUtensorMap* map, const void* base, int D, long long rows, int heads, long long head_stride,
+                       int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(PC_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(heads)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(D) * 2, static_cast<cuuint64_t>(head_stride) * 2};
-  cuuint32_t box[3] = {64, BN, 1};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) return set_error(PC_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", static_cast<int>(rc));
   return PC_OK;
+}
+
+namespace {
+
+int make_map(CUtensorMap* map, const void* base, int D, long long rows, int heads, long long head_stride) {
+  return make_tensor_map_3d(map, base, D, rows, heads, head_stride, BN);
 }
 
 template <int D, int ROUND, bool ALIBI>
@@ -424,14 +434,15 @@ int launch_d(const pc_attn_params& p, cudaStream_t st) {
   float* part_ml = nullptr;
   if (n_splits > 1) {
     const size_t need = static_cast<size_t>(n_splits) * p.n_heads * p.q_len * (D + 2) * sizeof(float);
-    if (p.workspace == nullptr || p.workspace_bytes < need) {
+    const size_t avail = (p.workspace && p.workspace_bytes > kAttnCounterBytes) ? p.workspace_bytes - kAttnCounterBytes : 0;
+    if (avail < need) {
       // degrade to as many splits as the caller's workspace allows
       const size_t per = static_cast<size_t>(p.n_heads) * p.q_len * (D + 2) * sizeof(float);
-      n_splits = p.workspace ? static_cast<int>(p.workspace_bytes / per) : 1;
+      n_splits = static_cast<int>(avail / per);
       if (n_splits < 1) n_splits = 1;
     }
     if (n_splits > 1) {
-      part_o = static_cast<float*>(p.workspace);
+      part_o = reinterpret_cast<float*>(static_cast<char*>(p.workspace) + kAttnCounterBytes);
       part_ml = part_o + static_cast<size_t>(n_splits) * p.n_heads * p.q_len * D;
     }
   }

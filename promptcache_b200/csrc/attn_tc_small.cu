@@ -1,0 +1,455 @@
+// tcgen05 attention for SHORT suffixes (G*q <= 32 folded query rows per KV head): prefill of a few
+// uncached tokens over a long spliced cache, and single-token decode.  Same contract as attn_tc.cu.
+//
+// With 16 query rows a 128-row MMA tile would leave 112 TMEM lanes (and 3.5 of 4 softmax warps) idle and
+// the per-tile softmax would serialise on half a warp.  This kernel swaps the operands instead:
+//   S^T_j = K_j . Q^T      SS-MMA 128 keys x NPAD queries x D : TMEM lane = key, column = query row
+//   P^T_j                  one key per thread, NPAD scores each; the per-query max / sum over the 128 keys
+//                          of a tile is a warp butterfly + a 4-way exchange through shared memory
+//   O^T  += V_j^T . P^T_j  SS-MMA D x NPAD x 128 keys : A = V tile (MN-major), B = P^T from shared memory
+// so every softmax thread has NPAD elements of work per tile, the K/V stream is the only large traffic and
+// the kernel is HBM-bound.  Split-KV partials are merged by the LAST CTA of each KV head (arrival counter in
+// the workspace), so there is no separate combine launch.
+#include <cuda.h>
+#include <math.h>
+#include <stdlib.h>
+
+#include "pc_common.cuh"
+
+namespace pc {
+
+int make_tensor_map_3d(CUtensorMap* map, const void* base, int D, long long rows, int heads, long long head_stride,
+                       int box_rows);
+
+namespace {
+
+constexpr int BK = 128;  // keys per tile
+constexpr int D = 128;
+constexpr int kThreads = 192;
+constexpr int kStages = 3;
+constexpr int kTileBytes = BK * D * 2;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kRescaleThreshold = 8.0f;
+
+template <int NPAD>
+struct SCfg {
+  static constexpr int kQBytes = NPAD * D * 2;
+  static constexpr int kPBytes = NPAD * BK * 2;
+  static constexpr int kOffQ = kStages * 2 * kTileBytes;
+  static constexpr int kOffP = kOffQ + kQBytes;
+  static constexpr int kOffRed = kOffP + 2 * kPBytes;           // float red[2][4][NPAD]
+  static constexpr int kOffMisc = kOffRed + 2 * 4 * NPAD * 4;   // int rtab[NPAD]; float slopetab[NPAD]; int flag
+  static constexpr int kOffBars = kOffMisc + 2 * NPAD * 4 + 16;
+  static constexpr int kSmem = 1024 + kOffBars + 256;
+  static constexpr int kTmemCols = NPAD <= 16 ? 64 : 128;       // S^T x2 + O^T = 3*NPAD
+};
+
+struct SmallParams {
+  __half* out;
+  float* part_o;
+  float* part_ml;
+  int* counters;
+  const float* alibi_slopes;
+  const int* key_pos;
+  int n_heads, n_kv_heads, n_cached, q_len, n_splits, alibi_max_pos;
+  float scale;
+};
+
+__device__ __forceinline__ float round_h(float x) { return __half2float(__float2half_rn(x)); }
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void named_bar_sync(int id, int n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld_n(uint32_t addr, float (&v)[N]) {
+  if constexpr (N == 16) tmem_ld16(addr, reinterpret_cast<uint32_t(&)[16]>(v));
+  else tmem_ld32(addr, reinterpret_cast<uint32_t(&)[32]>(v));
+}
+template <int N>
+__device__ __forceinline__ void tmem_st_n(uint32_t addr, const float (&v)[N]) {
+  if constexpr (N == 16) tmem_st16(addr, reinterpret_cast<const uint32_t(&)[16]>(v));
+  else tmem_st32(addr, reinterpret_cast<const uint32_t(&)[32]>(v));
+}
+
+template <int NPAD, int ROUND, bool ALIBI>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                  const __grid_constant__ CUtensorMap map_v, const SmallParams p) {
+  using C = SCfg<NPAD>;
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  unsigned char* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  unsigned char* sKV = smem;
+  unsigned char* sQ = smem + C::kOffQ;
+  unsigned char* sP = smem + C::kOffP;
+  float* red = reinterpret_cast<float*>(smem + C::kOffRed);
+  int* rtab = reinterpret_cast<int*>(smem + C::kOffMisc);  // query row r of column c (c = g*q + r)
+  float* slopetab = reinterpret_cast<float*>(rtab + NPAD);  // ALiBi slope of column c
+  int* flag = reinterpret_cast<int*>(slopetab + NPAD);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBars);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* v_full = k_full + kStages;
+  uint64_t* kv_empty = v_full + kStages;
+  uint64_t* s_full = kv_empty + kStages;
+  uint64_t* p_full = s_full + 2;
+  uint64_t* o_full = p_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int G = p.n_heads / p.n_kv_heads;
+  const int cols_valid = G * p.q_len;  // <= NPAD
+  const int split = blockIdx.x % p.n_splits;
+  const int hk = blockIdx.x / p.n_splits;
+  const int tiles_total = (p.n_cached + p.q_len + BK - 1) / BK;
+  const int tile0 = static_cast<int>(static_cast<long long>(split) * tiles_total / p.n_splits);
+  const int tile1 = static_cast<int>(static_cast<long long>(split + 1) * tiles_total / p.n_splits);
+  const int T = tile1 - tile0;  // >= 1 (host guarantees n_splits <= tiles_total)
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_v);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&s_full[b], 1);
+      mbar_init(&p_full[b], 128);
+    }
+    mbar_init(o_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 5) tmem_alloc<C::kTmemCols>(tmem_slot);
+  if (tid < NPAD) {
+    rtab[tid] = tid < cols_valid ? tid % p.q_len : 0x3fffffff;  // padding columns: nothing is masked, never stored
+    slopetab[tid] = (ALIBI && tid < cols_valid) ? p.alibi_slopes[hk * G + tid / p.q_len] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + 2 * NPAD;
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, C::kQBytes);
+      for (int hf = 0; hf < 2; ++hf) tma_load_3d(sQ + hf * (NPAD * 128), &map_q, q_full, hf * 64, 0, hk);
+      for (int j = 0; j < T; ++j) {
+        const int s = j % kStages;
+        if (j >= kStages) mbar_wait(&kv_empty[s], static_cast<uint32_t>(((j / kStages) - 1) & 1));
+        unsigned char* dk = sKV + (2 * s) * kTileBytes;
+        unsigned char* dv = dk + kTileBytes;
+        const int key0 = (tile0 + j) * BK;
+        mbar_expect_tx(&k_full[s], kTileBytes);
+        for (int hf = 0; hf < 2; ++hf) tma_load_3d(dk + hf * 16384, &map_k, &k_full[s], hf * 64, key0, hk);
+        mbar_expect_tx(&v_full[s], kTileBytes);
+        for (int hf = 0; hf < 2; ++hf) tma_load_3d(dv + hf * 16384, &map_v, &v_full[s], hf * 64, key0, hk);
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_st = make_idesc_f16(BK, NPAD, 0, 0);  // S^T = K . Q^T, both K-major
+      constexpr uint32_t idesc_pv = make_idesc_f16(D, NPAD, 1, 1);   // O^T = V^T . P^T, both MN-major
+      const uint32_t q_addr = smem_u32(sQ);
+      auto issue_st = [&](int j) {
+        const int s = j % kStages;
+        mbar_wait(&k_full[s], static_cast<uint32_t>((j / kStages) & 1));
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sKV + (2 * s) * kTileBytes);
+        const uint32_t d = tmem_base + (j & 1) * NPAD;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_ss(d, make_smem_desc(k_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, 2),
+                  make_smem_desc(q_addr + (kk >> 2) * (NPAD * 128) + (kk & 3) * 32, 16, 1024, 2), idesc_st,
+                  kk > 0 ? 1u : 0u);
+        tc_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_full, 0);
+      issue_st(0);
+      for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) issue_st(j + 1);
+        const int s = j % kStages;
+        mbar_wait(&p_full[j & 1], static_cast<uint32_t>((j >> 1) & 1));
+        mbar_wait(&v_full[s], static_cast<uint32_t>((j / kStages) & 1));
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(sKV + (2 * s + 1) * kTileBytes);
+        const uint32_t p_addr = smem_u32(sP + (j & 1) * C::kPBytes);
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk)
+          umma_ss(tmem_o, make_smem_desc(v_addr + kk * 2048, 16384, 1024, 2),
+                  make_smem_desc(p_addr + kk * 256, 128, 2048, 0), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+        tc_commit(&kv_empty[s]);
+        tc_commit(o_full);
+      }
+    }
+  } else {
+    // ===================== softmax (thread = key) / correction / epilogue (thread = d) ==================
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    float m_col[NPAD], l_part[NPAD];
+#pragma unroll
+    for (int c = 0; c < NPAD; ++c) {
+      m_col[c] = -INFINITY;
+      l_part[c] = 0.f;
+    }
+
+    for (int j = 0; j < T; ++j) {
+      const int b = j & 1;
+      mbar_wait(&s_full[b], static_cast<uint32_t>((j >> 1) & 1));
+      tc_fence_after();
+      float x[NPAD];
+      tmem_ld_n<NPAD>(tmem_base + lane_base + b * NPAD, x);
+      tmem_ld_wait();
+      const int key = (tile0 + j) * BK + tid;
+      const bool need_mask = (tile0 + j + 1) * BK > p.n_cached;
+      float kp = 0.f;
+      if (ALIBI) kp = static_cast<float>(__ldg(p.key_pos + min(key, p.n_cached + p.q_len - 1)) - p.alibi_max_pos);
+      float wm[NPAD];
+#pragma unroll
+      for (int c = 0; c < NPAD; ++c) {
+        float v = x[c];
+        if (ROUND & PC_ROUND_QK) v = round_h(v);
+        v *= p.scale;
+        if (ROUND & PC_ROUND_SCALED) v = round_h(v);
+        if (ALIBI) v += slopetab[c] * kp;
+        v *= kLog2e;
+        if (need_mask && key - p.n_cached > rtab[c]) v = -INFINITY;  // key n_cached+t visible iff t <= r
+        x[c] = v;
+        wm[c] = v;
+      }
+      // per-query max over the 128 keys of the tile: warp butterfly, then 4 warps through smem
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int c = 0; c < NPAD; ++c) wm[c] = fmaxf(wm[c], __shfl_xor_sync(0xffffffffu, wm[c], o));
+      }
+      float* rb = red + b * 4 * NPAD;
+#pragma unroll
+      for (int c = 0; c < NPAD; ++c)
+        if (lane == c) rb[warp * NPAD + c] = wm[c];
+      named_bar_sync(1, 128);
+      bool any_grow = false;
+      float alpha[NPAD];
+#pragma unroll
+      for (int c = 0; c < NPAD; ++c) {
+        const float mt = fmaxf(fmaxf(rb[c], rb[NPAD + c]), fmaxf(rb[2 * NPAD + c], rb[3 * NPAD + c]));
+        const float m_new = fmaxf(m_col[c], mt);
+        alpha[c] = 1.f;
+        if (m_col[c] == -INFINITY) {
+          m_col[c] = m_new;  // nothing accumulated for this query yet
+        } else if (m_new - m_col[c] > kRescaleThreshold) {
+          alpha[c] = exp2f(m_col[c] - m_new);
+          m_col[c] = m_new;
+          l_part[c] *= alpha[c];
+          any_grow = true;
+        }
+      }
+      uint32_t pk[NPAD / 2];
+#pragma unroll
+      for (int c = 0; c < NPAD; c += 2) {
+        const float p0 = exp2f(x[c] - (m_col[c] == -INFINITY ? 0.f : m_col[c]));
+        const float p1 = exp2f(x[c + 1] - (m_col[c + 1] == -INFINITY ? 0.f : m_col[c + 1]));
+        l_part[c] += p0;
+        l_part[c + 1] += p1;
+        pk[c >> 1] = pack_h2(p0, p1);
+      }
+      unsigned char* pb = sP + b * C::kPBytes + tid * 16;
+#pragma unroll
+      for (int m8 = 0; m8 < NPAD / 8; ++m8)
+        *reinterpret_cast<uint4*>(pb + m8 * 2048) = make_uint4(pk[m8 * 4], pk[m8 * 4 + 1], pk[m8 * 4 + 2], pk[m8 * 4 + 3]);
+      fence_proxy_async_smem();
+      if (any_grow) {  // CTA-uniform: every thread derived the same maxima from the same smem values
+        mbar_wait(o_full, static_cast<uint32_t>((j - 1) & 1));
+        tc_fence_after();
+        float o[NPAD];
+        tmem_ld_n<NPAD>(tmem_o + lane_base, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < NPAD; ++c) o[c] *= alpha[c];
+        tmem_st_n<NPAD>(tmem_o + lane_base, o);
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(&p_full[b]);
+    }
+
+    // ---- per-query sums over all keys of this split ----
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int c = 0; c < NPAD; ++c) l_part[c] += __shfl_xor_sync(0xffffffffu, l_part[c], o);
+    }
+    named_bar_sync(1, 128);  // everyone is done reading `red` of the last tile
+#pragma unroll
+    for (int c = 0; c < NPAD; ++c)
+      if (lane == c) red[warp * NPAD + c] = l_part[c];
+    named_bar_sync(1, 128);
+    float l_col[NPAD];
+#pragma unroll
+    for (int c = 0; c < NPAD; ++c) l_col[c] = (red[c] + red[NPAD + c]) + (red[2 * NPAD + c] + red[3 * NPAD + c]);
+
+    // ---- epilogue: O^T (TMEM lane = d, column = query row) ----
+    mbar_wait(o_full, static_cast<uint32_t>((T - 1) & 1));
+    tc_fence_after();
+    float o[NPAD];
+    tmem_ld_n<NPAD>(tmem_o + lane_base, o);
+    tmem_ld_wait();
+    const int d = tid;
+    if (p.n_splits == 1) {
+#pragma unroll
+      for (int c = 0; c < NPAD; ++c) {
+        if (c < cols_valid) {
+          const int h = hk * G + c / p.q_len, r = c % p.q_len;
+          const float inv = l_col[c] > 0.f ? 1.f / l_col[c] : 0.f;
+          p.out[(static_cast<long long>(r) * p.n_heads + h) * D + d] = __float2half_rn(o[c] * inv);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < NPAD; ++c) {
+        if (c < cols_valid) {
+          const int h = hk * G + c / p.q_len, r = c % p.q_len;
+          const long long idx = (static_cast<long long>(split) * p.n_heads + h) * p.q_len + r;
+          p.part_o[idx * D + d] = o[c];
+          if (tid == c) {
+            p.part_ml[idx * 2] = m_col[c];
+            p.part_ml[idx * 2 + 1] = l_col[c];
+          }
+        }
+      }
+      // last CTA of this KV head merges the partials (no separate combine launch)
+      __threadfence();
+      named_bar_sync(1, 128);
+      if (tid == 0) {
+        const int old = atomicAdd(p.counters + hk, 1);
+        *flag = (old == p.n_splits - 1) ? 1 : 0;
+        if (old == p.n_splits - 1) p.counters[hk] = 0;  // self-cleaning for the next launch
+      }
+      named_bar_sync(1, 128);
+      if (*flag) {
+        __threadfence();
+        for (int c = 0; c < cols_valid; ++c) {
+          const int h = hk * G + c / p.q_len, r = c % p.q_len;
+          float m_star = -INFINITY;
+          for (int s = 0; s < p.n_splits; ++s)
+            m_star = fmaxf(m_star, __ldcg(p.part_ml + ((static_cast<long long>(s) * p.n_heads + h) * p.q_len + r) * 2));
+          float acc = 0.f, l = 0.f;
+          for (int s = 0; s < p.n_splits; ++s) {
+            const long long idx = (static_cast<long long>(s) * p.n_heads + h) * p.q_len + r;
+            const float m = __ldcg(p.part_ml + idx * 2);
+            if (m == -INFINITY) continue;
+            const float w = exp2f(m - m_star);
+            l += w * __ldcg(p.part_ml + idx * 2 + 1);
+            acc += w * __ldcg(p.part_o + idx * D + d);
+          }
+          p.out[(static_cast<long long>(r) * p.n_heads + h) * D + d] = __float2half_rn(l > 0.f ? acc / l : 0.f);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_free<C::kTmemCols>(tmem_base);
+  }
+}
+
+template <int NPAD, int ROUND, bool ALIBI>
+int launch_small_one(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const SmallParams& sp, int grid,
+                     cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    PC_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<NPAD, ROUND, ALIBI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       SCfg<NPAD>::kSmem));
+    configured = true;
+  }
+  attn_small_kernel<NPAD, ROUND, ALIBI><<<grid, kThreads, SCfg<NPAD>::kSmem, st>>>(mq, mk, mv, sp);
+  PC_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return PC_OK;
+}
+
+template <int NPAD>
+int launch_small_n(const pc_attn_params& p, cudaStream_t st) {
+  const int G = p.n_heads / p.n_kv_heads;
+  const int tiles = (p.n_cached + p.q_len + BK - 1) / BK;
+  int n_splits = sm_count() / p.n_kv_heads;
+  if (const char* e = getenv("PC_ATTN_SPLITS")) n_splits = atoi(e);
+  if (n_splits > tiles) n_splits = tiles;
+  if (n_splits > 64) n_splits = 64;
+  if (n_splits < 1) n_splits = 1;
+  // workspace: [counters: 4096 B][part_o][part_ml]
+  const size_t ctr_bytes = kAttnCounterBytes;
+  if (static_cast<size_t>(p.n_kv_heads) * 4 > ctr_bytes)
+    return set_error(PC_ERR_UNSUPPORTED, "attn(tcgen05-small): %d KV heads exceed the counter region", p.n_kv_heads);
+  const size_t per_split = static_cast<size_t>(p.n_heads) * p.q_len * (D + 2) * sizeof(float);
+  if (n_splits > 1) {
+    const size_t avail = (p.workspace && p.workspace_bytes > ctr_bytes) ? p.workspace_bytes - ctr_bytes : 0;
+    if (avail < per_split * n_splits) n_splits = static_cast<int>(avail / per_split);
+    if (n_splits < 1) n_splits = 1;
+  }
+  SmallParams sp;
+  sp.out = static_cast<__half*>(p.out);
+  sp.counters = nullptr;
+  sp.part_o = nullptr;
+  sp.part_ml = nullptr;
+  if (n_splits > 1) {
+    sp.counters = static_cast<int*>(p.workspace);
+    sp.part_o = reinterpret_cast<float*>(static_cast<char*>(p.workspace) + ctr_bytes);
+    sp.part_ml = sp.part_o + static_cast<size_t>(n_splits) * p.n_heads * p.q_len * D;
+  }
+  sp.alibi_slopes = p.alibi_slopes;
+  sp.key_pos = p.key_pos;
+  sp.n_heads = p.n_heads;
+  sp.n_kv_heads = p.n_kv_heads;
+  sp.n_cached = p.n_cached;
+  sp.q_len = p.q_len;
+  sp.n_splits = n_splits;
+  sp.alibi_max_pos = p.alibi_max_pos;
+  sp.scale = p.scale;
+
+  const int rows_total = G * p.q_len;
+  CUtensorMap mq, mk, mv;
+  if (int rc = make_tensor_map_3d(&mq, p.q, D, rows_total, p.n_kv_heads, static_cast<long long>(rows_total) * D, NPAD)) return rc;
+  const long long kv_rows = static_cast<long long>(p.n_cached) + p.q_len;
+  if (int rc = make_tensor_map_3d(&mk, p.k, D, kv_rows, p.n_kv_heads, static_cast<long long>(p.max_ctx) * D, BK)) return rc;
+  if (int rc = make_tensor_map_3d(&mv, p.v, D, kv_rows, p.n_kv_heads, static_cast<long long>(p.max_ctx) * D, BK)) return rc;
+  const int grid = p.n_kv_heads * n_splits;
+  const bool alibi = p.alibi_slopes != nullptr;
+  if (p.rounding == 0)
+    return alibi ? launch_small_one<NPAD, 0, true>(mq, mk, mv, sp, grid, st) : launch_small_one<NPAD, 0, false>(mq, mk, mv, sp, grid, st);
+  return alibi ? launch_small_one<NPAD, 3, true>(mq, mk, mv, sp, grid, st) : launch_small_one<NPAD, 3, false>(mq, mk, mv, sp, grid, st);
+}
+
+}  // namespace
+
+bool attn_small_supported(const pc_attn_params& p) {
+  const int G = p.n_heads / p.n_kv_heads;
+  return p.head_dim == 128 && G * p.q_len <= 32 && (p.rounding == 0 || p.rounding == PC_ROUND_LLAMA);
+}
+
+// up to 64 splits of fp32 partials (the counter region is added by the caller)
+size_t attn_small_partial_bytes(int n_heads, int q_len, int head_dim) {
+  if (head_dim != 128 || q_len > 32) return 0;
+  long long splits = sm_count();  // worst case: one KV head
+  if (splits > 64) splits = 64;
+  return static_cast<size_t>(splits) * n_heads * q_len * (head_dim + 2) * sizeof(float);
+}
+
+int launch_attn_small(const pc_attn_params& p, cudaStream_t st) {
+  const int G = p.n_heads / p.n_kv_heads;
+  if (G * p.q_len <= 16) return launch_small_n<16>(p, st);
+  return launch_small_n<32>(p, st);
+}
+
+}  // namespace pc

@@ -15,6 +15,9 @@ namespace pc {
 int set_error(int code, const char* fmt, ...);
 void count_launch(int n = 1);
 int sm_count();
+// Both tcgen05 attention kernels keep their split-KV arrival counters in the first bytes of the caller's
+// workspace (zero-initialised once by the caller; the kernels leave them zeroed) and the fp32 partials behind.
+constexpr size_t kAttnCounterBytes = 4096;
 
 #define PC_CHECK_CUDA(expr)                                                                    \
   do {                                                                                         \

@@ -1,0 +1,116 @@
+// Support kernels around the hot path (norms / activation are unchanged by
+// prompt caching and stay outside the parity scope, but as ~25 eager launches per layer they made the
+// TTFT step launch-bound).  Rounding points follow the reference so the residual stream stays within
+// fp16 round-off of promptcache/model/llama2.py:
+//   pc_add_rmsnorm : x = half(x + delta)  (llama2.py:636,644 residual adds), then LlamaRMSNorm.forward
+//                    (llama2.py:104-109): fp32 statistics, round to fp16, multiply by the fp16 weight.
+//   pc_silu_mul    : half(silu(gate)) * up in fp16 (llama2.py:241, act_fn = SiLU evaluated in fp32).
+#include "pc_common.cuh"
+
+namespace {
+
+constexpr int kNormThreads = 256;
+
+__global__ void __launch_bounds__(kNormThreads)
+add_rmsnorm_kernel(__half* __restrict__ x, const __half* __restrict__ delta, const __half* __restrict__ weight,
+                   __half* __restrict__ h_out, int hidden, float eps) {
+  __shared__ float red[kNormThreads / 32];
+  const int row = blockIdx.x;
+  __half* xr = x + static_cast<long long>(row) * hidden;
+  const __half* dr = delta ? delta + static_cast<long long>(row) * hidden : nullptr;
+  __half* hr = h_out + static_cast<long long>(row) * hidden;
+  float ss = 0.f;
+  // pass 1: residual add (written back) + sum of squares; 8 halfs per thread per step
+  for (int i = threadIdx.x * 8; i < hidden; i += kNormThreads * 8) {
+    uint4 xv = *reinterpret_cast<const uint4*>(xr + i);
+    __half2* xh = reinterpret_cast<__half2*>(&xv);
+    if (dr) {
+      uint4 dv = *reinterpret_cast<const uint4*>(dr + i);
+      const __half2* dh = reinterpret_cast<const __half2*>(&dv);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) xh[k] = __hadd2_rn(xh[k], dh[k]);
+      *reinterpret_cast<uint4*>(xr + i) = xv;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(xh[k]);
+      ss = fmaf(f.x, f.x, ss);
+      ss = fmaf(f.y, f.y, ss);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < kNormThreads / 32; ++w) tot += red[w];
+  const float inv = rsqrtf(tot / static_cast<float>(hidden) + eps);
+  // pass 2: normalise (fp32) -> fp16 -> * weight (fp16)
+  for (int i = threadIdx.x * 8; i < hidden; i += kNormThreads * 8) {
+    uint4 xv = *reinterpret_cast<const uint4*>(xr + i);
+    uint4 wv = *reinterpret_cast<const uint4*>(weight + i);
+    __half2* xh = reinterpret_cast<__half2*>(&xv);
+    const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(xh[k]);
+      xh[k] = __hmul2_rn(wh[k], __floats2half2_rn(f.x * inv, f.y * inv));
+    }
+    *reinterpret_cast<uint4*>(hr + i) = xv;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+silu_mul_kernel(const __half* __restrict__ gate_up, __half* __restrict__ out, int inter, long long row_stride) {
+  const int row = blockIdx.y;
+  const int i = (blockIdx.x * 256 + threadIdx.x) * 8;
+  if (i >= inter) return;
+  const __half* g = gate_up + row * row_stride + i;
+  uint4 gv = *reinterpret_cast<const uint4*>(g);
+  uint4 uv = *reinterpret_cast<const uint4*>(g + inter);
+  __half2* gh = reinterpret_cast<__half2*>(&gv);
+  const __half2* uh = reinterpret_cast<const __half2*>(&uv);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 f = __half22float2(gh[k]);
+    const float sx = f.x / (1.f + expf(-f.x));
+    const float sy = f.y / (1.f + expf(-f.y));
+    gh[k] = __hmul2_rn(__floats2half2_rn(sx, sy), uh[k]);
+  }
+  *reinterpret_cast<uint4*>(out + static_cast<long long>(row) * inter + i) = gv;
+}
+
+}  // namespace
+
+PC_API int pc_add_rmsnorm(void* x, const void* delta, const void* weight, void* h_out, int rows, int hidden, float eps,
+                          void* stream) {
+  if (rows == 0) return PC_OK;
+  PC_REQUIRE(x && weight && h_out, "pc_add_rmsnorm: null tensor");
+  PC_REQUIRE(rows > 0 && hidden > 0 && hidden % 8 == 0, "pc_add_rmsnorm: hidden %d must be a positive multiple of 8", hidden);
+  const uintptr_t align = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(delta) |
+                          reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(h_out);
+  PC_REQUIRE(align % 16 == 0, "pc_add_rmsnorm: tensors must be 16B aligned");
+  add_rmsnorm_kernel<<<rows, kNormThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__half*>(x), static_cast<const __half*>(delta), static_cast<const __half*>(weight),
+      static_cast<__half*>(h_out), hidden, eps);
+  PC_CHECK_CUDA(cudaGetLastError());
+  pc::count_launch();
+  return PC_OK;
+}
+
+PC_API int pc_silu_mul(const void* gate_up, void* out, int rows, int inter, int64_t row_stride, void* stream) {
+  if (rows == 0) return PC_OK;
+  PC_REQUIRE(gate_up && out, "pc_silu_mul: null tensor");
+  PC_REQUIRE(rows > 0 && inter > 0 && inter % 8 == 0 && row_stride % 8 == 0 && row_stride >= 2LL * inter,
+             "pc_silu_mul: inter %d / row_stride %lld must be multiples of 8 with row_stride >= 2*inter", inter,
+             static_cast<long long>(row_stride));
+  PC_REQUIRE((reinterpret_cast<uintptr_t>(gate_up) | reinterpret_cast<uintptr_t>(out)) % 16 == 0,
+             "pc_silu_mul: tensors must be 16B aligned");
+  PC_REQUIRE(rows <= 65535, "pc_silu_mul: too many rows");
+  dim3 grid((inter / 8 + 255) / 256, rows);
+  silu_mul_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(gate_up),
+                                                                       static_cast<__half*>(out), inter, row_stride);
+  PC_CHECK_CUDA(cudaGetLastError());
+  pc::count_launch();
+  return PC_OK;
+}

@@ -141,7 +141,8 @@ class LlamaForCausalLM(nn.Module):
         if need == 0:
             return None
         if self._ws is None or self._ws.numel() < need or self._ws.device != self.device:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            # zero-initialised once: the first bytes hold split-KV arrival counters the kernels leave zeroed
+            self._ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
         return self._ws
 
     # ---- forward --------------------------------------------------------------------------------------
@@ -150,24 +151,28 @@ class LlamaForCausalLM(nn.Module):
         H, Hkv, D = self.n_heads, self.n_kv_heads, self.head_dim
         kv = resolve_kv(past, q_len, self.n_layers, Hkv, D, self.device)
         N = kv.n_cached
-        x = F.embedding(ids, self.embed_tokens)  # [q, hidden]
+        x = F.embedding(ids, self.embed_tokens)  # [q, hidden]: the residual stream, updated in place
+        h = torch.empty_like(x)
         q_rot = torch.empty(H, q_len, D, dtype=torch.float16, device=self.device)
         attn_out = torch.empty(q_len, H * D, dtype=torch.float16, device=self.device)
-        ws = self._workspace(q_len)
         inter = self.config.intermediate_size
+        act = torch.empty(q_len, inter, dtype=torch.float16, device=self.device)
+        ws = self._workspace(q_len)
+        delta = None
         for l in range(self.n_layers):
-            h = rms_norm(x, self.ln1[l], self.eps)
-            qkv = F.linear(h, self.wqkv[l])  # [q, (H+2Hkv)*D]
+            nat.add_rmsnorm(x, delta, self.ln1[l], h, self.eps)          # x += mlp(l-1); h = norm(x)
+            qkv = F.linear(h, self.wqkv[l])                              # [q, (H+2Hkv)*D]
             nat.rope_append(qkv[:, :H * D], qkv[:, H * D:(H + Hkv) * D], qkv[:, (H + Hkv) * D:], pos, self._cos,
                             self._sin, q_rot, kv.k[l], kv.v[l], N, H, Hkv, D)
             nat.attention(q_rot, kv.k[l], kv.v[l], attn_out, N, q_len, H, Hkv, D, self.scale, self.rounding,
                           workspace=ws, impl=self.attn_impl, decode=(q_len == 1))
-            x = x + F.linear(attn_out, self.wo[l])
-            h = rms_norm(x, self.ln2[l], self.eps)
+            delta = F.linear(attn_out, self.wo[l])
+            nat.add_rmsnorm(x, delta, self.ln2[l], h, self.eps)          # x += attn; h = norm(x)
             gu = F.linear(h, self.w_gate_up[l])
-            x = x + F.linear(F.silu(gu[:, :inter]) * gu[:, inter:], self.w_down[l])
-        x = rms_norm(x, self.norm, self.eps)
-        logits = F.linear(x, self.lm_head).float()
+            nat.silu_mul(gu, act, inter)
+            delta = F.linear(act, self.w_down[l])
+        nat.add_rmsnorm(x, delta, self.norm, h, self.eps)
+        logits = F.linear(h, self.lm_head).float()
         return logits, (kv.views(N + q_len) if use_cache else None)
 
     @torch.inference_mode()

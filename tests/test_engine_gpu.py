@@ -171,7 +171,15 @@ def test_llama7b_shaped_layers_match_oracle(native):
     print("7B-shaped 2-layer logits rel err", err)
     assert err < 3e-3
     # the encode path produced the cached KV: compare with the oracle's monolithic encode of the scaffold
-    scaf_ids = list(itertools.chain(*[m.token_sequence.token_ids() for m in eng.prompt_cache.staged]))
-    _, enc = O.llama_forward(sd, ocfg, torch.tensor([scaf_ids], device=DEV), torch.arange(2048, device=DEV).unsqueeze(0),
-                             cos=model._cos, sin=model._sin)
-    assert _rel(cache[0][0], enc[0][0][0]) < 2e-3 and _rel(cache[1][1], enc[1][1][0]) < 5e-3
+    # (schema order, positions 0..2047); the spliced rows follow the reference's reverse-DFS segment order
+    schema = eng.get_schema(case.name)
+    scaf = schema.get_scaffold()
+    _, enc = O.llama_forward(sd, ocfg, torch.tensor([scaf.token_ids()], device=DEV),
+                             torch.tensor([scaf.position_ids()], device=DEV), cos=model._cos, sin=model._sin)
+    row = 0
+    for m in eng.prompt_cache.staged:
+        off, n = m.token_sequence.offset, len(m)
+        assert _rel(cache[0][0][:, row:row + n], enc[0][0][0][:, off:off + n]) < 2e-3
+        assert _rel(cache[1][1][:, row:row + n], enc[1][1][0][:, off:off + n]) < 5e-3
+        row += n
+    assert row == 2048

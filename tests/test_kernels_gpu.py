@@ -173,6 +173,12 @@ CASES = [
     (8, 8, 128, 200, 0),      # no-cache prefill, 2 row blocks, causal only
     (71, 1, 64, 21, 256),     # Falcon MQA fold (71*21 rows)
     (8, 2, 128, 40, 500),     # GQA fold
+    (8, 2, 128, 4, 700),      # GQA fold on the short-suffix kernel (G*q = 16)
+    (4, 4, 128, 32, 1000),    # short-suffix kernel, 32 columns
+    (4, 4, 128, 17, 129),     # short-suffix kernel, padded columns, suffix straddles a tile boundary
+    (4, 4, 128, 5, 0),        # short-suffix kernel without any cached rows
+    (32, 32, 128, 32, 8192),  # C5
+    (40, 40, 128, 32, 4096),  # C3 (Llama-2-13B heads)
 ]
 
 
@@ -182,7 +188,7 @@ def test_attention_llama_rounding(native, impl, H, Hkv, D, q, N):
     Q, K, V = _attn_case(H, Hkv, D, q, N, seed=H * 1000 + q, std=1.28)
     out = torch.empty(q, H * D, dtype=torch.half, device=DEV)
     ws_bytes = native.attn_workspace_bytes(H, q, D)
-    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=DEV)
+    ws = torch.zeros(max(ws_bytes, 1), dtype=torch.uint8, device=DEV)
     native.attention(Q, K, V, out, N, q, H, Hkv, D, native.softmax_scale(D), native.PC_ROUND_LLAMA, workspace=ws,
                      impl=native.PC_ATTN_SIMT if impl == "simt" else native.PC_ATTN_TCGEN05, decode=(q == 1))
     torch.cuda.synchronize()
@@ -197,7 +203,7 @@ def test_attention_llama_rounding(native, impl, H, Hkv, D, q, N):
 def test_attention_exact_mode(native, impl, H, Hkv, D, q, N):
     Q, K, V = _attn_case(H, Hkv, D, q, N, seed=H * 77 + q)
     out = torch.empty(q, H * D, dtype=torch.half, device=DEV)
-    ws = torch.empty(max(native.attn_workspace_bytes(H, q, D), 1), dtype=torch.uint8, device=DEV)
+    ws = torch.zeros(max(native.attn_workspace_bytes(H, q, D), 1), dtype=torch.uint8, device=DEV)
     native.attention(Q, K, V, out, N, q, H, Hkv, D, 1.0 / math.sqrt(D), 0, workspace=ws,
                      impl=native.PC_ATTN_SIMT if impl == "simt" else native.PC_ATTN_TCGEN05, decode=(q == 1))
     torch.cuda.synchronize()
@@ -215,7 +221,7 @@ def test_attention_alibi(native, impl):
     slopes = O.mpt_alibi_slopes(H, 8, DEV)
     scale = 1.0 / math.sqrt(D)
     out = torch.empty(q, H * D, dtype=torch.half, device=DEV)
-    ws = torch.empty(max(native.attn_workspace_bytes(H, q, D), 1), dtype=torch.uint8, device=DEV)
+    ws = torch.zeros(max(native.attn_workspace_bytes(H, q, D), 1), dtype=torch.uint8, device=DEV)
     native.attention(Q, K, V, out, N, q, H, Hkv, D, scale, native.PC_ROUND_MPT, workspace=ws, alibi_slopes=slopes,
                      key_pos=key_pos, alibi_max_pos=int(key_pos.max()),
                      impl=native.PC_ATTN_SIMT if impl == "simt" else native.PC_ATTN_TCGEN05)
@@ -223,3 +229,18 @@ def test_attention_alibi(native, impl):
     ctx, _, _ = O.mpt_attention_core(Q.unsqueeze(0), K[:, N:N + q].unsqueeze(0), V[:, N:N + q].unsqueeze(0),
                                      K[:, :N].unsqueeze(0), V[:, :N].unsqueeze(0), key_pos.long().view(1, -1), scale)
     assert _rel(out, ctx[0]) <= 1e-3, _rel(out, ctx[0])
+
+
+def test_attention_workspace_is_left_clean_and_reusable(native):
+    """Split-KV arrival counters are self-cleaning: the same workspace serves alternating shapes/kernels."""
+    H = Hkv = 8
+    D = 128
+    ws = torch.zeros(native.attn_workspace_bytes(H, 64, D), dtype=torch.uint8, device=DEV)
+    for q, N in [(16, 900), (64, 900), (1, 901), (16, 300), (1, 5000)]:
+        Q, K, V = _attn_case(H, Hkv, D, q, N, seed=q + N, std=1.28)
+        out = torch.empty(q, H * D, dtype=torch.half, device=DEV)
+        for _ in range(2):
+            native.attention(Q, K, V, out, N, q, H, Hkv, D, native.softmax_scale(D), native.PC_ROUND_LLAMA, workspace=ws,
+                             decode=(q == 1))
+            assert _rel(out, _oracle_llama(Q, K, V, N, q)) <= 1e-3
+        assert int(ws[:4096].view(torch.int32).abs().max()) == 0

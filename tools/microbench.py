@@ -73,7 +73,7 @@ def bench_attn():
         V = torch.randn(L, Hkv, max_ctx, D, device=DEV).half()
         Q = torch.randn(H, q, D, device=DEV).half()
         out = torch.empty(q, H * D, dtype=torch.half, device=DEV)
-        ws = torch.empty(max(nat.attn_workspace_bytes(H, q, D), 1), dtype=torch.uint8, device=DEV)
+        ws = torch.zeros(max(nat.attn_workspace_bytes(H, q, D), 1), dtype=torch.uint8, device=DEV)
         state = {"i": 0}
         for impl, nm in [(nat.PC_ATTN_TCGEN05, "tcgen05"), (nat.PC_ATTN_SIMT, "simt")]:
             if impl == nat.PC_ATTN_SIMT and q > 64:
