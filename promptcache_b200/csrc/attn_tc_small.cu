@@ -4,8 +4,10 @@
 // With 16 query rows a 128-row MMA tile would leave 112 TMEM lanes (and 3.5 of 4 softmax warps) idle and
 // the per-tile softmax would serialise on half a warp.  This kernel swaps the operands instead:
 //   S^T_j = K_j . Q^T      SS-MMA 128 keys x NPAD queries x D : TMEM lane = key, column = query row
-//   P^T_j                  one key per thread, NPAD scores each; the per-query max / sum over the 128 keys
-//                          of a tile is a warp butterfly + a 4-way exchange through shared memory
+//   P^T_j                  8 softmax warps: a thread owns one key and NPAD/2 query columns (two warps per
+//                          TMEM lane quarter, i.e. two warps per scheduler to hide instruction latency); the
+//                          per-query max / sum over the 128 keys of a tile is a halving warp butterfly
+//                          (NPAD/2+1 shuffles) + a 4-way exchange through shared memory
 //   O^T  += V_j^T . P^T_j  SS-MMA D x NPAD x 128 keys : A = V tile (MN-major), B = P^T from shared memory
 // so every softmax thread has NPAD elements of work per tile, the K/V stream is the only large traffic and
 // the kernel is HBM-bound.  Split-KV partials are merged by the LAST CTA of each KV head (arrival counter in
@@ -25,7 +27,9 @@ namespace {
 
 constexpr int BK = 128;  // keys per tile
 constexpr int D = 128;
-constexpr int kThreads = 192;
+constexpr int kSoftmaxWarps = 8;
+constexpr int kSoftmaxThreads = kSoftmaxWarps * 32;
+constexpr int kThreads = kSoftmaxThreads + 64;  // + TMA warp + MMA warp
 constexpr int kStages = 3;
 constexpr int kTileBytes = BK * D * 2;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -63,15 +67,60 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 __device__ __forceinline__ void named_bar_sync(int id, int n) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
+__device__ __forceinline__ float ex2(float x) {  // 2^x, one MUFU; ex2(-inf) = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 template <int N>
 __device__ __forceinline__ void tmem_ld_n(uint32_t addr, float (&v)[N]) {
-  if constexpr (N == 16) tmem_ld16(addr, reinterpret_cast<uint32_t(&)[16]>(v));
-  else tmem_ld32(addr, reinterpret_cast<uint32_t(&)[32]>(v));
+  if constexpr (N == 8) tmem_ld8(addr, reinterpret_cast<uint32_t(&)[8]>(v));
+  else tmem_ld16(addr, reinterpret_cast<uint32_t(&)[16]>(v));
 }
 template <int N>
 __device__ __forceinline__ void tmem_st_n(uint32_t addr, const float (&v)[N]) {
-  if constexpr (N == 16) tmem_st16(addr, reinterpret_cast<const uint32_t(&)[16]>(v));
-  else tmem_st32(addr, reinterpret_cast<const uint32_t(&)[32]>(v));
+  if constexpr (N == 8) tmem_st8(addr, reinterpret_cast<const uint32_t(&)[8]>(v));
+  else tmem_st16(addr, reinterpret_cast<const uint32_t(&)[16]>(v));
+}
+// Reduce N per-lane values across the 32 lanes of a warp with N/2 + N/4 + ... + 1 (+ log2(32/N)) shuffles: at each
+// step a lane keeps one half of its vector and hands the other half to its partner.  Returns the reduction of
+// column ((lane >> (5 - log2 N)) & (N-1)); v is destroyed.
+template <int N, bool IS_MAX>
+__device__ __forceinline__ float warp_reduce_vec(float (&v)[N], int lane) {
+  int off = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1, off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = upper ? v[i] : v[i + n / 2];
+      const float keep = upper ? v[i + n / 2] : v[i];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+      v[i] = IS_MAX ? fmaxf(keep, recv) : keep + recv;
+    }
+  }
+#pragma unroll
+  for (; off > 0; off >>= 1) {
+    const float recv = __shfl_xor_sync(0xffffffffu, v[0], off);
+    v[0] = IS_MAX ? fmaxf(v[0], recv) : v[0] + recv;
+  }
+  return v[0];
+}
+template <int N>
+__device__ __forceinline__ int reduced_column(int lane) {
+  constexpr int sh = N == 8 ? 2 : 1;  // 5 - log2(N)
+  return (lane >> sh) & (N - 1);
 }
 
 template <int NPAD, int ROUND, bool ALIBI>
@@ -109,7 +158,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   const int tile1 = static_cast<int>(static_cast<long long>(split + 1) * tiles_total / p.n_splits);
   const int T = tile1 - tile0;  // >= 1 (host guarantees n_splits <= tiles_total)
 
-  if (warp == 4 && lane == 0) {
+  if (warp == kSoftmaxWarps && lane == 0) {
     tma_prefetch_desc(&map_q);
     tma_prefetch_desc(&map_k);
     tma_prefetch_desc(&map_v);
@@ -121,12 +170,12 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&s_full[b], 1);
-      mbar_init(&p_full[b], 128);
+      mbar_init(&p_full[b], kSoftmaxThreads);
     }
     mbar_init(o_full, 1);
     mbar_fence_init();
   }
-  if (warp == 5) tmem_alloc<C::kTmemCols>(tmem_slot);
+  if (warp == kSoftmaxWarps + 1) tmem_alloc<C::kTmemCols>(tmem_slot);
   if (tid < NPAD) {
     rtab[tid] = tid < cols_valid ? tid % p.q_len : 0x3fffffff;  // padding columns: nothing is masked, never stored
     slopetab[tid] = (ALIBI && tid < cols_valid) ? p.alibi_slopes[hk * G + tid / p.q_len] : 0.f;
@@ -137,7 +186,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + 2 * NPAD;
 
-  if (warp == 4) {
+  if (warp == kSoftmaxWarps) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       mbar_expect_tx(q_full, C::kQBytes);
@@ -154,7 +203,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         for (int hf = 0; hf < 2; ++hf) tma_load_3d(dv + hf * 16384, &map_v, &v_full[s], hf * 64, key0, hk);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kSoftmaxWarps + 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc_st = make_idesc_f16(BK, NPAD, 0, 0);  // S^T = K . Q^T, both K-major
@@ -192,89 +241,92 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
     }
   } else {
-    // ===================== softmax (thread = key) / correction / epilogue (thread = d) ==================
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    float m_col[NPAD], l_part[NPAD];
+    // ============ softmax (thread = key x half of the columns) / correction / epilogue (thread = d) ============
+    constexpr int NH = NPAD / 2;
+    const int quad = warp & 3, ch = warp >> 2;           // TMEM lane quarter, column half
+    const int kl = quad * 32 + lane;                      // key within the tile == TMEM lane == output d
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    const int c0 = ch * NH;                               // first column owned by this thread
+    const int my_col = c0 + reduced_column<NH>(lane);     // column whose warp-reduction this lane ends up holding
+    float m_col[NH], l_part[NH];
 #pragma unroll
-    for (int c = 0; c < NPAD; ++c) {
-      m_col[c] = -INFINITY;
-      l_part[c] = 0.f;
+    for (int i = 0; i < NH; ++i) {
+      m_col[i] = -INFINITY;
+      l_part[i] = 0.f;
     }
 
     for (int j = 0; j < T; ++j) {
       const int b = j & 1;
       mbar_wait(&s_full[b], static_cast<uint32_t>((j >> 1) & 1));
       tc_fence_after();
-      float x[NPAD];
-      tmem_ld_n<NPAD>(tmem_base + lane_base + b * NPAD, x);
+      float x[NH];
+      tmem_ld_n<NH>(tmem_base + lane_base + b * NPAD + c0, x);
       tmem_ld_wait();
-      const int key = (tile0 + j) * BK + tid;
-      const bool need_mask = (tile0 + j + 1) * BK > p.n_cached;
+      const int key = (tile0 + j) * BK + kl;
       float kp = 0.f;
       if (ALIBI) kp = static_cast<float>(__ldg(p.key_pos + min(key, p.n_cached + p.q_len - 1)) - p.alibi_max_pos);
-      float wm[NPAD];
 #pragma unroll
-      for (int c = 0; c < NPAD; ++c) {
-        float v = x[c];
+      for (int i = 0; i < NH; ++i) {
+        float v = x[i];
         if (ROUND & PC_ROUND_QK) v = round_h(v);
         v *= p.scale;
         if (ROUND & PC_ROUND_SCALED) v = round_h(v);
-        if (ALIBI) v += slopetab[c] * kp;
-        v *= kLog2e;
-        if (need_mask && key - p.n_cached > rtab[c]) v = -INFINITY;  // key n_cached+t visible iff t <= r
-        x[c] = v;
-        wm[c] = v;
+        if (ALIBI) v += slopetab[c0 + i] * kp;
+        x[i] = v * kLog2e;
       }
-      // per-query max over the 128 keys of the tile: warp butterfly, then 4 warps through smem
+      if ((tile0 + j + 1) * BK > p.n_cached) {  // tile touches the suffix: key n_cached+t is visible to row r iff t <= r
+        const int t = key - p.n_cached;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int c = 0; c < NPAD; ++c) wm[c] = fmaxf(wm[c], __shfl_xor_sync(0xffffffffu, wm[c], o));
+        for (int i = 0; i < NH; ++i)
+          if (t > rtab[c0 + i]) x[i] = -INFINITY;
       }
+      // per-query max over the 128 keys of the tile
+      float wm[NH];
+#pragma unroll
+      for (int i = 0; i < NH; ++i) wm[i] = x[i];
+      const float wmax = warp_reduce_vec<NH, true>(wm, lane);
       float* rb = red + b * 4 * NPAD;
-#pragma unroll
-      for (int c = 0; c < NPAD; ++c)
-        if (lane == c) rb[warp * NPAD + c] = wm[c];
-      named_bar_sync(1, 128);
+      if ((lane & (32 / NH - 1)) == 0) rb[quad * NPAD + my_col] = wmax;
+      named_bar_sync(1, kSoftmaxThreads);
       bool any_grow = false;
-      float alpha[NPAD];
+      float alpha[NH];
 #pragma unroll
-      for (int c = 0; c < NPAD; ++c) {
+      for (int i = 0; i < NH; ++i) {
+        const int c = c0 + i;
         const float mt = fmaxf(fmaxf(rb[c], rb[NPAD + c]), fmaxf(rb[2 * NPAD + c], rb[3 * NPAD + c]));
-        const float m_new = fmaxf(m_col[c], mt);
-        alpha[c] = 1.f;
-        if (m_col[c] == -INFINITY) {
-          m_col[c] = m_new;  // nothing accumulated for this query yet
-        } else if (m_new - m_col[c] > kRescaleThreshold) {
-          alpha[c] = exp2f(m_col[c] - m_new);
-          m_col[c] = m_new;
-          l_part[c] *= alpha[c];
-          any_grow = true;
-        }
+        const float m_new = fmaxf(m_col[i], mt);
+        // first finite max of a column: (m_new - (-inf)) = +inf > threshold and alpha = 2^(-inf) = 0
+        const bool grow = (m_new - m_col[i]) > kRescaleThreshold;  // NaN (both -inf) compares false
+        alpha[i] = grow ? ex2(m_col[i] - m_new) : 1.f;
+        m_col[i] = grow ? m_new : m_col[i];
+        l_part[i] *= alpha[i];
+        any_grow |= grow;
       }
-      uint32_t pk[NPAD / 2];
+      uint32_t pk[NH / 2];
 #pragma unroll
-      for (int c = 0; c < NPAD; c += 2) {
-        const float p0 = exp2f(x[c] - (m_col[c] == -INFINITY ? 0.f : m_col[c]));
-        const float p1 = exp2f(x[c + 1] - (m_col[c + 1] == -INFINITY ? 0.f : m_col[c + 1]));
-        l_part[c] += p0;
-        l_part[c + 1] += p1;
-        pk[c >> 1] = pack_h2(p0, p1);
+      for (int i = 0; i < NH; i += 2) {
+        const float p0 = ex2(x[i] - (m_col[i] == -INFINITY ? 0.f : m_col[i]));
+        const float p1 = ex2(x[i + 1] - (m_col[i + 1] == -INFINITY ? 0.f : m_col[i + 1]));
+        l_part[i] += p0;
+        l_part[i + 1] += p1;
+        pk[i >> 1] = pack_h2(p0, p1);
       }
-      unsigned char* pb = sP + b * C::kPBytes + tid * 16;
+      // P^T tile in shared memory, MN-major core matrices: 16 B (8 columns) per key, column blocks 2048 B apart
+      unsigned char* pb = sP + b * C::kPBytes + (c0 / 8) * 2048 + kl * 16;
 #pragma unroll
-      for (int m8 = 0; m8 < NPAD / 8; ++m8)
+      for (int m8 = 0; m8 < NH / 8; ++m8)
         *reinterpret_cast<uint4*>(pb + m8 * 2048) = make_uint4(pk[m8 * 4], pk[m8 * 4 + 1], pk[m8 * 4 + 2], pk[m8 * 4 + 3]);
       fence_proxy_async_smem();
-      if (any_grow) {  // CTA-uniform: every thread derived the same maxima from the same smem values
+      // CTA-uniform per column half: every thread of a half derived the same maxima from the same smem values
+      if (__any_sync(0xffffffffu, any_grow) && j > 0) {
         mbar_wait(o_full, static_cast<uint32_t>((j - 1) & 1));
         tc_fence_after();
-        float o[NPAD];
-        tmem_ld_n<NPAD>(tmem_o + lane_base, o);
+        float o[NH];
+        tmem_ld_n<NH>(tmem_o + lane_base + c0, o);
         tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < NPAD; ++c) o[c] *= alpha[c];
-        tmem_st_n<NPAD>(tmem_o + lane_base, o);
+        for (int i = 0; i < NH; ++i) o[i] *= alpha[i];
+        tmem_st_n<NH>(tmem_o + lane_base + c0, o);
         tmem_st_wait();
       }
       tc_fence_before();
@@ -282,61 +334,60 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
 
     // ---- per-query sums over all keys of this split ----
+    const float lsum = warp_reduce_vec<NH, false>(l_part, lane);
+    named_bar_sync(1, kSoftmaxThreads);  // everyone is done reading `red` of the last tile
+    if ((lane & (32 / NH - 1)) == 0) red[quad * NPAD + my_col] = lsum;
+    named_bar_sync(1, kSoftmaxThreads);
+    float l_col[NH];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int c = 0; c < NPAD; ++c) l_part[c] += __shfl_xor_sync(0xffffffffu, l_part[c], o);
+    for (int i = 0; i < NH; ++i) {
+      const int c = c0 + i;
+      l_col[i] = (red[c] + red[NPAD + c]) + (red[2 * NPAD + c] + red[3 * NPAD + c]);
     }
-    named_bar_sync(1, 128);  // everyone is done reading `red` of the last tile
-#pragma unroll
-    for (int c = 0; c < NPAD; ++c)
-      if (lane == c) red[warp * NPAD + c] = l_part[c];
-    named_bar_sync(1, 128);
-    float l_col[NPAD];
-#pragma unroll
-    for (int c = 0; c < NPAD; ++c) l_col[c] = (red[c] + red[NPAD + c]) + (red[2 * NPAD + c] + red[3 * NPAD + c]);
 
     // ---- epilogue: O^T (TMEM lane = d, column = query row) ----
     mbar_wait(o_full, static_cast<uint32_t>((T - 1) & 1));
     tc_fence_after();
-    float o[NPAD];
-    tmem_ld_n<NPAD>(tmem_o + lane_base, o);
+    float o[NH];
+    tmem_ld_n<NH>(tmem_o + lane_base + c0, o);
     tmem_ld_wait();
-    const int d = tid;
+    const int d = kl;
     if (p.n_splits == 1) {
 #pragma unroll
-      for (int c = 0; c < NPAD; ++c) {
+      for (int i = 0; i < NH; ++i) {
+        const int c = c0 + i;
         if (c < cols_valid) {
           const int h = hk * G + c / p.q_len, r = c % p.q_len;
-          const float inv = l_col[c] > 0.f ? 1.f / l_col[c] : 0.f;
-          p.out[(static_cast<long long>(r) * p.n_heads + h) * D + d] = __float2half_rn(o[c] * inv);
+          const float inv = l_col[i] > 0.f ? 1.f / l_col[i] : 0.f;
+          p.out[(static_cast<long long>(r) * p.n_heads + h) * D + d] = __float2half_rn(o[i] * inv);
         }
       }
     } else {
 #pragma unroll
-      for (int c = 0; c < NPAD; ++c) {
+      for (int i = 0; i < NH; ++i) {
+        const int c = c0 + i;
         if (c < cols_valid) {
           const int h = hk * G + c / p.q_len, r = c % p.q_len;
           const long long idx = (static_cast<long long>(split) * p.n_heads + h) * p.q_len + r;
-          p.part_o[idx * D + d] = o[c];
-          if (tid == c) {
-            p.part_ml[idx * 2] = m_col[c];
-            p.part_ml[idx * 2 + 1] = l_col[c];
+          p.part_o[idx * D + d] = o[i];
+          if (kl == i) {
+            p.part_ml[idx * 2] = m_col[i];
+            p.part_ml[idx * 2 + 1] = l_col[i];
           }
         }
       }
       // last CTA of this KV head merges the partials (no separate combine launch)
       __threadfence();
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kSoftmaxThreads);
       if (tid == 0) {
         const int old = atomicAdd(p.counters + hk, 1);
         *flag = (old == p.n_splits - 1) ? 1 : 0;
         if (old == p.n_splits - 1) p.counters[hk] = 0;  // self-cleaning for the next launch
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kSoftmaxThreads);
       if (*flag) {
         __threadfence();
-        for (int c = 0; c < cols_valid; ++c) {
+        for (int c = ch; c < cols_valid; c += 2) {  // the two column halves interleave over the valid columns
           const int h = hk * G + c / p.q_len, r = c % p.q_len;
           float m_star = -INFINITY;
           for (int s = 0; s < p.n_splits; ++s)
@@ -358,7 +409,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kSoftmaxWarps + 1) {
     tc_fence_after();
     tmem_free<C::kTmemCols>(tmem_base);
   }
