@@ -42,8 +42,8 @@ struct SCfg {
   static constexpr int kOffQ = kStages * 2 * kTileBytes;
   static constexpr int kOffP = kOffQ + kQBytes;
   static constexpr int kOffRed = kOffP + 2 * kPBytes;           // float red[2][4][NPAD]
-  static constexpr int kOffMisc = kOffRed + 2 * 4 * NPAD * 4;   // int rtab[NPAD]; float slopetab[NPAD]; int flag
-  static constexpr int kOffBars = kOffMisc + 2 * NPAD * 4 + 16;
+  static constexpr int kOffMisc = kOffRed + 2 * 4 * NPAD * 4;   // rtab, slopetab, otab, ptab [NPAD] each; int flag
+  static constexpr int kOffBars = kOffMisc + 4 * NPAD * 4 + 16;
   static constexpr int kSmem = 1024 + kOffBars + 256;
   static constexpr int kTmemCols = NPAD <= 16 ? 64 : 128;       // S^T x2 + O^T = 3*NPAD
 };
@@ -57,7 +57,18 @@ struct SmallParams {
   const int* key_pos;
   int n_heads, n_kv_heads, n_cached, q_len, n_splits, alibi_max_pos;
   float scale;
+  unsigned long long* trace;  // debug: %globaltimer stamps of CTA 0 (PC_ATTN_TRACE_PTR), else nullptr
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define PC_TRACE(slot)                                                   \
+  do {                                                                   \
+    if (p.trace != nullptr && blockIdx.x == 0) p.trace[(slot)] = gtime(); \
+  } while (0)
 
 __device__ __forceinline__ float round_h(float x) { return __half2float(__float2half_rn(x)); }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
@@ -137,7 +148,9 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   float* red = reinterpret_cast<float*>(smem + C::kOffRed);
   int* rtab = reinterpret_cast<int*>(smem + C::kOffMisc);  // query row r of column c (c = g*q + r)
   float* slopetab = reinterpret_cast<float*>(rtab + NPAD);  // ALiBi slope of column c
-  int* flag = reinterpret_cast<int*>(slopetab + NPAD);
+  int* otab = reinterpret_cast<int*>(slopetab + NPAD);     // out row of column c:  r*H + h
+  int* ptab = otab + NPAD;                                 // partial row of column c: h*q + r
+  int* flag = ptab + NPAD;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBars);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;
@@ -157,6 +170,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   const int tile0 = static_cast<int>(static_cast<long long>(split) * tiles_total / p.n_splits);
   const int tile1 = static_cast<int>(static_cast<long long>(split + 1) * tiles_total / p.n_splits);
   const int T = tile1 - tile0;  // >= 1 (host guarantees n_splits <= tiles_total)
+  if (tid == 0) PC_TRACE(0);
 
   if (warp == kSoftmaxWarps && lane == 0) {
     tma_prefetch_desc(&map_q);
@@ -179,12 +193,16 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   if (tid < NPAD) {
     rtab[tid] = tid < cols_valid ? tid % p.q_len : 0x3fffffff;  // padding columns: nothing is masked, never stored
     slopetab[tid] = (ALIBI && tid < cols_valid) ? p.alibi_slopes[hk * G + tid / p.q_len] : 0.f;
+    const int h = hk * G + tid / p.q_len, r = tid % p.q_len;
+    otab[tid] = r * p.n_heads + h;
+    ptab[tid] = h * p.q_len + r;
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + 2 * NPAD;
+  if (tid == 0) PC_TRACE(1);  // setup done
 
   if (warp == kSoftmaxWarps) {
     // ===================== TMA producer =====================
@@ -223,7 +241,9 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         tc_commit(&s_full[j & 1]);
       };
       mbar_wait(q_full, 0);
+      PC_TRACE(5);  // Q landed
       issue_st(0);
+      PC_TRACE(6);  // first K landed and S^T_0 issued
       for (int j = 0; j < T; ++j) {
         if (j + 1 < T) issue_st(j + 1);
         const int s = j % kStages;
@@ -259,6 +279,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       const int b = j & 1;
       mbar_wait(&s_full[b], static_cast<uint32_t>((j >> 1) & 1));
       tc_fence_after();
+      if (tid == 0 && j < 8) PC_TRACE(8 + 4 * j);  // S^T_j landed
       float x[NH];
       tmem_ld_n<NH>(tmem_base + lane_base + b * NPAD + c0, x);
       tmem_ld_wait();
@@ -288,6 +309,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       float* rb = red + b * 4 * NPAD;
       if ((lane & (32 / NH - 1)) == 0) rb[quad * NPAD + my_col] = wmax;
       named_bar_sync(1, kSoftmaxThreads);
+      if (tid == 0 && j < 8) PC_TRACE(9 + 4 * j);  // tile max exchanged
       bool any_grow = false;
       float alpha[NH];
 #pragma unroll
@@ -331,9 +353,10 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
       tc_fence_before();
       mbar_arrive(&p_full[b]);
+      if (tid == 0 && j < 8) PC_TRACE(10 + 4 * j);  // P^T_j published
     }
 
-    // ---- per-query sums over all keys of this split ----
+    // ---- per-query sums over all keys of this split (independent of the last P.V, so done first) ----
     const float lsum = warp_reduce_vec<NH, false>(l_part, lane);
     named_bar_sync(1, kSoftmaxThreads);  // everyone is done reading `red` of the last tile
     if ((lane & (32 / NH - 1)) == 0) red[quad * NPAD + my_col] = lsum;
@@ -348,18 +371,19 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     // ---- epilogue: O^T (TMEM lane = d, column = query row) ----
     mbar_wait(o_full, static_cast<uint32_t>((T - 1) & 1));
     tc_fence_after();
+    if (tid == 0) PC_TRACE(2);  // last PV landed
     float o[NH];
     tmem_ld_n<NH>(tmem_o + lane_base + c0, o);
     tmem_ld_wait();
     const int d = kl;
+    const int HQ = p.n_heads * p.q_len;
     if (p.n_splits == 1) {
 #pragma unroll
       for (int i = 0; i < NH; ++i) {
         const int c = c0 + i;
         if (c < cols_valid) {
-          const int h = hk * G + c / p.q_len, r = c % p.q_len;
           const float inv = l_col[i] > 0.f ? 1.f / l_col[i] : 0.f;
-          p.out[(static_cast<long long>(r) * p.n_heads + h) * D + d] = __float2half_rn(o[i] * inv);
+          p.out[static_cast<long long>(otab[c]) * D + d] = __float2half_rn(o[i] * inv);
         }
       }
     } else {
@@ -367,46 +391,77 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       for (int i = 0; i < NH; ++i) {
         const int c = c0 + i;
         if (c < cols_valid) {
-          const int h = hk * G + c / p.q_len, r = c % p.q_len;
-          const long long idx = (static_cast<long long>(split) * p.n_heads + h) * p.q_len + r;
+          const long long idx = static_cast<long long>(split) * HQ + ptab[c];
           p.part_o[idx * D + d] = o[i];
-          if (kl == i) {
-            p.part_ml[idx * 2] = m_col[i];
-            p.part_ml[idx * 2 + 1] = l_col[i];
-          }
+          if (kl == i) *reinterpret_cast<float2*>(p.part_ml + idx * 2) = make_float2(m_col[i], l_col[i]);
         }
       }
-      // last CTA of this KV head merges the partials (no separate combine launch)
-      __threadfence();
+      // The LAST CTA of this KV head merges the partials (no separate combine launch).  bar.sync orders every
+      // thread's partial stores before thread 0's gpu-scope fence + arrival (fence cumulativity).
       named_bar_sync(1, kSoftmaxThreads);
       if (tid == 0) {
+        __threadfence();
         const int old = atomicAdd(p.counters + hk, 1);
-        *flag = (old == p.n_splits - 1) ? 1 : 0;
-        if (old == p.n_splits - 1) p.counters[hk] = 0;  // self-cleaning for the next launch
+        const int last = (old == p.n_splits - 1) ? 1 : 0;
+        if (last) p.counters[hk] = 0;  // self-cleaning for the next launch
+        __threadfence();
+        *flag = last;
       }
       named_bar_sync(1, kSoftmaxThreads);
+      if (tid == 0) PC_TRACE(3);  // partials published
       if (*flag) {
-        __threadfence();
-        for (int c = ch; c < cols_valid; c += 2) {  // the two column halves interleave over the valid columns
-          const int h = hk * G + c / p.q_len, r = c % p.q_len;
+        // stage (m, l) of every split x column in shared memory (reuses the P^T buffers: all MMAs are done)
+        float2* ml_s = reinterpret_cast<float2*>(sP);  // [n_splits][NPAD]
+        for (int e = tid; e < p.n_splits * cols_valid; e += kSoftmaxThreads) {
+          const int s = e / cols_valid, c = e - s * cols_valid;
+          ml_s[s * NPAD + c] = __ldcg(reinterpret_cast<const float2*>(p.part_ml) + static_cast<long long>(s) * HQ + ptab[c]);
+        }
+        named_bar_sync(1, kSoftmaxThreads);
+        if (tid < cols_valid) {  // weights w_s = 2^(m_s - m*) / sum_s 2^(m_s - m*) l_s, written over m
           float m_star = -INFINITY;
-          for (int s = 0; s < p.n_splits; ++s)
-            m_star = fmaxf(m_star, __ldcg(p.part_ml + ((static_cast<long long>(s) * p.n_heads + h) * p.q_len + r) * 2));
-          float acc = 0.f, l = 0.f;
+          for (int s = 0; s < p.n_splits; ++s) m_star = fmaxf(m_star, ml_s[s * NPAD + tid].x);
+          float l = 0.f;
           for (int s = 0; s < p.n_splits; ++s) {
-            const long long idx = (static_cast<long long>(s) * p.n_heads + h) * p.q_len + r;
-            const float m = __ldcg(p.part_ml + idx * 2);
-            if (m == -INFINITY) continue;
-            const float w = exp2f(m - m_star);
-            l += w * __ldcg(p.part_ml + idx * 2 + 1);
-            acc += w * __ldcg(p.part_o + idx * D + d);
+            const float2 v = ml_s[s * NPAD + tid];
+            const float w = v.x == -INFINITY ? 0.f : exp2f(v.x - m_star);
+            l += w * v.y;
+            ml_s[s * NPAD + tid].x = w;
           }
-          p.out[(static_cast<long long>(r) * p.n_heads + h) * D + d] = __float2half_rn(l > 0.f ? acc / l : 0.f);
+          const float inv = l > 0.f ? 1.f / l : 0.f;
+          for (int s = 0; s < p.n_splits; ++s) ml_s[s * NPAD + tid].x *= inv;
+        }
+        named_bar_sync(1, kSoftmaxThreads);
+        float acc[NH];
+#pragma unroll
+        for (int i = 0; i < NH; ++i) acc[i] = 0.f;
+        for (int s0 = 0; s0 < p.n_splits; s0 += 4) {
+          float v[NH][4];
+#pragma unroll
+          for (int i = 0; i < NH; ++i) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {  // NH*4 independent L2 loads in flight per thread
+              const int s = s0 + u, c = c0 + i;
+              v[i][u] = (s < p.n_splits && c < cols_valid)
+                            ? __ldcg(p.part_o + (static_cast<long long>(s) * HQ + ptab[c]) * D + d) : 0.f;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < NH; ++i) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (s0 + u < p.n_splits) acc[i] = fmaf(ml_s[(s0 + u) * NPAD + c0 + i].x, v[i][u], acc[i]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NH; ++i) {
+          const int c = c0 + i;
+          if (c < cols_valid) p.out[static_cast<long long>(otab[c]) * D + d] = __float2half_rn(acc[i]);
         }
       }
     }
   }
 
+  if (tid == 0) PC_TRACE(4);  // softmax group done (incl. merge if last)
   tc_fence_before();
   __syncthreads();
   if (warp == kSoftmaxWarps + 1) {
@@ -468,6 +523,8 @@ int launch_small_n(const pc_attn_params& p, cudaStream_t st) {
   sp.n_splits = n_splits;
   sp.alibi_max_pos = p.alibi_max_pos;
   sp.scale = p.scale;
+  sp.trace = nullptr;
+  if (const char* e = getenv("PC_ATTN_TRACE_PTR")) sp.trace = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
 
   const int rows_total = G * p.q_len;
   CUtensorMap mq, mk, mv;

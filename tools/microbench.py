@@ -17,6 +17,31 @@ except Exception:
     pass
 
 
+def timeit_graph(fn, reps=16, iters=10):
+    """GPU-side time per call: capture `reps` back-to-back calls in a CUDA graph (no host launch overhead)."""
+    fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        fn()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(reps):
+                fn()
+    torch.cuda.synchronize()
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        g.replay()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / (iters * reps)
+
+
 def timeit(fn, iters=20, warmup=3):
     for _ in range(warmup):
         fn()
@@ -83,7 +108,7 @@ def bench_attn():
                 state["i"] += 1
                 nat.attention(Q, K[l], V[l], out, N, q, H, Hkv, D, nat.softmax_scale(D), nat.PC_ROUND_LLAMA, workspace=ws,
                               impl=impl, decode=(q == 1))
-            ms = timeit(run, iters=16, warmup=3)
+            ms = timeit_graph(run, reps=16, iters=10)
             G = H // Hkv
             # causal-aware flop count: key j>=N visible to rows r>=j-N
             vis = q * N + q * (q + 1) // 2
