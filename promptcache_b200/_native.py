@@ -112,8 +112,18 @@ def _require_cuda(*tensors: torch.Tensor) -> None:
             raise NativeError("promptcache_b200 kernels take CUDA tensors only (no CPU path exists)")
 
 
+_replayed_launches = 0
+
+
+def note_replayed_launches(n: int) -> None:
+    """Kernels of this library re-launched by a CUDA-graph replay (they do not pass through the C ABI again)."""
+    global _replayed_launches
+    _replayed_launches += int(n)
+
+
 def launch_count() -> int:
-    return int(load().pc_launch_count())
+    """Kernels of this library launched by this process: direct C-ABI launches + graph-replayed ones."""
+    return int(load().pc_launch_count()) + _replayed_launches
 
 
 def splice_kv(segments: Sequence[tuple], cache: torch.Tensor) -> None:

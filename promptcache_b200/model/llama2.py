@@ -86,6 +86,12 @@ class LlamaForCausalLM(nn.Module):
         self.lm_head = w(c.vocab_size, hid)
         self._cos = self._sin = None
         self._ws = None
+        # CUDA graphs of the whole single-sequence forward, keyed by (q_len, n_cached, KV buffer): the per-layer
+        # launch sequence is fixed once those are, so a repeated request shape is replayed with one launch
+        self.use_cuda_graphs = True
+        self._graphs = {}
+        self._graph_seen = {}
+        self.max_graphs = 8
         self.attn_impl = nat.PC_ATTN_AUTO
         self.rounding = nat.PC_ROUND_LLAMA
         self.scale = nat.softmax_scale(self.head_dim)
@@ -134,6 +140,7 @@ class LlamaForCausalLM(nn.Module):
         rows = max(int(rows), int(getattr(self.config, "max_position_embeddings", 2048)))
         if self._cos is None or self._cos.shape[0] < rows or self._cos.device != self.device:
             rows = ((rows + 1023) // 1024) * 1024
+            self._graphs.clear()  # captured graphs hold the old table pointers
             self._cos, self._sin = build_rope_tables(self.head_dim, rows, self.theta, self.device)
 
     def _workspace(self, q_len: int) -> Optional[torch.Tensor]:
@@ -142,14 +149,48 @@ class LlamaForCausalLM(nn.Module):
             return None
         if self._ws is None or self._ws.numel() < need or self._ws.device != self.device:
             # zero-initialised once: the first bytes hold split-KV arrival counters the kernels leave zeroed
+            self._graphs.clear()  # captured graphs hold the old workspace pointer
             self._ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
         return self._ws
 
     # ---- forward --------------------------------------------------------------------------------------
     def _forward_one(self, ids: torch.Tensor, pos: torch.Tensor, past, use_cache: bool):
         q_len = ids.shape[0]
+        kv = resolve_kv(past, q_len, self.n_layers, self.n_kv_heads, self.head_dim, self.device)
+        N = kv.n_cached
+        key = (q_len, N, kv.k[0].data_ptr(), kv.max_ctx)
+        if self.use_cuda_graphs and N > 0 and q_len > 1 and not torch.cuda.is_current_stream_capturing():
+            entry = self._graphs.get(key)
+            if entry is None and self._graph_seen.get(key, 0) >= 1:
+                entry = self._capture(key, ids, pos, kv)
+            self._graph_seen[key] = self._graph_seen.get(key, 0) + 1
+            if entry is not None:
+                graph, s_ids, s_pos, s_logits, n_native = entry
+                s_ids.copy_(ids, non_blocking=True)
+                s_pos.copy_(pos, non_blocking=True)
+                graph.replay()
+                nat.note_replayed_launches(n_native)
+                return s_logits.clone(), (kv.views(N + q_len) if use_cache else None)
+        logits = self._layers(ids, pos, kv)
+        return logits, (kv.views(N + q_len) if use_cache else None)
+
+    def _capture(self, key, ids, pos, kv):
+        """Record the forward for this (q_len, n_cached, KV buffer) once; later calls replay it."""
+        if len(self._graphs) >= self.max_graphs:
+            self._graphs.pop(next(iter(self._graphs)))
+        s_ids, s_pos = ids.clone(), pos.clone()
+        self._layers(s_ids, s_pos, kv)  # warm-up on the capture inputs (function attributes, workspaces, cuBLAS)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        before = nat.launch_count()
+        with torch.cuda.graph(graph):
+            s_logits = self._layers(s_ids, s_pos, kv)
+        self._graphs[key] = (graph, s_ids, s_pos, s_logits, nat.launch_count() - before)
+        return self._graphs[key]
+
+    def _layers(self, ids: torch.Tensor, pos: torch.Tensor, kv) -> torch.Tensor:
+        q_len = ids.shape[0]
         H, Hkv, D = self.n_heads, self.n_kv_heads, self.head_dim
-        kv = resolve_kv(past, q_len, self.n_layers, Hkv, D, self.device)
         N = kv.n_cached
         x = F.embedding(ids, self.embed_tokens)  # [q, hidden]: the residual stream, updated in place
         h = torch.empty_like(x)
@@ -172,8 +213,7 @@ class LlamaForCausalLM(nn.Module):
             nat.silu_mul(gu, act, inter)
             delta = F.linear(act, self.w_down[l])
         nat.add_rmsnorm(x, delta, self.norm, h, self.eps)
-        logits = F.linear(h, self.lm_head).float()
-        return logits, (kv.views(N + q_len) if use_cache else None)
+        return F.linear(h, self.lm_head).float()
 
     @torch.inference_mode()
     def forward(self, input_ids: torch.Tensor = None, attention_mask: Optional[torch.Tensor] = None,

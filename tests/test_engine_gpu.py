@@ -183,3 +183,35 @@ def test_llama7b_shaped_layers_match_oracle(native):
         assert _rel(cache[1][1][:, row:row + n], enc[1][1][0][:, off:off + n]) < 5e-3
         row += n
     assert row == 2048
+
+
+def test_cuda_graph_replay_matches_eager(native, gold):
+    """A repeated request shape is served from a captured CUDA graph; results equal the eager launches."""
+    from promptcache_b200 import CacheEngine, Prompt
+    lm = _tiny_lm(gold, native)
+    eng = CacheEngine(64, lm)
+    eng.add_schema(gold["schema"])
+    model = lm.hf_model
+    outs = []
+    for i in range(4):
+        ids, pos, _, cache = eng.process(Prompt(gold["prompt"]))
+        out = lm(input_ids=torch.tensor([ids], device=DEV), position_ids=torch.tensor([pos], device=DEV),
+                 past_key_values=[(k.unsqueeze(0), v.unsqueeze(0)) for k, v in cache], use_cache=True)
+        outs.append(out.logits.clone())
+    assert len(model._graphs) == 1  # captured on the second occurrence, replayed afterwards
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    model.use_cuda_graphs = False
+    ids, pos, _, cache = eng.process(Prompt(gold["prompt"]))
+    eager = lm(input_ids=torch.tensor([ids], device=DEV), position_ids=torch.tensor([pos], device=DEV),
+               past_key_values=[(k.unsqueeze(0), v.unsqueeze(0)) for k, v in cache], use_cache=True).logits
+    assert torch.equal(eager, outs[0])
+    # different suffix tokens through the same graph
+    model.use_cuda_graphs = True
+    ids2 = [(t + 1) % 100 + 4 for t in ids]
+    a = lm(input_ids=torch.tensor([ids2], device=DEV), position_ids=torch.tensor([pos], device=DEV),
+           past_key_values=[(k.unsqueeze(0), v.unsqueeze(0)) for k, v in eng.process(Prompt(gold["prompt"]))[3]], use_cache=True).logits
+    model.use_cuda_graphs = False
+    b = lm(input_ids=torch.tensor([ids2], device=DEV), position_ids=torch.tensor([pos], device=DEV),
+           past_key_values=[(k.unsqueeze(0), v.unsqueeze(0)) for k, v in eng.process(Prompt(gold["prompt"]))[3]], use_cache=True).logits
+    assert torch.equal(a, b) and not torch.equal(a, outs[0])
