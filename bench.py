@@ -214,7 +214,13 @@ def main():
     max_ctx = ((case.n_cached + case.q_len + 256 + 127) // 128) * 128
     eng = CacheEngine(max_ctx, lm)
     eng.prompt_cache.retain_prefix = False  # every step splices every segment
-    eng.add_schema(case.schema_xml)
+    from promptcache_b200 import parallel
+    if world > 1:
+        # rank 0 encodes the schema once; the segment store reaches the other GPUs over NCCL (NVLink)
+        eng.add_schema(case.schema_xml, no_cache=(rank != 0))
+        parallel.broadcast_schema(eng.schemas[case.name], src=0, device=dev)
+    else:
+        eng.add_schema(case.schema_xml)
     # each rank serves its own prompt (same modules, its own suffix tokens)
     if world > 1:
         mine = flat_schema(case.name, seg_lens, case.q_len, md["vocab_size"], seed=1002 + 17 * rank)

@@ -1,0 +1,95 @@
+"""Batch partition across the GPUs of one node.
+
+Prompts are independent, so the hot path shards with NO data-path collective: prompt b is served by rank
+b mod G, every rank holds the full weights and its own HBM copy of the schema's segment store.  NCCL (over
+NVLink 5 / NVSwitch) is used for two things only:
+  * `broadcast_schema`  one-time broadcast of the segment store rank `src` encoded, so that `add_schema`
+                        runs the scaffold forwards once per node instead of once per GPU;
+  * `gather_results`    all-gather of the per-rank outputs / timings at the end of a batch.
+The reference has no distributed code at all; it runs one OS process per GPU over a dataset
+(eval_acc.py:240-262, scripts/run_benchmarks.py:48-62) -- this module is the in-process equivalent.
+"""
+from __future__ import annotations
+
+from typing import Any, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank() -> int:
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def shard_indices(n_items: int, rank_: Optional[int] = None, world_: Optional[int] = None) -> List[int]:
+    """Indices of the prompts rank `rank_` serves: b mod G == rank (round-robin keeps shards within one item)."""
+    r = rank() if rank_ is None else rank_
+    w = world() if world_ is None else world_
+    return list(range(r, n_items, w))
+
+
+def gather_results(local: Any) -> List[Any]:
+    """All ranks' `local` objects, in rank order (a list of length 1 without a process group)."""
+    if world() == 1:
+        return [local]
+    out: List[Any] = [None] * world()
+    dist.all_gather_object(out, local)
+    return out
+
+
+def merge_sharded(per_rank: Sequence[Sequence[Any]], n_items: int) -> List[Any]:
+    """Inverse of shard_indices: interleave the per-rank result lists back into prompt order."""
+    w = len(per_rank)
+    merged: List[Any] = [None] * n_items
+    for r, items in enumerate(per_rank):
+        for k, item in enumerate(items):
+            merged[r + k * w] = item
+    return merged
+
+
+def max_over_ranks(value_ms: float, device=None) -> float:
+    """Timing rule: a multi-GPU step takes as long as its slowest rank."""
+    if world() == 1:
+        return float(value_ms)
+    t = torch.tensor([value_ms], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def broadcast_schema(schema_cache, src: int = 0, device=None) -> None:
+    """Make every rank hold the segment store rank `src` encoded.
+
+    `schema_cache` is a SchemaCache built with the same schema on every rank (`no_cache=True` on ranks other
+    than `src`, so only `src` ran the scaffold forwards).  Segments are matched by (offset, length, token ids),
+    which every rank derives identically from the schema, and moved with one broadcast per segment (each is a
+    single packed [L,2,Hkv,len,D] allocation)."""
+    from .cache_engine import TokenSequenceCache
+    if world() == 1:
+        return
+    schema = schema_cache.schema
+    seqs = []
+    for path in schema_cache.scaffold_paths():
+        for seq in schema.get_scaffold(path).select(path).all_token_sequences():
+            if len(seq) > 0 and all(seq is not s for s in seqs):
+                seqs.append(seq)
+    # shape header from the source rank
+    meta: List[Any] = [None]
+    if rank() == src:
+        first = next(iter(schema_cache.cache_l1.values()))
+        L, two, hkv, _, d = first.packed.shape
+        meta = [(int(L), int(hkv), int(d), str(first.packed.dtype).replace("torch.", ""))]
+    dist.broadcast_object_list(meta, src=src)
+    L, hkv, d, dtype_name = meta[0]
+    dtype = getattr(torch, dtype_name)
+    for seq in seqs:
+        if rank() == src:
+            buf = schema_cache.cache_l1[id(seq)].packed
+        else:
+            buf = torch.empty(L, 2, hkv, len(seq), d, dtype=dtype, device=device if device is not None else "cpu")
+        dist.broadcast(buf, src=src)
+        if rank() != src:
+            schema_cache.cache_l1[id(seq)] = TokenSequenceCache(seq, buf)
