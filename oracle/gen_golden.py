@@ -109,7 +109,50 @@ def attn_cores():
     print("attn_cores.pt:", list(gold))
 
 
+def falcon_mpt_tiny():
+    """Reference Falcon (7B layout: MQA, parallel attn, rotary) and MPT (ALiBi) tiny models, fp32 on CPU: a prefix
+    forward builds the past, then a suffix forward with discontiguous position ids runs over it."""
+    ref_shim.load_reference()
+    gold = {}
+    prefix_ids = torch.tensor([[5, 9, 33, 77, 12, 8, 101, 64, 3, 90]])
+    prefix_pos = torch.tensor([[0, 1, 2, 3, 10, 11, 12, 13, 14, 15]])
+    suffix_ids = torch.tensor([[44, 45, 46, 47, 48]])
+    suffix_pos = torch.tensor([[4, 5, 30, 31, 32]])
+    # ---- Falcon
+    cfg = ref_shim.tiny_falcon_config(layers=2, heads=2, head_dim=64, vocab=128, max_pos=256)
+    lm = ref_shim.make_reference_lm("falcon", cfg, seed=5)
+    with torch.no_grad():
+        o1 = lm(input_ids=prefix_ids, position_ids=prefix_pos, use_cache=True)
+        o2 = lm(input_ids=suffix_ids, position_ids=suffix_pos, past_key_values=o1.past_key_values, use_cache=True)
+    gold["falcon"] = dict(state_dict={k: v.clone() for k, v in lm.hf_model.state_dict().items() if k != "lm_head.weight"},
+                          config=dict(layers=2, heads=2, head_dim=64, vocab=128, eps=cfg.layer_norm_epsilon),
+                          prefix_ids=prefix_ids, prefix_pos=prefix_pos, suffix_ids=suffix_ids, suffix_pos=suffix_pos,
+                          prefix_logits=o1.logits.clone(), suffix_logits=o2.logits.clone(),
+                          past=[(k.clone(), v.clone()) for k, v in o1.past_key_values],
+                          present=[(k.clone(), v.clone()) for k, v in o2.past_key_values])
+    # ---- MPT (full position ids: cached rows then new tokens)
+    cfg = ref_shim.tiny_mpt_config(layers=2, heads=2, head_dim=64, vocab=128, max_seq_len=256)
+    lm = ref_shim.make_reference_lm("mpt", cfg, seed=6)
+    full_pos = torch.cat([prefix_pos, suffix_pos], dim=1)
+    with torch.no_grad():
+        o1 = lm.hf_model(prefix_ids, prefix_pos, use_cache=True)
+        o2 = lm.hf_model(suffix_ids, full_pos, past_key_values=o1.past_key_values, use_cache=True)
+    gold["mpt"] = dict(state_dict={k: v.clone() for k, v in lm.hf_model.state_dict().items() if k != "lm_head.weight"},
+                       config=dict(layers=2, heads=2, head_dim=64, vocab=128, eps=cfg.layer_norm_epsilon),
+                       prefix_ids=prefix_ids, prefix_pos=prefix_pos, suffix_ids=suffix_ids, full_pos=full_pos,
+                       prefix_logits=o1.logits.clone(), suffix_logits=o2.logits.clone(),
+                       past=[(k.clone(), v.clone()) for k, v in o1.past_key_values],
+                       present=[(k.clone(), v.clone()) for k, v in o2.past_key_values])
+    torch.save(gold, os.path.join(OUT, "falcon_mpt_tiny.pt"))
+    print("falcon_mpt_tiny.pt:", {k: tuple(v["suffix_logits"].shape) for k, v in gold.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    llama_tiny()
-    attn_cores()
+    only = sys.argv[1:] or ["llama", "cores", "falcon_mpt"]
+    if "llama" in only:
+        llama_tiny()
+    if "cores" in only:
+        attn_cores()
+    if "falcon_mpt" in only:
+        falcon_mpt_tiny()

@@ -1,0 +1,155 @@
+"""Shared plumbing of the B200 model families: HF-style forward signature, in-place KV buffers, RoPE tables,
+attention workspace and CUDA-graph replay of the single-sequence forward."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _native as nat
+from ._kv import CausalLMOutput, resolve_kv
+
+
+def build_rope_tables(head_dim: int, rows: int, theta: float, device, dtype=torch.float16):
+    """cos/sin tables as LlamaRotaryEmbedding._set_cos_sin_cache (llama2.py:128-137) and
+    FalconRotaryEmbedding._set_cos_sin_cache (falcon.py:104-118) build them: fp32 angles, cast at the end."""
+    inv_freq = 1.0 / (theta ** (torch.arange(0, head_dim, 2, device=device).float() / head_dim))
+    t = torch.arange(rows, device=device, dtype=inv_freq.dtype)
+    freqs = torch.einsum("i,j->ij", t, inv_freq)
+    emb = torch.cat((freqs, freqs), dim=-1)
+    return emb.cos().to(dtype).contiguous(), emb.sin().to(dtype).contiguous()
+
+
+class B200CausalLM(nn.Module):
+    """Subclasses set n_layers/n_heads/n_kv_heads/head_dim/vocab_size, `rotary` and implement `_layers`."""
+
+    accepts_max_position = True   # forward() takes the host-known max position id (avoids a device sync)
+    full_position_ids = False     # MPT: position_ids cover cached + new tokens (mpt.py:172)
+    rotary = True
+
+    def _init_runtime(self):
+        self._cos = self._sin = None
+        self._ws = None
+        self.attn_impl = nat.PC_ATTN_AUTO
+        # CUDA graphs of the whole single-sequence forward, keyed by (q_len, n_cached, KV buffer): the per-layer
+        # launch sequence is fixed once those are, so a repeated request shape is replayed with one launch
+        self.use_cuda_graphs = True
+        self._graphs = {}
+        self._graph_seen = {}
+        self.max_graphs = 8
+
+    @property
+    def device(self) -> torch.device:
+        return next(self.parameters()).device
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return next(self.parameters()).dtype
+
+    # ---- RoPE tables / workspace -------------------------------------------------------------------------
+    def ensure_rope(self, rows: int) -> None:
+        """Grow-on-demand like llama2.py:141-142, but driven by host-known ids (no device sync)."""
+        if not self.rotary:
+            return
+        rows = max(int(rows), int(getattr(self.config, "max_position_embeddings", 2048)))
+        if self._cos is None or self._cos.shape[0] < rows or self._cos.device != self.device:
+            rows = ((rows + 1023) // 1024) * 1024
+            self._graphs.clear()  # captured graphs hold the old table pointers
+            self._cos, self._sin = build_rope_tables(self.head_dim, rows, self.theta, self.device)
+
+    def _workspace(self, q_len: int) -> Optional[torch.Tensor]:
+        need = nat.attn_workspace_bytes(self.n_heads, q_len, self.head_dim)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != self.device:
+            # zero-initialised once: the first bytes hold split-KV arrival counters the kernels leave zeroed
+            self._graphs.clear()  # captured graphs hold the old workspace pointer
+            self._ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # ---- forward ---------------------------------------------------------------------------------------
+    def _layers(self, ids: torch.Tensor, pos: torch.Tensor, kv, extra) -> torch.Tensor:
+        raise NotImplementedError
+
+    def _graph_extra(self, pos_host_max: int):
+        """Host scalars baked into kernel parameters besides (q_len, n_cached); part of the graph key."""
+        return ()
+
+    def _forward_one(self, ids: torch.Tensor, pos: torch.Tensor, past, use_cache: bool, max_position: int):
+        q_len = ids.shape[0]
+        kv = resolve_kv(past, q_len, self.n_layers, self.n_kv_heads, self.head_dim, self.device)
+        N = kv.n_cached
+        extra = self._graph_extra(max_position)
+        key = (q_len, N, kv.k[0].data_ptr(), kv.max_ctx, pos.shape[0]) + tuple(extra)
+        if self.use_cuda_graphs and N > 0 and q_len > 1 and not torch.cuda.is_current_stream_capturing():
+            entry = self._graphs.get(key)
+            if entry is None and self._graph_seen.get(key, 0) >= 1:
+                entry = self._capture(key, ids, pos, kv, extra)
+            self._graph_seen[key] = self._graph_seen.get(key, 0) + 1
+            if entry is not None:
+                graph, s_ids, s_pos, s_logits, n_native = entry
+                s_ids.copy_(ids, non_blocking=True)
+                s_pos.copy_(pos, non_blocking=True)
+                graph.replay()
+                nat.note_replayed_launches(n_native)
+                return s_logits.clone(), (kv.views(N + q_len) if use_cache else None)
+        logits = self._layers(ids, pos, kv, extra)
+        return logits, (kv.views(N + q_len) if use_cache else None)
+
+    def _capture(self, key, ids, pos, kv, extra):
+        """Record the forward for this (q_len, n_cached, KV buffer) once; later calls replay it."""
+        if len(self._graphs) >= self.max_graphs:
+            self._graphs.pop(next(iter(self._graphs)))
+        s_ids, s_pos = ids.clone(), pos.clone()
+        self._layers(s_ids, s_pos, kv, extra)  # warm-up on the capture inputs (function attributes, workspaces, cuBLAS)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        before = nat.launch_count()
+        with torch.cuda.graph(graph):
+            s_logits = self._layers(s_ids, s_pos, kv, extra)
+        self._graphs[key] = (graph, s_ids, s_pos, s_logits, nat.launch_count() - before)
+        return self._graphs[key]
+
+    @torch.inference_mode()
+    def forward(self, input_ids: torch.Tensor = None, position_ids: Optional[torch.Tensor] = None,
+                past_key_values=None, attention_mask: Optional[torch.Tensor] = None, inputs_embeds=None, labels=None,
+                use_cache: Optional[bool] = None, output_attentions=None, output_hidden_states=None,
+                return_dict=None, max_position: Optional[int] = None, **_):
+        if input_ids is None:
+            raise ValueError("promptcache_b200 models need input_ids")
+        if not input_ids.is_cuda:
+            raise nat.NativeError("promptcache_b200 models run on CUDA only (no CPU fallback)")
+        use_cache = True if use_cache is None else use_cache
+        bsz, q_len = input_ids.shape
+        past_len = 0 if not past_key_values else int(past_key_values[0][0].shape[-2])
+        if position_ids is None:
+            first = 0 if self.full_position_ids else past_len
+            position_ids = torch.arange(first, past_len + q_len, device=input_ids.device).unsqueeze(0).expand(bsz, -1)
+        position_ids = position_ids.view(bsz, -1).long()
+        want = past_len + q_len if self.full_position_ids else q_len
+        if position_ids.shape[1] != want:
+            raise ValueError(f"position_ids has {position_ids.shape[1]} entries, expected {want}")
+        if max_position is None:
+            max_position = int(position_ids.max())  # device sync; GenerationEngine passes the host value instead
+        self.ensure_rope(max_position + 1)
+        if bsz == 1:
+            logits, pkv = self._forward_one(input_ids[0], position_ids[0].contiguous(), past_key_values, use_cache,
+                                            max_position)
+            return CausalLMOutput(logits.unsqueeze(0), pkv)
+        # batch > 1 (schema encoding with right padding, cache_engine.py:240-248): rows are independent
+        if past_key_values:
+            raise ValueError("batched forward with past_key_values is not supported")
+        lens = [q_len] * bsz if attention_mask is None else [int(v) for v in attention_mask.to(torch.int64).sum(-1).tolist()]
+        logits = torch.zeros(bsz, q_len, self.vocab_size, dtype=torch.float32, device=input_ids.device)
+        pk = [[None] * bsz for _ in range(self.n_layers)]
+        pv = [[None] * bsz for _ in range(self.n_layers)]
+        for b in range(bsz):
+            n = max(lens[b], 1)
+            lg, pkv = self._forward_one(input_ids[b, :n], position_ids[b, :n].contiguous(), None, True,
+                                        int(position_ids[b, :n].max()))
+            logits[b, :n] = lg
+            for l, (k, v) in enumerate(pkv):
+                pk[l][b] = F.pad(k[0], (0, 0, 0, q_len - n))
+                pv[l][b] = F.pad(v[0], (0, 0, 0, q_len - n))
+        pkv = tuple((torch.stack(pk[l]), torch.stack(pv[l])) for l in range(self.n_layers)) if use_cache else None
+        return CausalLMOutput(logits, pkv)

@@ -1,0 +1,127 @@
+"""Falcon (MQA, rotary, SDPA rounding) and MPT (ALiBi at key ids, full position ids) adapters on the GPU against the
+oracle in fp16 on the same device and against goldens produced by the reference's own models (fp32, CPU)."""
+import pytest
+import torch
+
+from oracle import pc_oracle as O
+from tests.helpers import WordTokenizer, load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-12))
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return load_golden("falcon_mpt_tiny.pt")
+
+
+def _falcon(g):
+    from promptcache_b200.model.falcon import FalconConfigLite, FalconForCausalLM
+    c = g["config"]
+    m = FalconForCausalLM(FalconConfigLite(vocab_size=c["vocab"], hidden_size=c["heads"] * c["head_dim"], num_hidden_layers=c["layers"],
+                                           num_attention_heads=c["heads"], layer_norm_epsilon=c["eps"]), device=DEV)
+    m.load_hf_state_dict(g["state_dict"])
+    return m
+
+
+def _mpt(g):
+    from promptcache_b200.model.mpt import MptConfigLite, MptForCausalLM
+    c = g["config"]
+    m = MptForCausalLM(MptConfigLite(d_model=c["heads"] * c["head_dim"], n_heads=c["heads"], n_layers=c["layers"], vocab_size=c["vocab"],
+                                     layer_norm_epsilon=c["eps"], expansion_ratio=2), device=DEV)
+    m.load_hf_state_dict(g["state_dict"])
+    return m
+
+
+def test_falcon_prefix_then_suffix(native, gold):
+    g = gold["falcon"]
+    m = _falcon(g)
+    sd16 = {k: v.to(DEV).half() for k, v in g["state_dict"].items()}
+    cfg = dict(n_layers=2, n_heads=g["config"]["heads"], eps=g["config"]["eps"], theta=10000.0)
+    pre_ids, pre_pos = g["prefix_ids"].to(DEV), g["prefix_pos"].to(DEV)
+    suf_ids, suf_pos = g["suffix_ids"].to(DEV), g["suffix_pos"].to(DEV)
+    o1 = m(input_ids=pre_ids, position_ids=pre_pos, use_cache=True)
+    assert o1.past_key_values[0][0].shape == (1, 1, 10, 64)  # cache shape (L, 1, head_dim), model/__init__.py:256-258
+    r1, rp = O.falcon_forward(sd16, cfg, pre_ids, pre_pos, cos=m._cos, sin=m._sin)
+    assert _rel(o1.logits, r1) < 2e-3
+    assert _rel(o1.logits.cpu(), g["prefix_logits"]) < 2e-2
+    assert torch.equal(o1.past_key_values[0][0], rp[0][0]) or _rel(o1.past_key_values[0][0], rp[0][0]) < 1e-3
+    o2 = m(input_ids=suf_ids, position_ids=suf_pos, past_key_values=o1.past_key_values, use_cache=True)
+    r2, _ = O.falcon_forward(sd16, cfg, suf_ids, suf_pos, rp, cos=m._cos, sin=m._sin)
+    assert _rel(o2.logits, r2) < 2e-3
+    assert _rel(o2.logits.cpu(), g["suffix_logits"]) < 2e-2
+    assert o2.past_key_values[1][1].shape == (1, 1, 15, 64)
+    assert _rel(o2.past_key_values[1][0].cpu(), g["present"][1][0]) < 1e-2
+
+
+def test_mpt_prefix_then_suffix_full_position_ids(native, gold):
+    g = gold["mpt"]
+    m = _mpt(g)
+    sd16 = {k: v.to(DEV).half() for k, v in g["state_dict"].items()}
+    cfg = dict(n_layers=2, n_heads=g["config"]["heads"], eps=g["config"]["eps"])
+    pre_ids, pre_pos = g["prefix_ids"].to(DEV), g["prefix_pos"].to(DEV)
+    suf_ids, full_pos = g["suffix_ids"].to(DEV), g["full_pos"].to(DEV)
+    o1 = m(pre_ids, pre_pos, use_cache=True)  # MPT takes position_ids positionally 2nd (mpt.py:654-666)
+    r1, rp = O.mpt_forward(sd16, cfg, pre_ids, pre_pos)
+    assert _rel(o1.logits, r1) < 2e-3 and _rel(o1.logits.cpu(), g["prefix_logits"]) < 2e-2
+    o2 = m(suf_ids, full_pos, past_key_values=o1.past_key_values, use_cache=True)
+    r2, _ = O.mpt_forward(sd16, cfg, suf_ids, full_pos, rp)
+    assert _rel(o2.logits, r2) < 2e-3 and _rel(o2.logits.cpu(), g["suffix_logits"]) < 2e-2
+    with pytest.raises(ValueError):
+        m(suf_ids, g["suffix_ids"].to(DEV), past_key_values=o2.past_key_values)  # needs the full id list
+
+
+def test_falcon_engine_parameterized_prompt(native, gold):
+    """C4 shape in miniature: parameter slots filled at interior positions, non-monotone suffix ids, MQA cache."""
+    from promptcache_b200 import CacheEngine, GenerationEngine, GenerationParameters, Prompt
+    from promptcache_b200.model import Falcon
+    g = gold["falcon"]
+    lm = Falcon("tiny-falcon", model=_falcon(g), tokenizer=WordTokenizer(128))
+    assert lm.get_cache_shape() == (2, 1, 64)
+    eng = CacheEngine(128, lm)
+    eng.add_schema('<schema name="trip"><module name="sys">you plan trips well</module><module name="plan">a trip of'
+                   '<parameter name="duration" length="4"/>days to<parameter name="city" length="5"/>please</module></schema>')
+    ids, pos, _, cache = eng.process(Prompt('<prompt schema="trip"><sys/><plan duration="three" city="new york"/>now go</prompt>'))
+    assert pos == [7, 13, 14, 19, 20] and cache[0][0].shape == (1, 14, 64)
+    sd16 = {k: v.to(DEV).half() for k, v in g["state_dict"].items()}
+    cfg = dict(n_layers=2, n_heads=g["config"]["heads"], eps=g["config"]["eps"], theta=10000.0)
+    past = [(k.clone().unsqueeze(0), v.clone().unsqueeze(0)) for k, v in cache]
+    ref, _ = O.falcon_forward(sd16, cfg, torch.tensor([ids], device=DEV), torch.tensor([pos], device=DEV), past,
+                              cos=lm.hf_model._cos, sin=lm.hf_model._sin)
+    out = lm(input_ids=torch.tensor([ids], device=DEV), position_ids=torch.tensor([pos], device=DEV),
+             past_key_values=[(k.unsqueeze(0), v.unsqueeze(0)) for k, v in cache], use_cache=True)
+    assert _rel(out.logits, ref) < 2e-3
+    params = GenerationParameters(temperature=0.0, max_new_tokens=3, stop_token_ids=[], stop_str=[])
+    outs = list(GenerationEngine(lm).generate(ids, pos, params, eng.process(Prompt(
+        '<prompt schema="trip"><sys/><plan duration="three" city="new york"/>now go</prompt>'))[3], stream_interval=1))
+    assert len(outs) == 3
+
+
+def test_mpt_engine_full_ids_generate(native, gold):
+    from promptcache_b200 import CacheEngine, GenerationEngine, GenerationParameters, Prompt
+    from promptcache_b200.model import Mpt
+    g = gold["mpt"]
+    lm = Mpt("tiny-mpt", model=_mpt(g), tokenizer=WordTokenizer(128))
+    assert lm.use_full_position_ids and lm.get_cache_shape() == (2, 2, 64)
+    eng = CacheEngine(128, lm)
+    eng.add_schema('<schema name="u"><module name="h">a b c</module><union><module name="m1">d e f g h</module>'
+                   '<module name="m2">i j</module></union><module name="t">k l</module></schema>')
+    xml = '<prompt schema="u"><h/><m2/><t/>what is next</prompt>'
+    ids, pos, _, cache = eng.process(Prompt(xml), return_full_position_ids=True)
+    n = cache[0][0].shape[1]
+    assert n == 7 and len(pos) == n + len(ids) and pos[-3:] == [10, 11, 12]
+    sd16 = {k: v.to(DEV).half() for k, v in g["state_dict"].items()}
+    cfg = dict(n_layers=2, n_heads=g["config"]["heads"], eps=g["config"]["eps"])
+    past = [(k.clone().unsqueeze(0), v.clone().unsqueeze(0)) for k, v in cache]
+    ref, _ = O.mpt_forward(sd16, cfg, torch.tensor([ids], device=DEV), torch.tensor([pos], device=DEV), past)
+    out = lm(input_ids=torch.tensor([ids], device=DEV), position_ids=torch.tensor([pos], device=DEV),
+             past_key_values=[(k.unsqueeze(0), v.unsqueeze(0)) for k, v in cache], use_cache=True)
+    assert _rel(out.logits, ref) < 2e-3
+    params = GenerationParameters(temperature=0.0, max_new_tokens=3, stop_token_ids=[], stop_str=[])
+    ids, pos, _, cache = eng.process(Prompt(xml), return_full_position_ids=True)
+    outs = list(GenerationEngine(lm).generate(ids, pos, params, cache, stream_interval=1, use_full_position_ids=True))
+    assert len(outs) == 3

@@ -111,3 +111,33 @@ def test_rope_three_roundings_is_what_the_reference_does():
     a = (q.float() * c).half().float()
     b = (O.rotate_half(q).float() * s).half().float()
     assert torch.equal((a + b).half(), ref)
+
+
+def _fm_cfg(g):
+    c = g["config"]
+    return dict(n_layers=c["layers"], n_heads=c["heads"], eps=c["eps"], theta=10000.0)
+
+
+def test_falcon_forward_reproduces_reference():
+    """Oracle Falcon (MQA, parallel block, rotary at discontiguous ids, SDPA) vs the reference model, fp32 CPU."""
+    g = load_golden("falcon_mpt_tiny.pt")["falcon"]
+    sd, cfg = g["state_dict"], _fm_cfg(g)
+    lg1, past = O.falcon_forward(sd, cfg, g["prefix_ids"], g["prefix_pos"])
+    assert torch.equal(lg1, g["prefix_logits"])
+    for l in range(2):
+        assert torch.equal(past[l][0], g["past"][l][0]) and torch.equal(past[l][1], g["past"][l][1])
+    lg2, present = O.falcon_forward(sd, cfg, g["suffix_ids"], g["suffix_pos"], g["past"])
+    assert torch.equal(lg2, g["suffix_logits"])
+    for l in range(2):
+        assert torch.equal(present[l][0], g["present"][l][0]) and torch.equal(present[l][1], g["present"][l][1])
+
+
+def test_mpt_forward_reproduces_reference():
+    g = load_golden("falcon_mpt_tiny.pt")["mpt"]
+    sd, cfg = g["state_dict"], _fm_cfg(g)
+    lg1, past = O.mpt_forward(sd, cfg, g["prefix_ids"], g["prefix_pos"])
+    assert torch.equal(lg1, g["prefix_logits"])
+    lg2, present = O.mpt_forward(sd, cfg, g["suffix_ids"], g["full_pos"], g["past"])
+    assert torch.equal(lg2, g["suffix_logits"])
+    for l in range(2):
+        assert torch.equal(present[l][0], g["present"][l][0]) and torch.equal(present[l][1], g["present"][l][1])
