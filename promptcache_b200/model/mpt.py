@@ -63,7 +63,7 @@ class MptForCausalLM(B200CausalLM):
         self.alibi_bias_max = bias_max if bias_max is not None else getattr(c, "alibi_bias_max", 8)
         scale = getattr(attn_cfg, "softmax_scale", None) if attn_cfg is not None else getattr(c, "softmax_scale", None)
         self.scale = float(scale) if scale is not None else 1.0 / math.sqrt(self.head_dim)  # mpt.py:127-129
-        self.inter = int(getattr(c, "expansion_ratio", 4)) * hid
+        self.inter = 4 * hid  # the reference hard-codes 4x (mpt.py:195-197), whatever expansion_ratio says
         std = getattr(c, "initializer_range", 0.02)
 
         def w(*shape):

@@ -32,7 +32,7 @@ def _mpt(g):
     from promptcache_b200.model.mpt import MptConfigLite, MptForCausalLM
     c = g["config"]
     m = MptForCausalLM(MptConfigLite(d_model=c["heads"] * c["head_dim"], n_heads=c["heads"], n_layers=c["layers"], vocab_size=c["vocab"],
-                                     layer_norm_epsilon=c["eps"], expansion_ratio=2), device=DEV)
+                                     layer_norm_epsilon=c["eps"]), device=DEV)
     m.load_hf_state_dict(g["state_dict"])
     return m
 
@@ -86,7 +86,7 @@ def test_falcon_engine_parameterized_prompt(native, gold):
     eng.add_schema('<schema name="trip"><module name="sys">you plan trips well</module><module name="plan">a trip of'
                    '<parameter name="duration" length="4"/>days to<parameter name="city" length="5"/>please</module></schema>')
     ids, pos, _, cache = eng.process(Prompt('<prompt schema="trip"><sys/><plan duration="three" city="new york"/>now go</prompt>'))
-    assert pos == [7, 13, 14, 19, 20] and cache[0][0].shape == (1, 14, 64)
+    assert pos == [7, 13, 14, 19, 20] and cache[0][0].shape == (1, 10, 64)  # parameter slots are not cached rows
     sd16 = {k: v.to(DEV).half() for k, v in g["state_dict"].items()}
     cfg = dict(n_layers=2, n_heads=g["config"]["heads"], eps=g["config"]["eps"], theta=10000.0)
     past = [(k.clone().unsqueeze(0), v.clone().unsqueeze(0)) for k, v in cache]
