@@ -39,6 +39,7 @@ int launch_attn_simt(const pc_attn_params& p, cudaStream_t st);
 int launch_attn_tc(const pc_attn_params& p, cudaStream_t st);
 size_t attn_tc_workspace_bytes(int n_heads, int q_len, int head_dim);
 int launch_attn_small(const pc_attn_params& p, cudaStream_t st);
+int launch_attn_pp(const pc_attn_params& p, cudaStream_t st);
 bool attn_small_supported(const pc_attn_params& p);
 size_t attn_small_partial_bytes(int n_heads, int q_len, int head_dim);
 
@@ -80,7 +81,9 @@ static int attn_dispatch(const pc_attn_params* p, void* stream, const char* who)
   if (impl == PC_ATTN_TCGEN05) {
     const char* e = getenv("PC_ATTN_SMALL");
     if (attn_small_supported(*p) && !(e && e[0] == '0')) return launch_attn_small(*p, st);
-    return launch_attn_tc(*p, st);
+    const char* v1 = getenv("PC_ATTN_V1");  // A/B switch: the single-tile kernel of attn_tc.cu
+    if (v1 && v1[0] == '1') return launch_attn_tc(*p, st);
+    return launch_attn_pp(*p, st);
   }
   return set_error(PC_ERR_INVALID, "%s: unknown impl %d", who, p->impl);
 }

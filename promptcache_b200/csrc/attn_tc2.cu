@@ -1,0 +1,514 @@
+// tcgen05 / TMEM attention for LONG suffixes (more than 32 folded query rows per KV head): no-cache prefill, long
+// uncached suffixes, Falcon's MQA (71 heads folded into M).  Same contract as attn_tc_small.cu; this is the
+// tensor-bound regime (G*q FLOP per KV byte above the ~254 FLOP/B ridge).
+//
+// One CTA = (kv head, PAIR of 128-row query tiles A and B, KV split).  Both tiles share every K/V tile, and two
+// softmax warpgroups ping-pong against one MMA thread so that the tensor core is never waiting on a softmax:
+//
+//   MMA thread :  S_A(0) S_B(0) | PV_A(0) S_A(1) | PV_B(0) S_B(1) | PV_A(1) S_A(2) | ...
+//   WG0 (tile A):        softmax A(0)        |      softmax A(1)       | ...
+//   WG1 (tile B):               softmax B(0)        |      softmax B(1)       | ...
+//
+//   S_X = Q_X . K_j^T   SS-MMA 128x128xD, accumulator in TMEM columns of tile X
+//   P_X                 one TMEM lane = one query row per thread; packed fp16 written back over S_X
+//   O_X += P_X . V_j    TS-MMA (A = P_X from TMEM, B = V tile MN-major), accumulator in TMEM
+//
+// TMEM: S_A[0,128) S_B[128,256) O_A[256,256+D) O_B[256+D,256+2D) = 512 columns at D=128.
+// Softmax is two passes over TMEM (no 128-register score array): pass 1 reads S and keeps only the row maximum of
+// the RAW accumulators (the fp16-rounding + scale transform is monotone, so max(transform) = transform(max));
+// pass 2 re-reads S in 32-column chunks, applies the reference's roundings, exponentiates (ex2.approx) and writes
+// P.  Rescaling of O is lazy (only when the row maximum grew by more than 2^8).
+#include <cuda.h>
+#include <math.h>
+#include <stdlib.h>
+
+#include "pc_common.cuh"
+
+namespace pc {
+
+int make_tensor_map_3d(CUtensorMap* map, const void* base, int D, long long rows, int heads, long long head_stride,
+                       int box_rows);
+int launch_attn_combine(const float* part_o, const float* part_ml, void* out, int n_heads, int q_len, int n_splits,
+                        int head_dim, cudaStream_t st);
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 128;
+constexpr int kThreads = 320;  // WG0 (warps 0-3), WG1 (warps 4-7), TMA warp 8, MMA warp 9
+constexpr int kMaxSplits = 32;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kRescaleThreshold = 8.0f;
+
+template <int D>
+struct Cfg2 {
+  static constexpr int kTileBytes = BN * D * 2;  // one K, V or Q tile
+  static constexpr int kStages = D == 128 ? 2 : 3;
+  static constexpr int kOffKV = 2 * kTileBytes;  // Q_A, Q_B first
+  static constexpr int kOffBars = kOffKV + kStages * 2 * kTileBytes;
+  static constexpr int kSmem = 1024 + kOffBars + 256;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kColO = 256;
+};
+
+struct PpParams {
+  __half* out;
+  float* part_o;
+  float* part_ml;
+  const float* alibi_slopes;
+  const int* key_pos;
+  int n_heads, n_kv_heads, n_cached, q_len, n_splits, m_pairs, alibi_max_pos;
+  float scale;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// round two fp32 values to fp16 and back (one packed cvt + two unpacks)
+__device__ __forceinline__ void round_h2(float& a, float& b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(h);
+  a = f.x;
+  b = f.y;
+}
+__device__ __forceinline__ float round_h(float x) { return __half2float(__float2half_rn(x)); }
+
+// Walk the 4 x 32 columns of an S tile: the TMEM load of chunk ch+1 is in flight while chunk ch is processed.
+template <typename F>
+__device__ __forceinline__ void for_each_chunk(uint32_t tmem_s, F&& body) {
+  uint32_t va[32], vb[32];
+  tmem_ld32(tmem_s, va);
+  tmem_ld_wait();
+  tmem_ld32(tmem_s + 32, vb);
+  body(va, 0);
+  tmem_ld_wait();
+  tmem_ld32(tmem_s + 64, va);
+  body(vb, 1);
+  tmem_ld_wait();
+  tmem_ld32(tmem_s + 96, vb);
+  body(va, 2);
+  tmem_ld_wait();
+  body(vb, 3);
+}
+
+// Causal extent (exclusive key bound) of the 128-row tile starting at folded row `row_lo`.
+__device__ __forceinline__ int tile_kv_end(int row_lo, int rows_total, int q_len, int n_cached) {
+  if (row_lo >= rows_total) return 0;
+  const int row_hi = min(row_lo + BM, rows_total) - 1;
+  const int r_max = (row_lo / q_len == row_hi / q_len) ? row_hi % q_len : q_len - 1;
+  return n_cached + r_max + 1;
+}
+
+template <int D, int ROUND, bool ALIBI>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+               const __grid_constant__ CUtensorMap map_v, const PpParams p) {
+  using C = Cfg2<D>;
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  unsigned char* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  unsigned char* sQ = smem;  // [2][kTileBytes]
+  unsigned char* sKV = smem + C::kOffKV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBars);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* v_full = k_full + C::kStages;
+  uint64_t* kv_empty = v_full + C::kStages;
+  uint64_t* s_full = kv_empty + C::kStages;  // [2] per query tile
+  uint64_t* p_full = s_full + 2;             // [2]
+  uint64_t* o_full = p_full + 2;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int G = p.n_heads / p.n_kv_heads;
+  const int rows_total = G * p.q_len;
+
+  int bid = blockIdx.x;
+  const int split = bid % p.n_splits;
+  bid /= p.n_splits;
+  const int mp = bid % p.m_pairs;
+  const int hk = bid / p.m_pairs;
+
+  // per-tile KV tile counts; both tiles walk the same global tile indices [t0, t1)
+  const int row_lo[2] = {mp * 2 * BM, mp * 2 * BM + BM};
+  int TT[2];
+#pragma unroll
+  for (int x = 0; x < 2; ++x) TT[x] = (tile_kv_end(row_lo[x], rows_total, p.q_len, p.n_cached) + BN - 1) / BN;
+  const int TTmax = max(TT[0], TT[1]);
+  const int t0 = static_cast<int>(static_cast<long long>(split) * TTmax / p.n_splits);
+  const int t1 = static_cast<int>(static_cast<long long>(split + 1) * TTmax / p.n_splits);
+  int T[2];
+#pragma unroll
+  for (int x = 0; x < 2; ++x) T[x] = max(0, min(t1, TT[x]) - t0);
+  const int Tmax = max(T[0], T[1]);
+  int valid_warps[2];
+#pragma unroll
+  for (int x = 0; x < 2; ++x) valid_warps[x] = row_lo[x] < rows_total ? (min(BM, rows_total - row_lo[x]) + 31) / 32 : 0;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_v);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&s_full[x], 1);
+      mbar_init(&p_full[x], max(32 * valid_warps[x], 1));
+      mbar_init(&o_full[x], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 9) tmem_alloc<C::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ===================== TMA producer =====================
+    if (lane == 0 && Tmax > 0) {
+      const int nq = (T[0] > 0 ? 1 : 0) + (T[1] > 0 ? 1 : 0);
+      mbar_expect_tx(q_full, nq * C::kTileBytes);
+      for (int x = 0; x < 2; ++x)
+        if (T[x] > 0)
+          for (int hf = 0; hf < D / 64; ++hf)
+            tma_load_3d(sQ + x * C::kTileBytes + hf * 16384, &map_q, q_full, hf * 64, row_lo[x], hk);
+      for (int j = 0; j < Tmax; ++j) {
+        const int s = j % C::kStages;
+        if (j >= C::kStages) mbar_wait(&kv_empty[s], static_cast<uint32_t>(((j / C::kStages) - 1) & 1));
+        unsigned char* dk = sKV + (2 * s) * C::kTileBytes;
+        unsigned char* dv = dk + C::kTileBytes;
+        const int key0 = (t0 + j) * BN;
+        mbar_expect_tx(&k_full[s], C::kTileBytes);
+        for (int hf = 0; hf < D / 64; ++hf) tma_load_3d(dk + hf * 16384, &map_k, &k_full[s], hf * 64, key0, hk);
+        mbar_expect_tx(&v_full[s], C::kTileBytes);
+        for (int hf = 0; hf < D / 64; ++hf) tma_load_3d(dv + hf * 16384, &map_v, &v_full[s], hf * 64, key0, hk);
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && Tmax > 0) {
+      constexpr uint32_t idesc_qk = make_idesc_f16(BM, BN, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_f16(BM, D, 0, 1);
+      auto issue_s = [&](int x, int j) {  // S_x(j) = Q_x . K_j^T  (the caller has already waited on k_full of j)
+        const int s = j % C::kStages;
+        const uint32_t q_addr = smem_u32(sQ + x * C::kTileBytes);
+        const uint32_t k_addr = smem_u32(sKV + (2 * s) * C::kTileBytes);
+        const uint32_t d = tmem_base + x * 128;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
+          umma_ss(d, make_smem_desc(q_addr + off, 16, 1024, 2), make_smem_desc(k_addr + off, 16, 1024, 2), idesc_qk,
+                  kk > 0 ? 1u : 0u);
+        }
+        tc_commit(&s_full[x]);
+      };
+      auto issue_pv = [&](int x, int j) {  // O_x += P_x(j) . V_j
+        const int s = j % C::kStages;
+        const uint32_t v_addr = smem_u32(sKV + (2 * s + 1) * C::kTileBytes);
+        const uint32_t pa = tmem_base + x * 128;
+        const uint32_t d = tmem_base + C::kColO + x * D;
+#pragma unroll
+        for (int kk = 0; kk < BN / 16; ++kk)
+          umma_ts(d, pa + kk * 8, make_smem_desc(v_addr + kk * 2048, 16384, 1024, 2), idesc_pv,
+                  (j > 0 || kk > 0) ? 1u : 0u);
+        tc_commit(&o_full[x]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      for (int x = 0; x < 2; ++x)
+        if (T[x] > 0) issue_s(x, 0);
+      for (int j = 0; j < Tmax; ++j) {
+        const int s = j % C::kStages;
+        bool k_next_ready = false;
+        for (int x = 0; x < 2; ++x) {
+          if (j >= T[x]) continue;
+          mbar_wait(&p_full[x], static_cast<uint32_t>(j & 1));
+          if (x == 0 || T[0] <= j) mbar_wait(&v_full[s], static_cast<uint32_t>((j / C::kStages) & 1));
+          tc_fence_after();
+          issue_pv(x, j);
+          if (j + 1 < T[x]) {
+            if (!k_next_ready) {
+              mbar_wait(&k_full[(j + 1) % C::kStages], static_cast<uint32_t>(((j + 1) / C::kStages) & 1));
+              tc_fence_after();
+              k_next_ready = true;
+            }
+            issue_s(x, j + 1);
+          }
+        }
+        tc_commit(&kv_empty[s]);  // every MMA that read stage s has been issued
+      }
+    }
+  } else {
+    // ===================== softmax warpgroups (WG x owns query tile x) =====================
+    const int x = warp >> 2;
+    const int quad = warp & 3;
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tmem_s = tmem_base + lane_base + x * 128;
+    const uint32_t tmem_o = tmem_base + lane_base + C::kColO + x * D;
+    const int R = row_lo[x] + quad * 32 + lane;
+    const bool warp_valid = quad < valid_warps[x];
+    const bool row_valid = R < rows_total;
+    const int g = row_valid ? R / p.q_len : 0;
+    const int r = row_valid ? R % p.q_len : 0;
+    const int h = hk * G + g;
+    const int Tx = T[x];
+    const float slope = (ALIBI && row_valid) ? p.alibi_slopes[h] : 0.f;
+    const int vis_end = row_valid ? p.n_cached + r + 1 : 0;  // keys [0, vis_end) are visible to this row
+    const float scale_l2 = p.scale * kLog2e;
+    float m_run = -INFINITY, l_run = 0.f;  // m in the log2 domain
+
+    if (warp_valid) {
+      for (int j = 0; j < Tx; ++j) {
+        mbar_wait(&s_full[x], static_cast<uint32_t>(j & 1));
+        tc_fence_after();
+        const int key0 = (t0 + j) * BN;
+        const bool need_mask = key0 + BN > vis_end;
+
+        // ---- pass 1: row maximum ----
+        float mt;
+        if (!ALIBI) {
+          float raw_max = -INFINITY;
+          for_each_chunk(tmem_s, [&](const uint32_t(&v)[32], int ch) {
+            if (need_mask) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c)
+                if (key0 + ch * 32 + c < vis_end) raw_max = fmaxf(raw_max, __uint_as_float(v[c]));
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; c += 2)
+                raw_max = fmaxf(raw_max, fmaxf(__uint_as_float(v[c]), __uint_as_float(v[c + 1])));
+            }
+          });
+          // the score transform is monotone non-decreasing, so it commutes with max
+          float t = raw_max;
+          if (ROUND & PC_ROUND_QK) t = round_h(t);
+          t *= p.scale;
+          if (ROUND & PC_ROUND_SCALED) t = round_h(t);
+          mt = t * kLog2e;
+        } else {
+          mt = -INFINITY;
+          for_each_chunk(tmem_s, [&](const uint32_t(&v)[32], int ch) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const int kidx = key0 + ch * 32 + c;
+              float t = __uint_as_float(v[c]);
+              if (ROUND & PC_ROUND_QK) t = round_h(t);
+              t *= p.scale;
+              if (ROUND & PC_ROUND_SCALED) t = round_h(t);
+              t += slope * static_cast<float>(__ldg(p.key_pos + min(kidx, p.n_cached + p.q_len - 1)) - p.alibi_max_pos);
+              t *= kLog2e;
+              if (kidx < vis_end) mt = fmaxf(mt, t);
+            }
+          });
+        }
+
+        // ---- running maximum, lazy rescale of O ----
+        const float m_new = fmaxf(m_run, mt);
+        const bool grow = (m_new - m_run) > kRescaleThreshold;  // first finite max: +inf; both -inf: NaN -> false
+        const float alpha = grow ? ex2(m_run - m_new) : 1.f;
+        if (grow) {
+          m_run = m_new;
+          l_run *= alpha;
+        }
+        if (j > 0 && __any_sync(0xffffffffu, grow)) {
+          mbar_wait(&o_full[x], static_cast<uint32_t>((j - 1) & 1));  // PV_x(j-1) has landed
+          tc_fence_after();
+#pragma unroll
+          for (int ch = 0; ch < D / 32; ++ch) {
+            uint32_t o[32];
+            tmem_ld32(tmem_o + ch * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+            tmem_st32(tmem_o + ch * 32, o);
+          }
+        }
+        const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
+
+        // ---- pass 2: P = 2^(score - m), written over S as packed fp16 ----
+        float lt = 0.f;
+        for_each_chunk(tmem_s, [&](const uint32_t(&v)[32], int ch) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            float a = __uint_as_float(v[c]), b = __uint_as_float(v[c + 1]);
+            float ya, yb;
+            if (ROUND == 0 && !ALIBI) {
+              ya = fmaf(a, scale_l2, -m_use);
+              yb = fmaf(b, scale_l2, -m_use);
+            } else {
+              if (ROUND & PC_ROUND_QK) round_h2(a, b);
+              a *= p.scale;
+              b *= p.scale;
+              if (ROUND & PC_ROUND_SCALED) round_h2(a, b);
+              if (ALIBI) {
+                const int k0 = key0 + ch * 32 + c, kmax = p.n_cached + p.q_len - 1;
+                a += slope * static_cast<float>(__ldg(p.key_pos + min(k0, kmax)) - p.alibi_max_pos);
+                b += slope * static_cast<float>(__ldg(p.key_pos + min(k0 + 1, kmax)) - p.alibi_max_pos);
+              }
+              ya = fmaf(a, kLog2e, -m_use);
+              yb = fmaf(b, kLog2e, -m_use);
+            }
+            if (need_mask) {
+              if (key0 + ch * 32 + c >= vis_end) ya = -INFINITY;
+              if (key0 + ch * 32 + c + 1 >= vis_end) yb = -INFINITY;
+            }
+            const float p0 = ex2(ya), p1 = ex2(yb);
+            lt += p0 + p1;
+            pk[c >> 1] = pack_h2(p0, p1);
+          }
+          // P columns [16ch,16ch+16) only cover S columns of chunks <= ch, never the chunk still in flight
+          tmem_st16(tmem_s + ch * 16, pk);
+        });
+        l_run += lt;
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[x]);
+      }
+
+      // ---- epilogue ----
+      const int n_heads = p.n_heads;
+      if (Tx > 0) {
+        mbar_wait(&o_full[x], static_cast<uint32_t>((Tx - 1) & 1));
+        tc_fence_after();
+      }
+      const float inv_l = l_run > 0.f ? 1.f / l_run : 0.f;
+#pragma unroll
+      for (int ch = 0; ch < D / 32; ++ch) {
+        uint32_t o[32];
+        if (Tx > 0) {
+          tmem_ld32(tmem_o + ch * 32, o);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) o[c] = 0u;
+        }
+        if (row_valid) {
+          if (p.n_splits == 1) {
+            __half* dst = p.out + (static_cast<long long>(r) * n_heads + h) * D + ch * 32;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              uint4 w;
+              w.x = pack_h2(__uint_as_float(o[v * 8 + 0]) * inv_l, __uint_as_float(o[v * 8 + 1]) * inv_l);
+              w.y = pack_h2(__uint_as_float(o[v * 8 + 2]) * inv_l, __uint_as_float(o[v * 8 + 3]) * inv_l);
+              w.z = pack_h2(__uint_as_float(o[v * 8 + 4]) * inv_l, __uint_as_float(o[v * 8 + 5]) * inv_l);
+              w.w = pack_h2(__uint_as_float(o[v * 8 + 6]) * inv_l, __uint_as_float(o[v * 8 + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(dst + v * 8) = w;
+            }
+          } else {
+            float* dst = p.part_o + ((static_cast<long long>(split) * n_heads + h) * p.q_len + r) * D + ch * 32;
+#pragma unroll
+            for (int v = 0; v < 8; ++v)
+              *reinterpret_cast<uint4*>(dst + v * 4) = make_uint4(o[v * 4], o[v * 4 + 1], o[v * 4 + 2], o[v * 4 + 3]);
+          }
+        }
+      }
+      if (row_valid && p.n_splits > 1) {
+        float* ml = p.part_ml + ((static_cast<long long>(split) * n_heads + h) * p.q_len + r) * 2;
+        ml[0] = m_run;  // log2 domain; -inf with l = 0 when this split saw no visible key
+        ml[1] = l_run;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_free<C::kTmemCols>(tmem_base);
+  }
+}
+
+template <int D, int ROUND, bool ALIBI>
+int launch_pp_one(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const PpParams& pp, int grid,
+                  cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    PC_CHECK_CUDA(cudaFuncSetAttribute(attn_pp_kernel<D, ROUND, ALIBI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg2<D>::kSmem));
+    configured = true;
+  }
+  attn_pp_kernel<D, ROUND, ALIBI><<<grid, kThreads, Cfg2<D>::kSmem, st>>>(mq, mk, mv, pp);
+  PC_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return PC_OK;
+}
+
+template <int D>
+int launch_pp_d(const pc_attn_params& p, cudaStream_t st) {
+  const int G = p.n_heads / p.n_kv_heads;
+  const int rows_total = G * p.q_len;
+  const int m_pairs = (rows_total + 2 * BM - 1) / (2 * BM);
+  const int tiles = (p.n_cached + p.q_len + BN - 1) / BN;
+  const int base = p.n_kv_heads * m_pairs;
+  int n_splits = sm_count() / base;
+  if (const char* e = getenv("PC_ATTN_SPLITS")) n_splits = atoi(e);
+  if (n_splits > tiles) n_splits = tiles;
+  if (n_splits > kMaxSplits) n_splits = kMaxSplits;
+  if (n_splits < 1) n_splits = 1;
+  float* part_o = nullptr;
+  float* part_ml = nullptr;
+  if (n_splits > 1) {
+    const size_t per = static_cast<size_t>(p.n_heads) * p.q_len * (D + 2) * sizeof(float);
+    const size_t avail = (p.workspace && p.workspace_bytes > kAttnCounterBytes) ? p.workspace_bytes - kAttnCounterBytes : 0;
+    if (avail < per * n_splits) n_splits = static_cast<int>(avail / per);
+    if (n_splits < 1) n_splits = 1;
+    if (n_splits > 1) {
+      part_o = reinterpret_cast<float*>(static_cast<char*>(p.workspace) + kAttnCounterBytes);
+      part_ml = part_o + static_cast<size_t>(n_splits) * p.n_heads * p.q_len * D;
+    }
+  }
+  CUtensorMap mq, mk, mv;
+  if (int rc = make_tensor_map_3d(&mq, p.q, D, rows_total, p.n_kv_heads, static_cast<long long>(rows_total) * D, BM)) return rc;
+  const long long kv_rows = static_cast<long long>(p.n_cached) + p.q_len;
+  if (int rc = make_tensor_map_3d(&mk, p.k, D, kv_rows, p.n_kv_heads, static_cast<long long>(p.max_ctx) * D, BN)) return rc;
+  if (int rc = make_tensor_map_3d(&mv, p.v, D, kv_rows, p.n_kv_heads, static_cast<long long>(p.max_ctx) * D, BN)) return rc;
+  PpParams pp;
+  pp.out = static_cast<__half*>(p.out);
+  pp.part_o = part_o;
+  pp.part_ml = part_ml;
+  pp.alibi_slopes = p.alibi_slopes;
+  pp.key_pos = p.key_pos;
+  pp.n_heads = p.n_heads;
+  pp.n_kv_heads = p.n_kv_heads;
+  pp.n_cached = p.n_cached;
+  pp.q_len = p.q_len;
+  pp.n_splits = n_splits;
+  pp.m_pairs = m_pairs;
+  pp.alibi_max_pos = p.alibi_max_pos;
+  pp.scale = p.scale;
+  const int grid = base * n_splits;
+  const bool alibi = p.alibi_slopes != nullptr;
+  int rc;
+  if (p.rounding == 0)
+    rc = alibi ? launch_pp_one<D, 0, true>(mq, mk, mv, pp, grid, st) : launch_pp_one<D, 0, false>(mq, mk, mv, pp, grid, st);
+  else if (p.rounding == PC_ROUND_LLAMA)
+    rc = alibi ? launch_pp_one<D, 3, true>(mq, mk, mv, pp, grid, st) : launch_pp_one<D, 3, false>(mq, mk, mv, pp, grid, st);
+  else
+    return set_error(PC_ERR_UNSUPPORTED, "attn(tcgen05): rounding flags %d (supported: 0, %d)", p.rounding, PC_ROUND_LLAMA);
+  if (rc) return rc;
+  if (n_splits > 1) return launch_attn_combine(part_o, part_ml, p.out, p.n_heads, p.q_len, n_splits, D, st);
+  return PC_OK;
+}
+
+}  // namespace
+
+int launch_attn_pp(const pc_attn_params& p, cudaStream_t st) {
+  if (p.head_dim == 128) return launch_pp_d<128>(p, st);
+  if (p.head_dim == 64) return launch_pp_d<64>(p, st);
+  return set_error(PC_ERR_UNSUPPORTED, "attn(tcgen05): head_dim %d not in {64,128}", p.head_dim);
+}
+
+}  // namespace pc

@@ -178,6 +178,11 @@ CASES = [
     (4, 4, 128, 17, 129),     # short-suffix kernel, padded columns, suffix straddles a tile boundary
     (4, 4, 128, 5, 0),        # short-suffix kernel without any cached rows
     (32, 32, 128, 32, 8192),  # C5
+    (8, 8, 128, 300, 100),    # ping-pong kernel: 3 row tiles (pair + half pair), suffix-dominated causal part
+    (4, 4, 128, 64, 1000),    # ping-pong kernel with a single half-filled tile and split-KV
+    (2, 2, 128, 1024, 2048),  # long suffix, 4 tile pairs per head
+    (4, 1, 128, 100, 3000),   # MQA at D=128: 400 folded rows
+    (2, 2, 64, 130, 70),      # D=64, two tiles, tile B has 2 rows
     (40, 40, 128, 32, 4096),  # C3 (Llama-2-13B heads)
 ]
 
