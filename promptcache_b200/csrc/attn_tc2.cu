@@ -22,6 +22,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "pc_common.cuh"
 
 namespace pc {
@@ -267,6 +269,11 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const float slope = (ALIBI && row_valid) ? p.alibi_slopes[h] : 0.f;
     const int vis_end = row_valid ? p.n_cached + r + 1 : 0;  // keys [0, vis_end) are visible to this row
     const float scale_l2 = p.scale * kLog2e;
+    // fp32 scale split into two fp16 terms: half(half(acc)*scale) == hfma2(a16, s_hi, a16*s_lo) up to a
+    // double-rounding event of probability ~2e-4 per score (1 fp16 ulp when it happens)
+    const __half s_hi = __float2half_rn(p.scale);
+    const __half2 scale_hi = __half2half2(s_hi);
+    const __half2 scale_lo = __half2half2(__float2half_rn(p.scale - __half2float(s_hi)));
     float m_run = -INFINITY, l_run = 0.f;  // m in the log2 domain
 
     if (warp_valid) {
@@ -293,9 +300,14 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           });
           // the score transform is monotone non-decreasing, so it commutes with max
           float t = raw_max;
-          if (ROUND & PC_ROUND_QK) t = round_h(t);
-          t *= p.scale;
-          if (ROUND & PC_ROUND_SCALED) t = round_h(t);
+          if (ROUND == PC_ROUND_LLAMA) {
+            const __half2 a16 = __floats2half2_rn(t, t);
+            t = __low2float(__hfma2(a16, scale_hi, __hmul2(a16, scale_lo)));
+          } else {
+            if (ROUND & PC_ROUND_QK) t = round_h(t);
+            t *= p.scale;
+            if (ROUND & PC_ROUND_SCALED) t = round_h(t);
+          }
           mt = t * kLog2e;
         } else {
           mt = -INFINITY;
@@ -338,30 +350,41 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
 
         // ---- pass 2: P = 2^(score - m), written over S as packed fp16 ----
+        // The mask is only evaluated on tiles that reach the causal diagonal (warp-uniform decision).
         float lt = 0.f;
-        for_each_chunk(tmem_s, [&](const uint32_t(&v)[32], int ch) {
+        const bool warp_mask = __any_sync(0xffffffffu, need_mask);
+        auto pass2 = [&](const uint32_t(&v)[32], int ch, auto masked_tag) {
+          constexpr bool kMasked = decltype(masked_tag)::value;
           uint32_t pk[16];
 #pragma unroll
           for (int c = 0; c < 32; c += 2) {
-            float a = __uint_as_float(v[c]), b = __uint_as_float(v[c + 1]);
+            const float a = __uint_as_float(v[c]), b = __uint_as_float(v[c + 1]);
             float ya, yb;
             if (ROUND == 0 && !ALIBI) {
               ya = fmaf(a, scale_l2, -m_use);
               yb = fmaf(b, scale_l2, -m_use);
+            } else if (ROUND == PC_ROUND_LLAMA && !ALIBI) {
+              // half(half(acc) * scale) in packed fp16: scale = s_hi + s_lo (both fp16), one fused rounding
+              const __half2 a16 = __floats2half2_rn(a, b);
+              const __half2 sc = __hfma2(a16, scale_hi, __hmul2(a16, scale_lo));
+              const float2 f = __half22float2(sc);
+              ya = fmaf(f.x, kLog2e, -m_use);
+              yb = fmaf(f.y, kLog2e, -m_use);
             } else {
-              if (ROUND & PC_ROUND_QK) round_h2(a, b);
-              a *= p.scale;
-              b *= p.scale;
-              if (ROUND & PC_ROUND_SCALED) round_h2(a, b);
+              float ta = a, tb = b;
+              if (ROUND & PC_ROUND_QK) round_h2(ta, tb);
+              ta *= p.scale;
+              tb *= p.scale;
+              if (ROUND & PC_ROUND_SCALED) round_h2(ta, tb);
               if (ALIBI) {
                 const int k0 = key0 + ch * 32 + c, kmax = p.n_cached + p.q_len - 1;
-                a += slope * static_cast<float>(__ldg(p.key_pos + min(k0, kmax)) - p.alibi_max_pos);
-                b += slope * static_cast<float>(__ldg(p.key_pos + min(k0 + 1, kmax)) - p.alibi_max_pos);
+                ta += slope * static_cast<float>(__ldg(p.key_pos + min(k0, kmax)) - p.alibi_max_pos);
+                tb += slope * static_cast<float>(__ldg(p.key_pos + min(k0 + 1, kmax)) - p.alibi_max_pos);
               }
-              ya = fmaf(a, kLog2e, -m_use);
-              yb = fmaf(b, kLog2e, -m_use);
+              ya = fmaf(ta, kLog2e, -m_use);
+              yb = fmaf(tb, kLog2e, -m_use);
             }
-            if (need_mask) {
+            if (kMasked) {
               if (key0 + ch * 32 + c >= vis_end) ya = -INFINITY;
               if (key0 + ch * 32 + c + 1 >= vis_end) yb = -INFINITY;
             }
@@ -371,7 +394,11 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           }
           // P columns [16ch,16ch+16) only cover S columns of chunks <= ch, never the chunk still in flight
           tmem_st16(tmem_s + ch * 16, pk);
-        });
+        };
+        if (warp_mask)
+          for_each_chunk(tmem_s, [&](const uint32_t(&v)[32], int ch) { pass2(v, ch, std::true_type{}); });
+        else
+          for_each_chunk(tmem_s, [&](const uint32_t(&v)[32], int ch) { pass2(v, ch, std::false_type{}); });
         l_run += lt;
         tmem_st_wait();
         tc_fence_before();

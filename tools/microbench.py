@@ -86,12 +86,12 @@ def bench_splice():
         del segs, cache, big, big2
 
 
-def bench_attn():
-    for name, H, Hkv, D, q, N in [("C2 q16", 32, 32, 128, 16, 2048), ("C2 q64", 32, 32, 128, 64, 2048),
+def bench_attn(only=None):
+    for name, H, Hkv, D, q, N in [c for c in [("C2 q16", 32, 32, 128, 16, 2048), ("C2 q64", 32, 32, 128, 64, 2048),
                                   ("C2 q256", 32, 32, 128, 256, 2048), ("C2 q1024", 32, 32, 128, 1024, 2048),
                                   ("full prefill 2K", 32, 32, 128, 2048, 0), ("decode N=2064", 32, 32, 128, 1, 2064),
                                   ("C5 q32", 32, 32, 128, 32, 8192), ("C5 q1024 N8K", 32, 32, 128, 1024, 8192), ("falcon C4", 71, 1, 64, 21, 256),
-                                  ("falcon q256 N2K", 71, 1, 64, 256, 2048)]:
+                                  ("falcon q256 N2K", 71, 1, 64, 256, 2048)] if only is None or only in c[0]]:
         L = 8  # rotate over several layers' KV so the stream does not sit in L2
         max_ctx = ((N + q + 127) // 128) * 128
         K = (torch.randn(L, Hkv, max_ctx, D, device=DEV)).half()
@@ -124,4 +124,4 @@ if __name__ == "__main__":
     if what in ("splice", "all"):
         bench_splice()
     if what in ("attn", "all"):
-        bench_attn()
+        bench_attn(sys.argv[2] if len(sys.argv) > 2 else None)
