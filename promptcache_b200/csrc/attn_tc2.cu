@@ -5,15 +5,16 @@
 // One CTA = (kv head, PAIR of 128-row query tiles A and B, KV split).  Both tiles share every K/V tile, and two
 // softmax warpgroups ping-pong against one MMA thread so that the tensor core is never waiting on a softmax:
 //
-//   MMA thread :  S_A(0) S_B(0) | PV_A(0) S_A(1) | PV_B(0) S_B(1) | PV_A(1) S_A(2) | ...
-//   WG0 (tile A):        softmax A(0)        |      softmax A(1)       | ...
-//   WG1 (tile B):               softmax B(0)        |      softmax B(1)       | ...
+//   MMA thread :  S_A(0) S_B(0) S_A(1) S_B(1) | PV_A(0) S_A(2) | PV_B(0) S_B(2) | PV_A(1) S_A(3) | ...
+//   WG0 (tile A):   softmax A(0) | softmax A(1) | softmax A(2) | ...      (S_A(j+1) is already waiting when
+//   WG1 (tile B):   softmax B(0) | softmax B(1) | softmax B(2) | ...       softmax A(j) finishes)
 //
-//   S_X = Q_X . K_j^T   SS-MMA 128x128xD, accumulator in TMEM columns of tile X
+//   S_X = Q_X . K_j^T   SS-MMA 128 x 64 keys x D, accumulator in TMEM, TWO buffers per query tile
 //   P_X                 one TMEM lane = one query row per thread; packed fp16 written back over S_X
 //   O_X += P_X . V_j    TS-MMA (A = P_X from TMEM, B = V tile MN-major), accumulator in TMEM
 //
-// TMEM: S_A[0,128) S_B[128,256) O_A[256,256+D) O_B[256+D,256+2D) = 512 columns at D=128.
+// KV tiles are 64 keys so that each query tile can double-buffer S within the 512 TMEM columns:
+//   S_A0[0,64) S_A1[64,128) S_B0[128,192) S_B1[192,256) O_A[256,256+D) O_B[256+D,256+2D).
 // Softmax is two passes over TMEM (no 128-register score array): pass 1 reads S and keeps only the row maximum of
 // the RAW accumulators (the fp16-rounding + scale transform is monotone, so max(transform) = transform(max));
 // pass 2 re-reads S in 32-column chunks, applies the reference's roundings, exponentiates (ex2.approx) and writes
@@ -36,7 +37,7 @@ int launch_attn_combine(const float* part_o, const float* part_ml, void* out, in
 namespace {
 
 constexpr int BM = 128;
-constexpr int BN = 128;
+constexpr int BN = 64;
 constexpr int kThreads = 320;  // WG0 (warps 0-3), WG1 (warps 4-7), TMA warp 8, MMA warp 9
 constexpr int kMaxSplits = 32;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -44,9 +45,11 @@ constexpr float kRescaleThreshold = 8.0f;
 
 template <int D>
 struct Cfg2 {
-  static constexpr int kTileBytes = BN * D * 2;  // one K, V or Q tile
-  static constexpr int kStages = D == 128 ? 2 : 3;
-  static constexpr int kOffKV = 2 * kTileBytes;  // Q_A, Q_B first
+  static constexpr int kQBytes = BM * D * 2;     // one query tile
+  static constexpr int kTileBytes = BN * D * 2;  // one K or V tile
+  static constexpr int kHalfStride = BN * 128;   // bytes between the two 64-column halves of a K/V tile (D=128)
+  static constexpr int kStages = 4;
+  static constexpr int kOffKV = 2 * kQBytes;     // Q_A, Q_B first
   static constexpr int kOffBars = kOffKV + kStages * 2 * kTileBytes;
   static constexpr int kSmem = 1024 + kOffBars + 256;
   static constexpr int kTmemCols = 512;
@@ -81,7 +84,7 @@ __device__ __forceinline__ void round_h2(float& a, float& b) {
 }
 __device__ __forceinline__ float round_h(float x) { return __half2float(__float2half_rn(x)); }
 
-// Walk the 4 x 32 columns of an S tile: the TMEM load of chunk ch+1 is in flight while chunk ch is processed.
+// Walk the 2 x 32 columns of an S tile: the TMEM load of chunk 1 is in flight while chunk 0 is processed.
 template <typename F>
 __device__ __forceinline__ void for_each_chunk(uint32_t tmem_s, F&& body) {
   uint32_t va[32], vb[32];
@@ -90,13 +93,7 @@ __device__ __forceinline__ void for_each_chunk(uint32_t tmem_s, F&& body) {
   tmem_ld32(tmem_s + 32, vb);
   body(va, 0);
   tmem_ld_wait();
-  tmem_ld32(tmem_s + 64, va);
   body(vb, 1);
-  tmem_ld_wait();
-  tmem_ld32(tmem_s + 96, vb);
-  body(va, 2);
-  tmem_ld_wait();
-  body(vb, 3);
 }
 
 // Causal extent (exclusive key bound) of the 128-row tile starting at folded row `row_lo`.
@@ -122,20 +119,22 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   uint64_t* k_full = bars + 1;
   uint64_t* v_full = k_full + C::kStages;
   uint64_t* kv_empty = v_full + C::kStages;
-  uint64_t* s_full = kv_empty + C::kStages;  // [2] per query tile
-  uint64_t* p_full = s_full + 2;             // [2]
-  uint64_t* o_full = p_full + 2;             // [2]
+  uint64_t* s_full = kv_empty + C::kStages;  // [2 query tiles][2 S buffers]
+  uint64_t* p_full = s_full + 4;             // [2][2]
+  uint64_t* o_full = p_full + 4;             // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = p.n_heads / p.n_kv_heads;
   const int rows_total = G * p.q_len;
 
+  // Block order = longest work first: the causal extent grows with the row-pair index, so the last pairs of
+  // every head are dispatched first and the short ones fill the tail of the grid.
   int bid = blockIdx.x;
   const int split = bid % p.n_splits;
   bid /= p.n_splits;
-  const int mp = bid % p.m_pairs;
-  const int hk = bid / p.m_pairs;
+  const int hk = bid % p.n_kv_heads;
+  const int mp = p.m_pairs - 1 - bid / p.n_kv_heads;
 
   // per-tile KV tile counts; both tiles walk the same global tile indices [t0, t1)
   const int row_lo[2] = {mp * 2 * BM, mp * 2 * BM + BM};
@@ -164,8 +163,10 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       mbar_init(&kv_empty[s], 1);
     }
     for (int x = 0; x < 2; ++x) {
-      mbar_init(&s_full[x], 1);
-      mbar_init(&p_full[x], max(32 * valid_warps[x], 1));
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&s_full[x * 2 + b], 1);
+        mbar_init(&p_full[x * 2 + b], max(32 * valid_warps[x], 1));
+      }
       mbar_init(&o_full[x], 1);
     }
     mbar_fence_init();
@@ -180,11 +181,11 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0 && Tmax > 0) {
       const int nq = (T[0] > 0 ? 1 : 0) + (T[1] > 0 ? 1 : 0);
-      mbar_expect_tx(q_full, nq * C::kTileBytes);
+      mbar_expect_tx(q_full, nq * C::kQBytes);
       for (int x = 0; x < 2; ++x)
         if (T[x] > 0)
           for (int hf = 0; hf < D / 64; ++hf)
-            tma_load_3d(sQ + x * C::kTileBytes + hf * 16384, &map_q, q_full, hf * 64, row_lo[x], hk);
+            tma_load_3d(sQ + x * C::kQBytes + hf * 16384, &map_q, q_full, hf * 64, row_lo[x], hk);
       for (int j = 0; j < Tmax; ++j) {
         const int s = j % C::kStages;
         if (j >= C::kStages) mbar_wait(&kv_empty[s], static_cast<uint32_t>(((j / C::kStages) - 1) & 1));
@@ -192,9 +193,11 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         unsigned char* dv = dk + C::kTileBytes;
         const int key0 = (t0 + j) * BN;
         mbar_expect_tx(&k_full[s], C::kTileBytes);
-        for (int hf = 0; hf < D / 64; ++hf) tma_load_3d(dk + hf * 16384, &map_k, &k_full[s], hf * 64, key0, hk);
+        for (int hf = 0; hf < D / 64; ++hf)
+          tma_load_3d(dk + hf * C::kHalfStride, &map_k, &k_full[s], hf * 64, key0, hk);
         mbar_expect_tx(&v_full[s], C::kTileBytes);
-        for (int hf = 0; hf < D / 64; ++hf) tma_load_3d(dv + hf * 16384, &map_v, &v_full[s], hf * 64, key0, hk);
+        for (int hf = 0; hf < D / 64; ++hf)
+          tma_load_3d(dv + hf * C::kHalfStride, &map_v, &v_full[s], hf * 64, key0, hk);
       }
     }
   } else if (warp == 9) {
@@ -202,54 +205,60 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     if (lane == 0 && Tmax > 0) {
       constexpr uint32_t idesc_qk = make_idesc_f16(BM, BN, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_f16(BM, D, 0, 1);
-      auto issue_s = [&](int x, int j) {  // S_x(j) = Q_x . K_j^T  (the caller has already waited on k_full of j)
+      auto wait_k = [&](int j) {
+        mbar_wait(&k_full[j % C::kStages], static_cast<uint32_t>((j / C::kStages) & 1));
+        tc_fence_after();
+      };
+      auto issue_s = [&](int x, int j) {  // S_x(j) = Q_x . K_j^T into S buffer (x, j&1); k_full(j) already waited
         const int s = j % C::kStages;
-        const uint32_t q_addr = smem_u32(sQ + x * C::kTileBytes);
+        const uint32_t q_addr = smem_u32(sQ + x * C::kQBytes);
         const uint32_t k_addr = smem_u32(sKV + (2 * s) * C::kTileBytes);
-        const uint32_t d = tmem_base + x * 128;
+        const uint32_t d = tmem_base + x * 128 + (j & 1) * BN;
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
-          umma_ss(d, make_smem_desc(q_addr + off, 16, 1024, 2), make_smem_desc(k_addr + off, 16, 1024, 2), idesc_qk,
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_ss(d, make_smem_desc(q_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, 2),
+                  make_smem_desc(k_addr + (kk >> 2) * C::kHalfStride + (kk & 3) * 32, 16, 1024, 2), idesc_qk,
                   kk > 0 ? 1u : 0u);
-        }
-        tc_commit(&s_full[x]);
+        tc_commit(&s_full[x * 2 + (j & 1)]);
       };
       auto issue_pv = [&](int x, int j) {  // O_x += P_x(j) . V_j
         const int s = j % C::kStages;
         const uint32_t v_addr = smem_u32(sKV + (2 * s + 1) * C::kTileBytes);
-        const uint32_t pa = tmem_base + x * 128;
+        const uint32_t pa = tmem_base + x * 128 + (j & 1) * BN;
         const uint32_t d = tmem_base + C::kColO + x * D;
 #pragma unroll
         for (int kk = 0; kk < BN / 16; ++kk)
-          umma_ts(d, pa + kk * 8, make_smem_desc(v_addr + kk * 2048, 16384, 1024, 2), idesc_pv,
+          umma_ts(d, pa + kk * 8, make_smem_desc(v_addr + kk * 2048, C::kHalfStride, 1024, 2), idesc_pv,
                   (j > 0 || kk > 0) ? 1u : 0u);
         tc_commit(&o_full[x]);
       };
       mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      for (int x = 0; x < 2; ++x)
-        if (T[x] > 0) issue_s(x, 0);
+      for (int j = 0; j < 2 && j < Tmax; ++j) {  // two S tiles in flight per query tile
+        wait_k(j);
+        for (int x = 0; x < 2; ++x)
+          if (j < T[x]) issue_s(x, j);
+      }
       for (int j = 0; j < Tmax; ++j) {
         const int s = j % C::kStages;
-        bool k_next_ready = false;
+        bool v_ready = false, k_ready = false;
         for (int x = 0; x < 2; ++x) {
           if (j >= T[x]) continue;
-          mbar_wait(&p_full[x], static_cast<uint32_t>(j & 1));
-          if (x == 0 || T[0] <= j) mbar_wait(&v_full[s], static_cast<uint32_t>((j / C::kStages) & 1));
+          mbar_wait(&p_full[x * 2 + (j & 1)], static_cast<uint32_t>((j >> 1) & 1));
+          if (!v_ready) {
+            mbar_wait(&v_full[s], static_cast<uint32_t>((j / C::kStages) & 1));
+            v_ready = true;
+          }
           tc_fence_after();
           issue_pv(x, j);
-          if (j + 1 < T[x]) {
-            if (!k_next_ready) {
-              mbar_wait(&k_full[(j + 1) % C::kStages], static_cast<uint32_t>(((j + 1) / C::kStages) & 1));
-              tc_fence_after();
-              k_next_ready = true;
+          if (j + 2 < T[x]) {  // S buffer (x, j&1) is free again once PV_x(j) has been issued (in-order execution)
+            if (!k_ready) {
+              wait_k(j + 2);
+              k_ready = true;
             }
-            issue_s(x, j + 1);
+            issue_s(x, j + 2);
           }
         }
-        tc_commit(&kv_empty[s]);  // every MMA that read stage s has been issued
+        tc_commit(&kv_empty[s]);  // every MMA that reads stage s has been issued
       }
     }
   } else {
@@ -257,7 +266,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const int x = warp >> 2;
     const int quad = warp & 3;
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t tmem_s = tmem_base + lane_base + x * 128;
+    const uint32_t tmem_sx = tmem_base + lane_base + x * 128;
     const uint32_t tmem_o = tmem_base + lane_base + C::kColO + x * D;
     const int R = row_lo[x] + quad * 32 + lane;
     const bool warp_valid = quad < valid_warps[x];
@@ -278,7 +287,9 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
     if (warp_valid) {
       for (int j = 0; j < Tx; ++j) {
-        mbar_wait(&s_full[x], static_cast<uint32_t>(j & 1));
+        const int b = j & 1;
+        const uint32_t tmem_s = tmem_sx + b * BN;
+        mbar_wait(&s_full[x * 2 + b], static_cast<uint32_t>((j >> 1) & 1));
         tc_fence_after();
         const int key0 = (t0 + j) * BN;
         const bool need_mask = key0 + BN > vis_end;
@@ -335,7 +346,8 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           l_run *= alpha;
         }
         if (j > 0 && __any_sync(0xffffffffu, grow)) {
-          mbar_wait(&o_full[x], static_cast<uint32_t>((j - 1) & 1));  // PV_x(j-1) has landed
+          // PV_x(j-1) must have landed (S_x(j) was issued two tiles ahead, so this is not implied by s_full)
+          mbar_wait(&o_full[x], static_cast<uint32_t>((j - 1) & 1));
           tc_fence_after();
 #pragma unroll
           for (int ch = 0; ch < D / 32; ++ch) {
@@ -402,7 +414,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         l_run += lt;
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&p_full[x]);
+        mbar_arrive(&p_full[x * 2 + b]);
       }
 
       // ---- epilogue ----
