@@ -80,8 +80,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   uint64_t* kv_empty = v_full + C::kStages;
   uint64_t* s_full = kv_empty + C::kStages;  // [2]
   uint64_t* p_full = s_full + 2;             // [2]
-  uint64_t* o_full = p_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  // indexed by tile parity: a parity wait is only unambiguous within one phase of its barrier, and the softmax
+  // warps can be up to two P.V MMAs ahead
+  uint64_t* o_full = p_full + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = p.n_heads / p.n_kv_heads;
@@ -137,7 +139,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       mbar_init(&s_full[b], 1);
       mbar_init(&p_full[b], 32 * n_valid_warps);
     }
-    mbar_init(o_full, 1);
+    mbar_init(&o_full[0], 1);
+    mbar_init(&o_full[1], 1);
     mbar_fence_init();
   }
   if (warp == 5) tmem_alloc<C::kTmemCols>(tmem_slot);
@@ -200,7 +203,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           umma_ts(tmem_o, pa + kk * 8, make_smem_desc(v_addr + kk * 2048, 16384, 1024, 2), idesc_pv,
                   (j > 0 || kk > 0) ? 1u : 0u);
         tc_commit(&kv_empty[s]);
-        tc_commit(o_full);
+        tc_commit(&o_full[j & 1]);
       }
     }
   } else {
@@ -271,7 +274,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
         if (__any_sync(0xffffffffu, alpha != 1.f)) {
           // O += P.V of tile j-1 must have landed before O is rescaled
-          mbar_wait(o_full, static_cast<uint32_t>((j - 1) & 1));
+          mbar_wait(&o_full[(j - 1) & 1], static_cast<uint32_t>(((j - 1) >> 1) & 1));
           tc_fence_after();
 #pragma unroll
           for (int ch = 0; ch < D / 32; ++ch) {
@@ -291,7 +294,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
     // ---- epilogue: O (TMEM) -> out / partials ----
     if (warp_valid) {
-      mbar_wait(o_full, static_cast<uint32_t>((T - 1) & 1));
+      mbar_wait(&o_full[(T - 1) & 1], static_cast<uint32_t>(((T - 1) >> 1) & 1));
       tc_fence_after();
       const float inv_l = l_run > 0.f ? 1.f / l_run : 0.f;
 #pragma unroll

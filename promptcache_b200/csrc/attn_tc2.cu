@@ -64,6 +64,7 @@ struct PpParams {
   const int* key_pos;
   int n_heads, n_kv_heads, n_cached, q_len, n_splits, m_pairs, alibi_max_pos;
   float scale;
+  int debug;
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -121,8 +122,10 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   uint64_t* kv_empty = v_full + C::kStages;
   uint64_t* s_full = kv_empty + C::kStages;  // [2 query tiles][2 S buffers]
   uint64_t* p_full = s_full + 4;             // [2][2]
-  uint64_t* o_full = p_full + 4;             // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  // o_full is also indexed by tile parity: a softmax warpgroup may run two tiles ahead of the P.V MMAs, and a
+  // parity wait is only unambiguous within one phase of its barrier
+  uint64_t* o_full = p_full + 4;             // [2][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = p.n_heads / p.n_kv_heads;
@@ -166,8 +169,8 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       for (int b = 0; b < 2; ++b) {
         mbar_init(&s_full[x * 2 + b], 1);
         mbar_init(&p_full[x * 2 + b], max(32 * valid_warps[x], 1));
+        mbar_init(&o_full[x * 2 + b], 1);
       }
-      mbar_init(&o_full[x], 1);
     }
     mbar_fence_init();
   }
@@ -230,7 +233,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         for (int kk = 0; kk < BN / 16; ++kk)
           umma_ts(d, pa + kk * 8, make_smem_desc(v_addr + kk * 2048, C::kHalfStride, 1024, 2), idesc_pv,
                   (j > 0 || kk > 0) ? 1u : 0u);
-        tc_commit(&o_full[x]);
+        tc_commit(&o_full[x * 2 + (j & 1)]);
       };
       mbar_wait(q_full, 0);
       for (int j = 0; j < 2 && j < Tmax; ++j) {  // two S tiles in flight per query tile
@@ -241,7 +244,8 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       for (int j = 0; j < Tmax; ++j) {
         const int s = j % C::kStages;
         bool v_ready = false, k_ready = false;
-        for (int x = 0; x < 2; ++x) {
+        for (int xi = 0; xi < 2; ++xi) {
+          const int x = (p.debug & 1) ? 1 - xi : xi;
           if (j >= T[x]) continue;
           mbar_wait(&p_full[x * 2 + (j & 1)], static_cast<uint32_t>((j >> 1) & 1));
           if (!v_ready) {
@@ -347,7 +351,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
         if (j > 0 && __any_sync(0xffffffffu, grow)) {
           // PV_x(j-1) must have landed (S_x(j) was issued two tiles ahead, so this is not implied by s_full)
-          mbar_wait(&o_full[x], static_cast<uint32_t>((j - 1) & 1));
+          mbar_wait(&o_full[x * 2 + ((j - 1) & 1)], static_cast<uint32_t>(((j - 1) >> 1) & 1));
           tc_fence_after();
 #pragma unroll
           for (int ch = 0; ch < D / 32; ++ch) {
@@ -420,7 +424,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       // ---- epilogue ----
       const int n_heads = p.n_heads;
       if (Tx > 0) {
-        mbar_wait(&o_full[x], static_cast<uint32_t>((Tx - 1) & 1));
+        mbar_wait(&o_full[x * 2 + ((Tx - 1) & 1)], static_cast<uint32_t>(((Tx - 1) >> 1) & 1));
         tc_fence_after();
       }
       const float inv_l = l_run > 0.f ? 1.f / l_run : 0.f;
@@ -528,6 +532,8 @@ int launch_pp_d(const pc_attn_params& p, cudaStream_t st) {
   pp.m_pairs = m_pairs;
   pp.alibi_max_pos = p.alibi_max_pos;
   pp.scale = p.scale;
+  pp.debug = 0;
+  if (const char* e = getenv("PC_PP_DEBUG")) pp.debug = atoi(e);
   const int grid = base * n_splits;
   const bool alibi = p.alibi_slopes != nullptr;
   int rc;

@@ -158,8 +158,10 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   uint64_t* kv_empty = v_full + kStages;
   uint64_t* s_full = kv_empty + kStages;
   uint64_t* p_full = s_full + 2;
-  uint64_t* o_full = p_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  // indexed by tile parity: a parity wait is only unambiguous within one phase of its barrier, and the softmax
+  // warps can be up to two P.V MMAs ahead
+  uint64_t* o_full = p_full + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = p.n_heads / p.n_kv_heads;
@@ -186,7 +188,8 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       mbar_init(&s_full[b], 1);
       mbar_init(&p_full[b], kSoftmaxThreads);
     }
-    mbar_init(o_full, 1);
+    mbar_init(&o_full[0], 1);
+    mbar_init(&o_full[1], 1);
     mbar_fence_init();
   }
   if (warp == kSoftmaxWarps + 1) tmem_alloc<C::kTmemCols>(tmem_slot);
@@ -257,7 +260,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           umma_ss(tmem_o, make_smem_desc(v_addr + kk * 2048, 16384, 1024, 2),
                   make_smem_desc(p_addr + kk * 256, 128, 2048, 0), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
         tc_commit(&kv_empty[s]);
-        tc_commit(o_full);
+        tc_commit(&o_full[j & 1]);
       }
     }
   } else {
@@ -341,7 +344,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       fence_proxy_async_smem();
       // CTA-uniform per column half: every thread of a half derived the same maxima from the same smem values
       if (__any_sync(0xffffffffu, any_grow) && j > 0) {
-        mbar_wait(o_full, static_cast<uint32_t>((j - 1) & 1));
+        mbar_wait(&o_full[(j - 1) & 1], static_cast<uint32_t>(((j - 1) >> 1) & 1));
         tc_fence_after();
         float o[NH];
         tmem_ld_n<NH>(tmem_o + lane_base + c0, o);
@@ -369,7 +372,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
 
     // ---- epilogue: O^T (TMEM lane = d, column = query row) ----
-    mbar_wait(o_full, static_cast<uint32_t>((T - 1) & 1));
+    mbar_wait(&o_full[(T - 1) & 1], static_cast<uint32_t>(((T - 1) >> 1) & 1));
     tc_fence_after();
     if (tid == 0) PC_TRACE(2);  // last PV landed
     float o[NH];

@@ -183,6 +183,8 @@ CASES = [
     (2, 2, 128, 1024, 2048),  # long suffix, 4 tile pairs per head
     (4, 1, 128, 100, 3000),   # MQA at D=128: 400 folded rows
     (2, 2, 64, 130, 70),      # D=64, two tiles, tile B has 2 rows
+    (2, 2, 128, 256, 64),     # one tile pair per head, unequal KV extents (regression: o_full phase aliasing)
+    (2, 2, 128, 256, 192),
     (40, 40, 128, 32, 4096),  # C3 (Llama-2-13B heads)
 ]
 
