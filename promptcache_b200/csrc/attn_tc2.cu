@@ -15,10 +15,10 @@
 //
 // KV tiles are 64 keys so that each query tile can double-buffer S within the 512 TMEM columns:
 //   S_A0[0,64) S_A1[64,128) S_B0[128,192) S_B1[192,256) O_A[256,256+D) O_B[256+D,256+2D).
-// Softmax is two passes over TMEM (no 128-register score array): pass 1 reads S and keeps only the row maximum of
-// the RAW accumulators (the fp16-rounding + scale transform is monotone, so max(transform) = transform(max));
-// pass 2 re-reads S in 32-column chunks, applies the reference's roundings, exponentiates (ex2.approx) and writes
-// P.  Rescaling of O is lazy (only when the row maximum grew by more than 2^8).
+// Softmax reads a 64-key row of S from TMEM once (64 registers).  Pass 1 keeps only the row maximum of the RAW
+// accumulators (the fp16-rounding + scale transform is monotone, so max(transform) = transform(max)); pass 2
+// applies the reference's roundings in packed fp16, exponentiates (ex2.approx) and writes P.  Rescaling of O is
+// lazy (only when the row maximum grew by more than 2^8).
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
@@ -84,18 +84,6 @@ __device__ __forceinline__ void round_h2(float& a, float& b) {
   b = f.y;
 }
 __device__ __forceinline__ float round_h(float x) { return __half2float(__float2half_rn(x)); }
-
-// Walk the 2 x 32 columns of an S tile: the TMEM load of chunk 1 is in flight while chunk 0 is processed.
-template <typename F>
-__device__ __forceinline__ void for_each_chunk(uint32_t tmem_s, F&& body) {
-  uint32_t va[32], vb[32];
-  tmem_ld32(tmem_s, va);
-  tmem_ld_wait();
-  tmem_ld32(tmem_s + 32, vb);
-  body(va, 0);
-  tmem_ld_wait();
-  body(vb, 1);
-}
 
 // Causal extent (exclusive key bound) of the 128-row tile starting at folded row `row_lo`.
 __device__ __forceinline__ int tile_kv_end(int row_lo, int rows_total, int q_len, int n_cached) {
@@ -298,26 +286,31 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const int key0 = (t0 + j) * BN;
         const bool need_mask = key0 + BN > vis_end;
 
-        // ---- pass 1: row maximum ----
+        // ---- the whole 64-key row of S lives in registers: one TMEM read per tile ----
+        float sv[BN];
+        tmem_ld32(tmem_s, reinterpret_cast<uint32_t(&)[32]>(sv[0]));
+        tmem_ld32(tmem_s + 32, reinterpret_cast<uint32_t(&)[32]>(sv[32]));
+        tmem_ld_wait();
+        const bool warp_mask = __any_sync(0xffffffffu, need_mask);  // warp-uniform: mask code only near the diagonal
+
+        // ---- pass 1: row maximum (log2 domain) ----
         float mt;
         if (!ALIBI) {
+          // max over the RAW accumulators; the fp16-rounding + scale transform is monotone, so it commutes with max
           float raw_max = -INFINITY;
-          for_each_chunk(tmem_s, [&](const uint32_t(&v)[32], int ch) {
-            if (need_mask) {
+          if (warp_mask) {
 #pragma unroll
-              for (int c = 0; c < 32; ++c)
-                if (key0 + ch * 32 + c < vis_end) raw_max = fmaxf(raw_max, __uint_as_float(v[c]));
-            } else {
+            for (int c = 0; c < BN; ++c)
+              if (key0 + c < vis_end) raw_max = fmaxf(raw_max, sv[c]);
+          } else {
 #pragma unroll
-              for (int c = 0; c < 32; c += 2)
-                raw_max = fmaxf(raw_max, fmaxf(__uint_as_float(v[c]), __uint_as_float(v[c + 1])));
-            }
-          });
-          // the score transform is monotone non-decreasing, so it commutes with max
+            for (int c = 0; c < BN; c += 2) raw_max = fmaxf(raw_max, fmaxf(sv[c], sv[c + 1]));
+          }
           float t = raw_max;
           if (ROUND == PC_ROUND_LLAMA) {
             const __half2 a16 = __floats2half2_rn(t, t);
             t = __low2float(__hfma2(a16, scale_hi, __hmul2(a16, scale_lo)));
+            if (raw_max == -INFINITY) t = -INFINITY;  // (-inf)*s_lo may be +inf -> NaN in the fused form
           } else {
             if (ROUND & PC_ROUND_QK) t = round_h(t);
             t *= p.scale;
@@ -325,20 +318,19 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           }
           mt = t * kLog2e;
         } else {
+          // ALiBi adds a per-key bias: transform every score once (kept in sv, natural-log domain), then take the max
           mt = -INFINITY;
-          for_each_chunk(tmem_s, [&](const uint32_t(&v)[32], int ch) {
+          const int kmax = p.n_cached + p.q_len - 1;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const int kidx = key0 + ch * 32 + c;
-              float t = __uint_as_float(v[c]);
-              if (ROUND & PC_ROUND_QK) t = round_h(t);
-              t *= p.scale;
-              if (ROUND & PC_ROUND_SCALED) t = round_h(t);
-              t += slope * static_cast<float>(__ldg(p.key_pos + min(kidx, p.n_cached + p.q_len - 1)) - p.alibi_max_pos);
-              t *= kLog2e;
-              if (kidx < vis_end) mt = fmaxf(mt, t);
-            }
-          });
+          for (int c = 0; c < BN; ++c) {
+            float t = sv[c];
+            if (ROUND & PC_ROUND_QK) t = round_h(t);
+            t *= p.scale;
+            if (ROUND & PC_ROUND_SCALED) t = round_h(t);
+            t += slope * static_cast<float>(__ldg(p.key_pos + min(key0 + c, kmax)) - p.alibi_max_pos);
+            sv[c] = t;
+            if (key0 + c < vis_end) mt = fmaxf(mt, t * kLog2e);
+          }
         }
 
         // ---- running maximum, lazy rescale of O ----
@@ -365,56 +357,48 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
         const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
 
-        // ---- pass 2: P = 2^(score - m), written over S as packed fp16 ----
-        // The mask is only evaluated on tiles that reach the causal diagonal (warp-uniform decision).
+        // ---- pass 2: P = 2^(score - m), written over S as packed fp16 (32 columns) ----
         float lt = 0.f;
-        const bool warp_mask = __any_sync(0xffffffffu, need_mask);
-        auto pass2 = [&](const uint32_t(&v)[32], int ch, auto masked_tag) {
+        uint32_t pk[BN / 2];
+        auto pass2 = [&](auto masked_tag) {
           constexpr bool kMasked = decltype(masked_tag)::value;
-          uint32_t pk[16];
 #pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            const float a = __uint_as_float(v[c]), b = __uint_as_float(v[c + 1]);
+          for (int c = 0; c < BN; c += 2) {
+            const float a = sv[c], b2 = sv[c + 1];
             float ya, yb;
-            if (ROUND == 0 && !ALIBI) {
+            if (ALIBI) {
+              ya = fmaf(a, kLog2e, -m_use);
+              yb = fmaf(b2, kLog2e, -m_use);
+            } else if (ROUND == 0) {
               ya = fmaf(a, scale_l2, -m_use);
-              yb = fmaf(b, scale_l2, -m_use);
-            } else if (ROUND == PC_ROUND_LLAMA && !ALIBI) {
+              yb = fmaf(b2, scale_l2, -m_use);
+            } else if (ROUND == PC_ROUND_LLAMA) {
               // half(half(acc) * scale) in packed fp16: scale = s_hi + s_lo (both fp16), one fused rounding
-              const __half2 a16 = __floats2half2_rn(a, b);
-              const __half2 sc = __hfma2(a16, scale_hi, __hmul2(a16, scale_lo));
-              const float2 f = __half22float2(sc);
+              const __half2 a16 = __floats2half2_rn(a, b2);
+              const float2 f = __half22float2(__hfma2(a16, scale_hi, __hmul2(a16, scale_lo)));
               ya = fmaf(f.x, kLog2e, -m_use);
               yb = fmaf(f.y, kLog2e, -m_use);
             } else {
-              float ta = a, tb = b;
+              float ta = a, tb = b2;
               if (ROUND & PC_ROUND_QK) round_h2(ta, tb);
               ta *= p.scale;
               tb *= p.scale;
               if (ROUND & PC_ROUND_SCALED) round_h2(ta, tb);
-              if (ALIBI) {
-                const int k0 = key0 + ch * 32 + c, kmax = p.n_cached + p.q_len - 1;
-                ta += slope * static_cast<float>(__ldg(p.key_pos + min(k0, kmax)) - p.alibi_max_pos);
-                tb += slope * static_cast<float>(__ldg(p.key_pos + min(k0 + 1, kmax)) - p.alibi_max_pos);
-              }
               ya = fmaf(ta, kLog2e, -m_use);
               yb = fmaf(tb, kLog2e, -m_use);
             }
             if (kMasked) {
-              if (key0 + ch * 32 + c >= vis_end) ya = -INFINITY;
-              if (key0 + ch * 32 + c + 1 >= vis_end) yb = -INFINITY;
+              if (key0 + c >= vis_end) ya = -INFINITY;
+              if (key0 + c + 1 >= vis_end) yb = -INFINITY;
             }
             const float p0 = ex2(ya), p1 = ex2(yb);
             lt += p0 + p1;
             pk[c >> 1] = pack_h2(p0, p1);
           }
-          // P columns [16ch,16ch+16) only cover S columns of chunks <= ch, never the chunk still in flight
-          tmem_st16(tmem_s + ch * 16, pk);
         };
-        if (warp_mask)
-          for_each_chunk(tmem_s, [&](const uint32_t(&v)[32], int ch) { pass2(v, ch, std::true_type{}); });
-        else
-          for_each_chunk(tmem_s, [&](const uint32_t(&v)[32], int ch) { pass2(v, ch, std::false_type{}); });
+        if (warp_mask) pass2(std::true_type{});
+        else pass2(std::false_type{});
+        tmem_st32(tmem_s, pk);
         l_run += lt;
         tmem_st_wait();
         tc_fence_before();
