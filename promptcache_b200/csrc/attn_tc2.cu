@@ -2,8 +2,9 @@
 // uncached suffixes, Falcon's MQA (71 heads folded into M).  Same contract as attn_tc_small.cu; this is the
 // tensor-bound regime (G*q FLOP per KV byte above the ~254 FLOP/B ridge).
 //
-// One CTA = (kv head, PAIR of 128-row query tiles A and B, KV split).  Both tiles share every K/V tile, and two
-// softmax warpgroups ping-pong against one MMA thread so that the tensor core is never waiting on a softmax:
+// One CTA = (kv head, PAIR of 128-row query tiles A and B, KV split).  Both tiles share every K/V tile; each tile
+// has its own softmax warpgroup and its own MMA-issuing thread (a single thread could not issue the 24 MMAs per
+// 64 keys fast enough), so the tensor core always has the other tile's work queued while one softmax runs:
 //
 //   MMA thread :  S_A(0) S_B(0) S_A(1) S_B(1) | PV_A(0) S_A(2) | PV_B(0) S_B(2) | PV_A(1) S_A(3) | ...
 //   WG0 (tile A):   softmax A(0) | softmax A(1) | softmax A(2) | ...      (S_A(j+1) is already waiting when
@@ -38,7 +39,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BN = 64;
-constexpr int kThreads = 320;  // WG0 (warps 0-3), WG1 (warps 4-7), TMA warp 8, MMA warp 9
+constexpr int kThreads = 352;  // WG0 (warps 0-3), WG1 (warps 4-7), TMA warp 8, MMA warps 9 (tile A) and 10 (tile B)
 constexpr int kMaxSplits = 32;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;
@@ -107,8 +108,8 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;
   uint64_t* v_full = k_full + C::kStages;
-  uint64_t* kv_empty = v_full + C::kStages;
-  uint64_t* s_full = kv_empty + C::kStages;  // [2 query tiles][2 S buffers]
+  uint64_t* kv_empty = v_full + C::kStages;      // [2 query tiles][stages]: released by each tile's MMA thread
+  uint64_t* s_full = kv_empty + 2 * C::kStages;  // [2 query tiles][2 S buffers]
   uint64_t* p_full = s_full + 4;             // [2][2]
   // o_full is also indexed by tile parity: a softmax warpgroup may run two tiles ahead of the P.V MMAs, and a
   // parity wait is only unambiguous within one phase of its barrier
@@ -152,6 +153,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       mbar_init(&k_full[s], 1);
       mbar_init(&v_full[s], 1);
       mbar_init(&kv_empty[s], 1);
+      mbar_init(&kv_empty[C::kStages + s], 1);
     }
     for (int x = 0; x < 2; ++x) {
       for (int b = 0; b < 2; ++b) {
@@ -179,7 +181,11 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             tma_load_3d(sQ + x * C::kQBytes + hf * 16384, &map_q, q_full, hf * 64, row_lo[x], hk);
       for (int j = 0; j < Tmax; ++j) {
         const int s = j % C::kStages;
-        if (j >= C::kStages) mbar_wait(&kv_empty[s], static_cast<uint32_t>(((j / C::kStages) - 1) & 1));
+        if (j >= C::kStages) {  // both tiles' MMAs that read tile j-kStages must have completed
+          for (int x = 0; x < 2; ++x)
+            if (j - C::kStages < T[x])
+              mbar_wait(&kv_empty[x * C::kStages + s], static_cast<uint32_t>(((j / C::kStages) - 1) & 1));
+        }
         unsigned char* dk = sKV + (2 * s) * C::kTileBytes;
         unsigned char* dv = dk + C::kTileBytes;
         const int key0 = (t0 + j) * BN;
@@ -191,66 +197,58 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           tma_load_3d(dv + hf * C::kHalfStride, &map_v, &v_full[s], hf * 64, key0, hk);
       }
     }
-  } else if (warp == 9) {
-    // ===================== MMA issuer =====================
-    if (lane == 0 && Tmax > 0) {
+  } else if (warp == 9 || warp == 10) {
+    // ===================== MMA issuers: warp 9 drives query tile A, warp 10 tile B =====================
+    const int x = warp - 9;
+    const int Tx = T[x];
+    if (lane == 0 && Tx > 0) {
       constexpr uint32_t idesc_qk = make_idesc_f16(BM, BN, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_f16(BM, D, 0, 1);
+      // descriptors: everything but the start address is loop-invariant; offsets are added to the low word
+      const uint64_t q_desc = make_smem_desc(smem_u32(sQ + x * C::kQBytes), 16, 1024, 2);
+      const uint64_t k_desc0 = make_smem_desc(smem_u32(sKV), 16, 1024, 2);
+      const uint64_t v_desc0 = make_smem_desc(smem_u32(sKV + C::kTileBytes), C::kHalfStride, 1024, 2);
+      const uint32_t tmem_sx = tmem_base + x * 128;
+      const uint32_t tmem_ox = tmem_base + C::kColO + x * D;
       auto wait_k = [&](int j) {
         mbar_wait(&k_full[j % C::kStages], static_cast<uint32_t>((j / C::kStages) & 1));
         tc_fence_after();
       };
-      auto issue_s = [&](int x, int j) {  // S_x(j) = Q_x . K_j^T into S buffer (x, j&1); k_full(j) already waited
-        const int s = j % C::kStages;
-        const uint32_t q_addr = smem_u32(sQ + x * C::kQBytes);
-        const uint32_t k_addr = smem_u32(sKV + (2 * s) * C::kTileBytes);
-        const uint32_t d = tmem_base + x * 128 + (j & 1) * BN;
+      auto issue_s = [&](int j) {  // S_x(j) = Q_x . K_j^T into S buffer (x, j&1); k_full(j) already waited
+        const uint64_t k_desc = k_desc0 + static_cast<uint64_t>(((j % C::kStages) * 2 * C::kTileBytes) >> 4);
+        const uint32_t d = tmem_sx + (j & 1) * BN;
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)
-          umma_ss(d, make_smem_desc(q_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, 2),
-                  make_smem_desc(k_addr + (kk >> 2) * C::kHalfStride + (kk & 3) * 32, 16, 1024, 2), idesc_qk,
+          umma_ss(d, q_desc + static_cast<uint64_t>(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4),
+                  k_desc + static_cast<uint64_t>(((kk >> 2) * C::kHalfStride + (kk & 3) * 32) >> 4), idesc_qk,
                   kk > 0 ? 1u : 0u);
         tc_commit(&s_full[x * 2 + (j & 1)]);
       };
-      auto issue_pv = [&](int x, int j) {  // O_x += P_x(j) . V_j
-        const int s = j % C::kStages;
-        const uint32_t v_addr = smem_u32(sKV + (2 * s + 1) * C::kTileBytes);
-        const uint32_t pa = tmem_base + x * 128 + (j & 1) * BN;
-        const uint32_t d = tmem_base + C::kColO + x * D;
+      auto issue_pv = [&](int j) {  // O_x += P_x(j) . V_j
+        const uint64_t v_desc = v_desc0 + static_cast<uint64_t>(((j % C::kStages) * 2 * C::kTileBytes) >> 4);
+        const uint32_t pa = tmem_sx + (j & 1) * BN;
 #pragma unroll
         for (int kk = 0; kk < BN / 16; ++kk)
-          umma_ts(d, pa + kk * 8, make_smem_desc(v_addr + kk * 2048, C::kHalfStride, 1024, 2), idesc_pv,
+          umma_ts(tmem_ox, pa + kk * 8, v_desc + static_cast<uint64_t>((kk * 2048) >> 4), idesc_pv,
                   (j > 0 || kk > 0) ? 1u : 0u);
         tc_commit(&o_full[x * 2 + (j & 1)]);
       };
       mbar_wait(q_full, 0);
-      for (int j = 0; j < 2 && j < Tmax; ++j) {  // two S tiles in flight per query tile
+      for (int j = 0; j < 2 && j < Tx; ++j) {  // two S tiles in flight per query tile
         wait_k(j);
-        for (int x = 0; x < 2; ++x)
-          if (j < T[x]) issue_s(x, j);
+        issue_s(j);
       }
-      for (int j = 0; j < Tmax; ++j) {
+      for (int j = 0; j < Tx; ++j) {
         const int s = j % C::kStages;
-        bool v_ready = false, k_ready = false;
-        for (int xi = 0; xi < 2; ++xi) {
-          const int x = (p.debug & 1) ? 1 - xi : xi;
-          if (j >= T[x]) continue;
-          mbar_wait(&p_full[x * 2 + (j & 1)], static_cast<uint32_t>((j >> 1) & 1));
-          if (!v_ready) {
-            mbar_wait(&v_full[s], static_cast<uint32_t>((j / C::kStages) & 1));
-            v_ready = true;
-          }
-          tc_fence_after();
-          issue_pv(x, j);
-          if (j + 2 < T[x]) {  // S buffer (x, j&1) is free again once PV_x(j) has been issued (in-order execution)
-            if (!k_ready) {
-              wait_k(j + 2);
-              k_ready = true;
-            }
-            issue_s(x, j + 2);
-          }
+        mbar_wait(&p_full[x * 2 + (j & 1)], static_cast<uint32_t>((j >> 1) & 1));
+        mbar_wait(&v_full[s], static_cast<uint32_t>((j / C::kStages) & 1));
+        tc_fence_after();
+        issue_pv(j);
+        if (j + 2 < Tx) {  // S buffer (x, j&1) is free again once PV_x(j) has been issued (in-order execution)
+          wait_k(j + 2);
+          issue_s(j + 2);
         }
-        tc_commit(&kv_empty[s]);  // every MMA that reads stage s has been issued
+        tc_commit(&kv_empty[x * C::kStages + s]);  // this tile's MMAs on stage s have all been issued
       }
     }
   } else {
