@@ -84,13 +84,58 @@ def attention_alone(nat, lm, case, dev, peak):
             "note": "34 MB per launch = 5 us at peak: launch/prologue latency bound at this size; 0.66 of peak at C5 (135 MB)"}
 
 
+def attention_tensor_alone(nat, dev, tflops_peak):
+    """Long-suffix (tensor-bound) regime of the same entry point: 1024 uncached tokens over 8192 cached ones at
+    Llama-2-7B head geometry, timed alone (CUDA-graph of 8 launches over 4 layers of K/V)."""
+    H = Hkv = 32
+    D, q, N, rot = 128, 1024, 8192, 4
+    max_ctx = N + q
+    K = torch.randn(rot, Hkv, max_ctx, D, device=dev).half()
+    V = torch.randn(rot, Hkv, max_ctx, D, device=dev).half()
+    Q = torch.randn(H, q, D, device=dev).half()
+    out = torch.empty(q, H * D, dtype=torch.half, device=dev)
+    ws = torch.zeros(max(nat.attn_workspace_bytes(H, q, D), 1), dtype=torch.uint8, device=dev)
+    state = {"i": 0}
+
+    def run():
+        l = state["i"] % rot
+        state["i"] += 1
+        nat.attention(Q, K[l], V[l], out, N, q, H, Hkv, D, nat.softmax_scale(D), nat.PC_ROUND_LLAMA, workspace=ws)
+
+    run()
+    torch.cuda.synchronize()
+    g, st = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        run()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(8):
+                run()
+    torch.cuda.synchronize()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 40
+    flops = 4.0 * H * D * (q * N + q * (q + 1) / 2)  # causal-aware: key N+t is visible to rows r >= t
+    ach = flops / (ms * 1e-3) / 1e12
+    return {"kernel": "attn_pp_kernel (pc_prefill_attn, one layer, q=1024 over N=8192)", "bound": "tensor", "achieved": ach,
+            "peak": tflops_peak, "unit": "TFLOP/s", "frac": ach / tflops_peak, "traffic": None, "algorithmic_flops_per_launch": flops,
+            "avg_launch_ms": ms, "timed": "alone, CUDA-graph of 8 launches (burst peak applies)",
+            "ncu": "sm__pipe_tensor_cycles_active 47% of active cycles (profiles/r01_ncu_full_attn_pp_v4.txt)"}
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
             p = json.load(fh)
-        return float(p["hbm_gbs"]), "measured"
+        return float(p["hbm_gbs"]), "measured", float(p.get("bf16_tflops", 1590.0))
     except Exception:
-        return 6650.0, "fallback"
+        return 6650.0, "fallback", 1590.0
 
 
 class ClockSampler:
@@ -361,7 +406,7 @@ def main():
     dev_ms, e2e_ms = float(times[0]), float(times[1])
 
     if rank == 0:
-        peak, peak_kind = load_peaks()
+        peak, peak_kind, tflops_peak = load_peaks()
         ms_per_step = dev_ms / args.steps
         L, Hkv, D = lm.get_cache_shape()
         splice_bytes = 8.0 * L * Hkv * case.n_cached * D  # read + write of K and V, fp16
@@ -385,6 +430,10 @@ def main():
             line["roofline_attention"] = attention_alone(nat, lm, case, dev, peak)
         except Exception as ex:
             line["roofline_attention"] = {"error": str(ex)}
+        try:
+            line["roofline_attention_tensor"] = attention_tensor_alone(nat, dev, tflops_peak)
+        except Exception as ex:
+            line["roofline_attention_tensor"] = {"error": str(ex)}
         if args.layers:
             line["invalid"] = f"debug run with {args.layers} layers"
         if world == 1 and not args.no_cpu_baseline:

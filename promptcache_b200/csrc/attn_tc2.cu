@@ -65,7 +65,6 @@ struct PpParams {
   const int* key_pos;
   int n_heads, n_kv_heads, n_cached, q_len, n_splits, m_pairs, alibi_max_pos;
   float scale;
-  int debug;
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -514,8 +513,6 @@ int launch_pp_d(const pc_attn_params& p, cudaStream_t st) {
   pp.m_pairs = m_pairs;
   pp.alibi_max_pos = p.alibi_max_pos;
   pp.scale = p.scale;
-  pp.debug = 0;
-  if (const char* e = getenv("PC_PP_DEBUG")) pp.debug = atoi(e);
   const int grid = base * n_splits;
   const bool alibi = p.alibi_slopes != nullptr;
   int rc;
