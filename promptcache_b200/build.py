@@ -66,6 +66,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     link = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static",
             "-Xcompiler", "-fPIC"]
     subprocess.run(link, check=True)
+    # a shared library links with unresolved symbols; make them a build error (dlopen resolves everything eagerly)
+    import ctypes
+    ctypes.CDLL(LIB, mode=ctypes.RTLD_LOCAL | os.RTLD_NOW)
     with open(STAMP, "w") as fh:
         fh.write(digest)
     return LIB

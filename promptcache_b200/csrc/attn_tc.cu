@@ -494,6 +494,18 @@ int launch_d(const pc_attn_params& p, cudaStream_t st) {
 
 }  // namespace
 
+int launch_attn_combine(const float* part_o, const float* part_ml, void* out, int n_heads, int q_len, int n_splits,
+                        int head_dim, cudaStream_t st) {
+  dim3 cgrid(q_len, n_heads);
+  if (head_dim == 128)
+    attn_combine_kernel<128><<<cgrid, 128, 0, st>>>(part_o, part_ml, static_cast<__half*>(out), n_heads, q_len, n_splits);
+  else
+    attn_combine_kernel<64><<<cgrid, 64, 0, st>>>(part_o, part_ml, static_cast<__half*>(out), n_heads, q_len, n_splits);
+  PC_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return PC_OK;
+}
+
 // Upper bound of what the long-suffix kernels may use: the split count is largest when every query head shares
 // one KV head (MQA), i.e. base = ceil(H*q/256) CTAs (row-tile pairs of attn_tc2.cu) before splitting.
 size_t attn_tc_workspace_bytes(int n_heads, int q_len, int head_dim) {
