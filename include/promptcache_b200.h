@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PC_ABI_VERSION 1
+#define PC_ABI_VERSION 2
 
 enum {
   PC_OK = 0,
@@ -110,6 +110,14 @@ int pc_rope_append(const void* q_in, const void* k_in, const void* v_in, int64_t
                    const void* cos_dev, const void* sin_dev, int table_rows, void* q_out,
                    void* k_cache, void* v_cache, int max_ctx, int dst_row0, int n_heads,
                    int n_kv_heads, int head_dim, int q_len, void* stream);
+/* Same, but the destination row is read on the device from *dst_row0_dev at run time (clamped to
+ * max_ctx - q_len), so that a captured CUDA graph of a decode step can be replayed while the
+ * sequence grows (generation_engine.py:123-147). */
+int pc_rope_append_dyn(const void* q_in, const void* k_in, const void* v_in, int64_t q_stride,
+                       int64_t k_stride, int64_t v_stride, const int64_t* position_ids_dev,
+                       const void* cos_dev, const void* sin_dev, int table_rows, void* q_out,
+                       void* k_cache, void* v_cache, int max_ctx, const int32_t* dst_row0_dev,
+                       int n_heads, int n_kv_heads, int head_dim, int q_len, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Attention of the uncached suffix over the spliced cache (prefill) and of one token (decode)
@@ -138,6 +146,9 @@ typedef struct pc_attn_params {
   const int32_t* key_pos;    /* [n_cached+q_len] or NULL (required with alibi_slopes)        */
   int32_t alibi_max_pos;     /* max(position_ids) (mpt.py:522)                               */
   int32_t impl;              /* PC_ATTN_*                                                    */
+  const int32_t* n_cached_dev; /* optional: N is read from the device at run time (graph-replayable decode /  *
+                              * short suffixes, head_dim 128, G*q_len <= 32 only); `n_cached` is then an    *
+                              * upper bound used for sizing, all max_ctx rows of k/v must hold finite values */
   void* workspace;           /* split-KV scratch, >= pc_attn_workspace_bytes(...) or NULL;   *
                               * ZERO it once before first use (arrival counters; kernels     *
                               * leave them zeroed); one workspace per concurrent stream      */

@@ -26,7 +26,7 @@ PC_ATTN_SIMT = 1
 PC_ATTN_TCGEN05 = 2
 
 EXPORTS = ("pc_version", "pc_last_error", "pc_device_info", "pc_splice_kv", "pc_splice_kv_tensors",
-           "pc_rope_append", "pc_attn_workspace_bytes", "pc_prefill_attn", "pc_decode_attn", "pc_launch_count",
+           "pc_rope_append", "pc_rope_append_dyn", "pc_attn_workspace_bytes", "pc_prefill_attn", "pc_decode_attn", "pc_launch_count",
            "pc_add_rmsnorm", "pc_silu_mul")
 
 
@@ -50,7 +50,7 @@ class pc_attn_params(C.Structure):
                 ("n_cached", C.c_int32), ("q_len", C.c_int32), ("max_ctx", C.c_int32),
                 ("scale", C.c_float), ("rounding", C.c_int32),
                 ("alibi_slopes", C.c_void_p), ("key_pos", C.c_void_p),
-                ("alibi_max_pos", C.c_int32), ("impl", C.c_int32),
+                ("alibi_max_pos", C.c_int32), ("impl", C.c_int32), ("n_cached_dev", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
@@ -81,6 +81,10 @@ def load() -> C.CDLL:
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.pc_rope_append.restype = C.c_int
+    lib.pc_rope_append_dyn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.pc_rope_append_dyn.restype = C.c_int
     lib.pc_attn_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.pc_attn_workspace_bytes.restype = C.c_size_t
     lib.pc_prefill_attn.argtypes = [C.POINTER(pc_attn_params), C.c_void_p]
@@ -172,9 +176,10 @@ def splice_kv_tensors(copies: Sequence[tuple]) -> None:
 
 def rope_append(q_in: torch.Tensor, k_in: torch.Tensor, v_in: torch.Tensor, position_ids: Optional[torch.Tensor],
                 cos: Optional[torch.Tensor], sin: Optional[torch.Tensor], q_out: torch.Tensor,
-                k_cache: torch.Tensor, v_cache: torch.Tensor, dst_row0: int, n_heads: int, n_kv_heads: int,
+                k_cache: torch.Tensor, v_cache: torch.Tensor, dst_row0, n_heads: int, n_kv_heads: int,
                 head_dim: int) -> None:
-    """q_in/k_in/v_in: [q, H*D]-like 2-D views (row stride arbitrary, inner contiguous); caches [Hkv,max_ctx,D]."""
+    """q_in/k_in/v_in: [q, H*D]-like 2-D views (row stride arbitrary, inner contiguous); caches [Hkv,max_ctx,D].
+    `dst_row0` is a host int, or a CUDA int32 tensor read at run time (graph-replayable decode)."""
     lib = load()
     _require_cuda(q_in, k_in, v_in, q_out, k_cache, v_cache)
     q_len = q_in.shape[0]
@@ -193,6 +198,16 @@ def rope_append(q_in: torch.Tensor, k_in: torch.Tensor, v_in: torch.Tensor, posi
         table_rows = cos.shape[0]
         if position_ids.dtype != torch.int64 or not position_ids.is_contiguous():
             raise NativeError("rope_append: position_ids must be a contiguous int64 tensor")
+    if isinstance(dst_row0, torch.Tensor):
+        if dst_row0.dtype != torch.int32 or not dst_row0.is_cuda:
+            raise NativeError("rope_append: a run-time dst_row0 must be a CUDA int32 tensor")
+        _check(lib.pc_rope_append_dyn(q_in.data_ptr(), k_in.data_ptr(), v_in.data_ptr(), q_in.stride(0), k_in.stride(0),
+                                      v_in.stride(0), position_ids.data_ptr() if position_ids is not None else None,
+                                      cos.data_ptr() if cos is not None else None,
+                                      sin.data_ptr() if sin is not None else None, table_rows, q_out.data_ptr(),
+                                      k_cache.data_ptr(), v_cache.data_ptr(), max_ctx, dst_row0.data_ptr(), n_heads,
+                                      n_kv_heads, head_dim, q_len, _stream()), "pc_rope_append_dyn")
+        return
     _check(lib.pc_rope_append(q_in.data_ptr(), k_in.data_ptr(), v_in.data_ptr(), q_in.stride(0), k_in.stride(0),
                               v_in.stride(0), position_ids.data_ptr() if position_ids is not None else None,
                               cos.data_ptr() if cos is not None else None,
@@ -214,7 +229,7 @@ def attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, out
               q_len: int, n_heads: int, n_kv_heads: int, head_dim: int, scale: float, rounding: int,
               workspace: Optional[torch.Tensor] = None, alibi_slopes: Optional[torch.Tensor] = None,
               key_pos: Optional[torch.Tensor] = None, alibi_max_pos: int = 0, impl: int = PC_ATTN_AUTO,
-              decode: bool = False) -> None:
+              decode: bool = False, n_cached_dev: Optional[torch.Tensor] = None) -> None:
     """q: [H,q,D] fp16; caches [Hkv,max_ctx,D] (row-contiguous views allowed); out: [q,H*D] fp16."""
     lib = load()
     _require_cuda(q, k_cache, v_cache, out)
@@ -235,6 +250,10 @@ def attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, out
         p.alibi_slopes, p.key_pos = alibi_slopes.data_ptr(), key_pos.data_ptr()
     p.alibi_max_pos = int(alibi_max_pos)
     p.impl = impl
+    if n_cached_dev is not None:
+        if n_cached_dev.dtype != torch.int32 or not n_cached_dev.is_cuda:
+            raise NativeError("attention: n_cached_dev must be a CUDA int32 tensor")
+        p.n_cached_dev = n_cached_dev.data_ptr()
     if workspace is not None:
         p.workspace, p.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
     fn = lib.pc_decode_attn if decode else lib.pc_prefill_attn

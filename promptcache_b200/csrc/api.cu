@@ -77,6 +77,11 @@ static int attn_dispatch(const pc_attn_params* p, void* stream, const char* who)
     if (e && e[0] == 's') impl = PC_ATTN_SIMT;
     else impl = PC_ATTN_TCGEN05;
   }
+  if (p->n_cached_dev != nullptr) {
+    if (impl != PC_ATTN_TCGEN05 || !attn_small_supported(*p))
+      return set_error(PC_ERR_UNSUPPORTED, "%s: n_cached_dev needs the short-suffix tcgen05 kernel (head_dim 128, G*q <= 32)", who);
+    return launch_attn_small(*p, st);
+  }
   if (impl == PC_ATTN_SIMT) return launch_attn_simt(*p, st);
   if (impl == PC_ATTN_TCGEN05) {
     const char* e = getenv("PC_ATTN_SMALL");

@@ -55,6 +55,7 @@ struct SmallParams {
   int* counters;
   const float* alibi_slopes;
   const int* key_pos;
+  const int* n_cached_dev;  // optional run-time N (graph-replayable decode)
   int n_heads, n_kv_heads, n_cached, q_len, n_splits, alibi_max_pos;
   float scale;
   unsigned long long* trace;  // debug: %globaltimer stamps of CTA 0 (PC_ATTN_TRACE_PTR), else nullptr
@@ -137,8 +138,10 @@ __device__ __forceinline__ int reduced_column(int lane) {
 template <int NPAD, int ROUND, bool ALIBI>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                  const __grid_constant__ CUtensorMap map_v, const SmallParams p) {
+                  const __grid_constant__ CUtensorMap map_v, const SmallParams pin) {
   using C = SCfg<NPAD>;
+  SmallParams p = pin;
+  if (pin.n_cached_dev != nullptr) p.n_cached = max(0, min(__ldg(pin.n_cached_dev), pin.n_cached));
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   unsigned char* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -171,7 +174,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   const int tiles_total = (p.n_cached + p.q_len + BK - 1) / BK;
   const int tile0 = static_cast<int>(static_cast<long long>(split) * tiles_total / p.n_splits);
   const int tile1 = static_cast<int>(static_cast<long long>(split + 1) * tiles_total / p.n_splits);
-  const int T = tile1 - tile0;  // >= 1 (host guarantees n_splits <= tiles_total)
+  const int T = tile1 - tile0;  // 0 only when N is read at run time and this split has no tile
   if (tid == 0) PC_TRACE(0);
 
   if (warp == kSoftmaxWarps && lane == 0) {
@@ -245,7 +248,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       };
       mbar_wait(q_full, 0);
       PC_TRACE(5);  // Q landed
-      issue_st(0);
+      if (T > 0) issue_st(0);
       PC_TRACE(6);  // first K landed and S^T_0 issued
       for (int j = 0; j < T; ++j) {
         if (j + 1 < T) issue_st(j + 1);
@@ -372,12 +375,17 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
 
     // ---- epilogue: O^T (TMEM lane = d, column = query row) ----
-    mbar_wait(&o_full[(T - 1) & 1], static_cast<uint32_t>(((T - 1) >> 1) & 1));
-    tc_fence_after();
-    if (tid == 0) PC_TRACE(2);  // last PV landed
     float o[NH];
-    tmem_ld_n<NH>(tmem_o + lane_base + c0, o);
-    tmem_ld_wait();
+    if (T > 0) {
+      mbar_wait(&o_full[(T - 1) & 1], static_cast<uint32_t>(((T - 1) >> 1) & 1));
+      tc_fence_after();
+      if (tid == 0) PC_TRACE(2);  // last PV landed
+      tmem_ld_n<NH>(tmem_o + lane_base + c0, o);
+      tmem_ld_wait();
+    } else {  // empty split: neutral partial (m = -inf, l = 0)
+#pragma unroll
+      for (int i = 0; i < NH; ++i) o[i] = 0.f;
+    }
     const int d = kl;
     const int HQ = p.n_heads * p.q_len;
     if (p.n_splits == 1) {
@@ -491,7 +499,7 @@ int launch_small_one(const CUtensorMap& mq, const CUtensorMap& mk, const CUtenso
 template <int NPAD>
 int launch_small_n(const pc_attn_params& p, cudaStream_t st) {
   const int G = p.n_heads / p.n_kv_heads;
-  const int tiles = (p.n_cached + p.q_len + BK - 1) / BK;
+  const int tiles = (p.n_cached + p.q_len + BK - 1) / BK;  // with n_cached_dev: an upper bound
   int n_splits = sm_count() / p.n_kv_heads;
   if (const char* e = getenv("PC_ATTN_SPLITS")) n_splits = atoi(e);
   if (n_splits > tiles) n_splits = tiles;
@@ -519,6 +527,7 @@ int launch_small_n(const pc_attn_params& p, cudaStream_t st) {
   }
   sp.alibi_slopes = p.alibi_slopes;
   sp.key_pos = p.key_pos;
+  sp.n_cached_dev = p.n_cached_dev;
   sp.n_heads = p.n_heads;
   sp.n_kv_heads = p.n_kv_heads;
   sp.n_cached = p.n_cached;
@@ -532,7 +541,8 @@ int launch_small_n(const pc_attn_params& p, cudaStream_t st) {
   const int rows_total = G * p.q_len;
   CUtensorMap mq, mk, mv;
   if (int rc = make_tensor_map_3d(&mq, p.q, D, rows_total, p.n_kv_heads, static_cast<long long>(rows_total) * D, NPAD)) return rc;
-  const long long kv_rows = static_cast<long long>(p.n_cached) + p.q_len;
+  // run-time N: the maps cover the whole buffer (rows past N+q are masked; they must hold finite values)
+  const long long kv_rows = p.n_cached_dev ? static_cast<long long>(p.max_ctx) : static_cast<long long>(p.n_cached) + p.q_len;
   if (int rc = make_tensor_map_3d(&mk, p.k, D, kv_rows, p.n_kv_heads, static_cast<long long>(p.max_ctx) * D, BK)) return rc;
   if (int rc = make_tensor_map_3d(&mv, p.v, D, kv_rows, p.n_kv_heads, static_cast<long long>(p.max_ctx) * D, BK)) return rc;
   const int grid = p.n_kv_heads * n_splits;

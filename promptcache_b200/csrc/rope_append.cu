@@ -25,6 +25,7 @@ struct RopeParams {
   __half* k_cache;
   __half* v_cache;
   int max_ctx, dst_row0, n_heads, n_kv_heads, head_dim, q_len;
+  const int* dst_row0_dev;  // optional run-time destination row (graph-replayable decode)
 };
 
 __global__ void __launch_bounds__(128) rope_append_kernel(const RopeParams p) {
@@ -34,6 +35,8 @@ __global__ void __launch_bounds__(128) rope_append_kernel(const RopeParams p) {
   const int H = p.n_heads, Hkv = p.n_kv_heads, D = p.head_dim;
   if (vh >= H + 2 * Hkv) return;
   const int half_d = D >> 1;
+  int row0 = p.dst_row0;
+  if (p.dst_row0_dev != nullptr) row0 = max(0, min(__ldg(p.dst_row0_dev), p.max_ctx - p.q_len));
 
   const __half* src;
   __half* dst;
@@ -45,12 +48,12 @@ __global__ void __launch_bounds__(128) rope_append_kernel(const RopeParams p) {
   } else if (vh < H + Hkv) {
     const int h = vh - H;
     src = p.k_in + t * p.k_stride + static_cast<long long>(h) * D;
-    dst = p.k_cache + (static_cast<long long>(h) * p.max_ctx + p.dst_row0 + t) * D;
+    dst = p.k_cache + (static_cast<long long>(h) * p.max_ctx + row0 + t) * D;
     rotate = p.cos != nullptr;
   } else {
     const int h = vh - H - Hkv;
     src = p.v_in + t * p.v_stride + static_cast<long long>(h) * D;
-    dst = p.v_cache + (static_cast<long long>(h) * p.max_ctx + p.dst_row0 + t) * D;
+    dst = p.v_cache + (static_cast<long long>(h) * p.max_ctx + row0 + t) * D;
     rotate = false;
   }
 
@@ -82,11 +85,11 @@ __global__ void __launch_bounds__(128) rope_append_kernel(const RopeParams p) {
 
 }  // namespace
 
-PC_API int pc_rope_append(const void* q_in, const void* k_in, const void* v_in, int64_t q_stride,
-                              int64_t k_stride, int64_t v_stride, const int64_t* position_ids_dev,
-                              const void* cos_dev, const void* sin_dev, int table_rows, void* q_out,
-                              void* k_cache, void* v_cache, int max_ctx, int dst_row0, int n_heads,
-                              int n_kv_heads, int head_dim, int q_len, void* stream) {
+static int rope_append_impl(const void* q_in, const void* k_in, const void* v_in, int64_t q_stride,
+                            int64_t k_stride, int64_t v_stride, const int64_t* position_ids_dev,
+                            const void* cos_dev, const void* sin_dev, int table_rows, void* q_out,
+                            void* k_cache, void* v_cache, int max_ctx, int dst_row0, const int32_t* dst_row0_dev,
+                            int n_heads, int n_kv_heads, int head_dim, int q_len, void* stream) {
   PC_REQUIRE(q_len >= 0, "pc_rope_append: q_len < 0");
   if (q_len == 0) return PC_OK;
   PC_REQUIRE(q_in && k_in && v_in && q_out && k_cache && v_cache, "pc_rope_append: null tensor");
@@ -122,6 +125,7 @@ PC_API int pc_rope_append(const void* q_in, const void* k_in, const void* v_in, 
   p.v_cache = static_cast<__half*>(v_cache);
   p.max_ctx = max_ctx;
   p.dst_row0 = dst_row0;
+  p.dst_row0_dev = dst_row0_dev;
   p.n_heads = n_heads;
   p.n_kv_heads = n_kv_heads;
   p.head_dim = head_dim;
@@ -132,4 +136,22 @@ PC_API int pc_rope_append(const void* q_in, const void* k_in, const void* v_in, 
   PC_CHECK_CUDA(cudaGetLastError());
   pc::count_launch();
   return PC_OK;
+}
+
+PC_API int pc_rope_append(const void* q_in, const void* k_in, const void* v_in, int64_t q_stride, int64_t k_stride,
+                          int64_t v_stride, const int64_t* position_ids_dev, const void* cos_dev, const void* sin_dev,
+                          int table_rows, void* q_out, void* k_cache, void* v_cache, int max_ctx, int dst_row0,
+                          int n_heads, int n_kv_heads, int head_dim, int q_len, void* stream) {
+  return rope_append_impl(q_in, k_in, v_in, q_stride, k_stride, v_stride, position_ids_dev, cos_dev, sin_dev, table_rows,
+                          q_out, k_cache, v_cache, max_ctx, dst_row0, nullptr, n_heads, n_kv_heads, head_dim, q_len, stream);
+}
+
+PC_API int pc_rope_append_dyn(const void* q_in, const void* k_in, const void* v_in, int64_t q_stride, int64_t k_stride,
+                              int64_t v_stride, const int64_t* position_ids_dev, const void* cos_dev,
+                              const void* sin_dev, int table_rows, void* q_out, void* k_cache, void* v_cache, int max_ctx,
+                              const int32_t* dst_row0_dev, int n_heads, int n_kv_heads, int head_dim, int q_len,
+                              void* stream) {
+  if (dst_row0_dev == nullptr) return pc::set_error(PC_ERR_INVALID, "pc_rope_append_dyn: null dst_row0_dev");
+  return rope_append_impl(q_in, k_in, v_in, q_stride, k_stride, v_stride, position_ids_dev, cos_dev, sin_dev, table_rows,
+                          q_out, k_cache, v_cache, max_ctx, 0, dst_row0_dev, n_heads, n_kv_heads, head_dim, q_len, stream);
 }

@@ -75,10 +75,47 @@ class B200CausalLM(nn.Module):
         """Host scalars baked into kernel parameters besides (q_len, n_cached); part of the graph key."""
         return ()
 
+    supports_dynamic_n = False    # _layers(..., n_dev=) reads the cached length on the device (decode graph)
+
+    def _decode_replay(self, ids, pos, kv):
+        """One-token decode through ONE captured graph per KV buffer: the cached length is a device scalar the
+        kernels read at run time (pc_rope_append_dyn, pc_attn_params.n_cached_dev), so the same graph serves every
+        step of every request on that buffer (reference loop: generation_engine.py:123-147)."""
+        key = ("decode", kv.k[0].data_ptr(), kv.max_ctx)
+        entry = self._graphs.get(key)
+        if entry is None:
+            if self._graph_seen.get(key, 0) < 1:  # first decode step on this buffer runs eagerly
+                self._graph_seen[key] = 1
+                return None
+            if len(self._graphs) >= self.max_graphs:
+                self._graphs.pop(next(iter(self._graphs)))
+            s_ids, s_pos = ids.clone(), pos.clone()
+            s_n = torch.full((1,), kv.n_cached, dtype=torch.int32, device=self.device)
+            self._layers(s_ids, s_pos, kv, (), n_dev=s_n)  # warm-up; rewrites row n_cached with the same values
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            before = nat.launch_count()
+            with torch.cuda.graph(graph):
+                s_logits = self._layers(s_ids, s_pos, kv, (), n_dev=s_n)
+            entry = (graph, s_ids, s_pos, s_n, s_logits, nat.launch_count() - before)
+            self._graphs[key] = entry
+        graph, s_ids, s_pos, s_n, s_logits, n_native = entry
+        s_ids.copy_(ids, non_blocking=True)
+        s_pos.copy_(pos, non_blocking=True)
+        s_n.fill_(kv.n_cached)
+        graph.replay()
+        nat.note_replayed_launches(n_native)
+        return s_logits.clone()
+
     def _forward_one(self, ids: torch.Tensor, pos: torch.Tensor, past, use_cache: bool, max_position: int):
         q_len = ids.shape[0]
         kv = resolve_kv(past, q_len, self.n_layers, self.n_kv_heads, self.head_dim, self.device)
         N = kv.n_cached
+        if (q_len == 1 and N > 0 and self.use_cuda_graphs and self.supports_dynamic_n and not self.full_position_ids
+                and N + 1 < kv.max_ctx and not torch.cuda.is_current_stream_capturing()):
+            logits = self._decode_replay(ids, pos, kv)
+            if logits is not None:
+                return logits, (kv.views(N + 1) if use_cache else None)
         extra = self._graph_extra(max_position)
         key = (q_len, N, kv.k[0].data_ptr(), kv.max_ctx, pos.shape[0]) + tuple(extra)
         if self.use_cuda_graphs and N > 0 and q_len > 1 and not torch.cuda.is_current_stream_capturing():

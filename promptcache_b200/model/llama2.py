@@ -46,6 +46,10 @@ def rms_norm(x: torch.Tensor, weight: torch.Tensor, eps: float) -> torch.Tensor:
 class LlamaForCausalLM(B200CausalLM):
     """fp16 Llama with fused QKV / gate-up weights; attention runs in the sm_100a kernels."""
 
+    @property
+    def supports_dynamic_n(self) -> bool:  # the short-suffix kernel reads N on the device (D=128, G <= 32)
+        return self.head_dim == 128 and self.n_heads // self.n_kv_heads <= 32
+
     def __init__(self, config, device="cuda", dtype=torch.float16):
         super().__init__()
         self.config = config
@@ -109,7 +113,7 @@ class LlamaForCausalLM(B200CausalLM):
         return model
 
     # ---- forward (one sequence; batching, KV buffers and graph replay live in B200CausalLM) ---------------
-    def _layers(self, ids: torch.Tensor, pos: torch.Tensor, kv, extra=()) -> torch.Tensor:
+    def _layers(self, ids: torch.Tensor, pos: torch.Tensor, kv, extra=(), n_dev=None) -> torch.Tensor:
         q_len = ids.shape[0]
         H, Hkv, D = self.n_heads, self.n_kv_heads, self.head_dim
         N = kv.n_cached
@@ -124,10 +128,12 @@ class LlamaForCausalLM(B200CausalLM):
         for l in range(self.n_layers):
             nat.add_rmsnorm(x, delta, self.ln1[l], h, self.eps)          # x += mlp(l-1); h = norm(x)
             qkv = F.linear(h, self.wqkv[l])                              # [q, (H+2Hkv)*D]
+            # n_dev: run-time cached length (decode graph); N is then only the sizing upper bound
             nat.rope_append(qkv[:, :H * D], qkv[:, H * D:(H + Hkv) * D], qkv[:, (H + Hkv) * D:], pos, self._cos,
-                            self._sin, q_rot, kv.k[l], kv.v[l], N, H, Hkv, D)
-            nat.attention(q_rot, kv.k[l], kv.v[l], attn_out, N, q_len, H, Hkv, D, self.scale, self.rounding,
-                          workspace=ws, impl=self.attn_impl, decode=(q_len == 1))
+                            self._sin, q_rot, kv.k[l], kv.v[l], N if n_dev is None else n_dev, H, Hkv, D)
+            nat.attention(q_rot, kv.k[l], kv.v[l], attn_out, N if n_dev is None else kv.max_ctx - q_len, q_len, H, Hkv,
+                          D, self.scale, self.rounding, workspace=ws, decode=(q_len == 1), n_cached_dev=n_dev,
+                          impl=self.attn_impl if n_dev is None else nat.PC_ATTN_TCGEN05)
             delta = F.linear(attn_out, self.wo[l])
             nat.add_rmsnorm(x, delta, self.ln2[l], h, self.eps)          # x += attn; h = norm(x)
             gu = F.linear(h, self.w_gate_up[l])
