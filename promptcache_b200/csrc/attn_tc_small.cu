@@ -169,12 +169,16 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = p.n_heads / p.n_kv_heads;
   const int cols_valid = G * p.q_len;  // <= NPAD
-  const int split = blockIdx.x % p.n_splits;
-  const int hk = blockIdx.x / p.n_splits;
+  const int split = blockIdx.x % pin.n_splits;
+  const int hk = blockIdx.x / pin.n_splits;
   const int tiles_total = (p.n_cached + p.q_len + BK - 1) / BK;
+  // With a run-time N the grid was sized for an upper bound: only the first min(n_splits, tiles) splits work, the
+  // other CTAs leave before touching any barrier, TMEM or the arrival counter.
+  if (p.n_splits > tiles_total) p.n_splits = tiles_total;
+  if (split >= p.n_splits) return;
   const int tile0 = static_cast<int>(static_cast<long long>(split) * tiles_total / p.n_splits);
   const int tile1 = static_cast<int>(static_cast<long long>(split + 1) * tiles_total / p.n_splits);
-  const int T = tile1 - tile0;  // 0 only when N is read at run time and this split has no tile
+  const int T = tile1 - tile0;  // >= 1
   if (tid == 0) PC_TRACE(0);
 
   if (warp == kSoftmaxWarps && lane == 0) {
@@ -248,7 +252,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       };
       mbar_wait(q_full, 0);
       PC_TRACE(5);  // Q landed
-      if (T > 0) issue_st(0);
+      issue_st(0);
       PC_TRACE(6);  // first K landed and S^T_0 issued
       for (int j = 0; j < T; ++j) {
         if (j + 1 < T) issue_st(j + 1);
@@ -376,16 +380,11 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
     // ---- epilogue: O^T (TMEM lane = d, column = query row) ----
     float o[NH];
-    if (T > 0) {
-      mbar_wait(&o_full[(T - 1) & 1], static_cast<uint32_t>(((T - 1) >> 1) & 1));
-      tc_fence_after();
-      if (tid == 0) PC_TRACE(2);  // last PV landed
-      tmem_ld_n<NH>(tmem_o + lane_base + c0, o);
-      tmem_ld_wait();
-    } else {  // empty split: neutral partial (m = -inf, l = 0)
-#pragma unroll
-      for (int i = 0; i < NH; ++i) o[i] = 0.f;
-    }
+    mbar_wait(&o_full[(T - 1) & 1], static_cast<uint32_t>(((T - 1) >> 1) & 1));
+    tc_fence_after();
+    if (tid == 0) PC_TRACE(2);  // last PV landed
+    tmem_ld_n<NH>(tmem_o + lane_base + c0, o);
+    tmem_ld_wait();
     const int d = kl;
     const int HQ = p.n_heads * p.q_len;
     if (p.n_splits == 1) {
