@@ -9,7 +9,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import _native as nat
-from ._kv import CausalLMOutput, resolve_kv
+from ._kv import CausalLMOutput, PastKV, resolve_kv
 
 
 def build_rope_tables(head_dim: int, rows: int, theta: float, device, dtype=torch.float16):
@@ -158,7 +158,10 @@ class B200CausalLM(nn.Module):
             raise nat.NativeError("promptcache_b200 models run on CUDA only (no CPU fallback)")
         use_cache = True if use_cache is None else use_cache
         bsz, q_len = input_ids.shape
-        past_len = 0 if not past_key_values else int(past_key_values[0][0].shape[-2])
+        if isinstance(past_key_values, PastKV):
+            past_len = past_key_values.rows
+        else:
+            past_len = 0 if not past_key_values else int(past_key_values[0][0].shape[-2])
         if position_ids is None:
             first = 0 if self.full_position_ids else past_len
             position_ids = torch.arange(first, past_len + q_len, device=input_ids.device).unsqueeze(0).expand(bsz, -1)
@@ -188,5 +191,6 @@ class B200CausalLM(nn.Module):
             for l, (k, v) in enumerate(pkv):
                 pk[l][b] = F.pad(k[0], (0, 0, 0, q_len - n))
                 pv[l][b] = F.pad(v[0], (0, 0, 0, q_len - n))
+            del pkv
         pkv = tuple((torch.stack(pk[l]), torch.stack(pv[l])) for l in range(self.n_layers)) if use_cache else None
         return CausalLMOutput(logits, pkv)

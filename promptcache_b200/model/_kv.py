@@ -45,8 +45,34 @@ class LayerKV:
     def __init__(self, k: List[torch.Tensor], v: List[torch.Tensor], n_cached: int, max_ctx: int):
         self.k, self.v, self.n_cached, self.max_ctx = k, v, n_cached, max_ctx
 
-    def views(self, rows: int):
-        return tuple((k[:, :rows, :].unsqueeze(0), v[:, :rows, :].unsqueeze(0)) for k, v in zip(self.k, self.v))
+    def views(self, rows: int) -> "PastKV":
+        return PastKV(self, rows)
+
+
+class PastKV:
+    """`past_key_values` as the models hand it back: behaves like the reference's tuple of L (K, V) pairs, each
+    [1, Hkv, rows, D] (llama2.py:366), but the views are only materialised when somebody indexes them.  Passing it
+    back into the next forward is O(1): the buffers are recognised instead of re-validated tensor by tensor."""
+
+    def __init__(self, kv: LayerKV, rows: int):
+        self.kv, self.rows = kv, rows
+        self._views = {}
+
+    def __len__(self) -> int:
+        return len(self.kv.k)
+
+    def __getitem__(self, l):
+        if isinstance(l, slice):
+            return tuple(self[i] for i in range(*l.indices(len(self))))
+        if l < 0:
+            l += len(self)
+        if l not in self._views:
+            k, v = self.kv.k[l], self.kv.v[l]
+            self._views[l] = (k[:, :self.rows, :].unsqueeze(0), v[:, :self.rows, :].unsqueeze(0))
+        return self._views[l]
+
+    def __iter__(self):
+        return (self[l] for l in range(len(self)))
 
 
 def _as_strided_head_major(t: torch.Tensor, max_ctx: int) -> torch.Tensor:
@@ -58,6 +84,8 @@ def _as_strided_head_major(t: torch.Tensor, max_ctx: int) -> torch.Tensor:
 def resolve_kv(past: Optional[Sequence[Tuple[torch.Tensor, torch.Tensor]]], q_len: int, n_layers: int,
                n_kv_heads: int, head_dim: int, device, headroom: int = 256) -> LayerKV:
     """Find (or build) buffers that already hold the past rows and have room for q_len more."""
+    if isinstance(past, PastKV) and past.rows + q_len <= past.kv.max_ctx:
+        return LayerKV(past.kv.k, past.kv.v, past.rows, past.kv.max_ctx)  # our own buffers coming back: O(1)
     if past is None or len(past) == 0 or past[0] is None:
         n_cached = 0
     else:
