@@ -249,3 +249,41 @@ def test_decode_graph_with_runtime_length_matches_eager(native):
     ids, pos, _, cache = eng.process(Prompt(case.prompt_xml))
     list(GenerationEngine(lm).generate(ids, pos, params, cache, stream_interval=1))
     assert torch.equal(eng.prompt_cache.buffer[:, :, :, 677:677 + 9 + 11], k_graph)
+
+
+def test_pool_of_prompts_sharded_like_c5(native):
+    """C5 in miniature: a pool of 16 modules, 12 prompts each choosing 6 of them (seeded), served in the order a
+    2-rank batch partition would see them.  After every request the spliced cache must equal the oracle's splice of
+    the engine's own segments in usage order (bit-exact), and the suffix logits must match the oracle forward."""
+    import random
+    from promptcache_b200 import CacheEngine, Prompt, parallel
+    from promptcache_b200.model import Llama2, LlamaConfigLite, LlamaForCausalLM
+    from promptcache_b200.synthetic import IdTokenizer, pool_prompt, pool_schema
+    sd = O.random_llama_state_dict(512, 512, 1024, 2, 4, 4, seed=2, dtype=torch.float16, device=DEV)
+    cfg = LlamaConfigLite(vocab_size=512, hidden_size=512, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=4,
+                          max_position_embeddings=4096)
+    model = LlamaForCausalLM(cfg, device=DEV)
+    model.load_hf_state_dict(sd)
+    lm = Llama2("pool", model=model, tokenizer=IdTokenizer(512))
+    xml, names = pool_schema("pool", 16, 48, 512, seed=5)
+    eng = CacheEngine(1024, lm)
+    eng.add_schema(xml)
+    rng = random.Random(5)
+    prompts = [pool_prompt("pool", sorted(rng.sample(names, 6), key=names.index), 7, 512, seed=100 + b) for b in range(12)]
+    ocfg = dict(n_layers=2, n_heads=4, n_kv_heads=4, eps=1e-5, theta=10000.0, max_pos=4096)
+    for rank in range(2):
+        for b in parallel.shard_indices(len(prompts), rank, 2):
+            ids, pos, _, cache = eng.process(Prompt(prompts[b]))
+            staged = eng.prompt_cache.staged
+            counters = [m.usage_counter for m in staged]
+            assert counters == sorted(counters, reverse=True) and len(eng.prompt_cache) == 6 * 48
+            want, n = O.splice([m.cache for m in staged], [0] * len(staged), 1024)
+            for l in range(2):
+                assert torch.equal(cache[l][0], want[l][0]) and torch.equal(cache[l][1], want[l][1])
+            past = [(k.clone().unsqueeze(0), v.clone().unsqueeze(0)) for k, v in cache]
+            ref, _ = O.llama_forward(sd, ocfg, torch.tensor([ids], device=DEV), torch.tensor([pos], device=DEV), past,
+                                     cos=model._cos, sin=model._sin)
+            out = lm(input_ids=torch.tensor([ids], device=DEV), position_ids=torch.tensor([pos], device=DEV),
+                     past_key_values=[(k.unsqueeze(0), v.unsqueeze(0)) for k, v in cache], use_cache=True)
+            assert _rel(out.logits, ref) < 2e-3
+            assert pos == list(range(16 * 48, 16 * 48 + 7))  # trailing text sits after the whole schema
