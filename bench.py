@@ -235,7 +235,7 @@ def run_reference(args, case, dims, seg_lens):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    ref = CpuReference(dims, case.n_cached, case.q_len, seg_lens, 2, threads)
+    ref = CpuReference(dims, case.n_cached, case.q_len, seg_lens, int(os.environ.get("PC_BENCH_CPU_LAYERS", "2")), threads)
     recs = []
     for i in range(args.warmup + args.steps):
         r = ref.step()

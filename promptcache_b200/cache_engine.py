@@ -159,27 +159,56 @@ class SchemaCache:
                             paths.append(Path(here + [member.name]).next)
         return paths
 
+    reuse_prefix = True  # encode non-default union members over the default scaffold's KV prefix
+
+    def _forward(self, token_ids: List[int], position_ids: List[int], past=None):
+        device = self.lm.device
+        extra = {"max_position": max(position_ids)} if getattr(self.lm.hf_model, "accepts_max_position", False) else {}
+        return self.lm(input_ids=torch.tensor([token_ids], device=device, dtype=torch.long),
+                       position_ids=torch.tensor([position_ids], device=device, dtype=torch.long),
+                       attention_mask=torch.ones(1, len(token_ids), device=device, dtype=torch.float16),
+                       past_key_values=past, use_cache=True, **extra)
+
     @torch.inference_mode()
     def _process(self, batch_size: int = 1) -> None:
-        # One forward per scaffold path.  `batch_size` is accepted for API compatibility; right-padded batching
-        # gives the same per-path KV, so paths are encoded one at a time and sliced on the device.
-        device = self.lm.device
+        """One forward per scaffold path (reference :212-304).  `batch_size` is accepted for API compatibility;
+        right-padded batching gives the same per-path KV, so paths are encoded one at a time and sliced on the device.
+
+        The reference re-runs the WHOLE scaffold for every non-default union member.  Attention is causal, so the KV of
+        a member only depends on the tokens before it: with `reuse_prefix` the member's path is encoded as a cached
+        prefill over the longest token/position prefix it shares with the default scaffold, and stops at the last
+        token the path has to store -- prompt caching applied to its own encoder."""
+        full_ids = not getattr(self.lm, "use_full_position_ids", False)  # MPT wants cached + new ids: keep it simple
+        base_ids = base_pos = base_kv = None
         for path in self.scaffold_paths():
             scaffold = self.schema.get_scaffold(path)
             token_ids = scaffold.token_ids()
             position_ids = scaffold.position_ids()
             if len(token_ids) == 0:
                 continue
-            extra = {"max_position": max(position_ids)} if getattr(self.lm.hf_model, "accepts_max_position", False) else {}
-            out = self.lm(input_ids=torch.tensor([token_ids], device=device, dtype=torch.long),
-                          position_ids=torch.tensor([position_ids], device=device, dtype=torch.long),
-                          attention_mask=torch.ones(1, len(token_ids), device=device, dtype=torch.float16),
-                          use_cache=True, **extra)
-            kv = out.past_key_values
-            target = scaffold.select(path)
-            for seq in target.all_token_sequences():
-                if len(seq) == 0:
-                    continue
+            target = [seq for seq in scaffold.select(path).all_token_sequences() if len(seq) > 0]
+            first = 0
+            if self.reuse_prefix and full_ids and base_kv is not None and target:
+                common = 0
+                for a, b, c, d in zip(token_ids, base_ids, position_ids, base_pos):
+                    if a != b or c != d:
+                        break
+                    common += 1
+                starts = [position_ids.index(seq.offset) for seq in target]
+                lo, hi = min(starts), max(st + len(seq) for st, seq in zip(starts, target))
+                first = min(common, lo)
+                if first > 0 and hi > first:
+                    past = [(k[:, :, :first].contiguous(), v[:, :, :first].contiguous()) for k, v in base_kv]
+                    out = self._forward(token_ids[first:hi], position_ids[first:hi], past)
+                else:
+                    first = 0
+                    out = self._forward(token_ids, position_ids)
+            else:
+                out = self._forward(token_ids, position_ids)
+            kv = out.past_key_values  # rows [0, first) are the reused prefix, row i holds scaffold token i
+            if base_kv is None:
+                base_ids, base_pos, base_kv = token_ids, position_ids, kv
+            for seq in target:
                 st = position_ids.index(seq.offset)  # offsets and row order can differ (:275-279)
                 ed = st + len(seq)
                 ks = torch.stack([self.lm.store_k_hook(kv[l][0])[0, :, st:ed, :] for l in range(len(kv))])
@@ -187,6 +216,7 @@ class SchemaCache:
                 packed = torch.stack([ks, vs], dim=1).to(device=self.target_device, dtype=torch.half).contiguous()
                 self.cache_l1[id(seq)] = TokenSequenceCache(seq, packed)
             del out, kv
+        del base_kv
         gc.collect()
 
     def get_cache_l1(self, seq: TokenSequence) -> Optional[TokenSequenceCache]:

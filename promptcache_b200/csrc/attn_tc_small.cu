@@ -180,6 +180,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   const int tile1 = static_cast<int>(static_cast<long long>(split + 1) * tiles_total / p.n_splits);
   const int T = tile1 - tile0;  // >= 1
   if (tid == 0) PC_TRACE(0);
+  if (tid == 0 && p.trace != nullptr) p.trace[64 + 2 * blockIdx.x] = gtime();  // per-CTA start
 
   if (warp == kSoftmaxWarps && lane == 0) {
     tma_prefetch_desc(&map_q);
@@ -472,6 +473,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   }
 
   if (tid == 0) PC_TRACE(4);  // softmax group done (incl. merge if last)
+  if (tid == 0 && p.trace != nullptr) p.trace[64 + 2 * blockIdx.x + 1] = gtime();  // per-CTA end
   tc_fence_before();
   __syncthreads();
   if (warp == kSoftmaxWarps + 1) {

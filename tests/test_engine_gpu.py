@@ -287,3 +287,31 @@ def test_pool_of_prompts_sharded_like_c5(native):
                      past_key_values=[(k.unsqueeze(0), v.unsqueeze(0)) for k, v in cache], use_cache=True)
             assert _rel(out.logits, ref) < 2e-3
             assert pos == list(range(16 * 48, 16 * 48 + 7))  # trailing text sits after the whole schema
+
+
+def test_encode_with_prefix_reuse_matches_full_scaffold_encode(native, gold):
+    """Union members encoded over the default scaffold's KV prefix == the reference's whole-scaffold encode."""
+    from promptcache_b200 import CacheEngine
+    from promptcache_b200.cache_engine import SchemaCache
+    lm = _tiny_lm(gold, native)
+    xml = ('<schema name="n"><module name="o">x y z<union scaffold="i1"><module name="i1">p q r s</module><module name="i2">t u</module>'
+           '</union>tail one</module><union><module name="w1">a b c</module><module name="w2">d e f g h</module></union>'
+           '<module name="end">fin ish</module></schema>')
+    stores = {}
+    for reuse in (True, False):
+        SchemaCache.reuse_prefix = reuse
+        eng = CacheEngine(64, lm)
+        eng.add_schema(xml)
+        stores[reuse] = {(e.token_sequence.offset, len(e)): e.packed.clone() for e in eng.schemas["n"].cache_l1.values()}
+    SchemaCache.reuse_prefix = True
+    assert stores[True].keys() == stores[False].keys() and len(stores[True]) == 8
+    for key in stores[True]:
+        assert _rel(stores[True][key], stores[False][key]) < 2e-3, key
+    # and against the reference's own encode of the golden demo schema (fp32 CPU model)
+    eng = CacheEngine(64, lm)
+    eng.add_schema(gold["schema"])
+    by_key = {(s["offset"], len(s["token_ids"])): s["kv"] for s in gold["segments"]}
+    for e in eng.schemas["demo"].cache_l1.values():
+        ref = by_key[(e.token_sequence.offset, len(e))]
+        for l in range(2):
+            assert _rel(e.packed[l, 0].cpu(), ref[l][0]) < 5e-3 and _rel(e.packed[l, 1].cpu(), ref[l][1]) < 5e-3
