@@ -251,3 +251,66 @@ def test_attention_workspace_is_left_clean_and_reusable(native):
                              decode=(q == 1))
             assert _rel(out, _oracle_llama(Q, K, V, N, q)) <= 1e-3
         assert int(ws[:4096].view(torch.int32).abs().max()) == 0
+
+
+def test_splice_many_segments_chunked_launches(native):
+    """More segments than one launch's inline table holds (48): the API chunks the launches; ragged lengths 1..9."""
+    L, Hkv, D = 2, 2, 64
+    g = torch.Generator(device="cpu").manual_seed(3)
+    lens = [1 + (i * 7) % 9 for i in range(131)]
+    segs = [torch.randn(L, 2, Hkv, n, D, generator=g).half().to(DEV) for n in lens]
+    max_ctx = sum(lens) + 5
+    cache = torch.zeros(L, 2, Hkv, max_ctx, D, dtype=torch.half, device=DEV)
+    plan, row = [], 0
+    for s in segs:
+        plan.append((s, row))
+        row += s.shape[3]
+    native.splice_kv(plan, cache)
+    ref, n = O.splice([[(s[l, 0], s[l, 1]) for l in range(L)] for s in segs], [0] * len(segs), max_ctx)
+    for l in range(L):
+        assert torch.equal(cache[l, 0, :, :n], ref[l][0]) and torch.equal(cache[l, 1, :, :n], ref[l][1])
+    assert int(cache[:, :, :, n:].abs().max()) == 0
+
+
+def test_rope_append_runtime_row(native):
+    """pc_rope_append_dyn: destination row read from the device equals the host-row variant."""
+    H = Hkv = 4
+    D, q, N, max_ctx = 128, 3, 41, 64
+    g = torch.Generator(device="cpu").manual_seed(8)
+    qkv = torch.randn(q, 3 * H * D, generator=g).half().to(DEV)
+    pos = torch.tensor([5, 900, 17], device=DEV)
+    cos, sin = O.rope_tables(D, 1024, 10000.0, DEV, torch.float16)
+    cos, sin = cos.contiguous(), sin.contiguous()
+    outs = []
+    for row in (N, torch.tensor([N], dtype=torch.int32, device=DEV)):
+        kc = torch.zeros(Hkv, max_ctx, D, dtype=torch.half, device=DEV)
+        vc = torch.zeros_like(kc)
+        qo = torch.empty(H, q, D, dtype=torch.half, device=DEV)
+        native.rope_append(qkv[:, :H * D], qkv[:, H * D:2 * H * D], qkv[:, 2 * H * D:], pos, cos, sin, qo, kc, vc, row, H, Hkv, D)
+        outs.append((qo, kc, vc))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+
+
+def test_attention_runtime_length_equals_host_length(native):
+    """n_cached_dev (graph-replayable decode): same bits as the host-length launch, including surplus splits."""
+    H = Hkv = 8
+    D, max_ctx = 128, 2048
+    ws = torch.zeros(native.attn_workspace_bytes(H, 16, D), dtype=torch.uint8, device=DEV)
+    for q, N in [(1, 1900), (1, 130), (1, 5), (16, 700), (9, 1)]:
+        Q, K, V = _attn_case(H, Hkv, D, q, N, seed=N)
+        K2 = torch.zeros(Hkv, max_ctx, D, dtype=torch.half, device=DEV)
+        V2 = torch.zeros_like(K2)
+        K2[:, :N + q], V2[:, :N + q] = K[:, :N + q], V[:, :N + q]
+        a = torch.empty(q, H * D, dtype=torch.half, device=DEV)
+        b = torch.empty_like(a)
+        native.attention(Q, K2, V2, a, N, q, H, Hkv, D, native.softmax_scale(D), native.PC_ROUND_LLAMA, workspace=ws)
+        n_dev = torch.tensor([N], dtype=torch.int32, device=DEV)
+        native.attention(Q, K2, V2, b, max_ctx - q, q, H, Hkv, D, native.softmax_scale(D), native.PC_ROUND_LLAMA, workspace=ws,
+                         n_cached_dev=n_dev, impl=native.PC_ATTN_TCGEN05)
+        assert _rel(b, _oracle_llama(Q, K, V, N, q)) <= 1e-3
+        assert float((a.float() - b.float()).abs().max()) <= 2e-3  # split partition may differ (sized for the upper bound)
+    with pytest.raises(native.NativeError):  # long suffixes have no run-time-length path
+        Q, K, V = _attn_case(H, Hkv, D, 200, 100, seed=1)
+        native.attention(Q, K, V, torch.empty(200, H * D, dtype=torch.half, device=DEV), 100, 200, H, Hkv, D, 0.1, 3, workspace=ws,
+                         n_cached_dev=torch.tensor([100], dtype=torch.int32, device=DEV))
