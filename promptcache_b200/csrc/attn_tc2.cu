@@ -239,14 +239,13 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       }
       for (int j = 0; j < Tx; ++j) {
         const int s = j % C::kStages;
-        mbar_wait(&p_full[x * 2 + (j & 1)], static_cast<uint32_t>((j >> 1) & 1));
+        // operands first (they landed long ago), so that nothing but the MMA issue follows the arrival of P_x(j)
         mbar_wait(&v_full[s], static_cast<uint32_t>((j / C::kStages) & 1));
+        if (j + 2 < Tx) mbar_wait(&k_full[(j + 2) % C::kStages], static_cast<uint32_t>(((j + 2) / C::kStages) & 1));
+        mbar_wait(&p_full[x * 2 + (j & 1)], static_cast<uint32_t>((j >> 1) & 1));
         tc_fence_after();
         issue_pv(j);
-        if (j + 2 < Tx) {  // S buffer (x, j&1) is free again once PV_x(j) has been issued (in-order execution)
-          wait_k(j + 2);
-          issue_s(j + 2);
-        }
+        if (j + 2 < Tx) issue_s(j + 2);  // S buffer (x, j&1) is free once PV_x(j) has been issued (in-order execution)
         tc_commit(&kv_empty[x * C::kStages + s]);  // this tile's MMAs on stage s have all been issued
       }
     }
