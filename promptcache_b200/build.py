@@ -37,7 +37,8 @@ def _digest() -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    digest = _digest()
+    extra = os.environ.get("PC_NVCC_EXTRA", "").split()  # experiments only (e.g. -DPC_EXP_...); empty in normal builds
+    digest = _digest() + "|" + " ".join(extra)
     if not force and os.path.exists(LIB) and os.path.exists(STAMP):
         with open(STAMP) as fh:
             if fh.read().strip() == digest:
@@ -49,7 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for s in SOURCES:
         obj = os.path.join(HERE, "build", s.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, s), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)

@@ -282,6 +282,19 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const int key0 = (t0 + j) * BN;
         const bool need_mask = key0 + BN > vis_end;
 
+#if defined(PC_EXP_NO_SOFTMAX)  // experiment: MMA / barrier chain alone (P = garbage, no math)
+        {
+          uint32_t z[BN / 2];
+#pragma unroll
+          for (int c = 0; c < BN / 2; ++c) z[c] = 0x3c003c00u;
+          tmem_st32(tmem_s, z);
+          l_run += 1.f;
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&p_full[x * 2 + b]);
+          continue;
+        }
+#endif
         // ---- the whole 64-key row of S lives in registers: one TMEM read per tile ----
         float sv[BN];
         tmem_ld32(tmem_s, reinterpret_cast<uint32_t(&)[32]>(sv[0]));
@@ -387,7 +400,11 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
               if (key0 + c >= vis_end) ya = -INFINITY;
               if (key0 + c + 1 >= vis_end) yb = -INFINITY;
             }
+#if defined(PC_EXP_NO_MUFU)  // experiment: how much of the time is the exponential?
+            const float p0 = ya * 1e-3f, p1 = yb * 1e-3f;
+#else
             const float p0 = ex2(ya), p1 = ex2(yb);
+#endif
             lt += p0 + p1;
             pk[c >> 1] = pack_h2(p0, p1);
           }
