@@ -3,7 +3,7 @@
 // tensor-bound regime (G*q FLOP per KV byte above the ~254 FLOP/B ridge).
 //
 // One CTA = (kv head, PAIR of 128-row query tiles A and B, KV split).  Both tiles share every K/V tile; each tile
-// has its own two softmax warpgroups (one per 32-key half of a row) and its own MMA-issuing thread (a single thread could not issue the 24 MMAs per
+// has its own softmax warpgroup and its own MMA-issuing thread (a single thread could not issue the 24 MMAs per
 // 64 keys fast enough), so the tensor core always has the other tile's work queued while one softmax runs:
 //
 //   MMA thread :  S_A(0) S_B(0) S_A(1) S_B(1) | PV_A(0) S_A(2) | PV_B(0) S_B(2) | PV_A(1) S_A(3) | ...
@@ -39,9 +39,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BN = 64;
-constexpr int kSoftmaxWarps = 16;  // per query tile: 2 warpgroups, each owning one 32-key half of every 64-key S tile
-constexpr int kWarpTma = kSoftmaxWarps, kWarpMma0 = kSoftmaxWarps + 1;
-constexpr int kThreads = (kSoftmaxWarps + 3) * 32;  // + TMA warp + one MMA warp per query tile
+constexpr int kThreads = 352;  // WG0 (warps 0-3), WG1 (warps 4-7), TMA warp 8, MMA warps 9 (tile A) and 10 (tile B)
 constexpr int kMaxSplits = 32;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;
@@ -53,8 +51,7 @@ struct Cfg2 {
   static constexpr int kHalfStride = BN * 128;   // bytes between the two 64-column halves of a K/V tile (D=128)
   static constexpr int kStages = 4;
   static constexpr int kOffKV = 2 * kQBytes;     // Q_A, Q_B first
-  static constexpr int kOffXch = kOffKV + kStages * 2 * kTileBytes;  // float xch[2 parities][2 tiles][2 halves][128 rows]
-  static constexpr int kOffBars = kOffXch + 2 * 2 * 2 * BM * 4;
+  static constexpr int kOffBars = kOffKV + kStages * 2 * kTileBytes;
   static constexpr int kSmem = 1024 + kOffBars + 256;
   static constexpr int kTmemCols = 512;
   static constexpr int kColO = 256;
@@ -87,9 +84,6 @@ __device__ __forceinline__ void round_h2(float& a, float& b) {
   b = f.y;
 }
 __device__ __forceinline__ float round_h(float x) { return __half2float(__float2half_rn(x)); }
-__device__ __forceinline__ void named_bar_sync(int id, int n) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
-}
 
 // Causal extent (exclusive key bound) of the 128-row tile starting at folded row `row_lo`.
 __device__ __forceinline__ int tile_kv_end(int row_lo, int rows_total, int q_len, int n_cached) {
@@ -109,7 +103,6 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   unsigned char* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   unsigned char* sQ = smem;  // [2][kTileBytes]
   unsigned char* sKV = smem + C::kOffKV;
-  float* xch = reinterpret_cast<float*>(smem + C::kOffXch);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBars);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;
@@ -150,7 +143,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 #pragma unroll
   for (int x = 0; x < 2; ++x) valid_warps[x] = row_lo[x] < rows_total ? (min(BM, rows_total - row_lo[x]) + 31) / 32 : 0;
 
-  if (warp == kWarpTma && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&map_q);
     tma_prefetch_desc(&map_k);
     tma_prefetch_desc(&map_v);
@@ -164,19 +157,19 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     for (int x = 0; x < 2; ++x) {
       for (int b = 0; b < 2; ++b) {
         mbar_init(&s_full[x * 2 + b], 1);
-        mbar_init(&p_full[x * 2 + b], max(64 * valid_warps[x], 1));  // both key halves of every valid row quarter
+        mbar_init(&p_full[x * 2 + b], max(32 * valid_warps[x], 1));
         mbar_init(&o_full[x * 2 + b], 1);
       }
     }
     mbar_fence_init();
   }
-  if (warp == kWarpMma0) tmem_alloc<C::kTmemCols>(tmem_slot);
+  if (warp == 9) tmem_alloc<C::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == kWarpTma) {
+  if (warp == 8) {
     // ===================== TMA producer =====================
     if (lane == 0 && Tmax > 0) {
       const int nq = (T[0] > 0 ? 1 : 0) + (T[1] > 0 ? 1 : 0);
@@ -203,9 +196,9 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           tma_load_3d(dv + hf * C::kHalfStride, &map_v, &v_full[s], hf * 64, key0, hk);
       }
     }
-  } else if (warp == kWarpMma0 || warp == kWarpMma0 + 1) {
-    // ===================== MMA issuers: one warp (one elected thread) per query tile =====================
-    const int x = warp - kWarpMma0;
+  } else if (warp == 9 || warp == 10) {
+    // ===================== MMA issuers: warp 9 drives query tile A, warp 10 tile B =====================
+    const int x = warp - 9;
     const int Tx = T[x];
     if (lane == 0 && Tx > 0) {
       constexpr uint32_t idesc_qk = make_idesc_f16(BM, BN, 0, 0);
@@ -257,25 +250,19 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       }
     }
   } else {
-    // ===================== softmax: 2 warpgroups per query tile, each owns one 32-key half of a row =====================
-    // Four softmax warps per scheduler (instead of two) hide the dependent cvt/ffma/ex2 chains; the two threads of a
-    // row exchange their half-row maximum (and, at the end, their half-row sums) through shared memory.
-    const int x = warp >> 3;          // query tile
-    const int hf = (warp >> 2) & 1;   // key half of the 64-key tile
-    const int quad = warp & 3;        // TMEM lane quarter = 32 rows
-    constexpr int HK = BN / 2;        // 32 keys per thread per tile
-    const int row = quad * 32 + lane;
+    // ===================== softmax warpgroups (WG x owns query tile x) =====================
+    const int x = warp >> 2;
+    const int quad = warp & 3;
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t tmem_sx = tmem_base + lane_base + x * 128;
-    const uint32_t tmem_o = tmem_base + lane_base + C::kColO + x * D + hf * (D / 2);  // this thread's half of the O row
-    const int R = row_lo[x] + row;
+    const uint32_t tmem_o = tmem_base + lane_base + C::kColO + x * D;
+    const int R = row_lo[x] + quad * 32 + lane;
     const bool warp_valid = quad < valid_warps[x];
     const bool row_valid = R < rows_total;
     const int g = row_valid ? R / p.q_len : 0;
     const int r = row_valid ? R % p.q_len : 0;
     const int h = hk * G + g;
     const int Tx = T[x];
-    const int bar_id = 1 + x, bar_n = 64 * valid_warps[x];
     const float slope = (ALIBI && row_valid) ? p.alibi_slopes[h] : 0.f;
     const int vis_end = row_valid ? p.n_cached + r + 1 : 0;  // keys [0, vis_end) are visible to this row
     const float scale_l2 = p.scale * kLog2e;
@@ -284,7 +271,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const __half s_hi = __float2half_rn(p.scale);
     const __half2 scale_hi = __half2half2(s_hi);
     const __half2 scale_lo = __half2half2(__float2half_rn(p.scale - __half2float(s_hi)));
-    float m_run = -INFINITY, l_run = 0.f;  // m (log2 domain) is identical in both threads of a row; l is per half
+    float m_run = -INFINITY, l_run = 0.f;  // m in the log2 domain
 
     if (warp_valid) {
       for (int j = 0; j < Tx; ++j) {
@@ -292,58 +279,70 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const uint32_t tmem_s = tmem_sx + b * BN;
         mbar_wait(&s_full[x * 2 + b], static_cast<uint32_t>((j >> 1) & 1));
         tc_fence_after();
-        const int key0 = (t0 + j) * BN + hf * HK;  // first key of this thread's half
-        const bool need_mask = key0 + HK > vis_end;
+        const int key0 = (t0 + j) * BN;
+        const bool need_mask = key0 + BN > vis_end;
 
-        float sv[HK];
-        tmem_ld32(tmem_s + hf * HK, reinterpret_cast<uint32_t(&)[32]>(sv[0]));
+#if defined(PC_EXP_NO_SOFTMAX)  // experiment: MMA / barrier chain alone (P = garbage, no math)
+        {
+          uint32_t z[BN / 2];
+#pragma unroll
+          for (int c = 0; c < BN / 2; ++c) z[c] = 0x3c003c00u;
+          tmem_st32(tmem_s, z);
+          l_run += 1.f;
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&p_full[x * 2 + b]);
+          continue;
+        }
+#endif
+        // ---- the whole 64-key row of S lives in registers: one TMEM read per tile ----
+        float sv[BN];
+        tmem_ld32(tmem_s, reinterpret_cast<uint32_t(&)[32]>(sv[0]));
+        tmem_ld32(tmem_s + 32, reinterpret_cast<uint32_t(&)[32]>(sv[32]));
         tmem_ld_wait();
         const bool warp_mask = __any_sync(0xffffffffu, need_mask);  // warp-uniform: mask code only near the diagonal
 
-        // ---- pass 1: half-row maximum, exchanged with the other half ----
-        float hmax = -INFINITY;  // RAW accumulator max (monotone transform commutes with max); ALiBi: transformed
+        // ---- pass 1: row maximum (log2 domain) ----
+        float mt;
         if (!ALIBI) {
+          // max over the RAW accumulators; the fp16-rounding + scale transform is monotone, so it commutes with max
+          float raw_max = -INFINITY;
           if (warp_mask) {
 #pragma unroll
-            for (int c = 0; c < HK; ++c)
-              if (key0 + c < vis_end) hmax = fmaxf(hmax, sv[c]);
+            for (int c = 0; c < BN; ++c)
+              if (key0 + c < vis_end) raw_max = fmaxf(raw_max, sv[c]);
           } else {
 #pragma unroll
-            for (int c = 0; c < HK; c += 2) hmax = fmaxf(hmax, fmaxf(sv[c], sv[c + 1]));
+            for (int c = 0; c < BN; c += 2) raw_max = fmaxf(raw_max, fmaxf(sv[c], sv[c + 1]));
           }
+          float t = raw_max;
+          if (ROUND == PC_ROUND_LLAMA) {
+            const __half2 a16 = __floats2half2_rn(t, t);
+            t = __low2float(__hfma2(a16, scale_hi, __hmul2(a16, scale_lo)));
+            if (raw_max == -INFINITY) t = -INFINITY;  // (-inf)*s_lo may be +inf -> NaN in the fused form
+          } else {
+            if (ROUND & PC_ROUND_QK) t = round_h(t);
+            t *= p.scale;
+            if (ROUND & PC_ROUND_SCALED) t = round_h(t);
+          }
+          mt = t * kLog2e;
         } else {
+          // ALiBi adds a per-key bias: transform every score once (kept in sv, natural-log domain), then take the max
+          mt = -INFINITY;
           const int kmax = p.n_cached + p.q_len - 1;
 #pragma unroll
-          for (int c = 0; c < HK; ++c) {
+          for (int c = 0; c < BN; ++c) {
             float t = sv[c];
             if (ROUND & PC_ROUND_QK) t = round_h(t);
             t *= p.scale;
             if (ROUND & PC_ROUND_SCALED) t = round_h(t);
             t += slope * static_cast<float>(__ldg(p.key_pos + min(key0 + c, kmax)) - p.alibi_max_pos);
-            sv[c] = t;  // natural-log domain, reused by pass 2
-            if (key0 + c < vis_end) hmax = fmaxf(hmax, t * kLog2e);
+            sv[c] = t;
+            if (key0 + c < vis_end) mt = fmaxf(mt, t * kLog2e);
           }
-        }
-        float* xb = xch + ((b * 2 + x) * 2) * BM;  // [half][row] for this (parity, tile)
-        xb[hf * BM + row] = hmax;
-        // also orders the S loads of both halves before either half overwrites S columns with P
-        named_bar_sync(bar_id, bar_n);
-        float mt = fmaxf(hmax, xb[(1 - hf) * BM + row]);
-        if (!ALIBI) {
-          const float raw_max = mt;
-          if (ROUND == PC_ROUND_LLAMA) {
-            const __half2 a16 = __floats2half2_rn(mt, mt);
-            mt = __low2float(__hfma2(a16, scale_hi, __hmul2(a16, scale_lo)));
-            if (raw_max == -INFINITY) mt = -INFINITY;  // (-inf)*s_lo may be +inf -> NaN in the fused form
-          } else {
-            if (ROUND & PC_ROUND_QK) mt = round_h(mt);
-            mt *= p.scale;
-            if (ROUND & PC_ROUND_SCALED) mt = round_h(mt);
-          }
-          mt *= kLog2e;
         }
 
-        // ---- running maximum, lazy rescale of O (each thread rescales its half of the O row) ----
+        // ---- running maximum, lazy rescale of O ----
         const float m_new = fmaxf(m_run, mt);
         const bool grow = (m_new - m_run) > kRescaleThreshold;  // first finite max: +inf; both -inf: NaN -> false
         const float alpha = grow ? ex2(m_run - m_new) : 1.f;
@@ -356,7 +355,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           mbar_wait(&o_full[x * 2 + ((j - 1) & 1)], static_cast<uint32_t>(((j - 1) >> 1) & 1));
           tc_fence_after();
 #pragma unroll
-          for (int ch = 0; ch < D / 64; ++ch) {
+          for (int ch = 0; ch < D / 32; ++ch) {
             uint32_t o[32];
             tmem_ld32(tmem_o + ch * 32, o);
             tmem_ld_wait();
@@ -367,13 +366,13 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
         const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
 
-        // ---- pass 2: P = 2^(score - m) for this half, written over S as packed fp16 (16 columns) ----
+        // ---- pass 2: P = 2^(score - m), written over S as packed fp16 (32 columns) ----
         float lt = 0.f;
-        uint32_t pk[HK / 2];
+        uint32_t pk[BN / 2];
         auto pass2 = [&](auto masked_tag) {
           constexpr bool kMasked = decltype(masked_tag)::value;
 #pragma unroll
-          for (int c = 0; c < HK; c += 2) {
+          for (int c = 0; c < BN; c += 2) {
             const float a = sv[c], b2 = sv[c + 1];
             float ya, yb;
             if (ALIBI) {
@@ -412,27 +411,22 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         };
         if (warp_mask) pass2(std::true_type{});
         else pass2(std::false_type{});
-        tmem_st16(tmem_s + hf * (HK / 2), pk);  // P of keys [32hf, 32hf+32) = columns [16hf, 16hf+16)
+        tmem_st32(tmem_s, pk);
         l_run += lt;
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_full[x * 2 + b]);
       }
 
-      // ---- epilogue: total row sum = own half + the other half's ----
+      // ---- epilogue ----
       const int n_heads = p.n_heads;
-      float* xl = xch + (x * 2) * BM;  // parity-0 slot of this tile (all tile maxima have been consumed)
-      named_bar_sync(bar_id, bar_n);
-      xl[hf * BM + row] = l_run;
-      named_bar_sync(bar_id, bar_n);
-      const float l_tot = l_run + xl[(1 - hf) * BM + row];
       if (Tx > 0) {
         mbar_wait(&o_full[x * 2 + ((Tx - 1) & 1)], static_cast<uint32_t>(((Tx - 1) >> 1) & 1));
         tc_fence_after();
       }
-      const float inv_l = l_tot > 0.f ? 1.f / l_tot : 0.f;
+      const float inv_l = l_run > 0.f ? 1.f / l_run : 0.f;
 #pragma unroll
-      for (int ch = 0; ch < D / 64; ++ch) {  // this thread's half of the O row: D/2 columns
+      for (int ch = 0; ch < D / 32; ++ch) {
         uint32_t o[32];
         if (Tx > 0) {
           tmem_ld32(tmem_o + ch * 32, o);
@@ -442,9 +436,8 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           for (int c = 0; c < 32; ++c) o[c] = 0u;
         }
         if (row_valid) {
-          const int col0 = hf * (D / 2) + ch * 32;
           if (p.n_splits == 1) {
-            __half* dst = p.out + (static_cast<long long>(r) * n_heads + h) * D + col0;
+            __half* dst = p.out + (static_cast<long long>(r) * n_heads + h) * D + ch * 32;
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
               uint4 w;
@@ -455,24 +448,24 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
               *reinterpret_cast<uint4*>(dst + v * 8) = w;
             }
           } else {
-            float* dst = p.part_o + ((static_cast<long long>(split) * n_heads + h) * p.q_len + r) * D + col0;
+            float* dst = p.part_o + ((static_cast<long long>(split) * n_heads + h) * p.q_len + r) * D + ch * 32;
 #pragma unroll
             for (int v = 0; v < 8; ++v)
               *reinterpret_cast<uint4*>(dst + v * 4) = make_uint4(o[v * 4], o[v * 4 + 1], o[v * 4 + 2], o[v * 4 + 3]);
           }
         }
       }
-      if (row_valid && hf == 0 && p.n_splits > 1) {
+      if (row_valid && p.n_splits > 1) {
         float* ml = p.part_ml + ((static_cast<long long>(split) * n_heads + h) * p.q_len + r) * 2;
         ml[0] = m_run;  // log2 domain; -inf with l = 0 when this split saw no visible key
-        ml[1] = l_tot;
+        ml[1] = l_run;
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kWarpMma0) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_free<C::kTmemCols>(tmem_base);
   }
