@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PC_ABI_VERSION 2
+#define PC_ABI_VERSION 3
 
 enum {
   PC_OK = 0,
@@ -169,6 +169,53 @@ int pc_decode_attn(const pc_attn_params* p, void* stream);
 int pc_add_rmsnorm(void* x, const void* delta, const void* weight, void* h_out, int rows, int hidden,
                    float eps, void* stream);
 int pc_silu_mul(const void* gate_up, void* out, int rows, int inter, int64_t row_stride, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Skinny linear layers of the step: y = x . W^T for q_len <= 32 tokens,
+ * one weight-streaming stream-K tcgen05 kernel per layer with the following op fused into its epilogue.
+ *   q/k/v projections + RoPE + KV append   llama2.py:345-351,357-364   (PC_LIN_ROPE_APPEND)
+ *   o_proj, down_proj, lm_head             llama2.py:405,241,1050      (PC_LIN_PLAIN)
+ *   gate_proj/up_proj + SiLU * up          llama2.py:241               (PC_LIN_SILU_MUL)
+ * x is [q_len][k] fp16 contiguous; w is an nn.Linear weight [n_rows][k] fp16 row-major; accumulation is fp32
+ * (split-K partials included, added in a fixed order: results are deterministic), one rounding to fp16.
+ *   PLAIN        out[t][r] = half(sum)                                        out: [q_len][out_stride]
+ *   SILU_MUL     w = [gate rows (n_rows/2); up rows (n_rows/2)];  out[t][i] = half(silu_f32(half(gate_i))) * half(up_i)
+ *   ROPE_APPEND  w = [q heads; k heads; v heads] of head_dim 128; the fp16 projections get the same treatment as
+ *                pc_rope_append (bit-identical to it on the same fp16 inputs): rotated Q -> q_out[H][q_len][128],
+ *                rotated K and V -> rows [dst_row0, dst_row0+q_len) of k_cache/v_cache[Hkv][max_ctx][128];
+ *                cos == NULL skips the rotation; dst_row0_dev != NULL reads the row on the device.
+ * workspace: >= pc_linear_workspace_bytes() bytes, ZEROED once before first use (tile arrival counters; the
+ * kernel leaves them zeroed); one workspace per concurrent stream. */
+#define PC_LIN_PLAIN 0
+#define PC_LIN_SILU_MUL 1
+#define PC_LIN_ROPE_APPEND 2
+
+typedef struct pc_linear_params {
+  const void* x;
+  const void* w;
+  int64_t x_stride;  /* elements between rows of x; must equal k */
+  int32_t q_len, k, n_rows, epilogue;
+  void* out;         /* PLAIN / SILU_MUL */
+  int64_t out_stride;
+  const int64_t* position_ids; /* ROPE_APPEND: [q_len] int64 (device) */
+  const void* cos;             /* [table_rows][128] fp16 or NULL */
+  const void* sin;
+  int32_t table_rows;
+  int32_t max_ctx;
+  void* q_out;
+  void* k_cache;
+  void* v_cache;
+  int32_t dst_row0;
+  int32_t n_heads;
+  int32_t n_kv_heads;
+  int32_t reserved;
+  const int32_t* dst_row0_dev;
+  void* workspace;
+  size_t workspace_bytes;
+} pc_linear_params;
+
+size_t pc_linear_workspace_bytes(void);
+int pc_linear_small(const pc_linear_params* p, void* stream);
 
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 int64_t pc_launch_count(void);

@@ -27,7 +27,10 @@ PC_ATTN_TCGEN05 = 2
 
 EXPORTS = ("pc_version", "pc_last_error", "pc_device_info", "pc_splice_kv", "pc_splice_kv_tensors",
            "pc_rope_append", "pc_rope_append_dyn", "pc_attn_workspace_bytes", "pc_prefill_attn", "pc_decode_attn", "pc_launch_count",
-           "pc_add_rmsnorm", "pc_silu_mul")
+           "pc_add_rmsnorm", "pc_silu_mul", "pc_linear_workspace_bytes", "pc_linear_small")
+PC_LIN_PLAIN = 0
+PC_LIN_SILU_MUL = 1
+PC_LIN_ROPE_APPEND = 2
 
 
 class NativeError(RuntimeError):
@@ -52,6 +55,17 @@ class pc_attn_params(C.Structure):
                 ("alibi_slopes", C.c_void_p), ("key_pos", C.c_void_p),
                 ("alibi_max_pos", C.c_int32), ("impl", C.c_int32), ("n_cached_dev", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+class pc_linear_params(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("w", C.c_void_p), ("x_stride", C.c_int64),
+                ("q_len", C.c_int32), ("k", C.c_int32), ("n_rows", C.c_int32), ("epilogue", C.c_int32),
+                ("out", C.c_void_p), ("out_stride", C.c_int64),
+                ("position_ids", C.c_void_p), ("cos", C.c_void_p), ("sin", C.c_void_p),
+                ("table_rows", C.c_int32), ("max_ctx", C.c_int32),
+                ("q_out", C.c_void_p), ("k_cache", C.c_void_p), ("v_cache", C.c_void_p),
+                ("dst_row0", C.c_int32), ("n_heads", C.c_int32), ("n_kv_heads", C.c_int32), ("reserved", C.c_int32),
+                ("dst_row0_dev", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -96,6 +110,10 @@ def load() -> C.CDLL:
     lib.pc_add_rmsnorm.restype = C.c_int
     lib.pc_silu_mul.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]
     lib.pc_silu_mul.restype = C.c_int
+    lib.pc_linear_workspace_bytes.argtypes = []
+    lib.pc_linear_workspace_bytes.restype = C.c_size_t
+    lib.pc_linear_small.argtypes = [C.POINTER(pc_linear_params), C.c_void_p]
+    lib.pc_linear_small.restype = C.c_int
     _lib = lib
     return lib
 
@@ -278,3 +296,59 @@ def silu_mul(gate_up: torch.Tensor, out: torch.Tensor, inter: int) -> None:
         raise NativeError("silu_mul: tensors must be fp16 with contiguous rows")
     _check(load().pc_silu_mul(gate_up.data_ptr(), out.data_ptr(), gate_up.shape[0], inter, gate_up.stride(0), _stream()),
            "pc_silu_mul")
+
+
+def linear_workspace(device) -> torch.Tensor:
+    """Zero-initialised scratch of pc_linear_small (tile arrival counters + split-K partial slots)."""
+    return torch.zeros(int(load().pc_linear_workspace_bytes()), dtype=torch.uint8, device=device)
+
+
+def _linear_params(x: torch.Tensor, w: torch.Tensor, workspace: torch.Tensor, epilogue: int) -> pc_linear_params:
+    _require_cuda(x, w, workspace)
+    if x.dim() != 2 or w.dim() != 2 or x.dtype != torch.float16 or w.dtype != torch.float16 or not x.is_contiguous() \
+            or not w.is_contiguous() or x.shape[1] != w.shape[1]:
+        raise NativeError(f"linear_small: x {tuple(x.shape)} / w {tuple(w.shape)} must be contiguous fp16 [q,k] / [n,k]")
+    p = pc_linear_params()
+    p.x, p.w, p.x_stride = x.data_ptr(), w.data_ptr(), x.stride(0)
+    p.q_len, p.k, p.n_rows, p.epilogue = x.shape[0], x.shape[1], w.shape[0], epilogue
+    p.workspace, p.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    return p
+
+
+def linear_small(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, workspace: torch.Tensor, silu_mul: bool = False) -> None:
+    """out[q, n] = x[q, k] @ w[n, k]^T  (q <= 32), or with `silu_mul` out[q, n/2] = silu(x @ w[:n/2]^T) * (x @ w[n/2:]^T)."""
+    p = _linear_params(x, w, workspace, PC_LIN_SILU_MUL if silu_mul else PC_LIN_PLAIN)
+    _require_cuda(out)
+    cols = w.shape[0] // 2 if silu_mul else w.shape[0]
+    if out.dim() != 2 or out.dtype != torch.float16 or out.stride(1) != 1 or out.shape[0] != x.shape[0] or out.shape[1] != cols:
+        raise NativeError(f"linear_small: out {tuple(out.shape)} must be fp16 [{x.shape[0]},{cols}] with contiguous rows")
+    p.out, p.out_stride = out.data_ptr(), out.stride(0)
+    _check(load().pc_linear_small(C.byref(p), _stream()), "pc_linear_small")
+
+
+def linear_rope_append(x: torch.Tensor, wqkv: torch.Tensor, position_ids: Optional[torch.Tensor], cos: Optional[torch.Tensor],
+                       sin: Optional[torch.Tensor], q_out: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor,
+                       dst_row0, n_heads: int, n_kv_heads: int, workspace: torch.Tensor) -> None:
+    """Fused QKV projection + RoPE at `position_ids` + in-place KV append (head_dim 128 only).  Arguments as rope_append."""
+    p = _linear_params(x, wqkv, workspace, PC_LIN_ROPE_APPEND)
+    _require_cuda(q_out, k_cache, v_cache)
+    D = 128
+    if k_cache.stride(2) != 1 or k_cache.stride(1) != D or k_cache.stride(0) != v_cache.stride(0) or not q_out.is_contiguous():
+        raise NativeError("linear_rope_append: caches must be [Hkv,max_ctx,128] with contiguous rows, q_out contiguous")
+    if cos is not None:
+        if cos.dtype != torch.float16 or sin.dtype != torch.float16 or not cos.is_contiguous() or not sin.is_contiguous() \
+                or cos.shape[1] != D:
+            raise NativeError("linear_rope_append: cos/sin must be contiguous fp16 [T,128] tables")
+        if position_ids.dtype != torch.int64 or not position_ids.is_contiguous():
+            raise NativeError("linear_rope_append: position_ids must be a contiguous int64 tensor")
+        p.cos, p.sin, p.table_rows, p.position_ids = cos.data_ptr(), sin.data_ptr(), cos.shape[0], position_ids.data_ptr()
+    p.q_out, p.k_cache, p.v_cache = q_out.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr()
+    p.max_ctx = k_cache.stride(0) // D
+    p.n_heads, p.n_kv_heads = n_heads, n_kv_heads
+    if isinstance(dst_row0, torch.Tensor):
+        if dst_row0.dtype != torch.int32 or not dst_row0.is_cuda:
+            raise NativeError("linear_rope_append: a run-time dst_row0 must be a CUDA int32 tensor")
+        p.dst_row0, p.dst_row0_dev = 0, dst_row0.data_ptr()
+    else:
+        p.dst_row0 = int(dst_row0)
+    _check(load().pc_linear_small(C.byref(p), _stream()), "pc_linear_small")

@@ -1,0 +1,444 @@
+// Skinny-M linear layers of the prefill / decode step as ONE weight-streaming tcgen05 kernel (SURVEY.md
+// section 8 row a13: q/k/v/o projections, MLP and lm_head -- reference promptcache/model/llama2.py:345-351,
+// :405, :213-244, :1050).  With q <= 32 uncached tokens these GEMMs are pure HBM streams of the fp16 weights
+// (13.5 GB per Llama-2-7B forward = 74 % of the TTFT step); the library kernels reach 59-85 % of the copy
+// bandwidth on them and every epilogue (RoPE + KV append, SiLU*up) costs another launch.
+//
+//   D^T[128 out-features x NPAD tokens] += W[128 x 64] . X[NPAD x 64]^T        (operands swapped so that the
+//   weight tile fills the MMA's M = 128 and the few tokens are its N)
+//
+// * stream-K: the (tile, k-block) space is cut into gridDim.x equal contiguous ranges, so every SM streams the
+//   same number of weight bytes whatever the shape (32 tiles of o_proj as well as 172 of gate/up);
+// * one elected thread keeps an 10-11 stage TMA ring (16 KiB weight tile + the matching X tile, 128B-swizzled)
+//   full, one elected thread issues the SS-MMAs into one of two TMEM accumulators, four epilogue warps drain
+//   the other one;
+// * a range that covers only part of a tile's K writes its fp32 partial to a per-CTA slot; the LAST CTA to
+//   arrive at the tile (arrival counter, self-cleaning) adds the slots in a fixed order -- deterministic, no
+//   second launch;
+// * epilogues: plain fp16 store; half(silu(gate)) * up (llama2.py:241) with gate and up rows of the same
+//   features loaded into one tile; RoPE at explicit position ids + in-place KV append with the reference's
+//   three fp16 roundings (llama2.py:195-210,357-364) when a tile is one head (D = 128).
+#include <cuda.h>
+#include <math.h>
+#include <stdlib.h>
+
+#include "pc_common.cuh"
+
+namespace pc {
+
+int make_tensor_map_3d(CUtensorMap* map, const void* base, int D, long long rows, int heads, long long head_stride,
+                       int box_rows);
+
+namespace {
+
+constexpr int BM = 128;                 // out-features per tile (MMA M)
+constexpr int BKK = 64;                 // k per stage: one 128-byte swizzled row
+constexpr int kWBytes = BM * BKK * 2;   // 16 KiB
+constexpr int kEpiThreads = 128;
+constexpr int kThreads = 64 + kEpiThreads;  // TMA warp + MMA warp + 4 epilogue warps
+constexpr size_t kLinCounterBytes = 16384;  // 4096 tile arrival counters
+constexpr int kMaxTiles = 4096;
+
+template <int NPAD>
+struct LCfg {
+  static constexpr int kXBytes = NPAD * BKK * 2;
+  static constexpr int kStageBytes = kWBytes + kXBytes;
+  static constexpr int kStages = NPAD <= 16 ? 11 : 10;
+  static constexpr int kOffExch = kStages * kStageBytes;
+  static constexpr int kExchBytes = NPAD * BM * 2;
+  static constexpr int kOffBars = kOffExch + kExchBytes;
+  static constexpr int kSmem = 1024 + kOffBars + 512;
+  static constexpr int kTmemCols = 2 * NPAD <= 32 ? 32 : 64;
+};
+
+struct LinParams {
+  __half* out;
+  long long out_stride;
+  float* slots;
+  int* counters;
+  int n_out;             // valid output columns (PLAIN: weight rows; SILU: inter)
+  int q_len, kb_total, tile_row_stride, second_half_off;
+  long long units_total;
+  // RoPE + append epilogue
+  const long long* pos;
+  const __half* cos;
+  const __half* sin;
+  int table_rows;
+  __half* q_out;
+  __half* k_cache;
+  __half* v_cache;
+  int max_ctx, row0, n_heads, n_kv_heads;
+  const int* row0_dev;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
+// CTA whose unit range [c*U/G, (c+1)*U/G) holds unit u.
+__device__ __forceinline__ int cta_of_unit(long long u, long long U, int G) {
+  int c = static_cast<int>(((u + 1) * G + U - 1) / U) - 1;
+  if (c < 0) c = 0;
+  if (c > G - 1) c = G - 1;
+  while (c + 1 < G && (static_cast<long long>(c + 1) * U) / G <= u) ++c;
+  while (c > 0 && (static_cast<long long>(c) * U) / G > u) --c;
+  return c;
+}
+
+template <int N>
+__device__ __forceinline__ void tmem_ld_acc(uint32_t addr, float (&v)[N]) {
+  if constexpr (N == 16) tmem_ld16(addr, reinterpret_cast<uint32_t(&)[16]>(v));
+  else tmem_ld32(addr, reinterpret_cast<uint32_t(&)[32]>(v));
+}
+
+template <int NPAD, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const LinParams p) {
+  using C = LCfg<NPAD>;
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  unsigned char* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  __half* exch = reinterpret_cast<__half*>(smem + C::kOffExch);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBars);
+  uint64_t* full = bars;
+  uint64_t* empty = full + C::kStages;
+  uint64_t* acc_full = empty + C::kStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  int* flag = reinterpret_cast<int*>(tmem_slot + 1);  // [3]: last arriver?, first / last contributing CTA
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int KB = p.kb_total;
+  const long long U = p.units_total;
+  const int G = gridDim.x, c = blockIdx.x;
+  const long long u0 = (static_cast<long long>(c) * U) / G;
+  const long long u1 = (static_cast<long long>(c + 1) * U) / G;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_w);
+    tma_prefetch_desc(&map_x);
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], kEpiThreads);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: the weight stream =====================
+    if (lane == 0) {
+      int tile = static_cast<int>(u0 / KB), kb = static_cast<int>(u0 - static_cast<long long>(tile) * KB);
+      int i = 0;
+      for (long long u = u0; u < u1; ++u, ++i) {
+        const int s = i % C::kStages;
+        if (i >= C::kStages) mbar_wait(&empty[s], static_cast<uint32_t>(((i / C::kStages) - 1) & 1));
+        unsigned char* dw = smem + s * C::kStageBytes;
+        mbar_expect_tx(&full[s], C::kStageBytes);
+        const int row_a = tile * p.tile_row_stride;
+        tma_load_3d(dw, &map_w, &full[s], kb * BKK, row_a, 0);
+        tma_load_3d(dw + kWBytes / 2, &map_w, &full[s], kb * BKK, row_a + p.second_half_off, 0);
+        tma_load_3d(dw + kWBytes, &map_x, &full[s], kb * BKK, 0, 0);
+        if (++kb == KB) {
+          kb = 0;
+          ++tile;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM, NPAD, 0, 0);  // both operands K-major
+      int i = 0, seg = 0;
+      long long u = u0;
+      while (u < u1) {
+        const int kb0 = static_cast<int>(u % KB);
+        const int n = static_cast<int>(min(static_cast<long long>(KB - kb0), u1 - u));
+        const int buf = seg & 1;
+        if (seg >= 2) {
+          mbar_wait(&acc_empty[buf], static_cast<uint32_t>(((seg >> 1) - 1) & 1));
+          tc_fence_after();
+        }
+        const uint32_t d = tmem_base + buf * NPAD;
+        for (int j = 0; j < n; ++j, ++i) {
+          const int s = i % C::kStages;
+          mbar_wait(&full[s], static_cast<uint32_t>((i / C::kStages) & 1));
+          tc_fence_after();
+          const uint32_t w_addr = smem_u32(smem + s * C::kStageBytes);
+          const uint32_t x_addr = w_addr + kWBytes;
+#pragma unroll
+          for (int kk = 0; kk < BKK / 16; ++kk)
+            umma_ss(d, make_smem_desc(w_addr + kk * 32, 16, 1024, 2), make_smem_desc(x_addr + kk * 32, 16, 1024, 2), idesc,
+                    (j > 0 || kk > 0) ? 1u : 0u);
+          tc_commit(&empty[s]);
+        }
+        tc_commit(&acc_full[buf]);
+        u += n;
+        ++seg;
+      }
+    }
+  } else {
+    // ===================== epilogue: thread = out-feature row of the tile =====================
+    const int et = tid - 64;
+    const int quad = warp & 3;                 // TMEM lane quarter this warp may read
+    const int f = quad * 32 + lane;            // row of the tile == TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    int row0 = p.row0;
+    if (EPI == PC_LIN_ROPE_APPEND && p.row0_dev != nullptr) row0 = max(0, min(__ldg(p.row0_dev), p.max_ctx - p.q_len));
+    int seg = 0;
+    long long u = u0;
+    while (u < u1) {
+      const int tile = static_cast<int>(u / KB);
+      const int kb0 = static_cast<int>(u - static_cast<long long>(tile) * KB);
+      const int n = static_cast<int>(min(static_cast<long long>(KB - kb0), u1 - u));
+      const int buf = seg & 1;
+      mbar_wait(&acc_full[buf], static_cast<uint32_t>((seg >> 1) & 1));
+      tc_fence_after();
+      float v[NPAD];
+      tmem_ld_acc<NPAD>(tmem_base + lane_base + buf * NPAD, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&acc_empty[buf]);
+      bool finalize = true;
+      if (n != KB) {
+        // partial K range: park the fp32 partial; the last CTA to arrive at this tile adds them up
+        const int slot = (u == u0) ? 0 : 1;
+        float* sp = p.slots + (static_cast<size_t>(c) * 2 + slot) * NPAD * BM;
+#pragma unroll
+        for (int t = 0; t < NPAD; ++t)
+          if (t < p.q_len) __stcg(sp + t * BM + f, v[t]);
+        named_bar_sync(1, kEpiThreads);  // orders every thread's stores before thread 0's gpu-scope fence + arrival
+        if (et == 0) {
+          const int c_first = cta_of_unit(static_cast<long long>(tile) * KB, U, G);
+          const int c_last = cta_of_unit(static_cast<long long>(tile) * KB + KB - 1, U, G);
+          __threadfence();
+          const int old = atomicAdd(p.counters + tile, 1);
+          const int last = (old == c_last - c_first) ? 1 : 0;
+          if (last) p.counters[tile] = 0;  // self-cleaning for the next launch
+          __threadfence();
+          flag[0] = last;
+          flag[1] = c_first;
+          flag[2] = c_last;
+        }
+        named_bar_sync(1, kEpiThreads);
+        finalize = flag[0] != 0;
+        if (finalize) {
+          const int c_first = flag[1], c_last = flag[2];
+#pragma unroll
+          for (int t = 0; t < NPAD; ++t) v[t] = 0.f;
+          for (int cc = c_first; cc <= c_last; ++cc) {
+            const long long cu0 = (static_cast<long long>(cc) * U) / G;
+            const int slot_c = (cu0 / KB == tile) ? 0 : 1;
+            const float* rp = p.slots + (static_cast<size_t>(cc) * 2 + slot_c) * NPAD * BM;
+#pragma unroll
+            for (int t = 0; t < NPAD; ++t)
+              if (t < p.q_len) v[t] += __ldcg(rp + t * BM + f);
+          }
+        }
+      }
+      if (finalize) {
+        if constexpr (EPI == PC_LIN_PLAIN) {
+          const int col = tile * BM + f;
+          if (col < p.n_out) {
+#pragma unroll
+            for (int t = 0; t < NPAD; ++t)
+              if (t < p.q_len) p.out[t * p.out_stride + col] = __float2half_rn(v[t]);
+          }
+        } else if constexpr (EPI == PC_LIN_SILU_MUL) {
+          // rows [0,64) of the tile are gate features, rows [64,128) the up features of the same columns
+          if (f >= 64) {
+#pragma unroll
+            for (int t = 0; t < NPAD; ++t) exch[t * 64 + (f - 64)] = __float2half_rn(v[t]);
+          }
+          named_bar_sync(1, kEpiThreads);
+          const int col = tile * 64 + f;
+          if (f < 64 && col < p.n_out) {
+#pragma unroll
+            for (int t = 0; t < NPAD; ++t) {
+              if (t < p.q_len) {
+                const float g = __half2float(__float2half_rn(v[t]));  // gate_proj output is fp16
+                const float s = g / (1.f + expf(-g));
+                p.out[t * p.out_stride + col] = __hmul_rn(__float2half_rn(s), exch[t * 64 + f]);
+              }
+            }
+          }
+          named_bar_sync(1, kEpiThreads);
+        } else {
+          // one tile == one head of 128: [0,H) query heads, [H,H+Hkv) key heads, then value heads
+#pragma unroll
+          for (int t = 0; t < NPAD; ++t) exch[t * BM + f] = __float2half_rn(v[t]);
+          named_bar_sync(1, kEpiThreads);
+          const int H = p.n_heads, Hkv = p.n_kv_heads;
+          const bool rotate = (tile < H + Hkv) && p.cos != nullptr;
+          __half* dst;
+          long long tstride = BM;
+          if (tile < H) dst = p.q_out + static_cast<long long>(tile) * p.q_len * BM + f;
+          else if (tile < H + Hkv) dst = p.k_cache + (static_cast<long long>(tile - H) * p.max_ctx + row0) * BM + f;
+          else dst = p.v_cache + (static_cast<long long>(tile - H - Hkv) * p.max_ctx + row0) * BM + f;
+          if (tile < H + 2 * Hkv) {
+#pragma unroll
+            for (int t = 0; t < NPAD; ++t) {
+              if (t < p.q_len) {
+                const __half x = exch[t * BM + f];
+                __half r = x;
+                if (rotate) {
+                  long long pos = __ldg(p.pos + t);
+                  if (pos < 0) pos = 0;
+                  if (pos >= p.table_rows) pos = p.table_rows - 1;
+                  const __half cs = p.cos[pos * BM + f], sn = p.sin[pos * BM + f];
+                  const __half partner = exch[t * BM + (f ^ 64)];
+                  const __half rot = f < 64 ? __hneg(partner) : partner;  // rotate_half(x) = cat(-x2, x1)
+                  r = __hadd_rn(__hmul_rn(x, cs), __hmul_rn(rot, sn));
+                }
+                dst[t * tstride] = r;
+              }
+            }
+          }
+          named_bar_sync(1, kEpiThreads);
+        }
+      }
+      u += n;
+      ++seg;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_free<C::kTmemCols>(tmem_base);
+  }
+}
+
+template <int NPAD, int EPI>
+int launch_lin(const CUtensorMap& mw, const CUtensorMap& mx, const LinParams& lp, int grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    PC_CHECK_CUDA(cudaFuncSetAttribute(linear_small_kernel<NPAD, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       LCfg<NPAD>::kSmem));
+    configured = true;
+  }
+  linear_small_kernel<NPAD, EPI><<<grid, kThreads, LCfg<NPAD>::kSmem, st>>>(mw, mx, lp);
+  PC_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return PC_OK;
+}
+
+template <int NPAD>
+int launch_lin_n(int epi, const CUtensorMap& mw, const CUtensorMap& mx, const LinParams& lp, int grid, cudaStream_t st) {
+  switch (epi) {
+    case PC_LIN_PLAIN: return launch_lin<NPAD, PC_LIN_PLAIN>(mw, mx, lp, grid, st);
+    case PC_LIN_SILU_MUL: return launch_lin<NPAD, PC_LIN_SILU_MUL>(mw, mx, lp, grid, st);
+    default: return launch_lin<NPAD, PC_LIN_ROPE_APPEND>(mw, mx, lp, grid, st);
+  }
+}
+
+}  // namespace
+}  // namespace pc
+
+PC_API size_t pc_linear_workspace_bytes(void) {
+  return pc::kLinCounterBytes + static_cast<size_t>(pc::sm_count()) * 2 * 32 * pc::BM * sizeof(float);
+}
+
+PC_API int pc_linear_small(const pc_linear_params* p, void* stream) {
+  using namespace pc;
+  if (!p) return set_error(PC_ERR_INVALID, "pc_linear_small: null params");
+  if (p->q_len == 0) return PC_OK;
+  PC_REQUIRE(p->x && p->w && p->workspace, "pc_linear_small: null tensor / workspace");
+  PC_REQUIRE(p->q_len > 0 && p->q_len <= 32, "pc_linear_small: q_len %d must be in [1,32]", p->q_len);
+  PC_REQUIRE(p->k > 0 && p->k % BKK == 0, "pc_linear_small: k %d must be a positive multiple of 64", p->k);
+  PC_REQUIRE(p->n_rows > 0, "pc_linear_small: n_rows %d", p->n_rows);
+  PC_REQUIRE(p->x_stride == p->k, "pc_linear_small: x must be contiguous (x_stride %lld != k %d)",
+             static_cast<long long>(p->x_stride), p->k);
+  PC_REQUIRE((reinterpret_cast<uintptr_t>(p->x) | reinterpret_cast<uintptr_t>(p->w) | reinterpret_cast<uintptr_t>(p->workspace)) % 16 == 0,
+             "pc_linear_small: x / w / workspace must be 16B aligned");
+  PC_REQUIRE(p->workspace_bytes >= pc_linear_workspace_bytes(), "pc_linear_small: workspace of %zu bytes, need %zu",
+             p->workspace_bytes, pc_linear_workspace_bytes());
+  LinParams lp{};
+  lp.q_len = p->q_len;
+  lp.kb_total = p->k / BKK;
+  int n_tiles = 0;
+  switch (p->epilogue) {
+    case PC_LIN_PLAIN:
+      PC_REQUIRE(p->out && p->out_stride >= p->n_rows, "pc_linear_small: out / out_stride");
+      n_tiles = (p->n_rows + BM - 1) / BM;
+      lp.n_out = p->n_rows;
+      lp.tile_row_stride = BM;
+      lp.second_half_off = 64;
+      break;
+    case PC_LIN_SILU_MUL: {
+      PC_REQUIRE(p->n_rows % 2 == 0, "pc_linear_small(silu_mul): n_rows %d must be even (gate rows, then up rows)", p->n_rows);
+      const int inter = p->n_rows / 2;
+      PC_REQUIRE(p->out && p->out_stride >= inter, "pc_linear_small(silu_mul): out / out_stride");
+      n_tiles = (inter + 63) / 64;
+      lp.n_out = inter;
+      lp.tile_row_stride = 64;
+      lp.second_half_off = inter;
+      // a ragged last tile would pull up-rows into the gate half: keep it exact
+      PC_REQUIRE(inter % 64 == 0, "pc_linear_small(silu_mul): intermediate size %d must be a multiple of 64", inter);
+      break;
+    }
+    case PC_LIN_ROPE_APPEND:
+      PC_REQUIRE(p->n_heads > 0 && p->n_kv_heads > 0 && p->n_rows == (p->n_heads + 2 * p->n_kv_heads) * BM,
+                 "pc_linear_small(rope_append): n_rows %d must be (H + 2 Hkv) * 128", p->n_rows);
+      PC_REQUIRE(p->q_out && p->k_cache && p->v_cache, "pc_linear_small(rope_append): null q_out / cache");
+      PC_REQUIRE((p->cos == nullptr) == (p->sin == nullptr), "pc_linear_small(rope_append): cos/sin must both be set");
+      PC_REQUIRE(p->cos == nullptr || (p->position_ids != nullptr && p->table_rows > 0),
+                 "pc_linear_small(rope_append): rotary needs position ids and a table");
+      PC_REQUIRE(p->dst_row0 >= 0 && static_cast<long long>(p->dst_row0) + p->q_len <= p->max_ctx,
+                 "pc_linear_small(rope_append): rows [%d,%d) exceed max_ctx %d", p->dst_row0, p->dst_row0 + p->q_len, p->max_ctx);
+      n_tiles = p->n_heads + 2 * p->n_kv_heads;
+      lp.n_out = p->n_rows;
+      lp.tile_row_stride = BM;
+      lp.second_half_off = 64;
+      break;
+    default:
+      return set_error(PC_ERR_INVALID, "pc_linear_small: unknown epilogue %d", p->epilogue);
+  }
+  PC_REQUIRE(n_tiles <= kMaxTiles, "pc_linear_small: %d tiles exceed the counter region", n_tiles);
+  {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+      return set_error(PC_ERR_CUDA, "no CUDA device");
+    if (major != 10) return set_error(PC_ERR_UNSUPPORTED, "this library is built for sm_100a only");
+  }
+  lp.out = static_cast<__half*>(p->out);
+  lp.out_stride = p->out_stride;
+  lp.counters = static_cast<int*>(p->workspace);
+  lp.slots = reinterpret_cast<float*>(static_cast<char*>(p->workspace) + kLinCounterBytes);
+  lp.units_total = static_cast<long long>(n_tiles) * lp.kb_total;
+  lp.pos = reinterpret_cast<const long long*>(p->position_ids);
+  lp.cos = static_cast<const __half*>(p->cos);
+  lp.sin = static_cast<const __half*>(p->sin);
+  lp.table_rows = p->table_rows;
+  lp.q_out = static_cast<__half*>(p->q_out);
+  lp.k_cache = static_cast<__half*>(p->k_cache);
+  lp.v_cache = static_cast<__half*>(p->v_cache);
+  lp.max_ctx = p->max_ctx;
+  lp.row0 = p->dst_row0;
+  lp.row0_dev = p->dst_row0_dev;
+  lp.n_heads = p->n_heads;
+  lp.n_kv_heads = p->n_kv_heads;
+
+  int grid = sm_count();
+  if (const char* e = getenv("PC_LIN_GRID")) grid = atoi(e);
+  if (grid > sm_count()) grid = sm_count();
+  if (grid > lp.units_total) grid = static_cast<int>(lp.units_total);
+  if (grid < 1) grid = 1;
+  CUtensorMap mw, mx;
+  if (int rc = make_tensor_map_3d(&mw, p->w, p->k, p->n_rows, 1, static_cast<long long>(p->n_rows) * p->k, 64)) return rc;
+  const int npad = p->q_len <= 16 ? 16 : 32;
+  // rows >= q_len of the X box read as zeros
+  if (int rc = make_tensor_map_3d(&mx, p->x, p->k, p->q_len, 1, static_cast<long long>(p->q_len) * p->x_stride, npad)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (npad == 16) return launch_lin_n<16>(p->epilogue, mw, mx, lp, grid, st);
+  return launch_lin_n<32>(p->epilogue, mw, mx, lp, grid, st);
+}

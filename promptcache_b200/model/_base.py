@@ -2,6 +2,7 @@
 attention workspace and CUDA-graph replay of the single-sequence forward."""
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -32,7 +33,10 @@ class B200CausalLM(nn.Module):
     def _init_runtime(self):
         self._cos = self._sin = None
         self._ws = None
+        self._lin_ws = None
         self.attn_impl = nat.PC_ATTN_AUTO
+        # "native": skinny linears (q <= 32) run in pc_linear_small; "cublas": torch.nn.functional.linear everywhere
+        self.linear_impl = os.environ.get("PC_LINEAR", "native")
         # CUDA graphs of the whole single-sequence forward, keyed by (q_len, n_cached, KV buffer): the per-layer
         # launch sequence is fixed once those are, so a repeated request shape is replayed with one launch
         self.use_cuda_graphs = True
@@ -66,6 +70,12 @@ class B200CausalLM(nn.Module):
             self._graphs.clear()  # captured graphs hold the old workspace pointer
             self._ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
         return self._ws
+
+    def _linear_workspace(self) -> torch.Tensor:
+        if self._lin_ws is None or self._lin_ws.device != self.device:
+            self._graphs.clear()  # captured graphs hold the old workspace pointer
+            self._lin_ws = nat.linear_workspace(self.device)  # zeroed once; the kernel leaves its counters zeroed
+        return self._lin_ws
 
     # ---- forward ---------------------------------------------------------------------------------------
     def _layers(self, ids: torch.Tensor, pos: torch.Tensor, kv, extra) -> torch.Tensor:

@@ -124,20 +124,43 @@ class LlamaForCausalLM(B200CausalLM):
         inter = self.config.intermediate_size
         act = torch.empty(q_len, inter, dtype=torch.float16, device=self.device)
         ws = self._workspace(q_len)
+        # q <= 32: the linears are weight streams -> pc_linear_small (stream-K tcgen05, fused RoPE+append / SiLU*up);
+        # longer suffixes are compute-bound GEMMs and stay in cuBLAS
+        lin = self.linear_impl == "native" and q_len <= 32 and D == 128 and self.config.hidden_size % 64 == 0 \
+            and inter % 64 == 0
+        lws = self._linear_workspace() if lin else None
+        dbuf = torch.empty_like(x) if lin else None
         delta = None
         for l in range(self.n_layers):
             nat.add_rmsnorm(x, delta, self.ln1[l], h, self.eps)          # x += mlp(l-1); h = norm(x)
-            qkv = F.linear(h, self.wqkv[l])                              # [q, (H+2Hkv)*D]
             # n_dev: run-time cached length (decode graph); N is then only the sizing upper bound
-            nat.rope_append(qkv[:, :H * D], qkv[:, H * D:(H + Hkv) * D], qkv[:, (H + Hkv) * D:], pos, self._cos,
-                            self._sin, q_rot, kv.k[l], kv.v[l], N if n_dev is None else n_dev, H, Hkv, D)
+            if lin:
+                nat.linear_rope_append(h, self.wqkv[l], pos, self._cos, self._sin, q_rot, kv.k[l], kv.v[l],
+                                       N if n_dev is None else n_dev, H, Hkv, lws)
+            else:
+                qkv = F.linear(h, self.wqkv[l])                          # [q, (H+2Hkv)*D]
+                nat.rope_append(qkv[:, :H * D], qkv[:, H * D:(H + Hkv) * D], qkv[:, (H + Hkv) * D:], pos, self._cos,
+                                self._sin, q_rot, kv.k[l], kv.v[l], N if n_dev is None else n_dev, H, Hkv, D)
             nat.attention(q_rot, kv.k[l], kv.v[l], attn_out, N if n_dev is None else kv.max_ctx - q_len, q_len, H, Hkv,
                           D, self.scale, self.rounding, workspace=ws, decode=(q_len == 1), n_cached_dev=n_dev,
                           impl=self.attn_impl if n_dev is None else nat.PC_ATTN_TCGEN05)
-            delta = F.linear(attn_out, self.wo[l])
+            if lin:
+                nat.linear_small(attn_out, self.wo[l], dbuf, lws)
+                delta = dbuf
+            else:
+                delta = F.linear(attn_out, self.wo[l])
             nat.add_rmsnorm(x, delta, self.ln2[l], h, self.eps)          # x += attn; h = norm(x)
-            gu = F.linear(h, self.w_gate_up[l])
-            nat.silu_mul(gu, act, inter)
-            delta = F.linear(act, self.w_down[l])
+            if lin:
+                nat.linear_small(h, self.w_gate_up[l], act, lws, silu_mul=True)
+                nat.linear_small(act, self.w_down[l], dbuf, lws)
+                delta = dbuf
+            else:
+                gu = F.linear(h, self.w_gate_up[l])
+                nat.silu_mul(gu, act, inter)
+                delta = F.linear(act, self.w_down[l])
         nat.add_rmsnorm(x, delta, self.norm, h, self.eps)
+        if lin:
+            logits = torch.empty(q_len, self.vocab_size, dtype=torch.float16, device=self.device)
+            nat.linear_small(h, self.lm_head, logits, lws)
+            return logits.float()
         return F.linear(h, self.lm_head).float()

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol(native):
     assert declared == set(native.EXPORTS), declared ^ set(native.EXPORTS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.pc_version() == 2
+    assert lib.pc_version() == 3
     assert lib.pc_launch_count() >= 0
 
 

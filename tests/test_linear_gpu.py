@@ -1,0 +1,167 @@
+"""GPU parity of pc_linear_small (stream-K tcgen05 skinny linear + fused epilogues) through the C ABI.
+
+Reference semantics (promptcache/model/llama2.py): an fp16 nn.Linear = fp32-accumulated dot products rounded once to
+fp16 (:345-351, :405, :241, :1050); SiLU(gate)*up in fp16 (:241); RoPE at explicit ids + KV concat (:195-210,357-364).
+Integer-valued inputs make every fp32 partial sum exact, so those cases must match BIT FOR BIT whatever the
+summation order; random inputs are checked against an fp64 product within one fp16 rounding.
+"""
+import pytest
+import torch
+
+from oracle import pc_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _ints(shape, lo, hi, scale, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randint(lo, hi + 1, shape, generator=g).float() * scale).half().to(DEV)
+
+
+def _exact_linear(x, w):
+    return (x.double() @ w.double().t()).half()
+
+
+SHAPES = [  # (q, k, n)
+    (16, 4096, 4096),     # o_proj 7B
+    (1, 4096, 12288),     # decode, qkv-sized
+    (32, 11008, 4096),    # down_proj, NPAD 32
+    (7, 256, 512),        # tiny: fewer units than SMs
+    (16, 4544, 4672),     # Falcon hidden (71 k-blocks), rows not a multiple of 128
+    (16, 4096, 32000),    # lm_head
+    (3, 64, 128),         # a single unit
+    (17, 5120, 5120),     # 13B, NPAD 32 with ragged tokens
+]
+
+
+@pytest.mark.parametrize("q,k,n", SHAPES)
+def test_linear_plain_exact_on_integer_inputs(native, q, k, n):
+    x = _ints((q, k), -4, 4, 0.25, seed=q + k)
+    w = _ints((n, k), -2, 2, 0.125, seed=n + 1)
+    ws = native.linear_workspace(DEV)
+    out = torch.full((q, n), float("nan"), dtype=torch.half, device=DEV)
+    native.linear_small(x, w, out, ws)
+    torch.cuda.synchronize()
+    assert torch.equal(out, _exact_linear(x, w))
+    assert int(ws[:16384].view(torch.int32).abs().max()) == 0  # arrival counters are left zeroed
+    # replays on the same workspace give the same bits
+    out2 = torch.empty_like(out)
+    for _ in range(3):
+        native.linear_small(x, w, out2, ws)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("q,k,n", [(16, 4096, 4096), (32, 11008, 4096), (5, 4096, 22016)])
+def test_linear_plain_random_within_one_rounding(native, q, k, n):
+    g = torch.Generator(device="cpu").manual_seed(11)
+    x = torch.randn(q, k, generator=g).half().to(DEV)
+    w = (torch.randn(n, k, generator=g) * 0.02).half().to(DEV)
+    ws = native.linear_workspace(DEV)
+    out = torch.empty(q, n, dtype=torch.half, device=DEV)
+    native.linear_small(x, w, out, ws)
+    ref = x.double() @ w.double().t()
+    err = (out.double() - ref).abs()
+    # fp32 accumulation error is far below the final fp16 rounding (2^-11 relative) at these sizes
+    assert bool((err <= ref.abs() * 2.0 ** -10 + 1e-4).all()), float(err.max())
+    cub = torch.nn.functional.linear(x, w)
+    assert float((out.float() - cub.float()).abs().max()) <= 2e-3 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("q,k,inter", [(16, 4096, 11008), (32, 512, 192), (1, 5120, 13824)])
+def test_linear_silu_mul(native, q, k, inter):
+    x = _ints((q, k), -4, 4, 0.25, seed=3)
+    w = _ints((2 * inter, k), -2, 2, 1.0 / 64, seed=4)
+    ws = native.linear_workspace(DEV)
+    out = torch.empty(q, inter, dtype=torch.half, device=DEV)
+    native.linear_small(x, w, out, ws, silu_mul=True)
+    gu = _exact_linear(x, w)  # exact fp16 gate / up projections
+    want = torch.empty_like(out)
+    native.silu_mul(gu, want, inter)  # the unfused kernel on the same fp16 inputs
+    ref = (torch.nn.functional.silu(gu[:, :inter].float()).half() * gu[:, inter:])
+    torch.cuda.synchronize()
+    assert torch.allclose(out.float(), want.float(), rtol=1e-3, atol=1e-6)
+    assert torch.allclose(out.float(), ref.float(), rtol=2e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("q,H,Hkv,k,row0,rotary", [
+    (16, 32, 32, 4096, 2048, True),   # C2
+    (1, 32, 32, 4096, 777, True),     # decode
+    (32, 8, 2, 512, 5, True),         # GQA, NPAD 32
+    (9, 4, 4, 256, 0, False),         # MPT: no rotation, plain append
+])
+def test_linear_rope_append_bit_exact_vs_unfused(native, q, H, Hkv, k, row0, rotary):
+    D, max_ctx = 128, row0 + q + 3
+    x = _ints((q, k), -4, 4, 0.25, seed=5)
+    w = _ints(((H + 2 * Hkv) * D, k), -2, 2, 1.0 / 32, seed=6)
+    g = torch.Generator(device="cpu").manual_seed(7)
+    pos = torch.randint(0, 4096, (q,), generator=g).to(DEV)  # discontiguous, non-monotone ids
+    cos, sin = O.rope_tables(D, 4096, dtype=torch.float16)
+    cos, sin = cos.contiguous().to(DEV), sin.contiguous().to(DEV)
+    ws = native.linear_workspace(DEV)
+
+    def fresh():
+        return (torch.zeros(H, q, D, dtype=torch.half, device=DEV), torch.zeros(Hkv, max_ctx, D, dtype=torch.half, device=DEV),
+                torch.zeros(Hkv, max_ctx, D, dtype=torch.half, device=DEV))
+
+    q1, k1, v1 = fresh()
+    native.linear_rope_append(x, w, pos if rotary else None, cos if rotary else None, sin if rotary else None, q1, k1, v1,
+                              row0, H, Hkv, ws)
+    qkv = _exact_linear(x, w)
+    q2, k2, v2 = fresh()
+    native.rope_append(qkv[:, :H * D], qkv[:, H * D:(H + Hkv) * D], qkv[:, (H + Hkv) * D:], pos if rotary else None,
+                       cos if rotary else None, sin if rotary else None, q2, k2, v2, row0, H, Hkv, D)
+    torch.cuda.synchronize()
+    assert torch.equal(q1, q2) and torch.equal(k1, k2) and torch.equal(v1, v2)
+    # run-time destination row (graph-replayable decode)
+    q3, k3, v3 = fresh()
+    row_dev = torch.tensor([row0], dtype=torch.int32, device=DEV)
+    native.linear_rope_append(x, w, pos if rotary else None, cos if rotary else None, sin if rotary else None, q3, k3, v3,
+                              row_dev, H, Hkv, ws)
+    torch.cuda.synchronize()
+    assert torch.equal(q3, q2) and torch.equal(k3, k2) and torch.equal(v3, v2)
+
+
+def test_linear_rejects_bad_arguments(native):
+    ws = native.linear_workspace(DEV)
+    x = torch.zeros(33, 128, dtype=torch.half, device=DEV)
+    w = torch.zeros(128, 128, dtype=torch.half, device=DEV)
+    with pytest.raises(native.NativeError):
+        native.linear_small(x, w, torch.zeros(33, 128, dtype=torch.half, device=DEV), ws)  # q > 32
+    with pytest.raises(native.NativeError):
+        native.linear_small(x[:4, :96].contiguous(), w[:, :96].contiguous(), torch.zeros(4, 128, dtype=torch.half, device=DEV), ws)
+    with pytest.raises(native.NativeError):
+        native.linear_small(x[:4], w, torch.zeros(4, 128, dtype=torch.half, device=DEV), ws[:1024])  # workspace too small
+
+
+def test_model_native_linears_match_cublas_linears(native):
+    """The same 2-layer Llama-2-7B-shaped step with pc_linear_small and with cuBLAS linears: logits agree to fp16
+    round-off, the appended K/V rows agree, and a replayed CUDA graph of the native step equals its eager run."""
+    from promptcache_b200 import CacheEngine, Prompt
+    from promptcache_b200.model import Llama2, LlamaConfigLite, LlamaForCausalLM
+    from promptcache_b200.synthetic import IdTokenizer, make_case
+    sd = O.random_llama_state_dict(4000, 4096, 11008, 2, 32, 32, seed=0, dtype=torch.float16, device=DEV)
+    model = LlamaForCausalLM(LlamaConfigLite(vocab_size=4000, num_hidden_layers=2), device=DEV)
+    model.load_hf_state_dict(sd)
+    lm = Llama2("llama7b-2l", model=model, tokenizer=IdTokenizer(4000))
+    case = make_case("C2", vocab=4000)
+    eng = CacheEngine(2304, lm)
+    eng.add_schema(case.schema_xml)
+    res = {}
+    for impl in ("native", "cublas", "native", "native"):
+        model.linear_impl = impl
+        before = native.launch_count()
+        ids, pos, _, cache = eng.process(Prompt(case.prompt_xml))
+        out = lm(input_ids=torch.tensor([ids], device=DEV), position_ids=torch.tensor([pos], device=DEV),
+                 past_key_values=[(k.unsqueeze(0), v.unsqueeze(0)) for k, v in cache], use_cache=True)
+        torch.cuda.synchronize()
+        rows = eng.prompt_cache.buffer[:, :, :, 2048:2064].clone()
+        res.setdefault(impl, []).append((out.logits.clone(), rows, native.launch_count() - before))
+    a, b = res["native"][0], res["cublas"][0]
+    scale = float(b[0].abs().max())
+    assert float((a[0] - b[0]).abs().max()) < 3e-3 * scale
+    assert float((a[1].float() - b[1].float()).abs().max()) < 3e-3 * float(b[1].abs().max())
+    assert a[2] >= 2 * 7 and b[2] >= 2 * 5  # native: 7 launches of this library per layer; cuBLAS path: 5 (+4 library GEMMs)
+    for other in res["native"][1:]:  # eager, then captured and replayed
+        assert torch.equal(other[0], a[0]) and torch.equal(other[1], a[1])

@@ -1,4 +1,4 @@
-"""Kernel micro-benchmarks (CUDA events, inputs larger than L2).  Usage: python tools/microbench.py [splice|attn|all]"""
+"""Kernel micro-benchmarks (CUDA events, inputs larger than L2).  Usage: python tools/microbench.py [splice|attn|linear|all]"""
 import json
 import math
 import os
@@ -118,6 +118,75 @@ def bench_attn(only=None):
                   f"({byts/ms/1e6/PEAK:.2f} of HBM peak)", flush=True)
 
 
+def bench_linear(only=None):
+    """pc_linear_small vs cuBLAS (F.linear) on the Llama-2 step's linears; weights rotate over > L2 worth of copies."""
+    import torch.nn.functional as F
+    ws = nat.linear_workspace(DEV)
+    shapes = [("7B qkv+rope", 16, 4096, 12288, "rope"), ("7B o_proj", 16, 4096, 4096, "plain"),
+              ("7B gate_up+silu", 16, 4096, 22016, "silu"), ("7B down", 16, 11008, 4096, "plain"),
+              ("7B lm_head", 16, 4096, 32000, "plain"), ("7B qkv+rope q1", 1, 4096, 12288, "rope"),
+              ("7B down q32", 32, 11008, 4096, "plain"), ("13B gate_up+silu q32", 32, 5120, 27648, "silu")]
+    tot = {"native": 0.0, "cublas": 0.0}
+    for name, q, k, n, epi in [c for c in shapes if only is None or only in c[0]]:
+        rot = max(2, int(math.ceil(600e6 / (n * k * 2))))
+        W = (torch.randn(rot, n, k, device=DEV) * 0.02).half()
+        x = torch.randn(q, k, device=DEV).half()
+        byts = n * k * 2.0
+        state = {"i": 0}
+        if epi == "rope":
+            H = Hkv = n // 384
+            pos = torch.arange(2048, 2048 + q, device=DEV)
+            inv = 1.0 / (10000.0 ** (torch.arange(0, 128, 2, device=DEV).float() / 128))
+            fr = torch.outer(torch.arange(4096, device=DEV).float(), inv)
+            emb = torch.cat([fr, fr], -1)
+            cos, sin = emb.cos().half().contiguous(), emb.sin().half().contiguous()
+            q_rot = torch.empty(H, q, 128, dtype=torch.half, device=DEV)
+            kc = torch.zeros(Hkv, 2304, 128, dtype=torch.half, device=DEV)
+            vc = torch.zeros(Hkv, 2304, 128, dtype=torch.half, device=DEV)
+
+            def run_native():
+                i = state["i"] = (state["i"] + 1) % rot
+                nat.linear_rope_append(x, W[i], pos, cos, sin, q_rot, kc, vc, 2048, H, Hkv, ws)
+
+            def run_cublas():
+                i = state["i"] = (state["i"] + 1) % rot
+                qkv = F.linear(x, W[i])
+                nat.rope_append(qkv[:, :H * 128], qkv[:, H * 128:(H + Hkv) * 128], qkv[:, (H + Hkv) * 128:], pos, cos, sin, q_rot,
+                                kc, vc, 2048, H, Hkv, 128)
+        elif epi == "silu":
+            out = torch.empty(q, n // 2, dtype=torch.half, device=DEV)
+
+            def run_native():
+                i = state["i"] = (state["i"] + 1) % rot
+                nat.linear_small(x, W[i], out, ws, silu_mul=True)
+
+            def run_cublas():
+                i = state["i"] = (state["i"] + 1) % rot
+                nat.silu_mul(F.linear(x, W[i]), out, n // 2)
+        else:
+            out = torch.empty(q, n, dtype=torch.half, device=DEV)
+
+            def run_native():
+                i = state["i"] = (state["i"] + 1) % rot
+                nat.linear_small(x, W[i], out, ws)
+
+            def run_cublas():
+                i = state["i"] = (state["i"] + 1) % rot
+                F.linear(x, W[i])
+        ms_n = timeit_graph(run_native, reps=16, iters=10)
+        ms_c = timeit_graph(run_cublas, reps=16, iters=10)
+        if q == 16 and name.startswith("7B") and "lm_head" not in name:
+            tot["native"] += ms_n
+            tot["cublas"] += ms_c
+        print(f"linear {name} q={q} [{n}x{k}] {byts/1e6:.0f} MB: native {ms_n*1e3:.1f} us = {byts/ms_n/1e6:.0f} GB/s "
+              f"({byts/ms_n/1e6/PEAK:.2f} of HBM peak) | cuBLAS(+epilogue kernel) {ms_c*1e3:.1f} us = {byts/ms_c/1e6:.0f} GB/s "
+              f"({byts/ms_c/1e6/PEAK:.2f})", flush=True)
+        del W
+    if tot["native"] > 0:
+        print(f"linear 7B per layer (qkv+o+gate_up+down, q=16): native {tot['native']*1e3:.1f} us vs cuBLAS {tot['cublas']*1e3:.1f} us "
+              f"-> x32 layers {tot['native']*32:.3f} ms vs {tot['cublas']*32:.3f} ms", flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     print("device:", torch.cuda.get_device_name(0), flush=True)
@@ -125,3 +194,5 @@ if __name__ == "__main__":
         bench_splice()
     if what in ("attn", "all"):
         bench_attn(sys.argv[2] if len(sys.argv) > 2 else None)
+    if what in ("linear", "all"):
+        bench_linear(sys.argv[2] if len(sys.argv) > 2 and what == "linear" else None)
