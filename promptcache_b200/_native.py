@@ -352,3 +352,4 @@ def linear_rope_append(x: torch.Tensor, wqkv: torch.Tensor, position_ids: Option
     else:
         p.dst_row0 = int(dst_row0)
     _check(load().pc_linear_small(C.byref(p), _stream()), "pc_linear_small")
+

@@ -23,10 +23,25 @@ from typing import Dict, List, Optional, Tuple, Union
 import torch
 
 from . import _native as nat
+from .model._kv import LayerKV, PastKV
 from .prompt import ModuleRef, Prompt
 from .schema import Module, Path, Schema, TokenSequence, UnionModule
 
 KVCache = List[Tuple[torch.Tensor, torch.Tensor]]
+
+
+class SplicedKV(list):
+    """What `CacheEngine.process` returns as `KVCache`: a plain list of L `(K, V)` views `[Hkv, N, D]` into the
+    engine-owned buffers (reference cache_engine.py:161-165) that also remembers those buffers, so that
+    `GenerationEngine` can hand them to the model in O(1) instead of re-deriving 2L views and re-validating them on
+    every request (that host work sat between the splice and the prefill with the GPU idle)."""
+
+    layer_kv: Optional[LayerKV] = None
+    rows: int = 0
+
+    def batched(self) -> PastKV:
+        """The `[(k.unsqueeze(0), v.unsqueeze(0)) ...]` of generation_engine.py:101-102, materialised lazily."""
+        return PastKV(self.layer_kv, self.rows)
 
 
 def pad_batch(batch_list: List[List[int]], pad_id: int) -> Tuple[List[List[int]], List[List[int]]]:
@@ -83,6 +98,9 @@ class PromptCache:
         self.head_dim = head_dim
         # zero-initialised: rows past `length` are read (and masked) by whole-tile attention loads
         self.buffer = torch.zeros(num_layers, 2, num_head, max_ctx_length, head_dim, dtype=torch.half, device=device)
+        self._bases_k = [self.buffer[l, 0] for l in range(num_layers)]  # [Hkv, max_ctx, D] per layer, built once
+        self._bases_v = [self.buffer[l, 1] for l in range(num_layers)]
+        self._views: Dict[int, SplicedKV] = {}                          # spliced length -> the 2L views of that length
         self.staged: List[TokenSequenceCache] = []
         self.length = 0
         self.retain_prefix = True
@@ -124,8 +142,19 @@ class PromptCache:
 
     @property
     def cache(self) -> KVCache:
+        """Views [Hkv, N, D] of the spliced rows (reference :161-165).  The 2L view objects of a given length are
+        built once and handed out as a fresh list each time (callers may mutate the list, not the engine's copy)."""
         n = self.length
-        return [(self.buffer[l, 0, :, :n, :], self.buffer[l, 1, :, :n, :]) for l in range(self.num_layers)]
+        master = self._views.get(n)
+        if master is None:
+            if len(self._views) >= 64:
+                self._views.pop(next(iter(self._views)))
+            master = SplicedKV((self.buffer[l, 0, :, :n, :], self.buffer[l, 1, :, :n, :]) for l in range(self.num_layers))
+            self._views[n] = master
+        out = SplicedKV(master)
+        out.layer_kv = LayerKV(self._bases_k, self._bases_v, n, self.max_ctx_length)
+        out.rows = n
+        return out
 
 
 class SchemaCache:
@@ -237,6 +266,9 @@ class CacheEngine:
                                         head_dim=head_dim, target_device=self.target_device)
         if hasattr(lm.hf_model, "ensure_rope"):
             lm.hf_model.ensure_rope(max_ctx_length)
+        from .model import LanguageModel
+        self._identity_hooks = all(getattr(getattr(lm, name, None), "__func__", None) is getattr(LanguageModel, name)
+                                   for name in ("read_k_hook", "read_v_hook"))
 
     def add_schema(self, schema: Union[str, Schema], batch_size: int = 1, max_tokens: Optional[int] = None,
                    no_cache: bool = False) -> None:
@@ -342,7 +374,8 @@ class CacheEngine:
         end.record()
         torch.cuda.synchronize()
         cache_time = start.elapsed_time(end)
-        cache = [(self.lm.read_k_hook(k), self.lm.read_v_hook(v)) for k, v in cache]
+        if not self._identity_hooks:  # the reference's hooks are identities (model/__init__.py:116-126)
+            cache = [(self.lm.read_k_hook(k), self.lm.read_v_hook(v)) for k, v in cache]
         if return_full_position_ids:
             # ids of the cached rows IN BUFFER ORDER (equal to the reference's visit order, :517-519, whenever
             # the usage counters do not reorder the layout; the reference is wrong when they do)

@@ -140,7 +140,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                   const __grid_constant__ CUtensorMap map_v, const SmallParams pin) {
   using C = SCfg<NPAD>;
+  pdl_launch_dependents();  // programmatic dependent launch: see pc_common.cuh
   SmallParams p = pin;
+  if (pin.n_cached_dev != nullptr) pdl_wait();  // the run-time length is written by the previous kernels
   if (pin.n_cached_dev != nullptr) p.n_cached = max(0, min(__ldg(pin.n_cached_dev), pin.n_cached));
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -211,6 +213,8 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // barriers, TMEM and descriptors are ready; Q, the new K/V rows and the workspace come from the previous kernels
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + 2 * NPAD;
   if (tid == 0) PC_TRACE(1);  // setup done
@@ -491,8 +495,7 @@ int launch_small_one(const CUtensorMap& mq, const CUtensorMap& mk, const CUtenso
                                        SCfg<NPAD>::kSmem));
     configured = true;
   }
-  attn_small_kernel<NPAD, ROUND, ALIBI><<<grid, kThreads, SCfg<NPAD>::kSmem, st>>>(mq, mk, mv, sp);
-  PC_CHECK_CUDA(cudaGetLastError());
+  PC_CHECK_CUDA(launch_pdl(attn_small_kernel<NPAD, ROUND, ALIBI>, dim3(grid), dim3(kThreads), SCfg<NPAD>::kSmem, st, mq, mk, mv, sp));
   count_launch();
   return PC_OK;
 }

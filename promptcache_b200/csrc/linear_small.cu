@@ -14,7 +14,9 @@
 //   the other one;
 // * a range that covers only part of a tile's K writes its fp32 partial to a per-CTA slot; the LAST CTA to
 //   arrive at the tile (arrival counter, self-cleaning) adds the slots in a fixed order -- deterministic, no
-//   second launch;
+//   second launch; partial segments are visited before whole tiles so that this reduction overlaps the stream;
+// * programmatic dependent launch: the weights are static, so a CTA fills its ring with them while the previous
+//   kernel (the producer of X) is still finishing, and only then waits for it;
 // * epilogues: plain fp16 store; half(silu(gate)) * up (llama2.py:241) with gate and up rows of the same
 //   features loaded into one tile; RoPE at explicit position ids + in-place KV append with the reference's
 //   three fp16 roundings (llama2.py:195-210,357-364) when a tile is one head (D = 128).
@@ -69,7 +71,18 @@ struct LinParams {
   __half* v_cache;
   int max_ctx, row0, n_heads, n_kv_heads;
   const int* row0_dev;
+  unsigned long long* trace;  // debug: 8 %globaltimer stamps per CTA (PC_LIN_TRACE_PTR), else nullptr
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define LIN_TRACE(slot)                                                 \
+  do {                                                                  \
+    if (p.trace != nullptr) p.trace[blockIdx.x * 8 + (slot)] = gtime(); \
+  } while (0)
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
@@ -91,10 +104,61 @@ __device__ __forceinline__ void tmem_ld_acc(uint32_t addr, float (&v)[N]) {
   else tmem_ld32(addr, reinterpret_cast<uint32_t(&)[32]>(v));
 }
 
+// One CTA's share of the (tile, k-block) space, cut at tile boundaries.  Segments that cover only part of a
+// tile's K ("partial": at most the first and the last of the range) are visited FIRST, whole tiles last: the
+// cross-CTA reduction of a partial (publish -> arrival counter -> slot reads) then overlaps the streaming of the
+// whole tiles instead of sitting in the kernel's tail.
+struct Seg {
+  int tile, kb0, n;
+};
+struct SegIter {
+  long long u0, u1;
+  int KB, t_first, t_last, phase, cur;
+  bool first_partial, last_partial;
+  __device__ SegIter(long long u0_, long long u1_, int KB_) : u0(u0_), u1(u1_), KB(KB_) {
+    t_first = static_cast<int>(u0 / KB);
+    t_last = static_cast<int>((u1 - 1) / KB);
+    const long long first_end = min(u1, static_cast<long long>(t_first + 1) * KB);
+    first_partial = (u0 != static_cast<long long>(t_first) * KB) || (first_end - u0 != KB);
+    last_partial = (t_last > t_first) && (u1 != static_cast<long long>(t_last + 1) * KB);
+    phase = 0;
+    cur = first_partial ? t_first + 1 : t_first;
+  }
+  __device__ bool next(Seg& s) {
+    if (phase == 0) {
+      phase = 1;
+      if (last_partial) {
+        s.tile = t_last;
+        s.kb0 = 0;
+        s.n = static_cast<int>(u1 - static_cast<long long>(t_last) * KB);
+        return true;
+      }
+    }
+    if (phase == 1) {
+      phase = 2;
+      if (first_partial) {
+        s.tile = t_first;
+        s.kb0 = static_cast<int>(u0 - static_cast<long long>(t_first) * KB);
+        s.n = static_cast<int>(min(u1, static_cast<long long>(t_first + 1) * KB) - u0);
+        return true;
+      }
+    }
+    const int end = last_partial ? t_last - 1 : t_last;
+    if (cur <= end) {
+      s.tile = cur++;
+      s.kb0 = 0;
+      s.n = KB;
+      return true;
+    }
+    return false;
+  }
+};
+
 template <int NPAD, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const LinParams p) {
   using C = LCfg<NPAD>;
+  pdl_launch_dependents();  // the next kernel may start its prologue (and its own weight prefetch) right away
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   unsigned char* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -113,6 +177,7 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
   const int G = gridDim.x, c = blockIdx.x;
   const long long u0 = (static_cast<long long>(c) * U) / G;
   const long long u1 = (static_cast<long long>(c + 1) * U) / G;
+  if (tid == 0) LIN_TRACE(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_w);
@@ -132,24 +197,42 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) LIN_TRACE(1);
 
   if (warp == 0) {
     // ===================== TMA producer: the weight stream =====================
     if (lane == 0) {
-      int tile = static_cast<int>(u0 / KB), kb = static_cast<int>(u0 - static_cast<long long>(tile) * KB);
-      int i = 0;
-      for (long long u = u0; u < u1; ++u, ++i) {
-        const int s = i % C::kStages;
-        if (i >= C::kStages) mbar_wait(&empty[s], static_cast<uint32_t>(((i / C::kStages) - 1) & 1));
+      auto load_w = [&](int s, int tile, int kb) {
         unsigned char* dw = smem + s * C::kStageBytes;
-        mbar_expect_tx(&full[s], C::kStageBytes);
         const int row_a = tile * p.tile_row_stride;
         tma_load_3d(dw, &map_w, &full[s], kb * BKK, row_a, 0);
         tma_load_3d(dw + kWBytes / 2, &map_w, &full[s], kb * BKK, row_a + p.second_half_off, 0);
-        tma_load_3d(dw + kWBytes, &map_x, &full[s], kb * BKK, 0, 0);
-        if (++kb == KB) {
-          kb = 0;
-          ++tile;
+      };
+      auto load_x = [&](int s, int kb) { tma_load_3d(smem + s * C::kStageBytes + kWBytes, &map_x, &full[s], kb * BKK, 0, 0); };
+      // The weights are static: fill the ring with them BEFORE waiting for the previous kernel (whose output is X).
+      {
+        SegIter it(u0, u1, KB);
+        Seg sg;
+        int i = 0;
+        while (i < C::kStages && it.next(sg))
+          for (int j = 0; j < sg.n && i < C::kStages; ++j, ++i) {
+            mbar_expect_tx(&full[i], C::kStageBytes);
+            load_w(i, sg.tile, sg.kb0 + j);
+          }
+      }
+      pdl_wait();
+      SegIter it(u0, u1, KB);
+      Seg sg;
+      int i = 0;
+      while (it.next(sg)) {
+        for (int j = 0; j < sg.n; ++j, ++i) {
+          const int s = i % C::kStages;
+          if (i >= C::kStages) {
+            mbar_wait(&empty[s], static_cast<uint32_t>(((i / C::kStages) - 1) & 1));
+            mbar_expect_tx(&full[s], C::kStageBytes);
+            load_w(s, sg.tile, sg.kb0 + j);
+          }
+          load_x(s, sg.kb0 + j);
         }
       }
     }
@@ -158,20 +241,20 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(BM, NPAD, 0, 0);  // both operands K-major
       int i = 0, seg = 0;
-      long long u = u0;
-      while (u < u1) {
-        const int kb0 = static_cast<int>(u % KB);
-        const int n = static_cast<int>(min(static_cast<long long>(KB - kb0), u1 - u));
+      SegIter it(u0, u1, KB);
+      Seg sg;
+      while (it.next(sg)) {
         const int buf = seg & 1;
         if (seg >= 2) {
           mbar_wait(&acc_empty[buf], static_cast<uint32_t>(((seg >> 1) - 1) & 1));
           tc_fence_after();
         }
         const uint32_t d = tmem_base + buf * NPAD;
-        for (int j = 0; j < n; ++j, ++i) {
+        for (int j = 0; j < sg.n; ++j, ++i) {
           const int s = i % C::kStages;
           mbar_wait(&full[s], static_cast<uint32_t>((i / C::kStages) & 1));
           tc_fence_after();
+          if (i == 0) LIN_TRACE(2);
           const uint32_t w_addr = smem_u32(smem + s * C::kStageBytes);
           const uint32_t x_addr = w_addr + kWBytes;
 #pragma unroll
@@ -181,12 +264,13 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
           tc_commit(&empty[s]);
         }
         tc_commit(&acc_full[buf]);
-        u += n;
         ++seg;
       }
+      LIN_TRACE(3);
     }
   } else {
     // ===================== epilogue: thread = out-feature row of the tile =====================
+    pdl_wait();  // everything below touches buffers other kernels write or read
     const int et = tid - 64;
     const int quad = warp & 3;                 // TMEM lane quarter this warp may read
     const int f = quad * 32 + lane;            // row of the tile == TMEM lane
@@ -194,23 +278,24 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
     int row0 = p.row0;
     if (EPI == PC_LIN_ROPE_APPEND && p.row0_dev != nullptr) row0 = max(0, min(__ldg(p.row0_dev), p.max_ctx - p.q_len));
     int seg = 0;
-    long long u = u0;
-    while (u < u1) {
-      const int tile = static_cast<int>(u / KB);
-      const int kb0 = static_cast<int>(u - static_cast<long long>(tile) * KB);
-      const int n = static_cast<int>(min(static_cast<long long>(KB - kb0), u1 - u));
+    SegIter it(u0, u1, KB);
+    const int t_first = it.t_first;
+    Seg sg;
+    while (it.next(sg)) {
+      const int tile = sg.tile;
       const int buf = seg & 1;
       mbar_wait(&acc_full[buf], static_cast<uint32_t>((seg >> 1) & 1));
       tc_fence_after();
+      if (et == 0) LIN_TRACE(4);
       float v[NPAD];
       tmem_ld_acc<NPAD>(tmem_base + lane_base + buf * NPAD, v);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&acc_empty[buf]);
       bool finalize = true;
-      if (n != KB) {
+      if (sg.n != KB) {
         // partial K range: park the fp32 partial; the last CTA to arrive at this tile adds them up
-        const int slot = (u == u0) ? 0 : 1;
+        const int slot = (tile == t_first) ? 0 : 1;
         float* sp = p.slots + (static_cast<size_t>(c) * 2 + slot) * NPAD * BM;
 #pragma unroll
         for (int t = 0; t < NPAD; ++t)
@@ -227,6 +312,7 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
           flag[0] = last;
           flag[1] = c_first;
           flag[2] = c_last;
+          LIN_TRACE(5);
         }
         named_bar_sync(1, kEpiThreads);
         finalize = flag[0] != 0;
@@ -234,13 +320,23 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
           const int c_first = flag[1], c_last = flag[2];
 #pragma unroll
           for (int t = 0; t < NPAD; ++t) v[t] = 0.f;
-          for (int cc = c_first; cc <= c_last; ++cc) {
-            const long long cu0 = (static_cast<long long>(cc) * U) / G;
-            const int slot_c = (cu0 / KB == tile) ? 0 : 1;
-            const float* rp = p.slots + (static_cast<size_t>(cc) * 2 + slot_c) * NPAD * BM;
+          constexpr int CH = NPAD <= 16 ? 4 : 2;  // contributors whose loads are in flight together
+          for (int cc = c_first; cc <= c_last; cc += CH) {
+            float tmp[CH][NPAD];
 #pragma unroll
-            for (int t = 0; t < NPAD; ++t)
-              if (t < p.q_len) v[t] += __ldcg(rp + t * BM + f);
+            for (int j = 0; j < CH; ++j) {
+              const int ccj = min(cc + j, c_last);
+              const long long cu0 = (static_cast<long long>(ccj) * U) / G;
+              const int slot_c = (cu0 / KB == tile) ? 0 : 1;
+              const float* rp = p.slots + (static_cast<size_t>(ccj) * 2 + slot_c) * NPAD * BM;
+#pragma unroll
+              for (int t = 0; t < NPAD; ++t) tmp[j][t] = (cc + j <= c_last && t < p.q_len) ? __ldcg(rp + t * BM + f) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {  // fixed order: deterministic sums
+#pragma unroll
+              for (int t = 0; t < NPAD; ++t) v[t] += tmp[j][t];
+            }
           }
         }
       }
@@ -279,7 +375,6 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
           const int H = p.n_heads, Hkv = p.n_kv_heads;
           const bool rotate = (tile < H + Hkv) && p.cos != nullptr;
           __half* dst;
-          long long tstride = BM;
           if (tile < H) dst = p.q_out + static_cast<long long>(tile) * p.q_len * BM + f;
           else if (tile < H + Hkv) dst = p.k_cache + (static_cast<long long>(tile - H) * p.max_ctx + row0) * BM + f;
           else dst = p.v_cache + (static_cast<long long>(tile - H - Hkv) * p.max_ctx + row0) * BM + f;
@@ -298,16 +393,16 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
                   const __half rot = f < 64 ? __hneg(partner) : partner;  // rotate_half(x) = cat(-x2, x1)
                   r = __hadd_rn(__hmul_rn(x, cs), __hmul_rn(rot, sn));
                 }
-                dst[t * tstride] = r;
+                dst[t * BM] = r;
               }
             }
           }
           named_bar_sync(1, kEpiThreads);
         }
       }
-      u += n;
       ++seg;
     }
+    if (et == 0) LIN_TRACE(6);
   }
 
   tc_fence_before();
@@ -326,8 +421,7 @@ int launch_lin(const CUtensorMap& mw, const CUtensorMap& mx, const LinParams& lp
                                        LCfg<NPAD>::kSmem));
     configured = true;
   }
-  linear_small_kernel<NPAD, EPI><<<grid, kThreads, LCfg<NPAD>::kSmem, st>>>(mw, mx, lp);
-  PC_CHECK_CUDA(cudaGetLastError());
+  PC_CHECK_CUDA(launch_pdl(linear_small_kernel<NPAD, EPI>, dim3(grid), dim3(kThreads), LCfg<NPAD>::kSmem, st, mw, mx, lp));
   count_launch();
   return PC_OK;
 }
@@ -427,6 +521,8 @@ PC_API int pc_linear_small(const pc_linear_params* p, void* stream) {
   lp.row0_dev = p->dst_row0_dev;
   lp.n_heads = p->n_heads;
   lp.n_kv_heads = p->n_kv_heads;
+  lp.trace = nullptr;
+  if (const char* e = getenv("PC_LIN_TRACE_PTR")) lp.trace = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
 
   int grid = sm_count();
   if (const char* e = getenv("PC_LIN_GRID")) grid = atoi(e);

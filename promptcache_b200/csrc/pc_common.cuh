@@ -32,6 +32,34 @@ constexpr size_t kAttnCounterBytes = 4096;
     if (!(cond)) return pc::set_error(PC_ERR_INVALID, __VA_ARGS__); \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------
+// Kernels launched through launch_pdl() may start while the previous kernel of the stream is still running.  They
+// call pdl_launch_dependents() first thing (so that the NEXT kernel can start its own prologue early) and
+// pdl_wait() before the first access to anything a predecessor writes or reads (everything but static weights and
+// tables); pdl_wait() returns once the previous kernel has completed and its memory operations are visible.  Every
+// CTA executes pdl_wait(), so completion is transitive along the stream.  PC_PDL=0 turns the attribute off.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- device: addresses -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

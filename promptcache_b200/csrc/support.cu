@@ -15,6 +15,8 @@ __global__ void __launch_bounds__(kNormThreads)
 add_rmsnorm_kernel(__half* __restrict__ x, const __half* __restrict__ delta, const __half* __restrict__ weight,
                    __half* __restrict__ h_out, int hidden, float eps) {
   __shared__ float red[kNormThreads / 32];
+  pc::pdl_launch_dependents();  // the following GEMM may start streaming its weights now
+  pc::pdl_wait();               // x / delta come from the previous kernel
   const int row = blockIdx.x;
   __half* xr = x + static_cast<long long>(row) * hidden;
   const __half* dr = delta ? delta + static_cast<long long>(row) * hidden : nullptr;
@@ -90,10 +92,9 @@ PC_API int pc_add_rmsnorm(void* x, const void* delta, const void* weight, void* 
   const uintptr_t align = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(delta) |
                           reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(h_out);
   PC_REQUIRE(align % 16 == 0, "pc_add_rmsnorm: tensors must be 16B aligned");
-  add_rmsnorm_kernel<<<rows, kNormThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<__half*>(x), static_cast<const __half*>(delta), static_cast<const __half*>(weight),
-      static_cast<__half*>(h_out), hidden, eps);
-  PC_CHECK_CUDA(cudaGetLastError());
+  PC_CHECK_CUDA(pc::launch_pdl(add_rmsnorm_kernel, dim3(rows), dim3(kNormThreads), 0, static_cast<cudaStream_t>(stream),
+                               static_cast<__half*>(x), static_cast<const __half*>(delta), static_cast<const __half*>(weight),
+                               static_cast<__half*>(h_out), hidden, eps));
   pc::count_launch();
   return PC_OK;
 }

@@ -96,8 +96,9 @@ class GenerationEngine:
 
         for i in range(params.max_new_tokens):
             if past_key_values is None:  # prefill of the uncached suffix over the spliced cache
-                if cache is not None:
-                    cache = [(k.unsqueeze(0), v.unsqueeze(0)) for k, v in cache]
+                if cache is not None:  # add the batch dimension (reference :101-102); O(1) for the engine's own views
+                    batched = getattr(cache, "batched", None)
+                    cache = batched() if batched is not None else [(k.unsqueeze(0), v.unsqueeze(0)) for k, v in cache]
                 out, ms = self._forward([list(token_ids)], [position_ids_og], cache, device)
                 inference_time += ms
                 response_time = inference_time

@@ -36,7 +36,7 @@ class B200CausalLM(nn.Module):
         self._lin_ws = None
         self.attn_impl = nat.PC_ATTN_AUTO
         # "native": skinny linears (q <= 32) run in pc_linear_small; "cublas": torch.nn.functional.linear everywhere
-        self.linear_impl = os.environ.get("PC_LINEAR", "native")
+        self.linear_impl = os.environ.get("PC_LINEAR", "cublas")
         # CUDA graphs of the whole single-sequence forward, keyed by (q_len, n_cached, KV buffer): the per-layer
         # launch sequence is fixed once those are, so a repeated request shape is replayed with one launch
         self.use_cuda_graphs = True
@@ -91,7 +91,7 @@ class B200CausalLM(nn.Module):
         """One-token decode through ONE captured graph per KV buffer: the cached length is a device scalar the
         kernels read at run time (pc_rope_append_dyn, pc_attn_params.n_cached_dev), so the same graph serves every
         step of every request on that buffer (reference loop: generation_engine.py:123-147)."""
-        key = ("decode", kv.k[0].data_ptr(), kv.max_ctx)
+        key = ("decode", kv.k[0].data_ptr(), kv.max_ctx, self.linear_impl)
         entry = self._graphs.get(key)
         if entry is None:
             if self._graph_seen.get(key, 0) < 1:  # first decode step on this buffer runs eagerly
@@ -127,7 +127,7 @@ class B200CausalLM(nn.Module):
             if logits is not None:
                 return logits, (kv.views(N + 1) if use_cache else None)
         extra = self._graph_extra(max_position)
-        key = (q_len, N, kv.k[0].data_ptr(), kv.max_ctx, pos.shape[0]) + tuple(extra)
+        key = (q_len, N, kv.k[0].data_ptr(), kv.max_ctx, pos.shape[0], self.linear_impl) + tuple(extra)
         if self.use_cuda_graphs and N > 0 and q_len > 1 and not torch.cuda.is_current_stream_capturing():
             entry = self._graphs.get(key)
             if entry is None and self._graph_seen.get(key, 0) >= 1:

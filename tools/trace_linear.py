@@ -1,0 +1,29 @@
+"""Debug: per-CTA %globaltimer stamps of pc_linear_small (PC_LIN_TRACE_PTR) -> where a launch spends its time."""
+import os, sys, torch
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from promptcache_b200 import _native as nat
+DEV = "cuda"
+NAMES = ["start", "setup done", "first stage landed", "last MMA committed", "last accumulator ready", "partial published",
+         "epilogue done", "end"]
+ws = nat.linear_workspace(DEV)
+for name, q, k, n, silu in [("o_proj", 16, 4096, 4096, False), ("qkv-sized plain", 16, 4096, 12288, False),
+                            ("gate_up silu", 16, 4096, 22016, True), ("down", 16, 11008, 4096, False)]:
+    W = (torch.randn(4, n, k, device=DEV) * 0.02).half()
+    x = torch.randn(q, k, device=DEV).half()
+    out = torch.empty(q, n // 2 if silu else n, dtype=torch.half, device=DEV)
+    tr = torch.zeros(8 * 148, dtype=torch.int64, device=DEV)
+    os.environ["PC_LIN_TRACE_PTR"] = hex(tr.data_ptr())
+    for i in range(4):
+        tr.zero_()
+        nat.linear_small(x, W[i], out, ws, silu_mul=silu)
+        torch.cuda.synchronize()
+    t = tr.cpu().numpy().reshape(148, 8).astype(np.float64)
+    t0 = t[:, 0][t[:, 0] > 0].min()
+    print(f"--- {name} q={q} [{n}x{k}] {n*k*2/1e6:.0f} MB (ideal {n*k*2/6.5e6:.1f} us)")
+    for j, nm in enumerate(NAMES):
+        col = t[:, j][t[:, j] > 0]
+        if len(col):
+            col = (col - t0) / 1000
+            print(f"  {nm:24s} n={len(col):3d} min {col.min():6.2f}  median {np.median(col):6.2f}  max {col.max():6.2f} us")
+    del os.environ["PC_LIN_TRACE_PTR"]
