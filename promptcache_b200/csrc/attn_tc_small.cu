@@ -213,8 +213,6 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  // barriers, TMEM and descriptors are ready; Q, the new K/V rows and the workspace come from the previous kernels
-  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + 2 * NPAD;
   if (tid == 0) PC_TRACE(1);  // setup done
@@ -222,11 +220,8 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   if (warp == kSoftmaxWarps) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_expect_tx(q_full, C::kQBytes);
-      for (int hf = 0; hf < 2; ++hf) tma_load_3d(sQ + hf * (NPAD * 128), &map_q, q_full, hf * 64, 0, hk);
-      for (int j = 0; j < T; ++j) {
+      auto load_kv = [&](int j) {
         const int s = j % kStages;
-        if (j >= kStages) mbar_wait(&kv_empty[s], static_cast<uint32_t>(((j / kStages) - 1) & 1));
         unsigned char* dk = sKV + (2 * s) * kTileBytes;
         unsigned char* dv = dk + kTileBytes;
         const int key0 = (tile0 + j) * BK;
@@ -234,6 +229,19 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         for (int hf = 0; hf < 2; ++hf) tma_load_3d(dk + hf * 16384, &map_k, &k_full[s], hf * 64, key0, hk);
         mbar_expect_tx(&v_full[s], kTileBytes);
         for (int hf = 0; hf < 2; ++hf) tma_load_3d(dv + hf * 16384, &map_v, &v_full[s], hf * 64, key0, hk);
+      };
+      // Programmatic dependent launch: this CTA may be running while the previous kernels of the step (the QKV
+      // projection, RoPE + append) are still in flight.  Rows [0, n_cached) of this layer's K/V were written before
+      // the forward began (splice, earlier forwards) and nothing inside a forward touches them, so tiles that lie
+      // entirely in them are streamed into the ring right away; Q and the tiles holding new rows wait.
+      int pre = 0;
+      while (pre < T && pre < kStages && (tile0 + pre + 1) * BK <= p.n_cached) load_kv(pre++);
+      pdl_wait();
+      mbar_expect_tx(q_full, C::kQBytes);
+      for (int hf = 0; hf < 2; ++hf) tma_load_3d(sQ + hf * (NPAD * 128), &map_q, q_full, hf * 64, 0, hk);
+      for (int j = pre; j < T; ++j) {
+        if (j >= kStages) mbar_wait(&kv_empty[j % kStages], static_cast<uint32_t>(((j / kStages) - 1) & 1));
+        load_kv(j);
       }
     }
   } else if (warp == kSoftmaxWarps + 1) {
@@ -277,6 +285,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
   } else {
     // ============ softmax (thread = key x half of the columns) / correction / epilogue (thread = d) ============
+    pdl_wait();  // everything these warps read (key positions) or write (out, partials, counters) belongs to the step
     constexpr int NH = NPAD / 2;
     const int quad = warp & 3, ch = warp >> 2;           // TMEM lane quarter, column half
     const int kl = quad * 32 + lane;                      // key within the tile == TMEM lane == output d

@@ -29,6 +29,8 @@ struct RopeParams {
 };
 
 __global__ void __launch_bounds__(128) rope_append_kernel(const RopeParams p) {
+  // let the attention kernel behind us start its prologue and stream the cached K/V tiles while we run
+  pc::pdl_launch_dependents();
   const int t = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int vh = blockIdx.y * 4 + warp;  // virtual head: [0,H) Q, [H,H+Hkv) K, [H+Hkv,H+2Hkv) V
