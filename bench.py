@@ -80,7 +80,8 @@ def attention_alone(nat, lm, case, dev, peak):
     ach = byts / (ms * 1e-3) / 1e9
     return {"kernel": "attn_small_kernel (pc_prefill_attn, one layer)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
             "frac": ach / peak, "traffic": load_traffic("attn_small_kernel", "C2"), "algorithmic_bytes_per_launch": byts,
-            "avg_launch_ms": ms, "timed": "alone, CUDA-graph of 16 launches over 8 layers of K/V (inputs > L2)",
+            "avg_launch_ms": ms, "timed": "alone, CUDA-graph of 16 back-to-back launches over 8 layers of K/V (inputs > L2); "
+            "launches carry the programmatic-dependent-launch attribute as in the step, so a launch's prologue overlaps its predecessor's tail",
             "note": "34 MB per launch = 5 us at peak: launch/prologue latency bound at this size; 0.66 of peak at C5 (135 MB)"}
 
 
