@@ -69,3 +69,81 @@ def test_oracle_forward_equals_reference_model(ref_engine):
     assert torch.equal(logits, ref.logits)
     for l in range(2):
         assert torch.equal(past[l][0], ref.past_key_values[l][0]) and torch.equal(past[l][1], ref.past_key_values[l][1])
+
+
+# ---- the reference's own example schemas (examples/*.xml; demo.py:54, eval_sys.py) --------------------------------
+EXAMPLES = ["code_generation_bookstore.xml", "parameterized_prompts.xml", "persona_generation.xml", "personalization-education.xml"]
+
+
+class _FmtLM:
+    """Tokenizer-only LanguageModel stand-in with the Llama-2 conversation formatter of either code base."""
+
+    unk_token_id, eos_token_id = 0, 2
+
+    def __init__(self, fmt):
+        self.tok, self.fmt = ref_shim.WordTokenizer(32000), fmt
+
+    def encode(self, text):
+        return self.tok.encode(text.decode() if isinstance(text, bytes) else text)
+
+    def decode(self, ids):
+        return self.tok.decode(ids)
+
+    def get_formatter(self):
+        return self.fmt
+
+
+def _walk(node, out):
+    """(kind, name, offset, length[, token ids]) of every node, depth first -- same traversal for both code bases."""
+    for c in node.children:
+        kind = type(c).__name__
+        if kind == "TokenSequence":
+            out.append(("T", c.offset, len(c), tuple(c.token_ids())))
+        elif kind == "Parameter":
+            out.append(("P", c.name, c.offset, c.length))
+        elif kind == "UnionModule":
+            out.append(("U", c.offset, len(c), c.scaffold_name))
+            for m in c.modules:
+                out.append(("M", m.name, m.offset, len(m)))
+                _walk(m, out)
+        else:
+            out.append(("M", c.name, c.offset, len(c)))
+            _walk(c, out)
+    return out
+
+
+@pytest.mark.parametrize("name", EXAMPLES)
+@pytest.mark.parametrize("max_tokens", [None, 800])  # demo.py:54 truncates modules to 800 tokens
+def test_example_schema_layout_equals_reference(name, max_tokens):
+    """Module tree, offsets, lengths, token ids, parameter slots and the default scaffold of the reference's example
+    schemas: identical in both front-ends (the position ids a schema assigns are what the splice and RoPE consume)."""
+    import os
+    ref_shim.load_reference()
+    from promptcache.model import FormatLlama2Conversation as RefFmt
+    from promptcache.schema import Schema as RefSchema
+    from promptcache_b200.model import FormatLlama2Conversation
+    from promptcache_b200.schema import Schema
+    text = open(os.path.join(ref_shim.REFERENCE_ROOT, "examples", name)).read()
+    ref = RefSchema(text, _FmtLM(RefFmt()), max_tokens=max_tokens)
+    ours = Schema(text, _FmtLM(FormatLlama2Conversation()), max_tokens=max_tokens)
+    assert ours.name == ref.name and len(ours) == len(ref)
+    a, b = _walk(ref, []), _walk(ours, [])
+    assert len(a) > 5 and a == b
+    rs, os_ = ref.get_scaffold(), ours.get_scaffold()
+    assert list(rs.token_ids()) == list(os_.token_ids()) and list(rs.position_ids()) == list(os_.position_ids())
+
+
+def test_malformed_example_is_parsed_tolerantly():
+    """examples/code_generation_game.xml (the schema demo.py loads) holds raw `<` in code and needs lxml's recover
+    mode (schema.py:285); the stdlib parser behind the reference shim rejects it, so only OUR tolerant front-end can be
+    exercised here: it must parse, keep every module and assign contiguous offsets."""
+    import os
+    from promptcache_b200.model import FormatLlama2Conversation
+    from promptcache_b200.schema import Schema
+    text = open(os.path.join(ref_shim.REFERENCE_ROOT, "examples", "code_generation_game.xml")).read()
+    s = Schema(text, _FmtLM(FormatLlama2Conversation()), max_tokens=800)
+    nodes = _walk(s, [])
+    assert s.name == "code-generation-game" and len(s) > 300
+    assert sum(1 for n in nodes if n[0] == "M") >= 5
+    pos = s.get_scaffold().position_ids()
+    assert list(pos) == sorted(pos) and len(set(pos)) == len(pos)
