@@ -124,11 +124,16 @@ def test_example_schema_layout_equals_reference(name, max_tokens):
     from promptcache_b200.model import FormatLlama2Conversation
     from promptcache_b200.schema import Schema
     text = open(os.path.join(ref_shim.REFERENCE_ROOT, "examples", name)).read()
-    ref = RefSchema(text, _FmtLM(RefFmt()), max_tokens=max_tokens)
-    ours = Schema(text, _FmtLM(FormatLlama2Conversation()), max_tokens=max_tokens)
+    # demo.py:46-54: the model's conversation formatter is applied to the file, then the schema is parsed
+    ref_text, our_text = RefFmt()(text), FormatLlama2Conversation()(text)
+    assert ref_text == our_text
+    ref = RefSchema(ref_text, _FmtLM(RefFmt()), max_tokens=max_tokens)
+    ours = Schema(our_text, _FmtLM(FormatLlama2Conversation()), max_tokens=max_tokens)
     assert ours.name == ref.name and len(ours) == len(ref)
     a, b = _walk(ref, []), _walk(ours, [])
-    assert len(a) > 5 and a == b
+    assert sum(1 for n in a if n[0] == "M") >= 2 and a == b
+    # the un-preprocessed file (conversation tags kept as literal text, schema.py:362-363) must agree as well
+    assert _walk(RefSchema(text, _FmtLM(None)), []) == _walk(Schema(text, _FmtLM(None)), [])
     rs, os_ = ref.get_scaffold(), ours.get_scaffold()
     assert list(rs.token_ids()) == list(os_.token_ids()) and list(rs.position_ids()) == list(os_.position_ids())
 
@@ -141,7 +146,7 @@ def test_malformed_example_is_parsed_tolerantly():
     from promptcache_b200.model import FormatLlama2Conversation
     from promptcache_b200.schema import Schema
     text = open(os.path.join(ref_shim.REFERENCE_ROOT, "examples", "code_generation_game.xml")).read()
-    s = Schema(text, _FmtLM(FormatLlama2Conversation()), max_tokens=800)
+    s = Schema(FormatLlama2Conversation()(text), _FmtLM(None), max_tokens=800)
     nodes = _walk(s, [])
     assert s.name == "code-generation-game" and len(s) > 300
     assert sum(1 for n in nodes if n[0] == "M") >= 5
