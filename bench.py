@@ -203,10 +203,11 @@ class CpuReference:
                       for _ in range(self.L)] for n in seg_lens]
         self.buf = O.new_prompt_cache(self.L, H, n_cached + 256, D)  # preallocated once, like PromptCache.__init__
         self.sd = O.random_llama_state_dict(dims["vocab"], hid, dims["inter"], sample_layers, H, H, seed=0, dtype=torch.float32)
-        self.cfg = dict(n_layers=sample_layers, n_heads=H, n_kv_heads=H, eps=1e-5, theta=10000.0, max_pos=4096)
+        rope_rows = max(4096, ((n_cached + q_len + 1023) // 1024) * 1024)  # grown on demand like llama2.py:141-142
+        self.cfg = dict(n_layers=sample_layers, n_heads=H, n_kv_heads=H, eps=1e-5, theta=10000.0, max_pos=rope_rows)
         self.ids = torch.randint(3, dims["vocab"], (1, q_len), generator=g)
         self.pos = torch.arange(n_cached, n_cached + q_len).unsqueeze(0)
-        self.cos, self.sin = O.rope_tables(D, 4096)
+        self.cos, self.sin = O.rope_tables(D, rope_rows)
 
     def step(self):
         O = self.O
@@ -258,7 +259,8 @@ METRIC = "Llama-2-7B prefill tok/s (served prompt tokens / TTFT; TTFT = ms_per_s
 
 
 def config_dict(args, case):
-    return {"workload": f"{args.config}: Llama-2-7B, {case.n_segments} cached segments = {case.n_cached} tokens, "
+    from promptcache_b200.synthetic import CONFIGS
+    return {"workload": f"{args.config}: {CONFIGS[args.config]['model']}, {case.n_segments} cached segments = {case.n_cached} tokens, "
                         f"{case.q_len}-token uncached suffix, one request per GPU per step",
             "n_cached": case.n_cached, "q_len": case.q_len, "segments": case.n_segments,
             "l2": "inputs larger than L2 (1 GiB of segments + 13.5 GB of weights stream per step)",
