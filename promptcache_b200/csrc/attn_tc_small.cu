@@ -135,7 +135,10 @@ __device__ __forceinline__ int reduced_column(int lane) {
   return (lane >> sh) & (N - 1);
 }
 
-template <int NPAD, int ROUND, bool ALIBI>
+// CLUSTER: the n_splits CTAs of a KV head form one thread-block cluster (n_splits <= 8) and the split-KV merge goes
+// through the leader's shared memory (two cluster barriers + DSMEM stores, ~1.5 us) instead of global partials, an
+// arrival counter and the last CTA's L2 round trips (~5 us of the 11 us kernel at the C2 shape).
+template <int NPAD, int ROUND, bool ALIBI, bool CLUSTER>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                   const __grid_constant__ CUtensorMap map_v, const SmallParams pin) {
@@ -177,10 +180,12 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   // With a run-time N the grid was sized for an upper bound: only the first min(n_splits, tiles) splits work, the
   // other CTAs leave before touching any barrier, TMEM or the arrival counter.
   if (p.n_splits > tiles_total) p.n_splits = tiles_total;
-  if (split >= p.n_splits) return;
-  const int tile0 = static_cast<int>(static_cast<long long>(split) * tiles_total / p.n_splits);
-  const int tile1 = static_cast<int>(static_cast<long long>(split + 1) * tiles_total / p.n_splits);
-  const int T = tile1 - tile0;  // >= 1
+  if (!CLUSTER && split >= p.n_splits) return;
+  // in a cluster every CTA has to reach the cluster barriers: surplus splits stay, with no tiles and an empty partial
+  const bool active = split < p.n_splits;
+  const int tile0 = active ? static_cast<int>(static_cast<long long>(split) * tiles_total / p.n_splits) : 0;
+  const int tile1 = active ? static_cast<int>(static_cast<long long>(split + 1) * tiles_total / p.n_splits) : 0;
+  const int T = tile1 - tile0;  // >= 1 for active splits
   if (tid == 0) PC_TRACE(0);
   if (tid == 0 && p.trace != nullptr) p.trace[64 + 2 * blockIdx.x] = gtime();  // per-CTA start
 
@@ -216,10 +221,19 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + 2 * NPAD;
   if (tid == 0) PC_TRACE(1);  // setup done
+  constexpr int NH = NPAD / 2;
+  // per-thread result of this split (softmax warps only): O^T element d = kl of NH columns, their maxima and sums
+  float o[NH], m_col[NH], l_col[NH];
+#pragma unroll
+  for (int i = 0; i < NH; ++i) {
+    o[i] = 0.f;
+    m_col[i] = -INFINITY;
+    l_col[i] = 0.f;
+  }
 
   if (warp == kSoftmaxWarps) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (lane == 0 && T > 0) {
       auto load_kv = [&](int j) {
         const int s = j % kStages;
         unsigned char* dk = sKV + (2 * s) * kTileBytes;
@@ -246,7 +260,7 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
   } else if (warp == kSoftmaxWarps + 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && T > 0) {
       constexpr uint32_t idesc_st = make_idesc_f16(BK, NPAD, 0, 0);  // S^T = K . Q^T, both K-major
       constexpr uint32_t idesc_pv = make_idesc_f16(D, NPAD, 1, 1);   // O^T = V^T . P^T, both MN-major
       const uint32_t q_addr = smem_u32(sQ);
@@ -286,18 +300,14 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   } else {
     // ============ softmax (thread = key x half of the columns) / correction / epilogue (thread = d) ============
     pdl_wait();  // everything these warps read (key positions) or write (out, partials, counters) belongs to the step
-    constexpr int NH = NPAD / 2;
     const int quad = warp & 3, ch = warp >> 2;           // TMEM lane quarter, column half
     const int kl = quad * 32 + lane;                      // key within the tile == TMEM lane == output d
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     const int c0 = ch * NH;                               // first column owned by this thread
     const int my_col = c0 + reduced_column<NH>(lane);     // column whose warp-reduction this lane ends up holding
-    float m_col[NH], l_part[NH];
+    float l_part[NH];
 #pragma unroll
-    for (int i = 0; i < NH; ++i) {
-      m_col[i] = -INFINITY;
-      l_part[i] = 0.f;
-    }
+    for (int i = 0; i < NH; ++i) l_part[i] = 0.f;
 
     for (int j = 0; j < T; ++j) {
       const int b = j & 1;
@@ -385,7 +395,6 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     named_bar_sync(1, kSoftmaxThreads);  // everyone is done reading `red` of the last tile
     if ((lane & (32 / NH - 1)) == 0) red[quad * NPAD + my_col] = lsum;
     named_bar_sync(1, kSoftmaxThreads);
-    float l_col[NH];
 #pragma unroll
     for (int i = 0; i < NH; ++i) {
       const int c = c0 + i;
@@ -393,15 +402,18 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
 
     // ---- epilogue: O^T (TMEM lane = d, column = query row) ----
-    float o[NH];
-    mbar_wait(&o_full[(T - 1) & 1], static_cast<uint32_t>(((T - 1) >> 1) & 1));
-    tc_fence_after();
-    if (tid == 0) PC_TRACE(2);  // last PV landed
-    tmem_ld_n<NH>(tmem_o + lane_base + c0, o);
-    tmem_ld_wait();
+    if (T > 0) {
+      mbar_wait(&o_full[(T - 1) & 1], static_cast<uint32_t>(((T - 1) >> 1) & 1));
+      tc_fence_after();
+      if (tid == 0) PC_TRACE(2);  // last PV landed
+      tmem_ld_n<NH>(tmem_o + lane_base + c0, o);
+      tmem_ld_wait();
+    }
     const int d = kl;
     const int HQ = p.n_heads * p.q_len;
-    if (p.n_splits == 1) {
+    if constexpr (CLUSTER) {
+      // the merge happens after the role branches, where every thread of the CTA can reach the cluster barriers
+    } else if (p.n_splits == 1) {
 #pragma unroll
       for (int i = 0; i < NH; ++i) {
         const int c = c0 + i;
@@ -485,6 +497,61 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
   }
 
+  if constexpr (CLUSTER) {
+    // ---- split-KV merge through the leader's shared memory (rank 0 of the cluster = split 0 of this KV head) ----
+    const int n_ranks = pin.n_splits;                       // launched cluster size; surplus ranks carry m = -inf
+    const bool smx = warp < kSoftmaxWarps;
+    const int quad = warp & 3, ch = (warp >> 2) & 1;
+    const int kl = quad * 32 + lane, c0 = ch * NH, d = kl;
+    // receive area in the K/V ring, free once a CTA's own MMAs are done: fp32 O^T [rank][column][d], (m, l) [rank][column]
+    const uint32_t recv_o = smem_u32(sKV);
+    const uint32_t recv_ml = recv_o + 8u * NPAD * D * 4u;
+    cluster_sync_all();  // A: every CTA of the cluster has finished its tiles -> the leader's ring may be overwritten
+    if (smx && split != 0) {
+      const uint32_t ro = cluster_map_shared(recv_o + (static_cast<uint32_t>(split) * NPAD + c0) * D * 4u + d * 4u, 0);
+#pragma unroll
+      for (int i = 0; i < NH; ++i) st_cluster_f32(ro + i * D * 4u, o[i]);
+#pragma unroll
+      for (int i = 0; i < NH; ++i)
+        if (kl == i) st_cluster_v2f32(cluster_map_shared(recv_ml + (static_cast<uint32_t>(split) * NPAD + c0 + i) * 8u, 0), m_col[i], l_col[i]);
+    }
+    if (smx && split == 0) {
+      float2* ml_own = reinterpret_cast<float2*>(sKV + 8 * NPAD * D * 4);
+#pragma unroll
+      for (int i = 0; i < NH; ++i)
+        if (kl == i) ml_own[c0 + i] = make_float2(m_col[i], l_col[i]);
+    }
+    cluster_sync_all();  // B: the partials have landed in the leader's shared memory
+    if (tid == 0) PC_TRACE(3);
+    if (smx && split == 0) {
+      const float2* ml_s = reinterpret_cast<const float2*>(sKV + 8 * NPAD * D * 4);  // [rank][NPAD]
+      const float* po = reinterpret_cast<const float*>(sKV);                           // [rank][NPAD][D]
+      float* wtab = red;                                                               // [rank][NPAD], 8*NPAD floats
+      if (tid < cols_valid) {  // weights w_s = 2^(m_s - m*) / sum_s 2^(m_s - m*) l_s  (same order as the global merge)
+        float m_star = -INFINITY;
+        for (int s = 0; s < n_ranks; ++s) m_star = fmaxf(m_star, ml_s[s * NPAD + tid].x);
+        float l = 0.f;
+        for (int s = 0; s < n_ranks; ++s) {
+          const float2 v = ml_s[s * NPAD + tid];
+          const float w = v.x == -INFINITY ? 0.f : exp2f(v.x - m_star);
+          l += w * v.y;
+          wtab[s * NPAD + tid] = w;
+        }
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+        for (int s = 0; s < n_ranks; ++s) wtab[s * NPAD + tid] *= inv;
+      }
+      named_bar_sync(1, kSoftmaxThreads);
+#pragma unroll
+      for (int i = 0; i < NH; ++i) {
+        const int c = c0 + i;
+        float acc = 0.f;
+        acc = fmaf(wtab[c], o[i], acc);
+        for (int s = 1; s < n_ranks; ++s) acc = fmaf(wtab[s * NPAD + c], po[(s * NPAD + c) * D + d], acc);
+        if (c < cols_valid) p.out[static_cast<long long>(otab[c]) * D + d] = __float2half_rn(acc);
+      }
+    }
+  }
+
   if (tid == 0) PC_TRACE(4);  // softmax group done (incl. merge if last)
   if (tid == 0 && p.trace != nullptr) p.trace[64 + 2 * blockIdx.x + 1] = gtime();  // per-CTA end
   tc_fence_before();
@@ -495,16 +562,46 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   }
 }
 
+// Can `clusters` clusters of `cluster_x` CTAs of this kernel be resident at once?  (A cluster lives inside one GPC; with
+// one 211 KB CTA per SM that is a placement question the occupancy API answers.)  Cached per cluster size.
+template <int NPAD, int ROUND, bool ALIBI>
+bool clusters_fit(int cluster_x, int clusters) {
+  static int max_active[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // 0 = not queried yet, -1 = query failed
+  if (cluster_x < 2 || cluster_x > 8) return false;
+  if (max_active[cluster_x] == 0) {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[2];
+    fill_launch_config(cfg, attr, dim3(cluster_x * 64), dim3(kThreads), SCfg<NPAD>::kSmem, nullptr, cluster_x);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, attn_small_kernel<NPAD, ROUND, ALIBI, true>, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      n = -1;
+    }
+    max_active[cluster_x] = n > 0 ? n : -1;
+  }
+  return max_active[cluster_x] >= clusters;
+}
+
 template <int NPAD, int ROUND, bool ALIBI>
 int launch_small_one(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const SmallParams& sp, int grid,
                      cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    PC_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<NPAD, ROUND, ALIBI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PC_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<NPAD, ROUND, ALIBI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       SCfg<NPAD>::kSmem));
+    PC_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<NPAD, ROUND, ALIBI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        SCfg<NPAD>::kSmem));
     configured = true;
   }
-  PC_CHECK_CUDA(launch_pdl(attn_small_kernel<NPAD, ROUND, ALIBI>, dim3(grid), dim3(kThreads), SCfg<NPAD>::kSmem, st, mq, mk, mv, sp));
+  const char* e = getenv("PC_ATTN_CLUSTER");
+  const bool want_cluster = sp.n_splits >= 2 && sp.n_splits <= 8 && !(e && e[0] == '0');
+  if (want_cluster && clusters_fit<NPAD, ROUND, ALIBI>(sp.n_splits, grid / sp.n_splits)) {
+    PC_CHECK_CUDA(launch_pdl_cluster(attn_small_kernel<NPAD, ROUND, ALIBI, true>, sp.n_splits, dim3(grid), dim3(kThreads),
+                                     SCfg<NPAD>::kSmem, st, mq, mk, mv, sp));
+  } else {
+    PC_CHECK_CUDA(launch_pdl(attn_small_kernel<NPAD, ROUND, ALIBI, false>, dim3(grid), dim3(kThreads), SCfg<NPAD>::kSmem, st, mq, mk,
+                             mv, sp));
+  }
   count_launch();
   return PC_OK;
 }

@@ -40,18 +40,41 @@ constexpr size_t kAttnCounterBytes = 4096;
 // CTA executes pdl_wait(), so completion is transitive along the stream.  PC_PDL=0 turns the attribute off.
 bool pdl_enabled();
 
-template <typename... KArgs, typename... Args>
-cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
-  cudaLaunchConfig_t cfg = {};
+inline void fill_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute (&attr)[2], dim3 grid, dim3 block, size_t smem,
+                               cudaStream_t st, int cluster_x) {
+  cfg = cudaLaunchConfig_t{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (cluster_x > 1) {  // thread-block cluster of `cluster_x` consecutive CTAs along x
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = static_cast<unsigned>(cluster_x);
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[2];
+  fill_launch_config(cfg, attr, grid, block, smem, st, 1);
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// Same, as clusters of `cluster_x` CTAs (distributed shared memory between the CTAs of a cluster).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), int cluster_x, dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                               Args... args) {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[2];
+  fill_launch_config(cfg, attr, grid, block, smem, st, cluster_x);
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
@@ -59,6 +82,23 @@ __device__ __forceinline__ void pdl_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ---- device: thread-block clusters / distributed shared memory -----------------------------------------
+__device__ __forceinline__ uint32_t cluster_map_shared(uint32_t smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_v2f32(uint32_t cluster_addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
+}
+// Every thread of every CTA of the cluster must call this the same number of times.
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 // ---- device: addresses -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

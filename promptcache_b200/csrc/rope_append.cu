@@ -31,6 +31,7 @@ struct RopeParams {
 __global__ void __launch_bounds__(128) rope_append_kernel(const RopeParams p) {
   // let the attention kernel behind us start its prologue and stream the cached K/V tiles while we run
   pc::pdl_launch_dependents();
+  pc::pdl_wait();  // the projections come from the previous kernel
   const int t = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int vh = blockIdx.y * 4 + warp;  // virtual head: [0,H) Q, [H,H+Hkv) K, [H+Hkv,H+2Hkv) V
@@ -134,8 +135,7 @@ static int rope_append_impl(const void* q_in, const void* k_in, const void* v_in
   p.q_len = q_len;
   const int vheads = n_heads + 2 * n_kv_heads;
   dim3 grid(q_len, (vheads + 3) / 4);
-  rope_append_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
-  PC_CHECK_CUDA(cudaGetLastError());
+  PC_CHECK_CUDA(pc::launch_pdl(rope_append_kernel, grid, dim3(128), 0, static_cast<cudaStream_t>(stream), p));
   pc::count_launch();
   return PC_OK;
 }

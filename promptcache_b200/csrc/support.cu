@@ -64,6 +64,8 @@ add_rmsnorm_kernel(__half* __restrict__ x, const __half* __restrict__ delta, con
 
 __global__ void __launch_bounds__(256)
 silu_mul_kernel(const __half* __restrict__ gate_up, __half* __restrict__ out, int inter, long long row_stride) {
+  pc::pdl_launch_dependents();
+  pc::pdl_wait();  // gate/up come from the previous kernel
   const int row = blockIdx.y;
   const int i = (blockIdx.x * 256 + threadIdx.x) * 8;
   if (i >= inter) return;
@@ -109,9 +111,9 @@ PC_API int pc_silu_mul(const void* gate_up, void* out, int rows, int inter, int6
              "pc_silu_mul: tensors must be 16B aligned");
   PC_REQUIRE(rows <= 65535, "pc_silu_mul: too many rows");
   dim3 grid((inter / 8 + 255) / 256, rows);
-  silu_mul_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(gate_up),
-                                                                       static_cast<__half*>(out), inter, row_stride);
-  PC_CHECK_CUDA(cudaGetLastError());
+  PC_CHECK_CUDA(pc::launch_pdl(silu_mul_kernel, grid, dim3(256), 0, static_cast<cudaStream_t>(stream),
+                               static_cast<const __half*>(gate_up), static_cast<__half*>(out), inter,
+                               static_cast<long long>(row_stride)));
   pc::count_launch();
   return PC_OK;
 }

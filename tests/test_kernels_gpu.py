@@ -314,3 +314,55 @@ def test_attention_runtime_length_equals_host_length(native):
         Q, K, V = _attn_case(H, Hkv, D, 200, 100, seed=1)
         native.attention(Q, K, V, torch.empty(200, H * D, dtype=torch.half, device=DEV), 100, 200, H, Hkv, D, 0.1, 3, workspace=ws,
                          n_cached_dev=torch.tensor([100], dtype=torch.int32, device=DEV))
+
+
+@pytest.mark.parametrize("H,Hkv,q,N", [
+    (32, 32, 16, 2048),   # C2: 4 splits per KV head -> clusters of 4
+    (32, 32, 1, 2064),    # decode
+    (32, 32, 32, 8192),   # C5, 32 columns
+    (40, 40, 32, 4096),   # C3: 3 splits
+    (20, 20, 7, 1500),    # 7 splits
+    (64, 32, 4, 900),     # GQA fold, 4 splits
+    (24, 24, 9, 300),     # fewer tiles (3) than SMs / heads (6): 3 splits
+])
+def test_attention_cluster_merge_equals_global_merge(native, monkeypatch, H, Hkv, q, N):
+    """Split-KV merge through the cluster leader's shared memory (DSMEM) vs through global partials + arrival counter:
+    same partials, same summation order -> the same bits; both within the north-star tolerance of the reference."""
+    D = 128
+    Q, K, V = _attn_case(H, Hkv, D, q, N, seed=H + q + N, std=1.28)
+    ws = torch.zeros(max(native.attn_workspace_bytes(H, q, D), 1), dtype=torch.uint8, device=DEV)
+    outs = []
+    for flag in ("1", "0", "1"):
+        monkeypatch.setenv("PC_ATTN_CLUSTER", flag)
+        out = torch.full((q, H * D), float("nan"), dtype=torch.half, device=DEV)
+        native.attention(Q, K, V, out, N, q, H, Hkv, D, native.softmax_scale(D), native.PC_ROUND_LLAMA, workspace=ws,
+                         impl=native.PC_ATTN_TCGEN05, decode=(q == 1))
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert _rel(outs[0], _oracle_llama(Q, K, V, N, q)) <= 1e-3
+    assert int(ws[:4096].view(torch.int32).abs().max()) == 0
+
+
+def test_attention_cluster_merge_with_runtime_length_and_surplus_ranks(native, monkeypatch):
+    """Run-time N (decode graph): the cluster is sized for the upper bound, ranks without tiles contribute an empty
+    partial instead of leaving early."""
+    H = Hkv = 32
+    D, max_ctx = 128, 1024  # upper bound: 8 tiles -> 4 splits per head
+    ws = torch.zeros(native.attn_workspace_bytes(H, 16, D), dtype=torch.uint8, device=DEV)
+    for q, N in [(1, 1000), (1, 130), (1, 5), (16, 300), (9, 1)]:
+        Q, K, V = _attn_case(H, Hkv, D, q, N, seed=N + 3)
+        K2 = torch.zeros(Hkv, max_ctx, D, dtype=torch.half, device=DEV)
+        V2 = torch.zeros_like(K2)
+        K2[:, :N + q], V2[:, :N + q] = K[:, :N + q], V[:, :N + q]
+        n_dev = torch.tensor([N], dtype=torch.int32, device=DEV)
+        res = {}
+        for flag in ("1", "0"):
+            monkeypatch.setenv("PC_ATTN_CLUSTER", flag)
+            out = torch.full((q, H * D), float("nan"), dtype=torch.half, device=DEV)
+            native.attention(Q, K2, V2, out, max_ctx - q, q, H, Hkv, D, native.softmax_scale(D), native.PC_ROUND_LLAMA,
+                             workspace=ws, n_cached_dev=n_dev, impl=native.PC_ATTN_TCGEN05)
+            torch.cuda.synchronize()
+            res[flag] = out
+        assert torch.equal(res["1"], res["0"])
+        assert _rel(res["1"], _oracle_llama(Q, K, V, N, q)) <= 1e-3
