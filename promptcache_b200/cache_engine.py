@@ -266,6 +266,7 @@ class CacheEngine:
                                         head_dim=head_dim, target_device=self.target_device)
         if hasattr(lm.hf_model, "ensure_rope"):
             lm.hf_model.ensure_rope(max_ctx_length)
+        self._events = None
         from .model import LanguageModel
         self._identity_hooks = all(getattr(getattr(lm, name, None), "__func__", None) is getattr(LanguageModel, name)
                                    for name in ("read_k_hook", "read_v_hook"))
@@ -344,8 +345,9 @@ class CacheEngine:
 
     def process(self, prompt: Prompt, no_cache: bool = False, return_full_position_ids: bool = False) -> Tuple[
             List[int], List[int], float, Optional[KVCache]]:
-        start = torch.cuda.Event(enable_timing=True)
-        end = torch.cuda.Event(enable_timing=True)
+        if self._events is None:  # one pair, reused: process() is synchronous
+            self._events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        start, end = self._events
         start.record()
         cached, used, orig_ids, orig_pos, input_ids, position_ids = self.plan(
             prompt, collect_original=no_cache or return_full_position_ids)
@@ -356,7 +358,7 @@ class CacheEngine:
             pairs = sorted(zip(all_pos, all_ids))
             sorted_ids = tuple(tok for _, tok in pairs)
             end.record()
-            torch.cuda.synchronize()
+            end.synchronize()
             # positions are renumbered 0..n-1 (reference :491-493)
             return sorted_ids, list(range(len(pairs))), start.elapsed_time(end), None
 
@@ -372,7 +374,7 @@ class CacheEngine:
         self.prompt_cache.update(seq_caches)
         cache = self.prompt_cache.cache
         end.record()
-        torch.cuda.synchronize()
+        end.synchronize()
         cache_time = start.elapsed_time(end)
         if not self._identity_hooks:  # the reference's hooks are identities (model/__init__.py:116-126)
             cache = [(self.lm.read_k_hook(k), self.lm.read_v_hook(v)) for k, v in cache]

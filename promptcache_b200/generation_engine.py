@@ -66,17 +66,23 @@ class GenerationEngine:
     def __init__(self, lm):
         self.lm = lm
         self.verbose = False
+        self._events = None  # one (start, end) pair, reused: the loop is synchronous
 
     def _forward(self, ids: List[List[int]], pos: List[List[int]], past, device):
         extra = {"max_position": max(pos[0])} if getattr(self.lm.hf_model, "accepts_max_position", False) else {}
-        input_ids = torch.tensor(ids, device=device, dtype=torch.long)
-        position_ids = torch.tensor(pos, device=device, dtype=torch.long)
-        start = torch.cuda.Event(enable_timing=True)
-        end = torch.cuda.Event(enable_timing=True)
+        if len(ids[0]) == len(pos[0]):  # one host->device copy for both id lists
+            both = torch.tensor([ids[0], pos[0]], device=device, dtype=torch.long)
+            input_ids, position_ids = both[0:1], both[1:2]
+        else:  # full position ids (MPT): cached + new positions
+            input_ids = torch.tensor(ids, device=device, dtype=torch.long)
+            position_ids = torch.tensor(pos, device=device, dtype=torch.long)
+        if self._events is None:
+            self._events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        start, end = self._events
         start.record()
         out = self.lm(input_ids=input_ids, position_ids=position_ids, past_key_values=past, use_cache=True, **extra)
         end.record()
-        torch.cuda.synchronize()
+        end.synchronize()
         return out, start.elapsed_time(end)
 
     @torch.inference_mode()
