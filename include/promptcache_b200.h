@@ -169,6 +169,10 @@ int pc_decode_attn(const pc_attn_params* p, void* stream);
 int pc_add_rmsnorm(void* x, const void* delta, const void* weight, void* h_out, int rows, int hidden,
                    float eps, void* stream);
 int pc_silu_mul(const void* gate_up, void* out, int rows, int inter, int64_t row_stride, void* stream);
+/* pc_add_rmsnorm whose delta is the sum of `n_splits` fp32 partials [split][rows][hidden] (PC_LIN_PARTIALS output),
+ * added in split order and rounded to fp16 once before the fp16 residual add. */
+int pc_add_rmsnorm_partials(void* x, const void* delta_partials, int n_splits, const void* weight, void* h_out, int rows,
+                            int hidden, float eps, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Skinny linear layers of the step: y = x . W^T for q_len <= 32 tokens,
@@ -189,6 +193,10 @@ int pc_silu_mul(const void* gate_up, void* out, int rows, int inter, int64_t row
 #define PC_LIN_PLAIN 0
 #define PC_LIN_SILU_MUL 1
 #define PC_LIN_ROPE_APPEND 2
+/* PARTIALS: regular split-K without an in-kernel reduction.  `out` is fp32 [pc_linear_partial_splits(n_rows, k)][q_len][n_rows]
+ * (out_stride == n_rows); the consumer adds the splits in order and rounds once -- pc_add_rmsnorm_partials does that
+ * for the o_proj / down_proj outputs, whose only consumer is the residual add (llama2.py:636,644).  No workspace use. */
+#define PC_LIN_PARTIALS 3
 
 typedef struct pc_linear_params {
   const void* x;
@@ -212,10 +220,18 @@ typedef struct pc_linear_params {
   const int32_t* dst_row0_dev;
   void* workspace;
   size_t workspace_bytes;
+  const void* w_tiled; /* optional: the same weights re-laid out by pc_linear_tile_weights (k % 128 == 0).  The kernel  *
+                        * then streams them with one 32 KiB bulk copy per pipeline stage instead of 128-byte-row     *
+                        * tensor-map boxes (an SM pulls ~2x more per second that way); `w` is still required.         */
 } pc_linear_params;
 
 size_t pc_linear_workspace_bytes(void);
+int pc_linear_partial_splits(int n_rows, int k);
 int pc_linear_small(const pc_linear_params* p, void* stream);
+/* One-off re-layout of w[n_rows][k] for `epilogue` into pc_linear_tiled_bytes(n_rows, k, epilogue) bytes at w_tiled:
+ * the [tile][k-block] sequence of 16 KiB shared-memory images (128 rows x 64 columns, 128B-swizzled) the kernel consumes. */
+size_t pc_linear_tiled_bytes(int n_rows, int k, int epilogue);
+int pc_linear_tile_weights(const void* w, int n_rows, int k, int epilogue, void* w_tiled, void* stream);
 
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 int64_t pc_launch_count(void);

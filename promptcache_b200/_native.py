@@ -27,10 +27,12 @@ PC_ATTN_TCGEN05 = 2
 
 EXPORTS = ("pc_version", "pc_last_error", "pc_device_info", "pc_splice_kv", "pc_splice_kv_tensors",
            "pc_rope_append", "pc_rope_append_dyn", "pc_attn_workspace_bytes", "pc_prefill_attn", "pc_decode_attn", "pc_launch_count",
-           "pc_add_rmsnorm", "pc_silu_mul", "pc_linear_workspace_bytes", "pc_linear_small")
+           "pc_add_rmsnorm", "pc_silu_mul", "pc_linear_workspace_bytes", "pc_linear_small",
+           "pc_linear_tiled_bytes", "pc_linear_tile_weights", "pc_linear_partial_splits", "pc_add_rmsnorm_partials")
 PC_LIN_PLAIN = 0
 PC_LIN_SILU_MUL = 1
 PC_LIN_ROPE_APPEND = 2
+PC_LIN_PARTIALS = 3
 
 
 class NativeError(RuntimeError):
@@ -65,7 +67,8 @@ class pc_linear_params(C.Structure):
                 ("table_rows", C.c_int32), ("max_ctx", C.c_int32),
                 ("q_out", C.c_void_p), ("k_cache", C.c_void_p), ("v_cache", C.c_void_p),
                 ("dst_row0", C.c_int32), ("n_heads", C.c_int32), ("n_kv_heads", C.c_int32), ("reserved", C.c_int32),
-                ("dst_row0_dev", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+                ("dst_row0_dev", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+                ("w_tiled", C.c_void_p)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -114,6 +117,15 @@ def load() -> C.CDLL:
     lib.pc_linear_workspace_bytes.restype = C.c_size_t
     lib.pc_linear_small.argtypes = [C.POINTER(pc_linear_params), C.c_void_p]
     lib.pc_linear_small.restype = C.c_int
+    lib.pc_linear_partial_splits.argtypes = [C.c_int, C.c_int]
+    lib.pc_linear_partial_splits.restype = C.c_int
+    lib.pc_add_rmsnorm_partials.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float,
+                                            C.c_void_p]
+    lib.pc_add_rmsnorm_partials.restype = C.c_int
+    lib.pc_linear_tiled_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.pc_linear_tiled_bytes.restype = C.c_size_t
+    lib.pc_linear_tile_weights.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.pc_linear_tile_weights.restype = C.c_int
     _lib = lib
     return lib
 
@@ -280,8 +292,17 @@ def attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, out
 
 def add_rmsnorm(x: torch.Tensor, delta: Optional[torch.Tensor], weight: torch.Tensor, h_out: torch.Tensor,
                 eps: float) -> None:
-    """x[rows,hidden] += delta (in place, fp16), h_out = RMSNorm(x) * weight."""
+    """x[rows,hidden] += delta (in place, fp16), h_out = RMSNorm(x) * weight.  An fp32 3-D `delta` is a stack of split-K
+    partials [splits, rows, hidden] (linear_partials): they are added in order and rounded to fp16 first."""
     _require_cuda(x, weight, h_out)
+    if delta is not None and delta.dtype == torch.float32:
+        rows, hidden = x.shape
+        if not (x.is_contiguous() and h_out.is_contiguous() and delta.is_contiguous()) or x.dtype != torch.float16 \
+                or delta.dim() != 3 or tuple(delta.shape[1:]) != (rows, hidden):
+            raise NativeError("add_rmsnorm: partials must be contiguous fp32 [splits, rows, hidden]")
+        _check(load().pc_add_rmsnorm_partials(x.data_ptr(), delta.data_ptr(), delta.shape[0], weight.data_ptr(), h_out.data_ptr(),
+                                              rows, hidden, float(eps), _stream()), "pc_add_rmsnorm_partials")
+        return
     if not (x.is_contiguous() and h_out.is_contiguous() and (delta is None or delta.is_contiguous())) or x.dtype != torch.float16:
         raise NativeError("add_rmsnorm: tensors must be contiguous fp16")
     rows, hidden = x.shape
@@ -303,8 +324,23 @@ def linear_workspace(device) -> torch.Tensor:
     return torch.zeros(int(load().pc_linear_workspace_bytes()), dtype=torch.uint8, device=device)
 
 
-def _linear_params(x: torch.Tensor, w: torch.Tensor, workspace: torch.Tensor, epilogue: int) -> pc_linear_params:
-    _require_cuda(x, w, workspace)
+def tile_weights(w: torch.Tensor, epilogue: int = PC_LIN_PLAIN) -> Optional[torch.Tensor]:
+    """Pre-tiled copy of an nn.Linear weight for pc_linear_small (None when k is not a multiple of 128)."""
+    _require_cuda(w)
+    if w.dim() != 2 or w.dtype != torch.float16 or not w.is_contiguous():
+        raise NativeError("tile_weights: w must be a contiguous fp16 [n, k] tensor")
+    n = int(load().pc_linear_tiled_bytes(w.shape[0], w.shape[1], epilogue))
+    if n == 0:
+        return None
+    out = torch.empty(n, dtype=torch.uint8, device=w.device)
+    _check(load().pc_linear_tile_weights(w.data_ptr(), w.shape[0], w.shape[1], epilogue, out.data_ptr(), _stream()),
+           "pc_linear_tile_weights")
+    return out
+
+
+def _linear_params(x: torch.Tensor, w: torch.Tensor, workspace: torch.Tensor, epilogue: int,
+                   w_tiled: Optional[torch.Tensor] = None) -> pc_linear_params:
+    _require_cuda(x, w, workspace, w_tiled)
     if x.dim() != 2 or w.dim() != 2 or x.dtype != torch.float16 or w.dtype != torch.float16 or not x.is_contiguous() \
             or not w.is_contiguous() or x.shape[1] != w.shape[1]:
         raise NativeError(f"linear_small: x {tuple(x.shape)} / w {tuple(w.shape)} must be contiguous fp16 [q,k] / [n,k]")
@@ -312,12 +348,17 @@ def _linear_params(x: torch.Tensor, w: torch.Tensor, workspace: torch.Tensor, ep
     p.x, p.w, p.x_stride = x.data_ptr(), w.data_ptr(), x.stride(0)
     p.q_len, p.k, p.n_rows, p.epilogue = x.shape[0], x.shape[1], w.shape[0], epilogue
     p.workspace, p.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    if w_tiled is not None:
+        if w_tiled.numel() * w_tiled.element_size() != int(load().pc_linear_tiled_bytes(w.shape[0], w.shape[1], epilogue)):
+            raise NativeError("linear_small: w_tiled does not belong to this weight / epilogue")
+        p.w_tiled = w_tiled.data_ptr()
     return p
 
 
-def linear_small(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, workspace: torch.Tensor, silu_mul: bool = False) -> None:
+def linear_small(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, workspace: torch.Tensor, silu_mul: bool = False,
+                 w_tiled: Optional[torch.Tensor] = None) -> None:
     """out[q, n] = x[q, k] @ w[n, k]^T  (q <= 32), or with `silu_mul` out[q, n/2] = silu(x @ w[:n/2]^T) * (x @ w[n/2:]^T)."""
-    p = _linear_params(x, w, workspace, PC_LIN_SILU_MUL if silu_mul else PC_LIN_PLAIN)
+    p = _linear_params(x, w, workspace, PC_LIN_SILU_MUL if silu_mul else PC_LIN_PLAIN, w_tiled)
     _require_cuda(out)
     cols = w.shape[0] // 2 if silu_mul else w.shape[0]
     if out.dim() != 2 or out.dtype != torch.float16 or out.stride(1) != 1 or out.shape[0] != x.shape[0] or out.shape[1] != cols:
@@ -328,9 +369,10 @@ def linear_small(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, workspace:
 
 def linear_rope_append(x: torch.Tensor, wqkv: torch.Tensor, position_ids: Optional[torch.Tensor], cos: Optional[torch.Tensor],
                        sin: Optional[torch.Tensor], q_out: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor,
-                       dst_row0, n_heads: int, n_kv_heads: int, workspace: torch.Tensor) -> None:
+                       dst_row0, n_heads: int, n_kv_heads: int, workspace: torch.Tensor,
+                       w_tiled: Optional[torch.Tensor] = None) -> None:
     """Fused QKV projection + RoPE at `position_ids` + in-place KV append (head_dim 128 only).  Arguments as rope_append."""
-    p = _linear_params(x, wqkv, workspace, PC_LIN_ROPE_APPEND)
+    p = _linear_params(x, wqkv, workspace, PC_LIN_ROPE_APPEND, w_tiled)
     _require_cuda(q_out, k_cache, v_cache)
     D = 128
     if k_cache.stride(2) != 1 or k_cache.stride(1) != D or k_cache.stride(0) != v_cache.stride(0) or not q_out.is_contiguous():
@@ -353,3 +395,21 @@ def linear_rope_append(x: torch.Tensor, wqkv: torch.Tensor, position_ids: Option
         p.dst_row0 = int(dst_row0)
     _check(load().pc_linear_small(C.byref(p), _stream()), "pc_linear_small")
 
+
+
+def linear_partial_splits(n_rows: int, k: int) -> int:
+    return int(load().pc_linear_partial_splits(int(n_rows), int(k)))
+
+
+def linear_partials(x: torch.Tensor, w: torch.Tensor, part: torch.Tensor, workspace: torch.Tensor,
+                    w_tiled: Optional[torch.Tensor] = None) -> int:
+    """part[s, q, n] (fp32) = split-K partials of x @ w^T, s < linear_partial_splits(n, k); the consumer adds them
+    (add_rmsnorm(..., partials=part)).  Returns the number of splits written."""
+    p = _linear_params(x, w, workspace, PC_LIN_PARTIALS, w_tiled)
+    _require_cuda(part)
+    splits = linear_partial_splits(w.shape[0], w.shape[1])
+    if part.dtype != torch.float32 or not part.is_contiguous() or tuple(part.shape) != (splits, x.shape[0], w.shape[0]):
+        raise NativeError(f"linear_partials: part {tuple(part.shape)} must be contiguous fp32 [{splits},{x.shape[0]},{w.shape[0]}]")
+    p.out, p.out_stride = part.data_ptr(), w.shape[0]
+    _check(load().pc_linear_small(C.byref(p), _stream()), "pc_linear_small")
+    return splits

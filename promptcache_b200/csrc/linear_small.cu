@@ -37,15 +37,18 @@ constexpr int BM = 128;                 // out-features per tile (MMA M)
 constexpr int BKK = 64;                 // k per stage: one 128-byte swizzled row
 constexpr int kWBytes = BM * BKK * 2;   // 16 KiB
 constexpr int kEpiThreads = 128;
-constexpr int kThreads = 64 + kEpiThreads;  // TMA warp + MMA warp + 4 epilogue warps
+constexpr int kThreads = 64 + kEpiThreads + 32;  // W-TMA warp + MMA warp + 4 epilogue warps + X-TMA warp
 constexpr size_t kLinCounterBytes = 16384;  // 4096 tile arrival counters
 constexpr int kMaxTiles = 4096;
 
-template <int NPAD>
+// KPS = k-blocks per pipeline stage: 1 with tensor-map loads of the row-major weight, 2 with pre-tiled weights (one
+// 32 KiB bulk copy per stage).
+template <int NPAD, int KPS>
 struct LCfg {
   static constexpr int kXBytes = NPAD * BKK * 2;
-  static constexpr int kStageBytes = kWBytes + kXBytes;
-  static constexpr int kStages = NPAD <= 16 ? 11 : 10;
+  static constexpr int kStageBytes = KPS * (kWBytes + kXBytes);
+  // bytes in flight per SM bound its streaming rate (Little's law, ~2.5 us loaded latency): as many stages as fit
+  static constexpr int kStages = KPS == 2 ? (NPAD <= 16 ? 6 : 5) : (NPAD <= 16 ? 11 : 10);
   static constexpr int kOffExch = kStages * kStageBytes;
   static constexpr int kExchBytes = NPAD * BM * 2;
   static constexpr int kOffBars = kOffExch + kExchBytes;
@@ -60,6 +63,10 @@ struct LinParams {
   int* counters;
   int n_out;             // valid output columns (PLAIN: weight rows; SILU: inter)
   int q_len, kb_total, tile_row_stride, second_half_off;
+  int w_one_box;         // the weight tile is 128 consecutive rows: one TMA box instead of two
+  const unsigned char* w_tiled;  // TILED: weights re-laid out as [tile][k-block] 16 KiB shared-memory images
+  int splits;            // PARTIALS: regular split-K, CTA = (tile, split); fp32 partials go to part_out[split][t][col]
+  float* part_out;
   long long units_total;
   // RoPE + append epilogue
   const long long* pos;
@@ -154,10 +161,11 @@ struct SegIter {
   }
 };
 
-template <int NPAD, int EPI>
+template <int NPAD, int EPI, bool TILED>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const LinParams p) {
-  using C = LCfg<NPAD>;
+  constexpr int KPS = TILED ? 2 : 1;
+  using C = LCfg<NPAD, KPS>;
   pdl_launch_dependents();  // the next kernel may start its prologue (and its own weight prefetch) right away
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -172,18 +180,23 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
   int* flag = reinterpret_cast<int*>(tmem_slot + 1);  // [3]: last arriver?, first / last contributing CTA
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int KB = p.kb_total;
+  const int KB = p.kb_total / KPS;  // pipeline stages (units) per tile
   const long long U = p.units_total;
   const int G = gridDim.x, c = blockIdx.x;
-  const long long u0 = (static_cast<long long>(c) * U) / G;
-  const long long u1 = (static_cast<long long>(c + 1) * U) / G;
+  long long u0 = (static_cast<long long>(c) * U) / G;
+  long long u1 = (static_cast<long long>(c + 1) * U) / G;
+  if constexpr (EPI == PC_LIN_PARTIALS) {  // regular split-K: every tile is cut into `splits` equal K ranges
+    const int tile_c = c / p.splits, sp = c - tile_c * p.splits;
+    u0 = static_cast<long long>(tile_c) * KB + (static_cast<long long>(sp) * KB) / p.splits;
+    u1 = static_cast<long long>(tile_c) * KB + (static_cast<long long>(sp + 1) * KB) / p.splits;
+  }
   if (tid == 0) LIN_TRACE(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_w);
     tma_prefetch_desc(&map_x);
     for (int s = 0; s < C::kStages; ++s) {
-      mbar_init(&full[s], 1);
+      mbar_init(&full[s], 2);  // the weight producer and the X producer each arrive once (with their byte counts)
       mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -202,24 +215,35 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
   if (warp == 0) {
     // ===================== TMA producer: the weight stream =====================
     if (lane == 0) {
-      auto load_w = [&](int s, int tile, int kb) {
-        unsigned char* dw = smem + s * C::kStageBytes;
-        const int row_a = tile * p.tile_row_stride;
-        tma_load_3d(dw, &map_w, &full[s], kb * BKK, row_a, 0);
-        tma_load_3d(dw + kWBytes / 2, &map_w, &full[s], kb * BKK, row_a + p.second_half_off, 0);
-      };
-      auto load_x = [&](int s, int kb) { tma_load_3d(smem + s * C::kStageBytes + kWBytes, &map_x, &full[s], kb * BKK, 0, 0); };
-      // The weights are static: fill the ring with them BEFORE waiting for the previous kernel (whose output is X).
-      {
-        SegIter it(u0, u1, KB);
-        Seg sg;
-        int i = 0;
-        while (i < C::kStages && it.next(sg))
-          for (int j = 0; j < sg.n && i < C::kStages; ++j, ++i) {
-            mbar_expect_tx(&full[i], C::kStageBytes);
-            load_w(i, sg.tile, sg.kb0 + j);
+      // One TMA instruction costs this thread ~110 ns whatever its size, so the weight tile travels as ONE 128-row box
+      // when its rows are consecutive, and the X tiles are issued by a thread of their own (warp 6).  The weights are
+      // static: the ring is filled with them without waiting for the previous kernel (whose output is X).
+      SegIter it(u0, u1, KB);
+      Seg sg;
+      int i = 0;
+      while (it.next(sg)) {
+        for (int j = 0; j < sg.n; ++j, ++i) {
+          const int s = i % C::kStages;
+          if (i >= C::kStages) mbar_wait(&empty[s], static_cast<uint32_t>(((i / C::kStages) - 1) & 1));
+          unsigned char* dw = smem + s * C::kStageBytes;
+          const int row_a = sg.tile * p.tile_row_stride, k0 = (sg.kb0 + j) * BKK;
+          mbar_expect_tx(&full[s], KPS * kWBytes);
+          if constexpr (TILED) {
+            // the stage's weights are ONE contiguous 32 KiB block of the pre-tiled copy: a single 1-D bulk load
+            bulk_g2s(dw, p.w_tiled + (static_cast<long long>(sg.tile) * KB + sg.kb0 + j) * (KPS * kWBytes), KPS * kWBytes, &full[s]);
+          } else if (p.w_one_box) {
+            tma_load_3d(dw, &map_w, &full[s], k0, row_a, 0);
+          } else {
+            tma_load_3d(dw, &map_w, &full[s], k0, row_a, 0);
+            tma_load_3d(dw + kWBytes / 2, &map_w, &full[s], k0, row_a + p.second_half_off, 0);
           }
+        }
       }
+      pdl_wait();  // every CTA waits at least once: completion stays transitive along the stream
+    }
+  } else if (warp == 6) {
+    // ===================== TMA producer: the X tiles (output of the previous kernel) =====================
+    if (lane == 0) {
       pdl_wait();
       SegIter it(u0, u1, KB);
       Seg sg;
@@ -227,12 +251,12 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
       while (it.next(sg)) {
         for (int j = 0; j < sg.n; ++j, ++i) {
           const int s = i % C::kStages;
-          if (i >= C::kStages) {
-            mbar_wait(&empty[s], static_cast<uint32_t>(((i / C::kStages) - 1) & 1));
-            mbar_expect_tx(&full[s], C::kStageBytes);
-            load_w(s, sg.tile, sg.kb0 + j);
-          }
-          load_x(s, sg.kb0 + j);
+          if (i >= C::kStages) mbar_wait(&empty[s], static_cast<uint32_t>(((i / C::kStages) - 1) & 1));
+          mbar_expect_tx(&full[s], KPS * C::kXBytes);
+#pragma unroll
+          for (int sb = 0; sb < KPS; ++sb)
+            tma_load_3d(smem + s * C::kStageBytes + KPS * kWBytes + sb * C::kXBytes, &map_x, &full[s],
+                        ((sg.kb0 + j) * KPS + sb) * BKK, 0, 0);
         }
       }
     }
@@ -256,11 +280,14 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
           tc_fence_after();
           if (i == 0) LIN_TRACE(2);
           const uint32_t w_addr = smem_u32(smem + s * C::kStageBytes);
-          const uint32_t x_addr = w_addr + kWBytes;
+          const uint32_t x_addr = w_addr + KPS * kWBytes;
 #pragma unroll
-          for (int kk = 0; kk < BKK / 16; ++kk)
-            umma_ss(d, make_smem_desc(w_addr + kk * 32, 16, 1024, 2), make_smem_desc(x_addr + kk * 32, 16, 1024, 2), idesc,
-                    (j > 0 || kk > 0) ? 1u : 0u);
+          for (int sb = 0; sb < KPS; ++sb) {
+#pragma unroll
+            for (int kk = 0; kk < BKK / 16; ++kk)
+              umma_ss(d, make_smem_desc(w_addr + sb * kWBytes + kk * 32, 16, 1024, 2),
+                      make_smem_desc(x_addr + sb * C::kXBytes + kk * 32, 16, 1024, 2), idesc, (j > 0 || sb > 0 || kk > 0) ? 1u : 0u);
+          }
           tc_commit(&empty[s]);
         }
         tc_commit(&acc_full[buf]);
@@ -293,7 +320,17 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
       tc_fence_before();
       mbar_arrive(&acc_empty[buf]);
       bool finalize = true;
-      if (sg.n != KB) {
+      if constexpr (EPI == PC_LIN_PARTIALS) {
+        // no cross-CTA reduction here: the consumer (pc_add_rmsnorm_partials) adds the splits in a fixed order
+        finalize = false;
+        const int col = tile * BM + f;
+        float* po = p.part_out + static_cast<long long>(c - (c / p.splits) * p.splits) * p.q_len * p.n_out + col;
+        if (col < p.n_out) {
+#pragma unroll
+          for (int t = 0; t < NPAD; ++t)
+            if (t < p.q_len) po[static_cast<long long>(t) * p.n_out] = v[t];
+        }
+      } else if (sg.n != KB) {
         // partial K range: park the fp32 partial; the last CTA to arrive at this tile adds them up
         const int slot = (tile == t_first) ? 0 : 1;
         float* sp = p.slots + (static_cast<size_t>(c) * 2 + slot) * NPAD * BM;
@@ -341,7 +378,7 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
         }
       }
       if (finalize) {
-        if constexpr (EPI == PC_LIN_PLAIN) {
+        if constexpr (EPI == PC_LIN_PLAIN || EPI == PC_LIN_PARTIALS) {
           const int col = tile * BM + f;
           if (col < p.n_out) {
 #pragma unroll
@@ -379,22 +416,30 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
           else if (tile < H + Hkv) dst = p.k_cache + (static_cast<long long>(tile - H) * p.max_ctx + row0) * BM + f;
           else dst = p.v_cache + (static_cast<long long>(tile - H - Hkv) * p.max_ctx + row0) * BM + f;
           if (tile < H + 2 * Hkv) {
+            if (rotate) {
+              // all table gathers first (independent loads in flight together), then the arithmetic
+              __half cs[NPAD], sn[NPAD];
 #pragma unroll
-            for (int t = 0; t < NPAD; ++t) {
-              if (t < p.q_len) {
-                const __half x = exch[t * BM + f];
-                __half r = x;
-                if (rotate) {
-                  long long pos = __ldg(p.pos + t);
-                  if (pos < 0) pos = 0;
-                  if (pos >= p.table_rows) pos = p.table_rows - 1;
-                  const __half cs = p.cos[pos * BM + f], sn = p.sin[pos * BM + f];
+              for (int t = 0; t < NPAD; ++t) {
+                long long pos = t < p.q_len ? __ldg(p.pos + t) : 0;
+                if (pos < 0) pos = 0;
+                if (pos >= p.table_rows) pos = p.table_rows - 1;
+                cs[t] = __ldg(p.cos + pos * BM + f);
+                sn[t] = __ldg(p.sin + pos * BM + f);
+              }
+#pragma unroll
+              for (int t = 0; t < NPAD; ++t) {
+                if (t < p.q_len) {
+                  const __half x = exch[t * BM + f];
                   const __half partner = exch[t * BM + (f ^ 64)];
                   const __half rot = f < 64 ? __hneg(partner) : partner;  // rotate_half(x) = cat(-x2, x1)
-                  r = __hadd_rn(__hmul_rn(x, cs), __hmul_rn(rot, sn));
+                  dst[t * BM] = __hadd_rn(__hmul_rn(x, cs[t]), __hmul_rn(rot, sn[t]));
                 }
-                dst[t * BM] = r;
               }
+            } else {
+#pragma unroll
+              for (int t = 0; t < NPAD; ++t)
+                if (t < p.q_len) dst[t * BM] = exch[t * BM + f];
             }
           }
           named_bar_sync(1, kEpiThreads);
@@ -413,30 +458,125 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
   }
 }
 
-template <int NPAD, int EPI>
+template <int NPAD, int EPI, bool TILED>
 int launch_lin(const CUtensorMap& mw, const CUtensorMap& mx, const LinParams& lp, int grid, cudaStream_t st) {
+  using C = LCfg<NPAD, TILED ? 2 : 1>;
   static bool configured = false;
   if (!configured) {
-    PC_CHECK_CUDA(cudaFuncSetAttribute(linear_small_kernel<NPAD, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       LCfg<NPAD>::kSmem));
+    PC_CHECK_CUDA(cudaFuncSetAttribute(linear_small_kernel<NPAD, EPI, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
     configured = true;
   }
-  PC_CHECK_CUDA(launch_pdl(linear_small_kernel<NPAD, EPI>, dim3(grid), dim3(kThreads), LCfg<NPAD>::kSmem, st, mw, mx, lp));
+  PC_CHECK_CUDA(launch_pdl(linear_small_kernel<NPAD, EPI, TILED>, dim3(grid), dim3(kThreads), C::kSmem, st, mw, mx, lp));
   count_launch();
   return PC_OK;
 }
 
-template <int NPAD>
+template <int NPAD, bool TILED>
 int launch_lin_n(int epi, const CUtensorMap& mw, const CUtensorMap& mx, const LinParams& lp, int grid, cudaStream_t st) {
   switch (epi) {
-    case PC_LIN_PLAIN: return launch_lin<NPAD, PC_LIN_PLAIN>(mw, mx, lp, grid, st);
-    case PC_LIN_SILU_MUL: return launch_lin<NPAD, PC_LIN_SILU_MUL>(mw, mx, lp, grid, st);
-    default: return launch_lin<NPAD, PC_LIN_ROPE_APPEND>(mw, mx, lp, grid, st);
+    case PC_LIN_PLAIN: return launch_lin<NPAD, PC_LIN_PLAIN, TILED>(mw, mx, lp, grid, st);
+    case PC_LIN_SILU_MUL: return launch_lin<NPAD, PC_LIN_SILU_MUL, TILED>(mw, mx, lp, grid, st);
+    case PC_LIN_PARTIALS: return launch_lin<NPAD, PC_LIN_PARTIALS, TILED>(mw, mx, lp, grid, st);
+    default: return launch_lin<NPAD, PC_LIN_ROPE_APPEND, TILED>(mw, mx, lp, grid, st);
+  }
+}
+
+// One-off re-layout of a weight matrix into the [tile][k-block] sequence of 16 KiB shared-memory images the kernel's
+// pipeline consumes (128 rows x 64 columns, 128B-swizzled K-major, exactly what the tensor-map load produces -- it IS
+// produced by that load here and written back verbatim).
+__global__ void __launch_bounds__(32) tile_weights_kernel(const __grid_constant__ CUtensorMap map_w, unsigned char* __restrict__ out,
+                                                          long long units, int kb_total, int tile_row_stride, int second_half_off) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  unsigned char* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kWBytes);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    uint32_t phase = 0;
+    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+      const int tile = static_cast<int>(u / kb_total), kb = static_cast<int>(u - static_cast<long long>(tile) * kb_total);
+      const int row_a = tile * tile_row_stride;
+      mbar_expect_tx(bar, kWBytes);
+      tma_load_3d(smem, &map_w, bar, kb * BKK, row_a, 0);
+      tma_load_3d(smem + kWBytes / 2, &map_w, bar, kb * BKK, row_a + second_half_off, 0);
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      bulk_s2g(out + u * kWBytes, smem, kWBytes);
+      bulk_commit();
+      bulk_wait_read<0>();  // the buffer is re-filled by the next load
+    }
+    bulk_wait_all<0>();
+  }
+}
+
+struct TileGeom {
+  int n_tiles, tile_row_stride, second_half_off;
+};
+
+int tile_geometry(int n_rows, int epilogue, TileGeom* g) {
+  switch (epilogue) {
+    case PC_LIN_PLAIN:
+    case PC_LIN_PARTIALS:
+    case PC_LIN_ROPE_APPEND:
+      g->n_tiles = (n_rows + BM - 1) / BM;
+      g->tile_row_stride = BM;
+      g->second_half_off = 64;
+      return PC_OK;
+    case PC_LIN_SILU_MUL:
+      if (n_rows % 128 != 0) return set_error(PC_ERR_INVALID, "pc_linear(silu_mul): n_rows %d must be 2 * a multiple of 64", n_rows);
+      g->n_tiles = n_rows / 128;
+      g->tile_row_stride = 64;
+      g->second_half_off = n_rows / 2;
+      return PC_OK;
+    default:
+      return set_error(PC_ERR_INVALID, "pc_linear: unknown epilogue %d", epilogue);
   }
 }
 
 }  // namespace
 }  // namespace pc
+
+PC_API size_t pc_linear_tiled_bytes(int n_rows, int k, int epilogue) {
+  pc::TileGeom g;
+  if (n_rows <= 0 || k <= 0 || k % 128 != 0 || pc::tile_geometry(n_rows, epilogue, &g) != PC_OK) return 0;
+  return static_cast<size_t>(g.n_tiles) * (k / pc::BKK) * pc::kWBytes;
+}
+
+PC_API int pc_linear_tile_weights(const void* w, int n_rows, int k, int epilogue, void* w_tiled, void* stream) {
+  using namespace pc;
+  PC_REQUIRE(w && w_tiled, "pc_linear_tile_weights: null pointer");
+  PC_REQUIRE(n_rows > 0 && k > 0 && k % 128 == 0, "pc_linear_tile_weights: k %d must be a positive multiple of 128", k);
+  PC_REQUIRE((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(w_tiled)) % 16 == 0, "pc_linear_tile_weights: 16B alignment");
+  TileGeom g;
+  if (int rc = tile_geometry(n_rows, epilogue, &g)) return rc;
+  CUtensorMap mw;
+  if (int rc = make_tensor_map_3d(&mw, w, k, n_rows, 1, static_cast<long long>(n_rows) * k, 64)) return rc;
+  const int kb_total = k / BKK;
+  const long long units = static_cast<long long>(g.n_tiles) * kb_total;
+  static bool configured = false;
+  if (!configured) {
+    PC_CHECK_CUDA(cudaFuncSetAttribute(tile_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWBytes + 2048));
+    configured = true;
+  }
+  int grid = sm_count() * 8;
+  if (grid > units) grid = static_cast<int>(units);
+  tile_weights_kernel<<<grid, 32, kWBytes + 2048, static_cast<cudaStream_t>(stream)>>>(mw, static_cast<unsigned char*>(w_tiled), units,
+                                                                                       kb_total, g.tile_row_stride, g.second_half_off);
+  PC_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return PC_OK;
+}
+
+PC_API int pc_linear_partial_splits(int n_rows, int k) {
+  if (n_rows <= 0 || k <= 0) return 0;
+  const int n_tiles = (n_rows + pc::BM - 1) / pc::BM;
+  int s = pc::sm_count() / n_tiles;  // as many CTAs per row tile as fit at once ...
+  if (s > 8) s = 8;
+  if (s > k / 128) s = k / 128;      // ... with at least one pipeline stage (128 columns) each
+  if (s < 1) s = 1;
+  return s;
+}
 
 PC_API size_t pc_linear_workspace_bytes(void) {
   return pc::kLinCounterBytes + static_cast<size_t>(pc::sm_count()) * 2 * 32 * pc::BM * sizeof(float);
@@ -459,6 +599,9 @@ PC_API int pc_linear_small(const pc_linear_params* p, void* stream) {
   LinParams lp{};
   lp.q_len = p->q_len;
   lp.kb_total = p->k / BKK;
+  const bool tiled = p->w_tiled != nullptr;
+  PC_REQUIRE(!tiled || p->k % 128 == 0, "pc_linear_small: pre-tiled weights need k %% 128 == 0 (k = %d)", p->k);
+  PC_REQUIRE(!tiled || reinterpret_cast<uintptr_t>(p->w_tiled) % 16 == 0, "pc_linear_small: w_tiled must be 16B aligned");
   int n_tiles = 0;
   switch (p->epilogue) {
     case PC_LIN_PLAIN:
@@ -467,6 +610,15 @@ PC_API int pc_linear_small(const pc_linear_params* p, void* stream) {
       lp.n_out = p->n_rows;
       lp.tile_row_stride = BM;
       lp.second_half_off = 64;
+      break;
+    case PC_LIN_PARTIALS:
+      PC_REQUIRE(p->out && p->out_stride == p->n_rows, "pc_linear_small(partials): out must be fp32 [splits][q_len][n_rows]");
+      n_tiles = (p->n_rows + BM - 1) / BM;
+      lp.n_out = p->n_rows;
+      lp.tile_row_stride = BM;
+      lp.second_half_off = 64;
+      lp.splits = pc_linear_partial_splits(p->n_rows, p->k);
+      PC_REQUIRE(n_tiles * lp.splits <= sm_count(), "pc_linear_small(partials): %d row tiles exceed the SM count", n_tiles);
       break;
     case PC_LIN_SILU_MUL: {
       PC_REQUIRE(p->n_rows % 2 == 0, "pc_linear_small(silu_mul): n_rows %d must be even (gate rows, then up rows)", p->n_rows);
@@ -504,11 +656,15 @@ PC_API int pc_linear_small(const pc_linear_params* p, void* stream) {
       return set_error(PC_ERR_CUDA, "no CUDA device");
     if (major != 10) return set_error(PC_ERR_UNSUPPORTED, "this library is built for sm_100a only");
   }
+  lp.part_out = p->epilogue == PC_LIN_PARTIALS ? static_cast<float*>(p->out) : nullptr;
+  PC_REQUIRE(p->epilogue != PC_LIN_PARTIALS || (tiled ? lp.kb_total / 2 : lp.kb_total) >= lp.splits,
+             "pc_linear_small(partials): k %d is too short for %d splits", p->k, lp.splits);
   lp.out = static_cast<__half*>(p->out);
   lp.out_stride = p->out_stride;
   lp.counters = static_cast<int*>(p->workspace);
   lp.slots = reinterpret_cast<float*>(static_cast<char*>(p->workspace) + kLinCounterBytes);
-  lp.units_total = static_cast<long long>(n_tiles) * lp.kb_total;
+  lp.units_total = static_cast<long long>(n_tiles) * (tiled ? lp.kb_total / 2 : lp.kb_total);
+  lp.w_tiled = static_cast<const unsigned char*>(p->w_tiled);
   lp.pos = reinterpret_cast<const long long*>(p->position_ids);
   lp.cos = static_cast<const __half*>(p->cos);
   lp.sin = static_cast<const __half*>(p->sin);
@@ -524,17 +680,35 @@ PC_API int pc_linear_small(const pc_linear_params* p, void* stream) {
   lp.trace = nullptr;
   if (const char* e = getenv("PC_LIN_TRACE_PTR")) lp.trace = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
 
+  // Grid: an SM that is fed 16 KiB per TMA instruction pulls ~100 GB/s, so ~2/3 of the SMs saturate HBM.  When the
+  // tile count has a divisor in [sm/2, sm] every CTA gets WHOLE tiles (no split-K, no cross-CTA reduction: the tail
+  // is a plain epilogue); otherwise all SMs share the (tile, k-block) space evenly (stream-K, partial tiles reduced).
   int grid = sm_count();
-  if (const char* e = getenv("PC_LIN_GRID")) grid = atoi(e);
+  const int min_whole = tiled ? (sm_count() * 5) / 8 : sm_count();  // row-major tensor-map loads need every SM's TMA
+  for (int g = sm_count(); g >= min_whole; --g)
+    if (n_tiles % g == 0) {
+      grid = g;
+      break;
+    }
+  if (grid == sm_count() && n_tiles < sm_count()) {
+    // few tiles (o_proj, down_proj): a regular split-K, the same number of CTAs per tile, keeps the reduction groups small
+    const int per_tile = sm_count() / n_tiles;
+    if (per_tile >= 2 && per_tile * n_tiles >= (sm_count() * 3) / 4) grid = per_tile * n_tiles;
+  }
+  if (p->epilogue == PC_LIN_PARTIALS) grid = n_tiles * lp.splits;
+  else if (const char* e = getenv("PC_LIN_GRID")) grid = atoi(e);
   if (grid > sm_count()) grid = sm_count();
   if (grid > lp.units_total) grid = static_cast<int>(lp.units_total);
   if (grid < 1) grid = 1;
+  lp.w_one_box = (lp.second_half_off == 64) ? 1 : 0;
+  if (const char* e = getenv("PC_LIN_ONEBOX")) lp.w_one_box = lp.w_one_box && atoi(e) != 0;
   CUtensorMap mw, mx;
-  if (int rc = make_tensor_map_3d(&mw, p->w, p->k, p->n_rows, 1, static_cast<long long>(p->n_rows) * p->k, 64)) return rc;
+  if (int rc = make_tensor_map_3d(&mw, p->w, p->k, p->n_rows, 1, static_cast<long long>(p->n_rows) * p->k, lp.w_one_box ? 128 : 64))
+    return rc;
   const int npad = p->q_len <= 16 ? 16 : 32;
   // rows >= q_len of the X box read as zeros
   if (int rc = make_tensor_map_3d(&mx, p->x, p->k, p->q_len, 1, static_cast<long long>(p->q_len) * p->x_stride, npad)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (npad == 16) return launch_lin_n<16>(p->epilogue, mw, mx, lp, grid, st);
-  return launch_lin_n<32>(p->epilogue, mw, mx, lp, grid, st);
+  if (tiled) return npad == 16 ? launch_lin_n<16, true>(p->epilogue, mw, mx, lp, grid, st) : launch_lin_n<32, true>(p->epilogue, mw, mx, lp, grid, st);
+  return npad == 16 ? launch_lin_n<16, false>(p->epilogue, mw, mx, lp, grid, st) : launch_lin_n<32, false>(p->epilogue, mw, mx, lp, grid, st);
 }

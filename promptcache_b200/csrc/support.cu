@@ -11,9 +11,13 @@ namespace {
 
 constexpr int kNormThreads = 256;
 
+// `part` != nullptr: the residual delta arrives as `n_splits` fp32 split-K partials [split][row][hidden] of the
+// preceding linear layer (pc_linear_small, PC_LIN_PARTIALS); they are added in split order and rounded to fp16 once,
+// which is the fp16 output an nn.Linear would have produced.
 __global__ void __launch_bounds__(kNormThreads)
 add_rmsnorm_kernel(__half* __restrict__ x, const __half* __restrict__ delta, const __half* __restrict__ weight,
-                   __half* __restrict__ h_out, int hidden, float eps) {
+                   __half* __restrict__ h_out, int hidden, float eps, const float* __restrict__ part, int n_splits,
+                   long long split_stride) {
   __shared__ float red[kNormThreads / 32];
   pc::pdl_launch_dependents();  // the following GEMM may start streaming its weights now
   pc::pdl_wait();               // x / delta come from the previous kernel
@@ -26,7 +30,19 @@ add_rmsnorm_kernel(__half* __restrict__ x, const __half* __restrict__ delta, con
   for (int i = threadIdx.x * 8; i < hidden; i += kNormThreads * 8) {
     uint4 xv = *reinterpret_cast<const uint4*>(xr + i);
     __half2* xh = reinterpret_cast<__half2*>(&xv);
-    if (dr) {
+    if (part) {
+      const float* pr = part + static_cast<long long>(row) * hidden + i;
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int s = 0; s < n_splits; ++s) {
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(pr + s * split_stride));
+        const float4 b = __ldcg(reinterpret_cast<const float4*>(pr + s * split_stride) + 1);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+        acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) xh[k] = __hadd2_rn(xh[k], __floats2half2_rn(acc[2 * k], acc[2 * k + 1]));
+      *reinterpret_cast<uint4*>(xr + i) = xv;
+    } else if (dr) {
       uint4 dv = *reinterpret_cast<const uint4*>(dr + i);
       const __half2* dh = reinterpret_cast<const __half2*>(&dv);
 #pragma unroll
@@ -96,7 +112,23 @@ PC_API int pc_add_rmsnorm(void* x, const void* delta, const void* weight, void* 
   PC_REQUIRE(align % 16 == 0, "pc_add_rmsnorm: tensors must be 16B aligned");
   PC_CHECK_CUDA(pc::launch_pdl(add_rmsnorm_kernel, dim3(rows), dim3(kNormThreads), 0, static_cast<cudaStream_t>(stream),
                                static_cast<__half*>(x), static_cast<const __half*>(delta), static_cast<const __half*>(weight),
-                               static_cast<__half*>(h_out), hidden, eps));
+                               static_cast<__half*>(h_out), hidden, eps, static_cast<const float*>(nullptr), 0, 0LL));
+  pc::count_launch();
+  return PC_OK;
+}
+
+PC_API int pc_add_rmsnorm_partials(void* x, const void* delta_partials, int n_splits, const void* weight, void* h_out, int rows,
+                                   int hidden, float eps, void* stream) {
+  if (rows == 0) return PC_OK;
+  PC_REQUIRE(x && weight && h_out && delta_partials, "pc_add_rmsnorm_partials: null tensor");
+  PC_REQUIRE(rows > 0 && hidden > 0 && hidden % 8 == 0 && n_splits >= 1, "pc_add_rmsnorm_partials: bad shape");
+  const uintptr_t align = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(delta_partials) |
+                          reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(h_out);
+  PC_REQUIRE(align % 16 == 0, "pc_add_rmsnorm_partials: tensors must be 16B aligned");
+  PC_CHECK_CUDA(pc::launch_pdl(add_rmsnorm_kernel, dim3(rows), dim3(kNormThreads), 0, static_cast<cudaStream_t>(stream),
+                               static_cast<__half*>(x), static_cast<const __half*>(nullptr), static_cast<const __half*>(weight),
+                               static_cast<__half*>(h_out), hidden, eps, static_cast<const float*>(delta_partials), n_splits,
+                               static_cast<long long>(rows) * hidden));
   pc::count_launch();
   return PC_OK;
 }

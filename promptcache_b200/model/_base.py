@@ -36,7 +36,10 @@ class B200CausalLM(nn.Module):
         self._lin_ws = None
         self.attn_impl = nat.PC_ATTN_AUTO
         # "native": skinny linears (q <= 32) run in pc_linear_small; "cublas": torch.nn.functional.linear everywhere
-        self.linear_impl = os.environ.get("PC_LINEAR", "cublas")
+        self.linear_impl = os.environ.get("PC_LINEAR", "native")
+        self.linear_native_ops = set(os.environ.get("PC_LINEAR_OPS", "qkv,o,down,head").split(","))
+        self.linear_partials = os.environ.get("PC_LINEAR_PARTIALS", "1") != "0"
+        self.linear_tiled = os.environ.get("PC_LINEAR_TILED", "1") != "0"  # native linears stream pre-tiled weight copies
         # CUDA graphs of the whole single-sequence forward, keyed by (q_len, n_cached, KV buffer): the per-layer
         # launch sequence is fixed once those are, so a repeated request shape is replayed with one launch
         self.use_cuda_graphs = True
@@ -127,7 +130,7 @@ class B200CausalLM(nn.Module):
             if logits is not None:
                 return logits, (kv.views(N + 1) if use_cache else None)
         extra = self._graph_extra(max_position)
-        key = (q_len, N, kv.k[0].data_ptr(), kv.max_ctx, pos.shape[0], self.linear_impl) + tuple(extra)
+        key = (q_len, N, kv.k[0].data_ptr(), kv.max_ctx, pos.shape[0], self.linear_impl, tuple(sorted(self.linear_native_ops))) + tuple(extra)
         if self.use_cuda_graphs and N > 0 and q_len > 1 and not torch.cuda.is_current_stream_capturing():
             entry = self._graphs.get(key)
             if entry is None and self._graph_seen.get(key, 0) >= 1:

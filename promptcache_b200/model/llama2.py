@@ -79,6 +79,7 @@ class LlamaForCausalLM(B200CausalLM):
         self.norm = ones()
         self.lm_head = w(c.vocab_size, hid)
         self._init_runtime()
+        self._tiled = {}  # pre-tiled copies of the weights for pc_linear_small, built on first native use
         self.rounding = nat.PC_ROUND_LLAMA
         self.scale = nat.softmax_scale(self.head_dim)
 
@@ -87,6 +88,8 @@ class LlamaForCausalLM(B200CausalLM):
     def load_hf_state_dict(self, sd) -> None:
         """Load a HuggingFace Llama state dict (model.layers.N.self_attn.q_proj.weight ...)."""
         g = lambda k: sd[k].to(self.embed_tokens.device, self.embed_tokens.dtype)
+        self._tiled.clear()
+        self._graphs.clear()
         self.embed_tokens.copy_(g("model.embed_tokens.weight"))
         self.norm.copy_(g("model.norm.weight"))
         self.lm_head.copy_(g("lm_head.weight"))
@@ -112,6 +115,15 @@ class LlamaForCausalLM(B200CausalLM):
         model.load_hf_state_dict(hf.state_dict())
         return model
 
+    def _wt(self, key, w: torch.Tensor, epilogue: int):
+        """Pre-tiled copy of a weight (pc_linear_tile_weights): doubles the memory of the matrices it is used for, and
+        lets one SM stream ~1.5x more bytes per second than 128-byte-row tensor-map boxes do."""
+        t = self._tiled.get(key)
+        if t is None:
+            t = nat.tile_weights(w, epilogue) if self.linear_tiled else None
+            self._tiled[key] = t if t is not None else False
+        return t if t is not False else None
+
     # ---- forward (one sequence; batching, KV buffers and graph replay live in B200CausalLM) ---------------
     def _layers(self, ids: torch.Tensor, pos: torch.Tensor, kv, extra=(), n_dev=None) -> torch.Tensor:
         q_len = ids.shape[0]
@@ -130,13 +142,25 @@ class LlamaForCausalLM(B200CausalLM):
             and inter % 64 == 0
         lws = self._linear_workspace() if lin else None
         dbuf = torch.empty_like(x) if lin else None
+        hid = self.config.hidden_size
+        # o_proj / down_proj leave their split-K partials to the next pc_add_rmsnorm (no reduction tail in the GEMM)
+        pbuf_o = pbuf_d = None
+        if lin and self.linear_partials:
+            s_o, s_d = nat.linear_partial_splits(hid, hid), nat.linear_partial_splits(hid, inter)
+            if s_o >= 2:
+                pbuf_o = torch.empty(s_o, q_len, hid, dtype=torch.float32, device=self.device)
+            if s_d >= 2:
+                pbuf_d = torch.empty(s_d, q_len, hid, dtype=torch.float32, device=self.device)
+        which = self.linear_native_ops  # which linears run natively (A/B switch, PC_LINEAR_OPS)
+        lin_qkv, lin_o, lin_gu, lin_down, lin_head = (lin and k in which for k in ("qkv", "o", "gu", "down", "head"))
         delta = None
         for l in range(self.n_layers):
             nat.add_rmsnorm(x, delta, self.ln1[l], h, self.eps)          # x += mlp(l-1); h = norm(x)
             # n_dev: run-time cached length (decode graph); N is then only the sizing upper bound
-            if lin:
+            if lin_qkv:
                 nat.linear_rope_append(h, self.wqkv[l], pos, self._cos, self._sin, q_rot, kv.k[l], kv.v[l],
-                                       N if n_dev is None else n_dev, H, Hkv, lws)
+                                       N if n_dev is None else n_dev, H, Hkv, lws,
+                                       w_tiled=self._wt(("qkv", l), self.wqkv[l], nat.PC_LIN_ROPE_APPEND))
             else:
                 qkv = F.linear(h, self.wqkv[l])                          # [q, (H+2Hkv)*D]
                 nat.rope_append(qkv[:, :H * D], qkv[:, H * D:(H + Hkv) * D], qkv[:, (H + Hkv) * D:], pos, self._cos,
@@ -144,23 +168,32 @@ class LlamaForCausalLM(B200CausalLM):
             nat.attention(q_rot, kv.k[l], kv.v[l], attn_out, N if n_dev is None else kv.max_ctx - q_len, q_len, H, Hkv,
                           D, self.scale, self.rounding, workspace=ws, decode=(q_len == 1), n_cached_dev=n_dev,
                           impl=self.attn_impl if n_dev is None else nat.PC_ATTN_TCGEN05)
-            if lin:
-                nat.linear_small(attn_out, self.wo[l], dbuf, lws)
+            if lin_o and pbuf_o is not None:
+                nat.linear_partials(attn_out, self.wo[l], pbuf_o, lws, w_tiled=self._wt(("o", l), self.wo[l], nat.PC_LIN_PARTIALS))
+                delta = pbuf_o
+            elif lin_o:
+                nat.linear_small(attn_out, self.wo[l], dbuf, lws, w_tiled=self._wt(("o", l), self.wo[l], nat.PC_LIN_PLAIN))
                 delta = dbuf
             else:
                 delta = F.linear(attn_out, self.wo[l])
             nat.add_rmsnorm(x, delta, self.ln2[l], h, self.eps)          # x += attn; h = norm(x)
-            if lin:
-                nat.linear_small(h, self.w_gate_up[l], act, lws, silu_mul=True)
-                nat.linear_small(act, self.w_down[l], dbuf, lws)
-                delta = dbuf
+            if lin_gu:
+                nat.linear_small(h, self.w_gate_up[l], act, lws, silu_mul=True,
+                                 w_tiled=self._wt(("gu", l), self.w_gate_up[l], nat.PC_LIN_SILU_MUL))
             else:
                 gu = F.linear(h, self.w_gate_up[l])
                 nat.silu_mul(gu, act, inter)
+            if lin_down and pbuf_d is not None:
+                nat.linear_partials(act, self.w_down[l], pbuf_d, lws, w_tiled=self._wt(("down", l), self.w_down[l], nat.PC_LIN_PARTIALS))
+                delta = pbuf_d
+            elif lin_down:
+                nat.linear_small(act, self.w_down[l], dbuf, lws, w_tiled=self._wt(("down", l), self.w_down[l], nat.PC_LIN_PLAIN))
+                delta = dbuf
+            else:
                 delta = F.linear(act, self.w_down[l])
         nat.add_rmsnorm(x, delta, self.norm, h, self.eps)
-        if lin:
+        if lin_head:
             logits = torch.empty(q_len, self.vocab_size, dtype=torch.float16, device=self.device)
-            nat.linear_small(h, self.lm_head, logits, lws)
+            nat.linear_small(h, self.lm_head, logits, lws, w_tiled=self._wt(("lm_head", 0), self.lm_head, nat.PC_LIN_PLAIN))
             return logits.float()
         return F.linear(h, self.lm_head).float()

@@ -35,20 +35,32 @@ SHAPES = [  # (q, k, n)
 ]
 
 
+def _tiled(native, w, epi, tiled):
+    """Pre-tiled copy of the weight (1-D bulk-load path) or None (tensor-map path)."""
+    if not tiled:
+        return None
+    wt = native.tile_weights(w, epi)
+    if wt is None:
+        pytest.skip("k is not a multiple of 128: no pre-tiled layout")
+    return wt
+
+
+@pytest.mark.parametrize("tiled", [False, True])
 @pytest.mark.parametrize("q,k,n", SHAPES)
-def test_linear_plain_exact_on_integer_inputs(native, q, k, n):
+def test_linear_plain_exact_on_integer_inputs(native, q, k, n, tiled):
     x = _ints((q, k), -4, 4, 0.25, seed=q + k)
     w = _ints((n, k), -2, 2, 0.125, seed=n + 1)
     ws = native.linear_workspace(DEV)
+    wt = _tiled(native, w, native.PC_LIN_PLAIN, tiled)
     out = torch.full((q, n), float("nan"), dtype=torch.half, device=DEV)
-    native.linear_small(x, w, out, ws)
+    native.linear_small(x, w, out, ws, w_tiled=wt)
     torch.cuda.synchronize()
     assert torch.equal(out, _exact_linear(x, w))
     assert int(ws[:16384].view(torch.int32).abs().max()) == 0  # arrival counters are left zeroed
     # replays on the same workspace give the same bits
     out2 = torch.empty_like(out)
     for _ in range(3):
-        native.linear_small(x, w, out2, ws)
+        native.linear_small(x, w, out2, ws, w_tiled=wt)
     torch.cuda.synchronize()
     assert torch.equal(out, out2)
 
@@ -69,13 +81,14 @@ def test_linear_plain_random_within_one_rounding(native, q, k, n):
     assert float((out.float() - cub.float()).abs().max()) <= 2e-3 * float(ref.abs().max())
 
 
+@pytest.mark.parametrize("tiled", [False, True])
 @pytest.mark.parametrize("q,k,inter", [(16, 4096, 11008), (32, 512, 192), (1, 5120, 13824)])
-def test_linear_silu_mul(native, q, k, inter):
+def test_linear_silu_mul(native, q, k, inter, tiled):
     x = _ints((q, k), -4, 4, 0.25, seed=3)
     w = _ints((2 * inter, k), -2, 2, 1.0 / 64, seed=4)
     ws = native.linear_workspace(DEV)
     out = torch.empty(q, inter, dtype=torch.half, device=DEV)
-    native.linear_small(x, w, out, ws, silu_mul=True)
+    native.linear_small(x, w, out, ws, silu_mul=True, w_tiled=_tiled(native, w, native.PC_LIN_SILU_MUL, tiled))
     gu = _exact_linear(x, w)  # exact fp16 gate / up projections
     want = torch.empty_like(out)
     native.silu_mul(gu, want, inter)  # the unfused kernel on the same fp16 inputs
@@ -91,7 +104,8 @@ def test_linear_silu_mul(native, q, k, inter):
     (32, 8, 2, 512, 5, True),         # GQA, NPAD 32
     (9, 4, 4, 256, 0, False),         # MPT: no rotation, plain append
 ])
-def test_linear_rope_append_bit_exact_vs_unfused(native, q, H, Hkv, k, row0, rotary):
+@pytest.mark.parametrize("tiled", [False, True])
+def test_linear_rope_append_bit_exact_vs_unfused(native, q, H, Hkv, k, row0, rotary, tiled):
     D, max_ctx = 128, row0 + q + 3
     x = _ints((q, k), -4, 4, 0.25, seed=5)
     w = _ints(((H + 2 * Hkv) * D, k), -2, 2, 1.0 / 32, seed=6)
@@ -100,6 +114,7 @@ def test_linear_rope_append_bit_exact_vs_unfused(native, q, H, Hkv, k, row0, rot
     cos, sin = O.rope_tables(D, 4096, dtype=torch.float16)
     cos, sin = cos.contiguous().to(DEV), sin.contiguous().to(DEV)
     ws = native.linear_workspace(DEV)
+    wt = _tiled(native, w, native.PC_LIN_ROPE_APPEND, tiled)
 
     def fresh():
         return (torch.zeros(H, q, D, dtype=torch.half, device=DEV), torch.zeros(Hkv, max_ctx, D, dtype=torch.half, device=DEV),
@@ -107,7 +122,7 @@ def test_linear_rope_append_bit_exact_vs_unfused(native, q, H, Hkv, k, row0, rot
 
     q1, k1, v1 = fresh()
     native.linear_rope_append(x, w, pos if rotary else None, cos if rotary else None, sin if rotary else None, q1, k1, v1,
-                              row0, H, Hkv, ws)
+                              row0, H, Hkv, ws, w_tiled=wt)
     qkv = _exact_linear(x, w)
     q2, k2, v2 = fresh()
     native.rope_append(qkv[:, :H * D], qkv[:, H * D:(H + Hkv) * D], qkv[:, (H + Hkv) * D:], pos if rotary else None,
@@ -118,9 +133,34 @@ def test_linear_rope_append_bit_exact_vs_unfused(native, q, H, Hkv, k, row0, rot
     q3, k3, v3 = fresh()
     row_dev = torch.tensor([row0], dtype=torch.int32, device=DEV)
     native.linear_rope_append(x, w, pos if rotary else None, cos if rotary else None, sin if rotary else None, q3, k3, v3,
-                              row_dev, H, Hkv, ws)
+                              row_dev, H, Hkv, ws, w_tiled=wt)
     torch.cuda.synchronize()
     assert torch.equal(q3, q2) and torch.equal(k3, k2) and torch.equal(v3, v2)
+
+
+@pytest.mark.parametrize("tiled", [False, True])
+@pytest.mark.parametrize("q,k,n", [(16, 4096, 4096), (16, 11008, 4096), (1, 4096, 4096), (32, 13824, 5120), (5, 512, 256)])
+def test_linear_partials_and_consumer_side_reduction(native, q, k, n, tiled):
+    """PC_LIN_PARTIALS + pc_add_rmsnorm_partials == PC_LIN_PLAIN + pc_add_rmsnorm, bit for bit on integer-valued inputs:
+    the split-K partials are summed by the norm kernel instead of by the last CTA of the GEMM."""
+    x = _ints((q, k), -4, 4, 0.25, seed=q + 2 * k)
+    w = _ints((n, k), -2, 2, 0.125, seed=n + 7)
+    ws = native.linear_workspace(DEV)
+    S = native.linear_partial_splits(n, k)
+    assert S >= 2
+    part = torch.full((S, q, n), float("nan"), dtype=torch.float32, device=DEV)
+    assert native.linear_partials(x, w, part, ws, w_tiled=_tiled(native, w, native.PC_LIN_PARTIALS, tiled)) == S
+    torch.cuda.synchronize()
+    assert torch.equal(part.sum(0).half(), _exact_linear(x, w))
+    g = torch.Generator(device="cpu").manual_seed(5)
+    resid = torch.randn(q, n, generator=g).half().to(DEV)
+    wn = torch.randn(n, generator=g).half().to(DEV)
+    xa, xb = resid.clone(), resid.clone()
+    ha, hb = torch.empty_like(xa), torch.empty_like(xb)
+    native.add_rmsnorm(xa, part, wn, ha, 1e-5)
+    native.add_rmsnorm(xb, _exact_linear(x, w), wn, hb, 1e-5)
+    torch.cuda.synchronize()
+    assert torch.equal(xa, xb) and torch.equal(ha, hb)
 
 
 def test_linear_rejects_bad_arguments(native):

@@ -127,9 +127,13 @@ def bench_linear(only=None):
               ("7B lm_head", 16, 4096, 32000, "plain"), ("7B qkv+rope q1", 1, 4096, 12288, "rope"),
               ("7B down q32", 32, 11008, 4096, "plain"), ("13B gate_up+silu q32", 32, 5120, 27648, "silu")]
     tot = {"native": 0.0, "cublas": 0.0}
+    tiled = os.environ.get("PC_MB_TILED", "1") != "0"  # stream the pre-tiled copy of the weights (1-D bulk loads)
+    print(f"pc_linear_small weights: {'pre-tiled (bulk loads)' if tiled else 'row-major (tensor-map loads)'}", flush=True)
+    epi_code = {"plain": nat.PC_LIN_PLAIN, "silu": nat.PC_LIN_SILU_MUL, "rope": nat.PC_LIN_ROPE_APPEND}
     for name, q, k, n, epi in [c for c in shapes if only is None or only in c[0]]:
         rot = max(2, int(math.ceil(600e6 / (n * k * 2))))
         W = (torch.randn(rot, n, k, device=DEV) * 0.02).half()
+        WT = [nat.tile_weights(W[i], epi_code[epi]) if tiled else None for i in range(rot)]
         x = torch.randn(q, k, device=DEV).half()
         byts = n * k * 2.0
         state = {"i": 0}
@@ -146,7 +150,7 @@ def bench_linear(only=None):
 
             def run_native():
                 i = state["i"] = (state["i"] + 1) % rot
-                nat.linear_rope_append(x, W[i], pos, cos, sin, q_rot, kc, vc, 2048, H, Hkv, ws)
+                nat.linear_rope_append(x, W[i], pos, cos, sin, q_rot, kc, vc, 2048, H, Hkv, ws, w_tiled=WT[i])
 
             def run_cublas():
                 i = state["i"] = (state["i"] + 1) % rot
@@ -158,7 +162,7 @@ def bench_linear(only=None):
 
             def run_native():
                 i = state["i"] = (state["i"] + 1) % rot
-                nat.linear_small(x, W[i], out, ws, silu_mul=True)
+                nat.linear_small(x, W[i], out, ws, silu_mul=True, w_tiled=WT[i])
 
             def run_cublas():
                 i = state["i"] = (state["i"] + 1) % rot
@@ -168,7 +172,7 @@ def bench_linear(only=None):
 
             def run_native():
                 i = state["i"] = (state["i"] + 1) % rot
-                nat.linear_small(x, W[i], out, ws)
+                nat.linear_small(x, W[i], out, ws, w_tiled=WT[i])
 
             def run_cublas():
                 i = state["i"] = (state["i"] + 1) % rot
@@ -181,7 +185,7 @@ def bench_linear(only=None):
         print(f"linear {name} q={q} [{n}x{k}] {byts/1e6:.0f} MB: native {ms_n*1e3:.1f} us = {byts/ms_n/1e6:.0f} GB/s "
               f"({byts/ms_n/1e6/PEAK:.2f} of HBM peak) | cuBLAS(+epilogue kernel) {ms_c*1e3:.1f} us = {byts/ms_c/1e6:.0f} GB/s "
               f"({byts/ms_c/1e6/PEAK:.2f})", flush=True)
-        del W
+        del W, WT
     if tot["native"] > 0:
         print(f"linear 7B per layer (qkv+o+gate_up+down, q=16): native {tot['native']*1e3:.1f} us vs cuBLAS {tot['cublas']*1e3:.1f} us "
               f"-> x32 layers {tot['native']*32:.3f} ms vs {tot['cublas']*32:.3f} ms", flush=True)
