@@ -65,6 +65,7 @@ struct LinParams {
   int q_len, kb_total, tile_row_stride, second_half_off;
   int w_one_box;         // the weight tile is 128 consecutive rows: one TMA box instead of two
   const unsigned char* w_tiled;  // TILED: weights re-laid out as [tile][k-block] 16 KiB shared-memory images
+  int whole_per_cta;     // tiles [0, whole_per_cta * grid) are processed whole, the rest is the stream-K region
   int splits;            // PARTIALS: regular split-K, CTA = (tile, split); fp32 partials go to part_out[split][t][col]
   float* part_out;
   long long units_total;
@@ -117,12 +118,20 @@ __device__ __forceinline__ void tmem_ld_acc(uint32_t addr, float (&v)[N]) {
 // whole tiles instead of sitting in the kernel's tail.
 struct Seg {
   int tile, kb0, n;
+  int rel;  // tile index inside the stream-K region (what the split bookkeeping counts in), -1 for a whole tile of phase 2
 };
 struct SegIter {
   long long u0, u1;
   int KB, t_first, t_last, phase, cur;
   bool first_partial, last_partial;
   __device__ SegIter(long long u0_, long long u1_, int KB_) : u0(u0_), u1(u1_), KB(KB_) {
+    if (u0 >= u1) {  // empty range
+      t_first = t_last = 0;
+      first_partial = last_partial = false;
+      phase = 2;
+      cur = 1;
+      return;
+    }
     t_first = static_cast<int>(u0 / KB);
     t_last = static_cast<int>((u1 - 1) / KB);
     const long long first_end = min(u1, static_cast<long long>(t_first + 1) * KB);
@@ -161,6 +170,34 @@ struct SegIter {
   }
 };
 
+// A CTA's whole work list.  With more tiles than CTAs (gate/up, lm_head) the tiles [0, W*G) are dealt out WHOLE, W per
+// CTA, and only the remaining n_tiles - W*G tiles are shared stream-K fashion -- and those come first, so that their
+// cross-CTA reduction overlaps the streaming of the whole tiles and the kernel ends with a plain epilogue.
+struct WorkIter {
+  SegIter it;
+  int W, G, c, KB, rem_tile0, r;
+  __device__ WorkIter(long long u0, long long u1, int KB_, int W_, int G_, int c_) : it(u0, u1, KB_), W(W_), G(G_), c(c_), KB(KB_) {
+    rem_tile0 = W * G;
+    r = 0;
+  }
+  __device__ bool next(Seg& s) {
+    if (it.next(s)) {
+      s.rel = s.tile;
+      s.tile += rem_tile0;
+      return true;
+    }
+    if (r < W) {
+      s.tile = c + r * G;
+      s.rel = -1;
+      s.kb0 = 0;
+      s.n = KB;
+      ++r;
+      return true;
+    }
+    return false;
+  }
+};
+
 template <int NPAD, int EPI, bool TILED>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const LinParams p) {
@@ -183,8 +220,10 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
   const int KB = p.kb_total / KPS;  // pipeline stages (units) per tile
   const long long U = p.units_total;
   const int G = gridDim.x, c = blockIdx.x;
-  long long u0 = (static_cast<long long>(c) * U) / G;
-  long long u1 = (static_cast<long long>(c + 1) * U) / G;
+  // the stream-K region is shared by the first Gs CTAs (all of them unless it holds fewer units than there are CTAs)
+  const int Gs = static_cast<int>(min(static_cast<long long>(G), U));
+  long long u0 = c < Gs ? (static_cast<long long>(c) * U) / Gs : 0;
+  long long u1 = c < Gs ? (static_cast<long long>(c + 1) * U) / Gs : 0;
   if constexpr (EPI == PC_LIN_PARTIALS) {  // regular split-K: every tile is cut into `splits` equal K ranges
     const int tile_c = c / p.splits, sp = c - tile_c * p.splits;
     u0 = static_cast<long long>(tile_c) * KB + (static_cast<long long>(sp) * KB) / p.splits;
@@ -218,7 +257,7 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
       // One TMA instruction costs this thread ~110 ns whatever its size, so the weight tile travels as ONE 128-row box
       // when its rows are consecutive, and the X tiles are issued by a thread of their own (warp 6).  The weights are
       // static: the ring is filled with them without waiting for the previous kernel (whose output is X).
-      SegIter it(u0, u1, KB);
+      WorkIter it(u0, u1, KB, p.whole_per_cta, G, c);
       Seg sg;
       int i = 0;
       while (it.next(sg)) {
@@ -245,7 +284,7 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
     // ===================== TMA producer: the X tiles (output of the previous kernel) =====================
     if (lane == 0) {
       pdl_wait();
-      SegIter it(u0, u1, KB);
+      WorkIter it(u0, u1, KB, p.whole_per_cta, G, c);
       Seg sg;
       int i = 0;
       while (it.next(sg)) {
@@ -265,7 +304,7 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(BM, NPAD, 0, 0);  // both operands K-major
       int i = 0, seg = 0;
-      SegIter it(u0, u1, KB);
+      WorkIter it(u0, u1, KB, p.whole_per_cta, G, c);
       Seg sg;
       while (it.next(sg)) {
         const int buf = seg & 1;
@@ -305,8 +344,8 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
     int row0 = p.row0;
     if (EPI == PC_LIN_ROPE_APPEND && p.row0_dev != nullptr) row0 = max(0, min(__ldg(p.row0_dev), p.max_ctx - p.q_len));
     int seg = 0;
-    SegIter it(u0, u1, KB);
-    const int t_first = it.t_first;
+    WorkIter it(u0, u1, KB, p.whole_per_cta, G, c);
+    const int t_first = it.it.t_first;
     Seg sg;
     while (it.next(sg)) {
       const int tile = sg.tile;
@@ -332,15 +371,16 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
         }
       } else if (sg.n != KB) {
         // partial K range: park the fp32 partial; the last CTA to arrive at this tile adds them up
-        const int slot = (tile == t_first) ? 0 : 1;
+        const int rel = sg.rel;  // tile index inside the stream-K region
+        const int slot = (rel == t_first) ? 0 : 1;
         float* sp = p.slots + (static_cast<size_t>(c) * 2 + slot) * NPAD * BM;
 #pragma unroll
         for (int t = 0; t < NPAD; ++t)
           if (t < p.q_len) __stcg(sp + t * BM + f, v[t]);
         named_bar_sync(1, kEpiThreads);  // orders every thread's stores before thread 0's gpu-scope fence + arrival
         if (et == 0) {
-          const int c_first = cta_of_unit(static_cast<long long>(tile) * KB, U, G);
-          const int c_last = cta_of_unit(static_cast<long long>(tile) * KB + KB - 1, U, G);
+          const int c_first = cta_of_unit(static_cast<long long>(rel) * KB, U, Gs);
+          const int c_last = cta_of_unit(static_cast<long long>(rel) * KB + KB - 1, U, Gs);
           __threadfence();
           const int old = atomicAdd(p.counters + tile, 1);
           const int last = (old == c_last - c_first) ? 1 : 0;
@@ -363,8 +403,8 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
 #pragma unroll
             for (int j = 0; j < CH; ++j) {
               const int ccj = min(cc + j, c_last);
-              const long long cu0 = (static_cast<long long>(ccj) * U) / G;
-              const int slot_c = (cu0 / KB == tile) ? 0 : 1;
+              const long long cu0 = (static_cast<long long>(ccj) * U) / Gs;
+              const int slot_c = (cu0 / KB == sg.rel) ? 0 : 1;
               const float* rp = p.slots + (static_cast<size_t>(ccj) * 2 + slot_c) * NPAD * BM;
 #pragma unroll
               for (int t = 0; t < NPAD; ++t) tmp[j][t] = (cc + j <= c_last && t < p.q_len) ? __ldcg(rp + t * BM + f) : 0.f;
@@ -663,7 +703,9 @@ PC_API int pc_linear_small(const pc_linear_params* p, void* stream) {
   lp.out_stride = p->out_stride;
   lp.counters = static_cast<int*>(p->workspace);
   lp.slots = reinterpret_cast<float*>(static_cast<char*>(p->workspace) + kLinCounterBytes);
-  lp.units_total = static_cast<long long>(n_tiles) * (tiled ? lp.kb_total / 2 : lp.kb_total);
+  const int units_per_tile = tiled ? lp.kb_total / 2 : lp.kb_total;
+  lp.units_total = static_cast<long long>(n_tiles) * units_per_tile;
+  lp.whole_per_cta = 0;
   lp.w_tiled = static_cast<const unsigned char*>(p->w_tiled);
   lp.pos = reinterpret_cast<const long long*>(p->position_ids);
   lp.cos = static_cast<const __half*>(p->cos);
@@ -695,10 +737,17 @@ PC_API int pc_linear_small(const pc_linear_params* p, void* stream) {
     const int per_tile = sm_count() / n_tiles;
     if (per_tile >= 2 && per_tile * n_tiles >= (sm_count() * 3) / 4) grid = per_tile * n_tiles;
   }
+  const char* hy = getenv("PC_LIN_HYBRID");
   if (p->epilogue == PC_LIN_PARTIALS) grid = n_tiles * lp.splits;
   else if (const char* e = getenv("PC_LIN_GRID")) grid = atoi(e);
+  else if (n_tiles > sm_count() && !(hy && hy[0] == '0')) {
+    // more tiles than SMs: whole tiles first-come per CTA, the remainder shared stream-K (and processed first)
+    grid = sm_count();
+    lp.whole_per_cta = n_tiles / grid;
+    lp.units_total = static_cast<long long>(n_tiles - lp.whole_per_cta * grid) * units_per_tile;
+  }
   if (grid > sm_count()) grid = sm_count();
-  if (grid > lp.units_total) grid = static_cast<int>(lp.units_total);
+  if (lp.whole_per_cta == 0 && grid > lp.units_total) grid = static_cast<int>(lp.units_total);
   if (grid < 1) grid = 1;
   lp.w_one_box = (lp.second_half_off == 64) ? 1 : 0;
   if (const char* e = getenv("PC_LIN_ONEBOX")) lp.w_one_box = lp.w_one_box && atoi(e) != 0;

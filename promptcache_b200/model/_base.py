@@ -37,7 +37,7 @@ class B200CausalLM(nn.Module):
         self.attn_impl = nat.PC_ATTN_AUTO
         # "native": skinny linears (q <= 32) run in pc_linear_small; "cublas": torch.nn.functional.linear everywhere
         self.linear_impl = os.environ.get("PC_LINEAR", "native")
-        self.linear_native_ops = set(os.environ.get("PC_LINEAR_OPS", "qkv,o,down,head").split(","))
+        self.linear_native_ops = set(os.environ.get("PC_LINEAR_OPS", "qkv,o,gu,down,head").split(","))
         self.linear_partials = os.environ.get("PC_LINEAR_PARTIALS", "1") != "0"
         self.linear_tiled = os.environ.get("PC_LINEAR_TILED", "1") != "0"  # native linears stream pre-tiled weight copies
         # CUDA graphs of the whole single-sequence forward, keyed by (q_len, n_cached, KV buffer): the per-layer

@@ -32,6 +32,8 @@ SHAPES = [  # (q, k, n)
     (16, 4096, 32000),    # lm_head
     (3, 64, 128),         # a single unit
     (17, 5120, 5120),     # 13B, NPAD 32 with ragged tokens
+    (4, 256, 37888),      # 296 row tiles = 2 whole tiles per SM, empty stream-K remainder
+    (9, 384, 19200),      # 150 row tiles: one whole tile per SM + a 2-tile remainder shared by all SMs
 ]
 
 
