@@ -5,8 +5,8 @@
 
 One step = one request on BASELINE config C2 (code-generation-game shape: 7 cached segments [24,400x5,24] =
 2048 tokens, 16-token uncached suffix): request plan -> splice of ALL segments (retained-prefix shortcut off) ->
-32-layer prefill of the suffix over the spliced cache (RoPE at position ids + in-place append + tcgen05
-attention per layer; projections/MLP in cuBLAS) -> logits.  TTFT = ms_per_step; value = served prompt tokens/s
+32-layer prefill of the suffix over the spliced cache (per layer: QKV projection with RoPE at position ids + in-place
+append in its epilogue, tcgen05 attention, o_proj / MLP as weight-streaming tcgen05 kernels) -> logits.  TTFT = ms_per_step; value = served prompt tokens/s
 = n_gpus*(N+q)/TTFT.  Weights are seeded random fp16 at the real dims, token ids synthetic (no network).
 N>1: one rank per GPU, every rank serves its own prompt against its own HBM-resident segment store (weak
 scaling, no data-path collective); NCCL only for the barrier and the max-over-ranks time.

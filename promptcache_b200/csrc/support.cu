@@ -33,11 +33,22 @@ add_rmsnorm_kernel(__half* __restrict__ x, const __half* __restrict__ delta, con
     if (part) {
       const float* pr = part + static_cast<long long>(row) * hidden + i;
       float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int s = 0; s < n_splits; ++s) {
-        const float4 a = __ldcg(reinterpret_cast<const float4*>(pr + s * split_stride));
-        const float4 b = __ldcg(reinterpret_cast<const float4*>(pr + s * split_stride) + 1);
-        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-        acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+      for (int s0 = 0; s0 < n_splits; s0 += 4) {  // four splits' loads in flight together, added in split order
+        float4 a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool ok = s0 + u < n_splits;
+          const float4* q = reinterpret_cast<const float4*>(pr + (ok ? s0 + u : s0) * split_stride);
+          a[u] = ok ? __ldcg(q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          b[u] = ok ? __ldcg(q + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (s0 + u < n_splits) {
+            acc[0] += a[u].x; acc[1] += a[u].y; acc[2] += a[u].z; acc[3] += a[u].w;
+            acc[4] += b[u].x; acc[5] += b[u].y; acc[6] += b[u].z; acc[7] += b[u].w;
+          }
+        }
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) xh[k] = __hadd2_rn(xh[k], __floats2half2_rn(acc[2 * k], acc[2 * k + 1]));
