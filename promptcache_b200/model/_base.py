@@ -38,6 +38,7 @@ class B200CausalLM(nn.Module):
         # "native": skinny linears (q <= 32) run in pc_linear_small; "cublas": torch.nn.functional.linear everywhere
         self.linear_impl = os.environ.get("PC_LINEAR", "native")
         self.linear_native_ops = set(os.environ.get("PC_LINEAR_OPS", "qkv,o,gu,down,head").split(","))
+        self.linear_max_q = min(32, int(os.environ.get("PC_LINEAR_MAX_Q", "16")))
         self.linear_partials = os.environ.get("PC_LINEAR_PARTIALS", "1") != "0"
         self.linear_tiled = os.environ.get("PC_LINEAR_TILED", "1") != "0"  # native linears stream pre-tiled weight copies
         # CUDA graphs of the whole single-sequence forward, keyed by (q_len, n_cached, KV buffer): the per-layer

@@ -136,9 +136,10 @@ class LlamaForCausalLM(B200CausalLM):
         inter = self.config.intermediate_size
         act = torch.empty(q_len, inter, dtype=torch.float16, device=self.device)
         ws = self._workspace(q_len)
-        # q <= 32: the linears are weight streams -> pc_linear_small (stream-K tcgen05, fused RoPE+append / SiLU*up);
-        # longer suffixes are compute-bound GEMMs and stay in cuBLAS
-        lin = self.linear_impl == "native" and q_len <= 32 and D == 128 and self.config.hidden_size % 64 == 0 \
+        # few tokens: the linears are weight streams -> pc_linear_small (tcgen05, fused RoPE+append / SiLU*up); the kernel
+        # takes up to 32 tokens but only beats the library up to 16 (its 32-column variant has one pipeline stage less),
+        # longer suffixes are compute-bound GEMMs: both stay in cuBLAS
+        lin = self.linear_impl == "native" and q_len <= self.linear_max_q and D == 128 and self.config.hidden_size % 64 == 0 \
             and inter % 64 == 0
         lws = self._linear_workspace() if lin else None
         dbuf = torch.empty_like(x) if lin else None
