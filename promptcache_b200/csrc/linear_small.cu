@@ -1,25 +1,31 @@
 // Skinny-M linear layers of the prefill / decode step as ONE weight-streaming tcgen05 kernel (SURVEY.md
 // section 8 row a13: q/k/v/o projections, MLP and lm_head -- reference promptcache/model/llama2.py:345-351,
 // :405, :213-244, :1050).  With q <= 32 uncached tokens these GEMMs are pure HBM streams of the fp16 weights
-// (13.5 GB per Llama-2-7B forward = 74 % of the TTFT step); the library kernels reach 59-85 % of the copy
-// bandwidth on them and every epilogue (RoPE + KV append, SiLU*up) costs another launch.
+// (13.5 GB per Llama-2-7B forward, two thirds of the TTFT step) and every epilogue (RoPE + KV append, SiLU*up)
+// used to cost another launch.
 //
 //   D^T[128 out-features x NPAD tokens] += W[128 x 64] . X[NPAD x 64]^T        (operands swapped so that the
 //   weight tile fills the MMA's M = 128 and the few tokens are its N)
 //
-// * stream-K: the (tile, k-block) space is cut into gridDim.x equal contiguous ranges, so every SM streams the
-//   same number of weight bytes whatever the shape (32 tiles of o_proj as well as 172 of gate/up);
-// * one elected thread keeps an 10-11 stage TMA ring (16 KiB weight tile + the matching X tile, 128B-swizzled)
-//   full, one elected thread issues the SS-MMAs into one of two TMEM accumulators, four epilogue warps drain
-//   the other one;
-// * a range that covers only part of a tile's K writes its fp32 partial to a per-CTA slot; the LAST CTA to
-//   arrive at the tile (arrival counter, self-cleaning) adds the slots in a fixed order -- deterministic, no
-//   second launch; partial segments are visited before whole tiles so that this reduction overlaps the stream;
-// * programmatic dependent launch: the weights are static, so a CTA fills its ring with them while the previous
-//   kernel (the producer of X) is still finishing, and only then waits for it;
+// * weights: either the row-major nn.Linear matrix through 128B-swizzled tensor-map boxes (one SM's TMA sustains
+//   ~49 GB/s on such 128-byte rows), or -- the default of the models -- a pre-tiled copy (pc_linear_tile_weights:
+//   the [tile][k-block] sequence of 16 KiB shared-memory images) streamed with ONE 32 KiB bulk copy per stage
+//   (61 / 116 GB/s per SM with 16 / 32 KiB copies);
+// * roles: a weight-producer thread (never waits for the previous kernel: weights are static), an X-producer
+//   thread (waits: X is the previous kernel's output), an MMA-issuing thread with two TMEM accumulators, four
+//   epilogue warps; 6 (pre-tiled) or 10-11 (tensor-map) ring stages, i.e. ~190 KiB of weights in flight per SM;
+// * work partition (chosen on the host per shape, all expressed as a list of (tile, k-range) segments per CTA):
+//     - whole tiles per CTA when the tile count divides a grid of >= 5/8 of the SMs (QKV: 96 head tiles);
+//     - more tiles than SMs (gate/up, lm_head): whole tiles dealt out per CTA + the remainder shared stream-K
+//       fashion and visited FIRST, so that its reduction overlaps the streaming of the whole tiles;
+//     - PC_LIN_PARTIALS (o_proj, down_proj): regular split-K, NO reduction here -- the consumer
+//       (pc_add_rmsnorm_partials) adds the fp32 partials in split order and rounds once;
+//     - otherwise stream-K: equal contiguous ranges of the (tile, k-block) space; a range that covers only part of
+//       a tile's K parks its fp32 partial in a per-CTA slot and the LAST CTA to arrive at the tile (arrival counter,
+//       self-cleaning) adds the slots in a fixed order -- deterministic, no second launch;
 // * epilogues: plain fp16 store; half(silu(gate)) * up (llama2.py:241) with gate and up rows of the same
-//   features loaded into one tile; RoPE at explicit position ids + in-place KV append with the reference's
-//   three fp16 roundings (llama2.py:195-210,357-364) when a tile is one head (D = 128).
+//   features in one tile; RoPE at explicit position ids + in-place KV append with the reference's three fp16
+//   roundings (llama2.py:195-210,357-364) when a tile is one head (D = 128).
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
