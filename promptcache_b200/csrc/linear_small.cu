@@ -236,6 +236,11 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
     u1 = static_cast<long long>(tile_c) * KB + (static_cast<long long>(sp + 1) * KB) / p.splits;
   }
   if (tid == 0) LIN_TRACE(0);
+  if (tid == 0 && p.trace != nullptr) {  // slot 7: the SM this CTA runs on
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.trace[blockIdx.x * 8 + 7] = smid;
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_w);
