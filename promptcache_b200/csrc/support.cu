@@ -9,7 +9,7 @@
 
 namespace {
 
-constexpr int kNormThreads = 256;
+constexpr int kNormThreads = 512;  // one 8-column chunk per thread at hidden 4096: a single load wave per pass
 
 // `part` != nullptr: the residual delta arrives as `n_splits` fp32 split-K partials [split][row][hidden] of the
 // preceding linear layer (pc_linear_small, PC_LIN_PARTIALS); they are added in split order and rounded to fp16 once,
