@@ -34,6 +34,8 @@ SHAPES = [  # (q, k, n)
     (17, 5120, 5120),     # 13B, NPAD 32 with ragged tokens
     (4, 256, 37888),      # 296 row tiles = 2 whole tiles per SM, empty stream-K remainder
     (9, 384, 19200),      # 150 row tiles: one whole tile per SM + a 2-tile remainder shared by all SMs
+    (8, 256, 1000),       # ragged last row tile (CodeLlama-style vocabularies are not multiples of 128)
+    (16, 4096, 32016),    # CodeLlama lm_head: 251 row tiles, the last one 16 rows
 ]
 
 
