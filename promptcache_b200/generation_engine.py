@@ -6,7 +6,10 @@ use_full_position_ids)` yields `Output`s exactly like the reference, including i
   * `Output` is built positionally as (output, new_output, inference_time, response_time), so
     `.response_time` is the cumulative model time and `.elapsed_time` the prefill time (:53-58,201).
 What changes is underneath: the KV is appended in place (no torch.cat per step) and every forward runs
-pc_rope_append + pc_prefill_attn / pc_decode_attn.
+pc_rope_append + pc_prefill_attn / pc_decode_attn.  Greedy decoding without a repetition penalty additionally
+samples ON THE DEVICE: the argmax of a step feeds the next step's graph without going
+through the host, and the host reads the pending token ids only where the reference loop would yield
+(`i % stream_interval == 0`, the last step) -- same tokens, same texts, same per-step event times, fewer syncs.
 """
 from __future__ import annotations
 
@@ -67,6 +70,7 @@ class GenerationEngine:
         self.lm = lm
         self.verbose = False
         self._events = None  # one (start, end) pair, reused: the loop is synchronous
+        self.device_sampling = True  # greedy decoding keeps the sampled token on the device between yields
 
     def _forward(self, ids: List[List[int]], pos: List[List[int]], past, device):
         extra = {"max_position": max(pos[0])} if getattr(self.lm.hf_model, "accepts_max_position", False) else {}
@@ -85,10 +89,83 @@ class GenerationEngine:
         end.synchronize()
         return out, start.elapsed_time(end)
 
+    def _device_sampling_ok(self, params: GenerationParameters, use_full_position_ids: bool) -> bool:
+        greedy = params.temperature < 1e-5 or params.top_p < 1e-8
+        # top-p / top-k warpers mask tokens but never move the argmax; a repetition penalty does
+        return (self.device_sampling and greedy and params.repetition_penalty <= 1.0 and not use_full_position_ids
+                and not self.verbose and getattr(self.lm.hf_model, "accepts_max_position", False))
+
+    def _generate_greedy_on_device(self, token_ids, position_ids, params, cache, stream_interval):
+        """The loop of `generate` for greedy decoding, with the sampled token kept on the device between yields."""
+        device = self.lm.device
+        output_ids = list(token_ids)
+        new_output_ids: List[int] = []
+        position_offset = max(position_ids) + 1
+        n_max = params.max_new_tokens
+        # decode step i >= 1 runs at position position_offset + i (one position is skipped, reference :82,132)
+        pos_all = torch.arange(position_offset, position_offset + n_max + 1, device=device, dtype=torch.long).view(1, -1)
+        pool = [torch.cuda.Event(enable_timing=True) for _ in range(2 * (max(1, stream_interval) + 1))]
+        pending = []  # (token on the device, start event, end event) of the steps the host has not looked at yet
+        past = tok_dev = None
+        inference_time = response_time = 0.0
+        first = True
+        for i in range(n_max):
+            start, end = pool[2 * len(pending)], pool[2 * len(pending) + 1]
+            if past is None:
+                if cache is not None:
+                    batched = getattr(cache, "batched", None)
+                    cache = batched() if batched is not None else [(k.unsqueeze(0), v.unsqueeze(0)) for k, v in cache]
+                both = torch.tensor([list(token_ids), list(position_ids)], device=device, dtype=torch.long)
+                ids_t, pos_t, past_in, max_pos = both[0:1], both[1:2], cache, max(position_ids)
+            else:
+                ids_t, pos_t, past_in, max_pos = tok_dev.view(1, 1), pos_all[:, i:i + 1], past, position_offset + i
+            start.record()
+            out = self.lm(input_ids=ids_t, position_ids=pos_t, past_key_values=past_in, use_cache=True, max_position=max_pos)
+            end.record()
+            past = out.past_key_values
+            tok_dev = torch.argmax(out.logits[0, -1])
+            pending.append((tok_dev, start, end))
+            if not (i % stream_interval == 0 or i == n_max - 1):
+                continue  # the reference loop would not yield here (unless this token stops it: found at the next flush)
+            end.synchronize()
+            ids = torch.stack([p[0] for p in pending]).tolist()  # one device->host read for all pending steps
+            stopped = False
+            for (_, s_ev, e_ev), tid in zip(pending, ids):
+                inference_time += s_ev.elapsed_time(e_ev)
+                if first:
+                    response_time, first = inference_time, False
+                output_ids.append(tid)
+                new_output_ids.append(tid)
+                if tid in params.stop_token_ids:  # steps run past a stop token are dropped: their rows lie behind the sequence
+                    stopped = True
+                    break
+            pending = []
+            output = self.lm.decode(output_ids)
+            new_output = self.lm.decode(new_output_ids)
+            partially_stopped = False
+            for each_stop in params.stop_str:
+                pos_found = new_output.rfind(each_stop, 0)
+                if pos_found != -1:
+                    new_output = new_output[:pos_found]
+                    stopped = True
+                    break
+                partially_stopped = is_partial_stop(output, each_stop)
+                if partially_stopped:
+                    break
+            if not partially_stopped:
+                yield Output(output, new_output, inference_time, response_time)
+            if stopped:
+                break
+        del past
+        gc.collect()
+
     @torch.inference_mode()
     def generate(self, token_ids: List[int], position_ids: List[int], params: GenerationParameters,
                  cache: Optional[KVCache] = None, stream_interval: int = 2,
                  use_full_position_ids: bool = False) -> Generator[Output, None, None]:
+        if self._device_sampling_ok(params, use_full_position_ids) and params.max_new_tokens > 0:
+            yield from self._generate_greedy_on_device(token_ids, position_ids, params, cache, stream_interval)
+            return
         logits_processor = params.get_logits_processor()
         output_ids = list(token_ids)
         new_output_ids: List[int] = []

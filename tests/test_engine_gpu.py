@@ -251,6 +251,40 @@ def test_decode_graph_with_runtime_length_matches_eager(native):
     assert torch.equal(eng.prompt_cache.buffer[:, :, :, 677:677 + 9 + 11], k_graph)
 
 
+def test_device_side_greedy_sampling_equals_host_loop(native):
+    """Greedy decoding with the sampled token kept on the device between yields (section 8 row f3) gives the same
+    yields -- texts, token counts, stop behaviour -- as the reference-shaped loop that reads every token on the host."""
+    from promptcache_b200 import CacheEngine, GenerationEngine, GenerationParameters, Prompt
+    from promptcache_b200.model import Llama2, LlamaConfigLite, LlamaForCausalLM
+    from promptcache_b200.synthetic import IdTokenizer, flat_schema
+    sd = O.random_llama_state_dict(512, 512, 1024, 2, 4, 4, seed=2, dtype=torch.float16, device=DEV)
+    cfg = LlamaConfigLite(vocab_size=512, hidden_size=512, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=4,
+                          max_position_embeddings=2048)
+    model = LlamaForCausalLM(cfg, device=DEV)
+    model.load_hf_state_dict(sd)
+    lm = Llama2("d128", model=model, tokenizer=IdTokenizer(512))
+    case = flat_schema("smp", [64, 200, 33], 7, 512, seed=4)
+    eng = CacheEngine(1024, lm)
+    eng.add_schema(case.schema_xml)
+
+    def run(device_sampling, interval, stop_ids, n=14):
+        gen = GenerationEngine(lm)
+        gen.device_sampling = device_sampling
+        params = GenerationParameters(temperature=0.0, max_new_tokens=n, stop_token_ids=stop_ids, stop_str=[])
+        ids, pos, _, cache = eng.process(Prompt(case.prompt_xml))
+        return [(o.text, o.new_text) for o in gen.generate(ids, pos, params, cache, stream_interval=interval)]
+
+    free = run(False, 1, [])
+    tokens = free[-1][1].split()
+    assert len(tokens) == 14
+    for interval in (1, 2, 3, 5):
+        assert run(True, interval, []) == run(False, interval, [])
+        # a stop token in the middle of an interval: the device loop has already run past it and must drop the surplus
+        for stop_at in (3, 4, 6):
+            stop = [int(tokens[stop_at][1:])]
+            assert run(True, interval, stop) == run(False, interval, stop)
+
+
 def test_pool_of_prompts_sharded_like_c5(native):
     """C5 in miniature: a pool of 16 modules, 12 prompts each choosing 6 of them (seeded), served in the order a
     2-rank batch partition would see them.  After every request the spliced cache must equal the oracle's splice of
