@@ -13,7 +13,6 @@ through the host, and the host reads the pending token ids only where the refere
 """
 from __future__ import annotations
 
-import gc
 from dataclasses import dataclass, field
 from typing import Generator, List, Optional
 
@@ -156,8 +155,7 @@ class GenerationEngine:
                 yield Output(output, new_output, inference_time, response_time)
             if stopped:
                 break
-        del past
-        gc.collect()
+        del past  # the KV lives in the engine's buffers: nothing to collect (the reference runs gc.collect() here, :207-209)
 
     @torch.inference_mode()
     def generate(self, token_ids: List[int], position_ids: List[int], params: GenerationParameters,
@@ -226,5 +224,4 @@ class GenerationEngine:
             if stopped:
                 break
 
-        del past_key_values
-        gc.collect()
+        del past_key_values  # no gc.collect(): the KV lives in the engine's buffers (reference :207-209 collects, ~45 ms)
