@@ -7,7 +7,8 @@
  * pointers unless a comment says HOST; the caller owns every buffer and keeps it alive until the
  * stream has drained.  Every call is asynchronous on `stream` (a `cudaStream_t` passed as
  * `void*`; NULL = legacy default stream), re-entrant, keeps no state between calls other than
- * internal caches (TMA descriptors, a pinned staging ring) and never throws.
+ * per-stream internal caches (pc_splice_kv_tensors stages its descriptor table in a pinned buffer
+ * owned by the stream it is called on; concurrent calls must use different streams) and never throws.
  *
  * Return value: 0 on success, a negative `PC_ERR_*` otherwise; `pc_last_error()` returns the
  * thread-local message of the last failure.
@@ -51,6 +52,10 @@ enum {
 #define PC_ATTN_AUTO 0
 #define PC_ATTN_SIMT 1
 #define PC_ATTN_TCGEN05 2
+#define PC_ATTN_IMPL_MASK 0xff
+/* Flag OR-ed into `impl` (A/B and tests): the short-suffix kernel merges its split-KV partials through the global
+ * workspace + arrival counter instead of the thread-block cluster's shared memory (same arithmetic, same bits). */
+#define PC_ATTN_GLOBAL_MERGE 0x100
 
 int pc_version(void);
 const char* pc_last_error(void);

@@ -1,8 +1,10 @@
 """TEST INFRASTRUCTURE ONLY -- loader for the *unmodified* reference (yale-sys/prompt-cache).
 
-Imports ``promptcache`` from ``/root/reference`` (present only in the build container, never on the
-GPU box) through the shim set of SURVEY.md section 8c so that ``oracle/gen_golden.py`` can run the
-reference's own classes on CPU and freeze their outputs under ``tests/golden/``.
+Imports ``promptcache`` from ``oracle/_ref`` (the byte-for-byte copy staged by ``oracle/make_ref.py``; git-ignored,
+travels to the GPU box) or from ``/root/reference`` (build container only) through the shim set of SURVEY.md
+section 8c, so that ``oracle/gen_golden.py`` can freeze the reference's outputs under ``tests/golden/``, the
+``-m gpu`` tests can run the reference's own modules in fp16 on the B200 next to the CUDA path, and
+``bench.py --impl reference`` can time the reference's own classes on the host cores.
 
 Nothing under ``promptcache_b200/`` imports this file.  Only ``oracle/gen_golden.py`` and the
 "oracle vs live reference" tests (skipped when ``/root/reference`` is absent) do.
@@ -23,8 +25,20 @@ from typing import List, Optional
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("PC_REFERENCE_ROOT", "/root/reference")
-_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_shims")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIMS = os.path.join(_HERE, "_shims")
+
+
+def _find_reference() -> str:
+    """PC_REFERENCE_ROOT, else the staged byte-for-byte copy oracle/_ref (made by oracle/make_ref.py; the only one
+    that exists on the GPU box), else the read-only mount of the build container."""
+    for cand in (os.environ.get("PC_REFERENCE_ROOT"), os.path.join(_HERE, "_ref"), "/root/reference"):
+        if cand and os.path.isdir(os.path.join(cand, "promptcache")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference()
 
 
 def reference_available() -> bool:

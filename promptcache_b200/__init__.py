@@ -11,7 +11,8 @@ from .prompt import Prompt, CompactSpaces, read_file, apply_preproc
 from .schema import Schema
 from .cache_engine import CacheEngine, PromptCache, SchemaCache, TokenSequenceCache
 from .generation_engine import GenerationEngine, GenerationParameters, Output
+from .model._kv import StaleKVError
 
 __all__ = ["Prompt", "CompactSpaces", "read_file", "apply_preproc", "Schema", "CacheEngine", "PromptCache",
-           "SchemaCache", "TokenSequenceCache", "GenerationEngine", "GenerationParameters", "Output"]
+           "SchemaCache", "TokenSequenceCache", "GenerationEngine", "GenerationParameters", "Output", "StaleKVError"]
 __version__ = "0.1.0"

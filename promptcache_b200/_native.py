@@ -24,6 +24,7 @@ PC_ROUND_FALCON = 0
 PC_ATTN_AUTO = 0
 PC_ATTN_SIMT = 1
 PC_ATTN_TCGEN05 = 2
+PC_ATTN_GLOBAL_MERGE = 0x100
 
 EXPORTS = ("pc_version", "pc_last_error", "pc_device_info", "pc_splice_kv", "pc_splice_kv_tensors",
            "pc_rope_append", "pc_rope_append_dyn", "pc_attn_workspace_bytes", "pc_prefill_attn", "pc_decode_attn", "pc_launch_count",

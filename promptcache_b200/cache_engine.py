@@ -23,7 +23,7 @@ from typing import Dict, List, Optional, Tuple, Union
 import torch
 
 from . import _native as nat
-from .model._kv import LayerKV, PastKV
+from .model._kv import KVBuffer, PastKV
 from .prompt import ModuleRef, Prompt
 from .schema import Module, Path, Schema, TokenSequence, UnionModule
 
@@ -36,12 +36,13 @@ class SplicedKV(list):
     `GenerationEngine` can hand them to the model in O(1) instead of re-deriving 2L views and re-validating them on
     every request (that host work sat between the splice and the prefill with the GPU idle)."""
 
-    layer_kv: Optional[LayerKV] = None
+    kv_buffer: Optional[KVBuffer] = None
     rows: int = 0
+    epoch: int = 0  # of the buffer when process() handed the views out: a later process() makes them stale
 
     def batched(self) -> PastKV:
         """The `[(k.unsqueeze(0), v.unsqueeze(0)) ...]` of generation_engine.py:101-102, materialised lazily."""
-        return PastKV(self.layer_kv, self.rows)
+        return PastKV(self.kv_buffer, self.rows, self.epoch)
 
 
 def pad_batch(batch_list: List[List[int]], pad_id: int) -> Tuple[List[List[int]], List[List[int]]]:
@@ -100,6 +101,10 @@ class PromptCache:
         self.buffer = torch.zeros(num_layers, 2, num_head, max_ctx_length, head_dim, dtype=torch.half, device=device)
         self._bases_k = [self.buffer[l, 0] for l in range(num_layers)]  # [Hkv, max_ctx, D] per layer, built once
         self._bases_v = [self.buffer[l, 1] for l in range(num_layers)]
+        # append bookkeeping shared with the models: update() bumps its epoch, so a generation still running on the
+        # previous splice (or a `cache` kept from an earlier process()) raises StaleKVError instead of reading rows the
+        # new splice overwrote -- the reference's forward would hold a private torch.cat copy (llama2.py:361-364)
+        self.kv = KVBuffer(self._bases_k, self._bases_v, max_ctx_length, storage=self.buffer)
         self._views: Dict[int, SplicedKV] = {}                          # spliced length -> the 2L views of that length
         self.staged: List[TokenSequenceCache] = []
         self.length = 0
@@ -114,6 +119,7 @@ class PromptCache:
         """Forget the staged layout so the next update() moves every segment."""
         self.staged = []
         self.length = 0
+        self.kv.rewritten(0)
 
     @torch.inference_mode()
     def update(self, modules: List[TokenSequenceCache]) -> None:
@@ -136,6 +142,7 @@ class PromptCache:
         self.last_spliced_rows = sum(int(p.shape[3]) for p, _ in plan)
         self.staged = ordered
         self.length = row
+        self.kv.rewritten(row)  # rows >= `row` are scratch for the request being served; older pasts are stale now
 
     def __len__(self) -> int:
         return self.length
@@ -152,8 +159,7 @@ class PromptCache:
             master = SplicedKV((self.buffer[l, 0, :, :n, :], self.buffer[l, 1, :, :n, :]) for l in range(self.num_layers))
             self._views[n] = master
         out = SplicedKV(master)
-        out.layer_kv = LayerKV(self._bases_k, self._bases_v, n, self.max_ctx_length)
-        out.rows = n
+        out.kv_buffer, out.rows, out.epoch = self.kv, n, self.kv.epoch
         return out
 
 

@@ -25,7 +25,7 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 bool pdl_enabled() {
   static int on = -1;
   if (on < 0) {
-    const char* e = getenv("PC_PDL");
+    const char* e = dbg_env("PC_PDL");
     on = (e && e[0] == '0') ? 0 : 1;
   }
   return on != 0;
@@ -45,7 +45,6 @@ int sm_count() {
 }
 
 int launch_attn_simt(const pc_attn_params& p, cudaStream_t st);
-int launch_attn_tc(const pc_attn_params& p, cudaStream_t st);
 size_t attn_tc_workspace_bytes(int n_heads, int q_len, int head_dim);
 int launch_attn_small(const pc_attn_params& p, cudaStream_t st);
 int launch_attn_pp(const pc_attn_params& p, cudaStream_t st);
@@ -80,9 +79,9 @@ static int attn_dispatch(const pc_attn_params* p, void* stream, const char* who)
   PC_REQUIRE(align % 16 == 0, "%s: q/k/v/out must be 16B aligned", who);
   if (int rc = check_sm100()) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int impl = p->impl;
+  int impl = p->impl & PC_ATTN_IMPL_MASK;
   if (impl == PC_ATTN_AUTO) {
-    const char* e = getenv("PC_ATTN_IMPL");
+    const char* e = dbg_env("PC_ATTN_IMPL");
     if (e && e[0] == 's') impl = PC_ATTN_SIMT;
     else impl = PC_ATTN_TCGEN05;
   }
@@ -93,10 +92,8 @@ static int attn_dispatch(const pc_attn_params* p, void* stream, const char* who)
   }
   if (impl == PC_ATTN_SIMT) return launch_attn_simt(*p, st);
   if (impl == PC_ATTN_TCGEN05) {
-    const char* e = getenv("PC_ATTN_SMALL");
+    const char* e = dbg_env("PC_ATTN_SMALL");
     if (attn_small_supported(*p) && !(e && e[0] == '0')) return launch_attn_small(*p, st);
-    const char* v1 = getenv("PC_ATTN_V1");  // A/B switch: the single-tile kernel of attn_tc.cu
-    if (v1 && v1[0] == '1') return launch_attn_tc(*p, st);
     return launch_attn_pp(*p, st);
   }
   return set_error(PC_ERR_INVALID, "%s: unknown impl %d", who, p->impl);

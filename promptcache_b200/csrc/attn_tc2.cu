@@ -494,7 +494,7 @@ int launch_pp_d(const pc_attn_params& p, cudaStream_t st) {
   const int tiles = (p.n_cached + p.q_len + BN - 1) / BN;
   const int base = p.n_kv_heads * m_pairs;
   int n_splits = sm_count() / base;
-  if (const char* e = getenv("PC_ATTN_SPLITS")) n_splits = atoi(e);
+  if (const char* e = dbg_env("PC_ATTN_SPLITS")) n_splits = atoi(e);
   if (n_splits > tiles) n_splits = tiles;
   if (n_splits > kMaxSplits) n_splits = kMaxSplits;
   if (n_splits < 1) n_splits = 1;

@@ -58,7 +58,8 @@ struct SmallParams {
   const int* n_cached_dev;  // optional run-time N (graph-replayable decode)
   int n_heads, n_kv_heads, n_cached, q_len, n_splits, alibi_max_pos;
   float scale;
-  unsigned long long* trace;  // debug: %globaltimer stamps of CTA 0 (PC_ATTN_TRACE_PTR), else nullptr
+  unsigned long long* trace;  // PC_DEBUG builds: %globaltimer stamps of CTA 0 (PC_ATTN_TRACE_PTR), else nullptr
+  bool global_merge;          // PC_ATTN_GLOBAL_MERGE: merge split-KV partials through the workspace, not the cluster
 };
 
 __device__ __forceinline__ unsigned long long gtime() {
@@ -66,10 +67,14 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+#ifdef PC_DEBUG
 #define PC_TRACE(slot)                                                   \
   do {                                                                   \
     if (p.trace != nullptr && blockIdx.x == 0) p.trace[(slot)] = gtime(); \
   } while (0)
+#else
+#define PC_TRACE(slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ float round_h(float x) { return __half2float(__float2half_rn(x)); }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
@@ -593,8 +598,7 @@ int launch_small_one(const CUtensorMap& mq, const CUtensorMap& mk, const CUtenso
                                        SCfg<NPAD>::kSmem));
     configured = true;
   }
-  const char* e = getenv("PC_ATTN_CLUSTER");
-  const bool want_cluster = sp.n_splits >= 2 && sp.n_splits <= 8 && !(e && e[0] == '0');
+  const bool want_cluster = sp.n_splits >= 2 && sp.n_splits <= 8 && !sp.global_merge;
   if (want_cluster && clusters_fit<NPAD, ROUND, ALIBI>(sp.n_splits, grid / sp.n_splits)) {
     PC_CHECK_CUDA(launch_pdl_cluster(attn_small_kernel<NPAD, ROUND, ALIBI, true>, sp.n_splits, dim3(grid), dim3(kThreads),
                                      SCfg<NPAD>::kSmem, st, mq, mk, mv, sp));
@@ -611,7 +615,7 @@ int launch_small_n(const pc_attn_params& p, cudaStream_t st) {
   const int G = p.n_heads / p.n_kv_heads;
   const int tiles = (p.n_cached + p.q_len + BK - 1) / BK;  // with n_cached_dev: an upper bound
   int n_splits = sm_count() / p.n_kv_heads;
-  if (const char* e = getenv("PC_ATTN_SPLITS")) n_splits = atoi(e);
+  if (const char* e = dbg_env("PC_ATTN_SPLITS")) n_splits = atoi(e);
   if (n_splits > tiles) n_splits = tiles;
   if (n_splits > 64) n_splits = 64;
   if (n_splits < 1) n_splits = 1;
@@ -646,7 +650,8 @@ int launch_small_n(const pc_attn_params& p, cudaStream_t st) {
   sp.alibi_max_pos = p.alibi_max_pos;
   sp.scale = p.scale;
   sp.trace = nullptr;
-  if (const char* e = getenv("PC_ATTN_TRACE_PTR")) sp.trace = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
+  sp.global_merge = (p.impl & PC_ATTN_GLOBAL_MERGE) != 0;
+  if (const char* e = dbg_env("PC_ATTN_TRACE_PTR")) sp.trace = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
 
   const int rows_total = G * p.q_len;
   CUtensorMap mq, mk, mv;

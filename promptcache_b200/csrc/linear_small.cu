@@ -93,10 +93,14 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+#ifdef PC_DEBUG
 #define LIN_TRACE(slot)                                                 \
   do {                                                                  \
     if (p.trace != nullptr) p.trace[blockIdx.x * 8 + (slot)] = gtime(); \
   } while (0)
+#else
+#define LIN_TRACE(slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
@@ -731,7 +735,7 @@ PC_API int pc_linear_small(const pc_linear_params* p, void* stream) {
   lp.n_heads = p->n_heads;
   lp.n_kv_heads = p->n_kv_heads;
   lp.trace = nullptr;
-  if (const char* e = getenv("PC_LIN_TRACE_PTR")) lp.trace = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
+  if (const char* e = dbg_env("PC_LIN_TRACE_PTR")) lp.trace = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
 
   // Grid: an SM that is fed 16 KiB per TMA instruction pulls ~100 GB/s, so ~2/3 of the SMs saturate HBM.  When the
   // tile count has a divisor in [sm/2, sm] every CTA gets WHOLE tiles (no split-K, no cross-CTA reduction: the tail
@@ -748,9 +752,9 @@ PC_API int pc_linear_small(const pc_linear_params* p, void* stream) {
     const int per_tile = sm_count() / n_tiles;
     if (per_tile >= 2 && per_tile * n_tiles >= (sm_count() * 3) / 4) grid = per_tile * n_tiles;
   }
-  const char* hy = getenv("PC_LIN_HYBRID");
+  const char* hy = dbg_env("PC_LIN_HYBRID");
   if (p->epilogue == PC_LIN_PARTIALS) grid = n_tiles * lp.splits;
-  else if (const char* e = getenv("PC_LIN_GRID")) grid = atoi(e);
+  else if (const char* e = dbg_env("PC_LIN_GRID")) grid = atoi(e);
   else if (n_tiles > sm_count() && !(hy && hy[0] == '0')) {
     // more tiles than SMs: whole tiles first-come per CTA, the remainder shared stream-K (and processed first)
     grid = sm_count();
@@ -761,7 +765,7 @@ PC_API int pc_linear_small(const pc_linear_params* p, void* stream) {
   if (lp.whole_per_cta == 0 && grid > lp.units_total) grid = static_cast<int>(lp.units_total);
   if (grid < 1) grid = 1;
   lp.w_one_box = (lp.second_half_off == 64) ? 1 : 0;
-  if (const char* e = getenv("PC_LIN_ONEBOX")) lp.w_one_box = lp.w_one_box && atoi(e) != 0;
+  if (const char* e = dbg_env("PC_LIN_ONEBOX")) lp.w_one_box = lp.w_one_box && atoi(e) != 0;
   CUtensorMap mw, mx;
   if (int rc = make_tensor_map_3d(&mw, p->w, p->k, p->n_rows, 1, static_cast<long long>(p->n_rows) * p->k, lp.w_one_box ? 128 : 64))
     return rc;

@@ -1,6 +1,7 @@
 // Shared device helpers for the sm_100a kernels: mbarrier, TMA (bulk + tensor), tcgen05 / TMEM.
 // Everything is inline PTX; no CUTLASS dependency.
 #pragma once
+#include <stdlib.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -13,6 +14,13 @@ namespace pc {
 
 // ---- host-side error plumbing (api.cu) ---------------------------------------------------------
 int set_error(int code, const char* fmt, ...);
+// Experiment / A-B switches read from the environment exist only in debug builds (PC_NVCC_EXTRA=-DPC_DEBUG, used by
+// tools/); the product build has no getenv on its dispatch paths and never turns an environment string into a pointer.
+#ifdef PC_DEBUG
+inline const char* dbg_env(const char* name) { return getenv(name); }
+#else
+inline const char* dbg_env(const char*) { return nullptr; }
+#endif
 void count_launch(int n = 1);
 int sm_count();
 // Both tcgen05 attention kernels keep their split-KV arrival counters in the first bytes of the caller's

@@ -7,6 +7,7 @@
 // ring of kStages tiles per SM keeps kAhead loads plus (kStages-kAhead) stores in flight
 // (~96 KiB of reads in flight per SM, above the ~44 KiB Little's-law requirement at 6.5 TB/s).
 // Bound: HBM.  Algorithmic bytes = 2 * payload (read + write).
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -143,16 +144,17 @@ long long finish_descs(RunDesc* d, int n) {
   return t;
 }
 
-// Device-side descriptor table for pc_splice_kv_tensors (grown on demand, per process).
+// Device-side descriptor table for pc_splice_kv_tensors: one per stream (grown on demand), so calls on different
+// streams never wait on each other; a call only waits for the previous table of ITS OWN stream to be consumed.
 struct Staging {
-  std::mutex mu;
   RunDesc* host = nullptr;  // pinned
   RunDesc* dev = nullptr;
   size_t cap = 0;
   cudaEvent_t done = nullptr;
   bool pending = false;
 };
-Staging g_stage;
+std::mutex g_stage_mu;  // guards the map only
+std::map<cudaStream_t, Staging> g_stages;
 
 }  // namespace
 
@@ -218,8 +220,13 @@ PC_API int pc_splice_kv_tensors(const pc_copy2d* copies, int n_copies, void* str
   }
   if (int rc = configure()) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  std::lock_guard<std::mutex> lock(g_stage.mu);
-  if (g_stage.pending) {  // previous table may still be in flight on another stream
+  Staging* stage_ptr;
+  {
+    std::lock_guard<std::mutex> lock(g_stage_mu);
+    stage_ptr = &g_stages[st];  // std::map nodes are address-stable
+  }
+  Staging& g_stage = *stage_ptr;
+  if (g_stage.pending) {  // the previous table of this stream may still be in flight
     PC_CHECK_CUDA(cudaEventSynchronize(g_stage.done));
     g_stage.pending = false;
   }

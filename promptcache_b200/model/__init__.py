@@ -126,6 +126,14 @@ class Llama2(LanguageModel):
     def get_formatter(self) -> Callable[[str], str]:
         return self.formatter
 
+    def get_cache_shape(self) -> Tuple[int, int, int]:
+        """(L, KV heads, head_dim).  The reference returns num_attention_heads (model/__init__.py:110-114), which equals
+        the KV-head count for every Llama-2 7B/13B checkpoint it was run on; for grouped-query checkpoints (Llama-2-70B,
+        CodeLlama-34B) the cached K/V have num_key_value_heads heads, which is what the prompt cache must be sized for."""
+        c = self.config
+        hkv = getattr(c, "num_key_value_heads", None) or c.num_attention_heads
+        return c.num_hidden_layers, hkv, c.hidden_size // c.num_attention_heads
+
 
 class CodeLlama(Llama2):
     """model/__init__.py:164-182."""

@@ -91,15 +91,45 @@ class B200CausalLM(nn.Module):
 
     supports_dynamic_n = False    # _layers(..., n_dev=) reads the cached length on the device (decode graph)
 
+    def _launch_shape_key(self):
+        """Every switch that changes the launch sequence of `_layers`; part of each graph key so that toggling one
+        after a capture can never replay a stale sequence."""
+        return (self.linear_impl, tuple(sorted(self.linear_native_ops)), self.linear_max_q, self.linear_partials,
+                self.linear_tiled, self.attn_impl)
+
+    def _note_seen(self, key) -> None:
+        if len(self._graph_seen) >= 256:  # bounded: forked / short-lived buffers would otherwise grow it forever
+            self._graph_seen.clear()
+        self._graph_seen[key] = self._graph_seen.get(key, 0) + 1
+
+    def _weights_changed(self) -> None:
+        """Captured graphs and pre-tiled weight copies refer to the old parameter storage / values."""
+        self._graphs.clear()
+        tiled = getattr(self, "_tiled", None)
+        if tiled is not None:
+            tiled.clear()
+
+    def _apply(self, fn, *args, **kwargs):  # .to() / .half() / .cuda()
+        out = super()._apply(fn, *args, **kwargs)
+        if hasattr(self, "_graphs"):
+            self._weights_changed()
+            self._cos = self._sin = self._ws = self._lin_ws = None
+        return out
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._weights_changed()
+        return out
+
     def _decode_replay(self, ids, pos, kv):
         """One-token decode through ONE captured graph per KV buffer: the cached length is a device scalar the
         kernels read at run time (pc_rope_append_dyn, pc_attn_params.n_cached_dev), so the same graph serves every
         step of every request on that buffer (reference loop: generation_engine.py:123-147)."""
-        key = ("decode", kv.k[0].data_ptr(), kv.max_ctx, self.linear_impl)
+        key = ("decode", kv.buf.serial, kv.max_ctx) + self._launch_shape_key()
         entry = self._graphs.get(key)
         if entry is None:
             if self._graph_seen.get(key, 0) < 1:  # first decode step on this buffer runs eagerly
-                self._graph_seen[key] = 1
+                self._note_seen(key)
                 return None
             if len(self._graphs) >= self.max_graphs:
                 self._graphs.pop(next(iter(self._graphs)))
@@ -129,22 +159,25 @@ class B200CausalLM(nn.Module):
                 and N + 1 < kv.max_ctx and not torch.cuda.is_current_stream_capturing()):
             logits = self._decode_replay(ids, pos, kv)
             if logits is not None:
+                kv.wrote(N + 1)
                 return logits, (kv.views(N + 1) if use_cache else None)
         extra = self._graph_extra(max_position)
-        key = (q_len, N, kv.k[0].data_ptr(), kv.max_ctx, pos.shape[0], self.linear_impl, tuple(sorted(self.linear_native_ops))) + tuple(extra)
+        key = (q_len, N, kv.buf.serial, kv.max_ctx, pos.shape[0]) + self._launch_shape_key() + tuple(extra)
         if self.use_cuda_graphs and N > 0 and q_len > 1 and not torch.cuda.is_current_stream_capturing():
             entry = self._graphs.get(key)
             if entry is None and self._graph_seen.get(key, 0) >= 1:
                 entry = self._capture(key, ids, pos, kv, extra)
-            self._graph_seen[key] = self._graph_seen.get(key, 0) + 1
+            self._note_seen(key)
             if entry is not None:
                 graph, s_ids, s_pos, s_logits, n_native = entry
                 s_ids.copy_(ids, non_blocking=True)
                 s_pos.copy_(pos, non_blocking=True)
                 graph.replay()
                 nat.note_replayed_launches(n_native)
+                kv.wrote(N + q_len)
                 return s_logits.clone(), (kv.views(N + q_len) if use_cache else None)
         logits = self._layers(ids, pos, kv, extra)
+        kv.wrote(N + q_len)
         return logits, (kv.views(N + q_len) if use_cache else None)
 
     def _capture(self, key, ids, pos, kv, extra):

@@ -1,16 +1,32 @@
 """KV-buffer plumbing shared by the model families.
 
 The reference re-materialises the whole KV with torch.cat on every forward (llama2.py:361-364,
-falcon.py:446-452, mpt.py:148-151).  Here `past_key_values` are row-contiguous views
-[1,Hkv,N,D] of a buffer whose head stride (max_ctx*D) leaves room, and the new rows are written in place
-behind them by pc_rope_append; the tuple handed back is the same buffer viewed N+q rows long.
+falcon.py:446-452, mpt.py:148-151).  Here the KV of a sequence lives in a `KVBuffer` -- per-layer `[Hkv, max_ctx, D]`
+bases with room behind the valid rows -- and the new rows are written in place behind them by pc_rope_append (or the QKV
+projection's epilogue); the `past_key_values` handed back is the same buffer viewed N+q rows long.
+
+In-place appends must not change what a caller can observe compared with the reference's functional forward, so every
+buffer keeps two counters:
+  * `high`   rows written so far.  A past that ends BELOW it (the same past used twice, e.g. to score two continuations,
+             or a second generation started from the same spliced cache while the first is still running) is forked:
+             its rows are copied to a fresh buffer instead of clobbering what the first call appended;
+  * `epoch`  bumped whenever the owner re-writes the cached rows (PromptCache.update).  A past from an older epoch
+             refers to rows that no longer exist; using it raises `StaleKVError` instead of silently attending over
+             another request's segments (the reference's generator would still hold its private torch.cat copy).
+Only buffers the models / the engine created themselves are appended to in place; foreign tensors are copied once.
 """
 from __future__ import annotations
 
+import itertools
+import weakref
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
 import torch
+
+
+class StaleKVError(RuntimeError):
+    """`past_key_values` / a `process()` cache from before the engine re-spliced its buffer."""
 
 
 @dataclass
@@ -23,43 +39,74 @@ class CausalLMOutput:
         return (self.logits, self.past_key_values)[i]
 
 
-def _appendable(t: torch.Tensor, extra: int, head_dim: int) -> bool:
-    """Can `extra` rows be written behind view t = [1,Hkv,N,D] without leaving its storage?"""
-    if t.dim() != 4 or t.shape[0] != 1 or t.dtype != torch.float16 or not t.is_cuda:
-        return False
-    _, hkv, n, d = t.shape
-    if d != head_dim or t.stride(3) != 1 or t.stride(2) != d:
-        return False
-    hs = t.stride(1)  # sliced views keep the buffer's head stride even when Hkv == 1 (Falcon MQA)
-    if hs % d != 0 or hs < (n + extra) * d:
-        return False
-    if t.data_ptr() % 16 != 0:
-        return False
-    need = t.storage_offset() + (hkv - 1) * hs + (n + extra) * d
-    return t.untyped_storage().nbytes() // t.element_size() >= need
+_serial = itertools.count(1)
+_registry: "dict[int, weakref.ref]" = {}  # storage data_ptr -> KVBuffer (to recognise plain views of our own buffers)
+
+
+class KVBuffer:
+    """Per-layer K/V bases `[Hkv, max_ctx, D]` (strided views of one allocation) + the append bookkeeping."""
+
+    def __init__(self, k: List[torch.Tensor], v: List[torch.Tensor], max_ctx: int, storage: Optional[torch.Tensor] = None):
+        self.k, self.v, self.max_ctx = k, v, max_ctx
+        self.serial = next(_serial)   # never reused: identifies the buffer in CUDA-graph keys
+        self.epoch = 0
+        self.high = 0
+        self._storage = storage
+        if storage is not None:
+            _registry[storage.untyped_storage().data_ptr()] = weakref.ref(self)
+
+    def __del__(self):
+        try:
+            if self._storage is not None:
+                _registry.pop(self._storage.untyped_storage().data_ptr(), None)
+        except Exception:
+            pass
+
+    def rewritten(self, rows: int) -> None:
+        """The owner re-wrote rows [.., rows): everything handed out before is stale."""
+        self.epoch += 1
+        self.high = rows
+
+    @staticmethod
+    def allocate(n_layers: int, n_kv_heads: int, cap: int, head_dim: int, device) -> "KVBuffer":
+        buf = torch.zeros(n_layers, 2, n_kv_heads, cap, head_dim, dtype=torch.float16, device=device)
+        return KVBuffer([buf[l, 0] for l in range(n_layers)], [buf[l, 1] for l in range(n_layers)], cap, storage=buf)
+
+
+def buffer_of(t: torch.Tensor) -> Optional[KVBuffer]:
+    ref = _registry.get(t.untyped_storage().data_ptr())
+    return ref() if ref is not None else None
 
 
 class LayerKV:
-    """Per-forward view of the per-layer K/V buffers: base pointers as [Hkv, max_ctx, D] strided tensors."""
+    """What one forward works on: a buffer and the number of valid rows in front of the rows it will write."""
 
-    def __init__(self, k: List[torch.Tensor], v: List[torch.Tensor], n_cached: int, max_ctx: int):
-        self.k, self.v, self.n_cached, self.max_ctx = k, v, n_cached, max_ctx
+    def __init__(self, buf: KVBuffer, n_cached: int):
+        self.buf, self.n_cached = buf, n_cached
+
+    k = property(lambda self: self.buf.k)
+    v = property(lambda self: self.buf.v)
+    max_ctx = property(lambda self: self.buf.max_ctx)
 
     def views(self, rows: int) -> "PastKV":
-        return PastKV(self, rows)
+        return PastKV(self.buf, rows)
+
+    def wrote(self, rows: int) -> None:
+        self.buf.high = max(self.buf.high, rows)
 
 
 class PastKV:
     """`past_key_values` as the models hand it back: behaves like the reference's tuple of L (K, V) pairs, each
     [1, Hkv, rows, D] (llama2.py:366), but the views are only materialised when somebody indexes them.  Passing it
-    back into the next forward is O(1): the buffers are recognised instead of re-validated tensor by tensor."""
+    back into the next forward is O(1): the buffer is recognised instead of re-validated tensor by tensor."""
 
-    def __init__(self, kv: LayerKV, rows: int):
-        self.kv, self.rows = kv, rows
+    def __init__(self, buf: KVBuffer, rows: int, epoch: Optional[int] = None):
+        self.buf, self.rows = buf, rows
+        self.epoch = buf.epoch if epoch is None else epoch
         self._views = {}
 
     def __len__(self) -> int:
-        return len(self.kv.k)
+        return len(self.buf.k)
 
     def __getitem__(self, l):
         if isinstance(l, slice):
@@ -67,7 +114,7 @@ class PastKV:
         if l < 0:
             l += len(self)
         if l not in self._views:
-            k, v = self.kv.k[l], self.kv.v[l]
+            k, v = self.buf.k[l], self.buf.v[l]
             self._views[l] = (k[:, :self.rows, :].unsqueeze(0), v[:, :self.rows, :].unsqueeze(0))
         return self._views[l]
 
@@ -75,35 +122,56 @@ class PastKV:
         return (self[l] for l in range(len(self)))
 
 
-def _as_strided_head_major(t: torch.Tensor, max_ctx: int) -> torch.Tensor:
-    """[1,Hkv,N,D] view -> [Hkv,max_ctx,D] view over the same storage."""
-    _, hkv, _, d = t.shape
-    return t.as_strided((hkv, max_ctx, d), (max_ctx * d, d, 1), t.storage_offset())
+def _own_view_rows(past, head_dim: int) -> Optional[Tuple[KVBuffer, int]]:
+    """Is `past` a list of plain `[1,Hkv,N,D]` views that start at row 0 of every layer of one of OUR buffers (what
+    eval_sys.py:340 builds from `process()`'s cache)?  Returns (buffer, N)."""
+    k0 = past[0][0]
+    buf = buffer_of(k0)
+    if buf is None or len(past) != len(buf.k) or k0.dim() != 4 or k0.shape[0] != 1:
+        return None
+    n = int(k0.shape[2])
+    for l, (k, v) in enumerate(past):
+        for t, base in ((k, buf.k[l]), (v, buf.v[l])):
+            if (t.dim() != 4 or t.shape[0] != 1 or t.data_ptr() != base.data_ptr() or t.shape[2] != n or t.stride(3) != 1
+                    or t.stride(2) != head_dim or (t.shape[1] > 1 and t.stride(1) != base.stride(0))):
+                return None
+    return buf, n
+
+
+def _fork(src_k, src_v, n_cached: int, q_len: int, n_layers: int, n_kv_heads: int, head_dim: int, device,
+          headroom: int) -> LayerKV:
+    cap = ((n_cached + q_len + headroom + 127) // 128) * 128
+    buf = KVBuffer.allocate(n_layers, n_kv_heads, cap, head_dim, device)
+    if n_cached > 0:
+        for l in range(n_layers):
+            buf.k[l][:, :n_cached].copy_(src_k(l).reshape(n_kv_heads, n_cached, head_dim))
+            buf.v[l][:, :n_cached].copy_(src_v(l).reshape(n_kv_heads, n_cached, head_dim))
+    buf.high = n_cached
+    return LayerKV(buf, n_cached)
 
 
 def resolve_kv(past: Optional[Sequence[Tuple[torch.Tensor, torch.Tensor]]], q_len: int, n_layers: int,
                n_kv_heads: int, head_dim: int, device, headroom: int = 256) -> LayerKV:
-    """Find (or build) buffers that already hold the past rows and have room for q_len more."""
-    if isinstance(past, PastKV) and past.rows + q_len <= past.kv.max_ctx:
-        return LayerKV(past.kv.k, past.kv.v, past.rows, past.kv.max_ctx)  # our own buffers coming back: O(1)
+    """Find (or build) a buffer that already holds the past rows and has room for q_len more."""
+    buf = rows = None
+    if isinstance(past, PastKV):
+        if past.epoch != past.buf.epoch:
+            raise StaleKVError("this past_key_values / process() cache was handed out before the engine re-spliced its "
+                               "buffer (another CacheEngine.process ran); its rows no longer exist")
+        buf, rows = past.buf, past.rows
+    elif past is not None and len(past) > 0 and past[0] is not None and int(past[0][0].shape[-2]) > 0:
+        own = _own_view_rows(past, head_dim)
+        if own is not None:
+            buf, rows = own
+    if buf is not None:
+        if rows == buf.high and rows + q_len <= buf.max_ctx:
+            return LayerKV(buf, rows)                      # the tip of the sequence: append in place, O(1)
+        # somebody already appended behind these rows (or there is no room): continue on a private copy
+        return _fork(lambda l: buf.k[l][:, :rows], lambda l: buf.v[l][:, :rows], rows, q_len, n_layers, n_kv_heads,
+                     head_dim, device, headroom)
     if past is None or len(past) == 0 or past[0] is None:
         n_cached = 0
     else:
         n_cached = int(past[0][0].shape[-2])
-    if n_cached > 0:
-        ok = all(_appendable(k, q_len, head_dim) and _appendable(v, q_len, head_dim) for k, v in past)
-        if ok:
-            ok = len({t.stride(1) for kv in past for t in kv}) == 1
-        if ok:
-            max_ctx = past[0][0].stride(1) // head_dim
-            ks = [_as_strided_head_major(k, max_ctx) for k, _ in past]
-            vs = [_as_strided_head_major(v, max_ctx) for _, v in past]
-            return LayerKV(ks, vs, n_cached, max_ctx)
-    # own buffer (no past, or past without room: copy it once)
-    cap = ((n_cached + q_len + headroom + 127) // 128) * 128
-    buf = torch.zeros(n_layers, 2, n_kv_heads, cap, head_dim, dtype=torch.float16, device=device)
-    if n_cached > 0:
-        for l, (k, v) in enumerate(past):
-            buf[l, 0, :, :n_cached].copy_(k.reshape(n_kv_heads, n_cached, head_dim))
-            buf[l, 1, :, :n_cached].copy_(v.reshape(n_kv_heads, n_cached, head_dim))
-    return LayerKV([buf[l, 0] for l in range(n_layers)], [buf[l, 1] for l in range(n_layers)], n_cached, cap)
+    # no past, or foreign tensors: the forward stays functional (the caller's storage is never written)
+    return _fork(lambda l: past[l][0], lambda l: past[l][1], n_cached, q_len, n_layers, n_kv_heads, head_dim, device, headroom)

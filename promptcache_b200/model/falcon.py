@@ -75,6 +75,7 @@ class FalconForCausalLM(B200CausalLM):
 
     @torch.no_grad()
     def load_hf_state_dict(self, sd) -> None:
+        self._weights_changed()
         g = lambda k: sd[k].to(self.word_embeddings.device, self.word_embeddings.dtype)
         self.word_embeddings.copy_(g("transformer.word_embeddings.weight"))
         self.lnf_w.copy_(g("transformer.ln_f.weight"))

@@ -84,6 +84,7 @@ class MptForCausalLM(B200CausalLM):
 
     @torch.no_grad()
     def load_hf_state_dict(self, sd) -> None:
+        self._weights_changed()
         g = lambda k: sd[k].to(self.wte.device, self.wte.dtype)
         self.wte.copy_(g("transformer.wte.weight"))
         self.norm_f.copy_(g("transformer.norm_f.weight"))

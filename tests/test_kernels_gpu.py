@@ -332,11 +332,10 @@ def test_attention_cluster_merge_equals_global_merge(native, monkeypatch, H, Hkv
     Q, K, V = _attn_case(H, Hkv, D, q, N, seed=H + q + N, std=1.28)
     ws = torch.zeros(max(native.attn_workspace_bytes(H, q, D), 1), dtype=torch.uint8, device=DEV)
     outs = []
-    for flag in ("1", "0", "1"):
-        monkeypatch.setenv("PC_ATTN_CLUSTER", flag)
+    for flag in (0, native.PC_ATTN_GLOBAL_MERGE, 0):
         out = torch.full((q, H * D), float("nan"), dtype=torch.half, device=DEV)
         native.attention(Q, K, V, out, N, q, H, Hkv, D, native.softmax_scale(D), native.PC_ROUND_LLAMA, workspace=ws,
-                         impl=native.PC_ATTN_TCGEN05, decode=(q == 1))
+                         impl=native.PC_ATTN_TCGEN05 | flag, decode=(q == 1))
         torch.cuda.synchronize()
         outs.append(out)
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
@@ -358,10 +357,10 @@ def test_attention_cluster_merge_with_runtime_length_and_surplus_ranks(native, m
         n_dev = torch.tensor([N], dtype=torch.int32, device=DEV)
         res = {}
         for flag in ("1", "0"):
-            monkeypatch.setenv("PC_ATTN_CLUSTER", flag)
             out = torch.full((q, H * D), float("nan"), dtype=torch.half, device=DEV)
             native.attention(Q, K2, V2, out, max_ctx - q, q, H, Hkv, D, native.softmax_scale(D), native.PC_ROUND_LLAMA,
-                             workspace=ws, n_cached_dev=n_dev, impl=native.PC_ATTN_TCGEN05)
+                             workspace=ws, n_cached_dev=n_dev,
+                             impl=native.PC_ATTN_TCGEN05 | (native.PC_ATTN_GLOBAL_MERGE if flag == "0" else 0))
             torch.cuda.synchronize()
             res[flag] = out
         assert torch.equal(res["1"], res["0"])
