@@ -1,17 +1,25 @@
 #!/usr/bin/env python
 """Headline benchmark: Llama-2-7B TTFT (ms) and prefill tok/s on the prompt-cache hot path.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config C2]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config C1|C2|C3|C4|C5]
 
-One step = one request on BASELINE config C2 (code-generation-game shape: 7 cached segments [24,400x5,24] =
-2048 tokens, 16-token uncached suffix): request plan -> splice of ALL segments (retained-prefix shortcut off) ->
-32-layer prefill of the suffix over the spliced cache (per layer: QKV projection with RoPE at position ids + in-place
-append in its epilogue, tcgen05 attention, o_proj / MLP as weight-streaming tcgen05 kernels) -> logits.  TTFT = ms_per_step; value = served prompt tokens/s
-= n_gpus*(N+q)/TTFT.  Weights are seeded random fp16 at the real dims, token ids synthetic (no network).
-N>1: one rank per GPU, every rank serves its own prompt against its own HBM-resident segment store (weak
-scaling, no data-path collective); NCCL only for the barrier and the max-over-ranks time.
-`--impl reference` times the reference's algorithm for the same step on the host cores (oracle port: the
-reference itself cannot travel to the GPU box).
+One step = one request on BASELINE config C2 (code-generation-game shape: 7 cached segments [24,400x5,24] = 2048
+tokens, 16-token uncached suffix): request plan -> splice of ALL segments (retained-prefix shortcut off) -> 32-layer
+prefill of the suffix over the spliced cache (per layer: QKV projection with RoPE at position ids + in-place append in
+its epilogue, tcgen05 attention, o_proj / MLP as weight-streaming tcgen05 kernels) -> logits.  TTFT = ms_per_step;
+value = served prompt tokens/s = n_gpus*(N+q)/TTFT ("effective"); `computed_tok_s` = n_gpus*q/TTFT.  Weights are seeded
+random fp16 at the real dims, token ids synthetic (no network).
+
+N>1: one rank per GPU, every rank serves its own prompt against its own HBM-resident segment store (weak scaling, no
+data-path collective); NCCL only for the barrier, the max-over-ranks time and the one-time broadcast of the encoded
+segment store.  Every line also carries a `c5` block: BASELINE config C5 (B=64 prompts, each 32 of a 64-segment pool
+= 8192 cached tokens + 32-token suffix) served through `parallel.serve_batch`'s partition (prompt b -> rank b mod G),
+with the NCCL pool broadcast timed against the NVLink peer rate.  At N=1 the line also carries `c4` (Falcon-7B real
+dims, parameterized schema), the suffix sweep S and the CPU baseline.
+
+`--impl reference` runs the UNMODIFIED reference (oracle/_ref, staged by oracle/make_ref.py) through its own
+CacheEngine.process -> GenerationEngine.generate on the host cores, all layers (cpu_baseline.kind "reference"); only
+when the staged copy is missing does it fall back to the oracle port (kind "port").
 """
 import argparse
 import json
@@ -27,6 +35,8 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
+NVLINK_PEER_GBS = 770.0  # measured peer-copy rate per direction (B200_PROFILING.md); denominator of the pool broadcast
+
 
 def load_traffic(kernel, config):
     """DRAM traffic per launch measured once with `ncu --set full` (committed under profiles/), or None."""
@@ -36,98 +46,6 @@ def load_traffic(kernel, config):
         return float(t["bytes"]) if t and t.get("config") == config else None
     except Exception:
         return None
-
-
-def attention_alone(nat, lm, case, dev, peak):
-    """The per-layer attention kernel timed ALONE (16 launches captured in a CUDA graph, rotating over 8 layers of
-    K/V = 270 MB > L2) -- inside the step it runs within the forward graph and cannot be event-timed."""
-    L, Hkv, D = lm.get_cache_shape()
-    H, q, N = lm.hf_model.n_heads, case.q_len, case.n_cached
-    rot = 8
-    max_ctx = ((N + q + 127) // 128) * 128
-    K = torch.randn(rot, Hkv, max_ctx, D, device=dev).half()
-    V = torch.randn(rot, Hkv, max_ctx, D, device=dev).half()
-    Q = torch.randn(H, q, D, device=dev).half()
-    out = torch.empty(q, H * D, dtype=torch.half, device=dev)
-    ws = torch.zeros(max(nat.attn_workspace_bytes(H, q, D), 1), dtype=torch.uint8, device=dev)
-    state = {"i": 0}
-
-    def run():
-        l = state["i"] % rot
-        state["i"] += 1
-        nat.attention(Q, K[l], V[l], out, N, q, H, Hkv, D, nat.softmax_scale(D), nat.PC_ROUND_LLAMA, workspace=ws)
-
-    run()
-    torch.cuda.synchronize()
-    g, st = torch.cuda.CUDAGraph(), torch.cuda.Stream()
-    with torch.cuda.stream(st):
-        run()
-        torch.cuda.synchronize()
-        with torch.cuda.graph(g, stream=st):
-            for _ in range(16):
-                run()
-    torch.cuda.synchronize()
-    g.replay()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10):
-        g.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 160
-    byts = 4.0 * Hkv * (N + q) * D + 4.0 * H * q * D
-    ach = byts / (ms * 1e-3) / 1e9
-    return {"kernel": "attn_small_kernel (pc_prefill_attn, one layer)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-            "frac": ach / peak, "traffic": load_traffic("attn_small_kernel", "C2"), "algorithmic_bytes_per_launch": byts,
-            "avg_launch_ms": ms, "timed": "alone, CUDA-graph of 16 back-to-back launches over 8 layers of K/V (inputs > L2); "
-            "launches carry the programmatic-dependent-launch attribute as in the step, so a launch's prologue overlaps its predecessor's tail",
-            "note": "34 MB per launch = 5 us at peak: launch/prologue latency bound at this size; 0.66 of peak at C5 (135 MB)"}
-
-
-def attention_tensor_alone(nat, dev, tflops_peak):
-    """Long-suffix (tensor-bound) regime of the same entry point: 1024 uncached tokens over 8192 cached ones at
-    Llama-2-7B head geometry, timed alone (CUDA-graph of 8 launches over 4 layers of K/V)."""
-    H = Hkv = 32
-    D, q, N, rot = 128, 1024, 8192, 4
-    max_ctx = N + q
-    K = torch.randn(rot, Hkv, max_ctx, D, device=dev).half()
-    V = torch.randn(rot, Hkv, max_ctx, D, device=dev).half()
-    Q = torch.randn(H, q, D, device=dev).half()
-    out = torch.empty(q, H * D, dtype=torch.half, device=dev)
-    ws = torch.zeros(max(nat.attn_workspace_bytes(H, q, D), 1), dtype=torch.uint8, device=dev)
-    state = {"i": 0}
-
-    def run():
-        l = state["i"] % rot
-        state["i"] += 1
-        nat.attention(Q, K[l], V[l], out, N, q, H, Hkv, D, nat.softmax_scale(D), nat.PC_ROUND_LLAMA, workspace=ws)
-
-    run()
-    torch.cuda.synchronize()
-    g, st = torch.cuda.CUDAGraph(), torch.cuda.Stream()
-    with torch.cuda.stream(st):
-        run()
-        torch.cuda.synchronize()
-        with torch.cuda.graph(g, stream=st):
-            for _ in range(8):
-                run()
-    torch.cuda.synchronize()
-    g.replay()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(5):
-        g.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 40
-    flops = 4.0 * H * D * (q * N + q * (q + 1) / 2)  # causal-aware: key N+t is visible to rows r >= t
-    ach = flops / (ms * 1e-3) / 1e12
-    return {"kernel": "attn_pp_kernel (pc_prefill_attn, one layer, q=1024 over N=8192)", "bound": "tensor", "achieved": ach,
-            "peak": tflops_peak, "unit": "TFLOP/s", "frac": ach / tflops_peak, "traffic": None, "algorithmic_flops_per_launch": flops,
-            "avg_launch_ms": ms, "timed": "alone, CUDA-graph of 8 launches (burst peak applies)",
-            "ncu": "sm__pipe_tensor_cycles_active 47% of active cycles (profiles/r01_ncu_full_attn_pp_v4.txt)"}
 
 
 def load_peaks():
@@ -164,13 +82,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def stop(self, upto=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines[self.first:]:
+        for ln in self.lines[self.first:upto]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -187,13 +105,284 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the reference's algorithm (oracle port) on the host cores, bounded sample
+# workloads
 # ------------------------------------------------------------------------------------------------
-class CpuReference:
-    """TTFT of the reference's CPU path = splice (cache_engine.py:116-156, fp16 cache) + prefill forward
-    (llama2.py, fp32 weights as `Llama2(name, device_map=None)` loads them on CPU, eval_sys.py:45-51).
-    One step times the FULL splice and `sample_layers` of the L decoder layers (+ embedding, final norm,
-    lm_head) and scales the layer time by L/sample_layers."""
+SEG_LENS = {"C1": [24] + [92] * 6 + [24], "C2": [24] + [400] * 5 + [24], "C3": [512] * 8}
+
+
+def build_lm(model_key, dev, layers=None):
+    """The CUDA-path LanguageModel of a BASELINE config at real dims, seeded random fp16 weights."""
+    from promptcache_b200.model import Falcon, Llama2, LlamaConfigLite, LlamaForCausalLM
+    from promptcache_b200.model.falcon import FalconConfigLite, FalconForCausalLM
+    from promptcache_b200.synthetic import MODEL_DIMS, IdTokenizer
+    md = dict(MODEL_DIMS[model_key])
+    if layers:
+        md["num_hidden_layers"] = layers
+    torch.manual_seed(0)
+    tok = IdTokenizer(md["vocab_size"])
+    if model_key.startswith("falcon"):
+        return Falcon(model_key, model=FalconForCausalLM(FalconConfigLite(**md), device=dev), tokenizer=tok), md
+    return Llama2(model_key, model=LlamaForCausalLM(LlamaConfigLite(**md), device=dev), tokenizer=tok), md
+
+
+def weight_bytes(md, model_key):
+    """fp16 bytes of every matrix one forward streams once (embedding rows excluded: q rows only)."""
+    hid, L, V = md["hidden_size"], md["num_hidden_layers"], md["vocab_size"]
+    if model_key.startswith("falcon"):
+        D = hid // md["num_attention_heads"]
+        per = (hid + 2 * D) * hid + hid * hid + 8 * hid * hid
+    else:
+        per = 4 * hid * hid + 3 * hid * md["intermediate_size"]
+    return 2.0 * (L * per + V * hid)
+
+
+class RequestStep:
+    """One request of a flat BASELINE config (C1-C4) on one GPU: device-resident arm and public-API arm."""
+
+    def __init__(self, lm, case, dev, world, rank, seg_lens=None):
+        from promptcache_b200 import CacheEngine, GenerationEngine, GenerationParameters, Prompt, parallel
+        from promptcache_b200.synthetic import flat_schema
+        self.lm, self.case, self.dev = lm, case, dev
+        max_ctx = ((case.n_cached + case.q_len + 256 + 127) // 128) * 128
+        self.eng = eng = CacheEngine(max_ctx, lm)
+        eng.prompt_cache.retain_prefix = False  # every step splices every segment
+        self.broadcast = None
+        if world > 1:
+            # rank 0 encodes the schema once; the segment store reaches the other GPUs over NCCL (NVLink)
+            eng.add_schema(case.schema_xml, no_cache=(rank != 0))
+            self.broadcast = timed_broadcast(eng.schemas[case.name], dev)
+        else:
+            eng.add_schema(case.schema_xml)
+        prompt_xml = case.prompt_xml
+        if world > 1 and seg_lens is not None:  # each rank serves its own prompt (same modules, its own suffix tokens)
+            prompt_xml = flat_schema(case.name, seg_lens, case.q_len, lm.hf_tokenizer.vocab_size, seed=1002 + 17 * rank).prompt_xml
+        self.prompt = Prompt(prompt_xml)
+        self.gen = GenerationEngine(lm)
+        self.params = GenerationParameters(temperature=0.0, max_new_tokens=1, stop_token_ids=[], stop_str=[])
+        ids, pos, _, _ = eng.process(self.prompt)
+        self.q_len = len(ids)
+        self.ids_dev = torch.tensor([ids], device=dev)
+        self.pos_dev = torch.tensor([pos], device=dev)
+        cached, used, _, _, _, _ = eng.plan(self.prompt, collect_original=False)
+        self.seq_caches = [cached.get_cache_l1(s) for s in used if len(s) > 0]
+        self.max_pos = max(pos)
+        self.splice_ev = []
+
+    def device_step(self, record=False):
+        """ids already in HBM, no host sync inside the step."""
+        if record:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        self.eng.prompt_cache.update(self.seq_caches)
+        if record:
+            e1.record()
+            self.splice_ev.append((e0, e1))
+        return self.lm(input_ids=self.ids_dev, position_ids=self.pos_dev, past_key_values=self.eng.prompt_cache.cache.batched(),
+                       use_cache=True, max_position=self.max_pos)
+
+    def e2e_step(self):
+        """The public API with host inputs (token lists -> device) and the first token read back."""
+        i2, p2, _, cache = self.eng.process(self.prompt)
+        return next(self.gen.generate(i2, p2, self.params, cache, stream_interval=1))
+
+    def timed(self, fn, steps, sync_all):
+        sync_all()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(steps):
+            fn()
+        t1.record()
+        sync_all()
+        return t0.elapsed_time(t1) / steps
+
+
+def timed_broadcast(schema_cache, dev):
+    """NCCL broadcast of the encoded segment store from rank 0, device-timed, max over ranks."""
+    import torch.distributed as dist
+    from promptcache_b200 import parallel
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    moved = parallel.broadcast_schema(schema_cache, src=0, device=dev)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = parallel.max_over_ranks(e0.elapsed_time(e1), device=dev)
+    gbs = moved["bytes"] / (ms * 1e-3) / 1e9 if ms > 0 else None
+    return {"bytes": moved["bytes"], "segments": moved["segments"], "ms": ms, "GB/s": gbs, "peer_peak_GB/s": NVLINK_PEER_GBS,
+            "frac_of_peer_peak": (gbs / NVLINK_PEER_GBS) if gbs else None,
+            "note": "one ncclBroadcast per packed segment, rank 0 -> all; includes the object broadcast of the shape header"}
+
+
+def c5_block(lm, dev, world, rank, batch=64, pool=64, picks=32, seg_len=256, suffix=32):
+    """BASELINE configs[4]: Llama-2-7B, a pool of 64 segments x 256 tokens, B=64 prompts each choosing 32 (seed 5) ->
+    N=8192 cached tokens + 32-token suffix, sharded b mod G over the ranks.  Timed through the public calls
+    (CacheEngine.process + GenerationEngine.generate(max_new_tokens=1)), host id lists in, token out."""
+    import random
+    import torch.distributed as dist
+    from promptcache_b200 import CacheEngine, GenerationEngine, GenerationParameters, Prompt, parallel
+    from promptcache_b200.synthetic import pool_prompt, pool_schema
+    vocab = lm.hf_tokenizer.vocab_size
+    schema_xml, names = pool_schema("pool", pool, seg_len, vocab, seed=1005)
+    n_cached = picks * seg_len
+    max_ctx = ((n_cached + suffix + 256 + 127) // 128) * 128
+    eng = CacheEngine(max_ctx, lm)
+    t0 = time.perf_counter()
+    eng.add_schema(schema_xml, no_cache=(world > 1 and rank != 0))
+    torch.cuda.synchronize()
+    encode_s = time.perf_counter() - t0
+    bc = timed_broadcast(eng.schemas["pool"], dev) if world > 1 else None
+    rng = random.Random(5)
+    prompts = [Prompt(pool_prompt("pool", sorted(rng.sample(names, picks), key=lambda n: int(n[1:])), suffix, vocab, seed=5000 + b))
+               for b in range(batch)]
+    gen = GenerationEngine(lm)
+    params = GenerationParameters(temperature=0.0, max_new_tokens=1, stop_token_ids=[], stop_str=[])
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out = {}
+    for mode, retain in (("full_splice", False), ("retained_prefix", True)):
+        eng.prompt_cache.retain_prefix = retain
+        for m in eng.schemas["pool"].cache_l1.values():
+            m.usage_counter = 0
+        eng.prompt_cache.invalidate()
+        parallel.serve_batch(eng, gen, prompts[:2 * world], params)  # warm-up: graph capture of the (q, N) shape
+        for m in eng.schemas["pool"].cache_l1.values():
+            m.usage_counter = 0
+        eng.prompt_cache.invalidate()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        served = parallel.serve_batch(eng, gen, prompts, params)
+        e1.record()
+        sync_all()
+        ms = parallel.max_over_ranks(e0.elapsed_time(e1), device=dev)
+        ttft = [s.ttft_ms for s in served]
+        spliced = sum(s.spliced_rows for s in served)
+        out[mode] = {"batch_ms": ms, "tok_s": batch * (n_cached + suffix) / (ms * 1e-3), "computed_tok_s": batch * suffix / (ms * 1e-3),
+                     "ttft_ms_mean": statistics.mean(ttft), "ttft_ms_max": max(ttft),
+                     "cache_ms_mean": statistics.mean(s.cache_ms for s in served),
+                     "prefill_ms_mean": statistics.mean(s.prefill_ms for s in served),
+                     "spliced_rows": spliced, "retained_row_fraction": 1.0 - spliced / float(batch * n_cached),
+                     "prompts_per_rank": [sum(1 for s in served if s.rank == r) for r in range(world)]}
+    L, Hkv, D = lm.get_cache_shape()
+    res = {"workload": f"C5: {batch} prompts x ({picks} of a {pool}-segment pool x {seg_len} tokens = {n_cached} cached + {suffix} suffix), "
+                       f"prompt b -> rank b mod {world}; public API (process + generate(1)), max over ranks",
+           "n_gpus": world, "pool_bytes": 4.0 * L * Hkv * D * pool * seg_len, "encode_s_rank0": encode_s, "broadcast": bc, **out,
+           "note": "retained_prefix: usage-ordered layout + retained common prefix (cache_engine.py:121-131) on; "
+                   "full_splice: every request moves all 8192 rows (8 GiB of HBM traffic)"}
+    del eng
+    return res
+
+
+def c4_block(dev, steps, warmup):
+    """BASELINE configs[3]: Falcon-7B at real dims (H=71, Hkv=1, D=64, hidden 4544, 32 layers), parameterized schema:
+    5 segments = 256 cached tokens, 21-token suffix of which 5 sit at interior parameter slots (non-monotone ids)."""
+    from promptcache_b200.synthetic import make_case
+    lm, md = build_lm("falcon-7b", dev)
+    case = make_case("C4", vocab=md["vocab_size"])
+    w = RequestStep(lm, case, dev, 1, 0)
+    sync = torch.cuda.synchronize
+    for _ in range(warmup):
+        w.device_step()
+    dev_ms = w.timed(lambda: w.device_step(True), steps, sync)
+    for _ in range(warmup):
+        w.e2e_step()
+    e2e_ms = w.timed(w.e2e_step, steps, sync)
+    tokens = case.n_cached + w.q_len
+    wb = weight_bytes(md, "falcon-7b")
+    peak, _, _ = load_peaks()
+    res = {"workload": f"C4: falcon-7b, {case.n_segments} cached segments = {case.n_cached} tokens, {w.q_len}-token suffix "
+                       f"(position ids {w.pos_dev[0, :6].tolist()}..., non-monotone), one request per step",
+           "ttft_ms": dev_ms, "tok_s": tokens / (dev_ms * 1e-3), "computed_tok_s": w.q_len / (dev_ms * 1e-3),
+           "e2e_ttft_ms": e2e_ms, "e2e_tok_s": tokens / (e2e_ms * 1e-3),
+           "splice_ms": statistics.mean(a.elapsed_time(b) for a, b in w.splice_ev),
+           "roofline_step": {"bound": "hbm", "algorithmic_bytes": wb, "achieved": wb / (dev_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": wb / (dev_ms * 1e-3) / 1e9 / peak, "note": "weights only (14.4 GB); linears are cuBLAS for Falcon"}}
+    del w, lm
+    torch.cuda.empty_cache()
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
+# attention micro-benchmarks (kernel alone; the step's own attribution comes from the ablation runs in main)
+# ------------------------------------------------------------------------------------------------
+def attention_point(nat, dev, H, Hkv, D, q, N, peak, tflops_peak, rounding=None, launches=16):
+    """One (q, N) point of pc_prefill_attn timed ALONE: a CUDA graph of `launches` back-to-back launches rotating over
+    enough layers of K/V to exceed L2."""
+    rounding = nat.PC_ROUND_LLAMA if rounding is None else rounding
+    max_ctx = ((N + q + 127) // 128) * 128
+    per_layer = 4.0 * Hkv * max_ctx * D
+    rot = max(2, min(8, int(300e6 // per_layer) + 1))
+    K = torch.randn(rot, Hkv, max_ctx, D, device=dev).half()
+    V = torch.randn(rot, Hkv, max_ctx, D, device=dev).half()
+    Q = torch.randn(H, q, D, device=dev).half()
+    out = torch.empty(q, H * D, dtype=torch.half, device=dev)
+    ws = torch.zeros(max(nat.attn_workspace_bytes(H, q, D), 1), dtype=torch.uint8, device=dev)
+    state = {"i": 0}
+
+    def run():
+        l = state["i"] % rot
+        state["i"] += 1
+        nat.attention(Q, K[l], V[l], out, N, q, H, Hkv, D, nat.softmax_scale(D), rounding, workspace=ws, decode=(q == 1))
+
+    run()
+    torch.cuda.synchronize()
+    g, st = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        run()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(launches):
+                run()
+    torch.cuda.synchronize()
+    g.replay()
+    torch.cuda.synchronize()
+    reps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / (reps * launches)
+    byts = 4.0 * Hkv * (N + q) * D + 4.0 * H * q * D
+    flops = 4.0 * H * D * (q * N + q * (q + 1) / 2)  # causal-aware: key N+t is visible to rows r >= t
+    gbs, tf = byts / (ms * 1e-3) / 1e9, flops / (ms * 1e-3) / 1e12
+    G = H // Hkv
+    return {"q": q, "N": N, "H": H, "Hkv": Hkv, "D": D, "us": ms * 1e3, "GB/s": gbs, "frac_hbm": gbs / peak, "TFLOP/s": tf,
+            "frac_tensor": tf / tflops_peak, "bound": "hbm" if G * q < 254 else "tensor",
+            "algorithmic_bytes_per_launch": byts, "algorithmic_flops_per_launch": flops}
+
+
+def suffix_sweep(nat, dev, peak, tflops_peak):
+    """q in {16, 64, 256, 1024} over the C2 and C5 cached lengths, no-cache full prefill q=N, and the
+    Falcon MQA geometry."""
+    pts = []
+    for (H, Hkv, D, q, N, rnd, tag) in [(32, 32, 128, 16, 2048, None, "C2"), (32, 32, 128, 64, 2048, None, "C2"),
+                                        (32, 32, 128, 256, 2048, None, "C2"), (32, 32, 128, 1024, 2048, None, "C2"),
+                                        (32, 32, 128, 2048, 0, None, "C2 no-cache, q=N"), (32, 32, 128, 32, 8192, None, "C5"),
+                                        (32, 32, 128, 1024, 8192, None, "C5"), (71, 1, 64, 21, 256, 0, "C4 falcon"),
+                                        (71, 1, 64, 256, 2048, 0, "falcon MQA")]:
+        try:
+            p = attention_point(nat, dev, H, Hkv, D, q, N, peak, tflops_peak, rounding=rnd, launches=8 if q >= 256 else 16)
+            p["shape"] = tag
+            pts.append(p)
+        except Exception as ex:
+            pts.append({"q": q, "N": N, "shape": tag, "error": str(ex)})
+    return pts
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm
+# ------------------------------------------------------------------------------------------------
+class PortReference:
+    """Fallback when oracle/_ref is absent: the oracle restatement, 2 of L layers timed and scaled (kind "port")."""
+
+    kind = "port"
 
     def __init__(self, dims, n_cached, q_len, seg_lens, sample_layers, threads):
         from oracle import pc_oracle as O
@@ -205,13 +394,14 @@ class CpuReference:
         g = torch.Generator().manual_seed(0)
         self.segs = [[(torch.randn(H, n, D, generator=g).half(), torch.randn(H, n, D, generator=g).half())
                       for _ in range(self.L)] for n in seg_lens]
-        self.buf = O.new_prompt_cache(self.L, H, n_cached + 256, D)  # preallocated once, like PromptCache.__init__
+        self.buf = O.new_prompt_cache(self.L, H, n_cached + 256, D)
         self.sd = O.random_llama_state_dict(dims["vocab"], hid, dims["inter"], sample_layers, H, H, seed=0, dtype=torch.float32)
-        rope_rows = max(4096, ((n_cached + q_len + 1023) // 1024) * 1024)  # grown on demand like llama2.py:141-142
+        rope_rows = max(4096, ((n_cached + q_len + 1023) // 1024) * 1024)
         self.cfg = dict(n_layers=sample_layers, n_heads=H, n_kv_heads=H, eps=1e-5, theta=10000.0, max_pos=rope_rows)
         self.ids = torch.randint(3, dims["vocab"], (1, q_len), generator=g)
         self.pos = torch.arange(n_cached, n_cached + q_len).unsqueeze(0)
         self.cos, self.sin = O.rope_tables(D, rope_rows)
+        self.n_cached = n_cached
 
     def step(self):
         O = self.O
@@ -223,25 +413,64 @@ class CpuReference:
             t2 = time.perf_counter()
             O.llama_forward(self.sd, self.cfg, self.ids, self.pos, past, cos=self.cos, sin=self.sin)
             t3 = time.perf_counter()
-            # embedding + final norm + lm_head alone, to separate them from the per-layer time
             x = torch.nn.functional.embedding(self.ids, self.sd["model.embed_tokens.weight"])
             torch.nn.functional.linear(O.rms_norm(x, self.sd["model.norm.weight"], 1e-5), self.sd["lm_head.weight"]).float()
             t4 = time.perf_counter()
         head = t4 - t3
         layers = max((t3 - t2) - head, 0.0) * (self.L / self.sample_layers)
-        return dict(ttft_s=(t1 - t0) + layers + head, splice_s=t1 - t0, layers_s=layers, head_s=head)
+        return dict(ttft_s=(t1 - t0) + layers + head, cache_ms=(t1 - t0) * 1e3)
 
-    def describe(self, n_cached):
-        return (f"per step: full splice of {n_cached} rows x {self.L} layers (fp16 cache) + {self.sample_layers} of {self.L} "
-                f"decoder layers fp32 (time x{self.L // self.sample_layers}) + embedding/norm/lm_head; oracle port of the reference")
+    def describe(self):
+        return (f"oracle PORT (oracle/_ref missing): full splice of {self.n_cached} rows x {self.L} layers + {self.sample_layers} of "
+                f"{self.L} decoder layers fp32 (time x{self.L // self.sample_layers}) + embedding/norm/lm_head")
 
 
-def run_reference(args, case, dims, seg_lens):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+class RealReference:
+    """The unmodified reference's own classes on the host cores: fp32 weights as `Llama2(name, device_map=None)` loads
+    them (eval_sys.py:45-51), fp16 PromptCache (cache_engine.py:104-107), ALL layers, nothing extrapolated."""
+
+    kind = "reference"
+
+    def __init__(self, arch, md, case, threads, synthetic_segments):
+        from oracle import ref_runner
+        from promptcache_b200.synthetic import IdTokenizer
+        torch.set_num_threads(threads)
+        t0 = time.perf_counter()
+        self.lm = ref_runner.build_reference_lm(arch, md, IdTokenizer(md["vocab_size"]), dtype=torch.float32, device="cpu", seed=0)
+        self.build_s = time.perf_counter() - t0
+        max_ctx = ((case.n_cached + case.q_len + 256 + 127) // 128) * 128
+        self.run = ref_runner.ReferenceTTFT(self.lm, case.schema_xml, case.prompt_xml, max_ctx, device="cpu",
+                                            synthetic_segments=synthetic_segments)
+        self.synthetic_segments, self.case, self.layers = synthetic_segments, case, md["num_hidden_layers"]
+
+    def step(self):
+        with torch.inference_mode():
+            return self.run.step(invalidate=True)
+
+    def describe(self):
+        seg = ("segment K/V synthetic N(0,1) in the reference's own TokenSequenceCache objects (schema encode skipped: it is "
+               "outside the TTFT)" if self.synthetic_segments else f"schema encoded by the reference's add_schema ({self.run.encode_s:.0f} s, untimed)")
+        return (f"UNMODIFIED reference (oracle/_ref) CacheEngine.process + GenerationEngine.generate(max_new_tokens=1), all "
+                f"{self.layers} layers, fp32 weights / fp16 prompt cache on the host cores, every step re-splices all "
+                f"{self.case.n_cached} rows; {seg}")
+
+
+def make_cpu_reference(args, case, md, dims, seg_lens, threads, synthetic_segments):
+    from oracle import ref_shim
+    arch = "falcon" if args.config == "C4" else "llama"
+    want = os.environ.get("PC_BENCH_CPU", "reference")
+    if want == "reference" and ref_shim.reference_available():
+        return RealReference(arch, md, case, threads, synthetic_segments and arch == "llama")
+    if arch != "llama":
+        raise RuntimeError("the oracle port covers Llama only")
+    return PortReference(dims, case.n_cached, case.q_len, seg_lens, int(os.environ.get("PC_BENCH_CPU_LAYERS", "2")), threads)
+
+
+def run_reference(args, case, md, dims, seg_lens):
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     threads = os.cpu_count() or 1
-    ref = CpuReference(dims, case.n_cached, case.q_len, seg_lens, int(os.environ.get("PC_BENCH_CPU_LAYERS", "2")), threads)
+    ref = make_cpu_reference(args, case, md, dims, seg_lens, threads, synthetic_segments=False)
     recs = []
     for i in range(args.warmup + args.steps):
         r = ref.step()
@@ -249,17 +478,21 @@ def run_reference(args, case, dims, seg_lens):
             recs.append(r)
     ttft = statistics.mean(r["ttft_s"] for r in recs)
     tokens = case.n_cached + case.q_len
-    line = {"impl": "reference", "metric": METRIC, "value": tokens / ttft, "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ttft * 1e3, "ttft_ms": ttft * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 weights / f16 cache (CPU)", "data": "synthetic",
-            "config": config_dict(args, case),
-            "cpu_baseline": {"value": tokens / ttft, "unit": "tok/s", "cores": threads, "kind": "port", "sample": ref.describe(case.n_cached),
-                             "splice_ms": statistics.mean(r["splice_s"] for r in recs) * 1e3},
+    line = {"impl": "reference", "metric": metric_name(args), "value": tokens / ttft, "unit": "tok/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ttft * 1e3, "ttft_ms": ttft * 1e3,
+            "computed_tok_s": case.q_len / ttft, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 weights / f16 cache (CPU)", "data": "synthetic", "config": config_dict(args, case),
+            "cpu_baseline": {"value": tokens / ttft, "unit": "tok/s", "cores": threads, "kind": ref.kind, "sample": ref.describe(),
+                             "cache_ms": statistics.mean(r["cache_ms"] for r in recs),
+                             "ttft_ms_min": min(r["ttft_s"] for r in recs) * 1e3},
             "e2e": {"value": tokens / ttft, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-METRIC = "Llama-2-7B prefill tok/s (served prompt tokens / TTFT; TTFT = ms_per_step)"
+def metric_name(args):
+    from promptcache_b200.synthetic import CONFIGS
+    model = {"llama2-7b": "Llama-2-7B", "llama2-13b": "Llama-2-13B", "falcon-7b": "Falcon-7B"}[CONFIGS[args.config]["model"]]
+    return f"{model} prefill tok/s (served prompt tokens / TTFT; TTFT = ms_per_step)"
 
 
 def config_dict(args, case):
@@ -277,22 +510,32 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3"])
+    ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--layers", type=int, default=None, help="debug only: fewer layers (marks the line invalid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the c5 / c4 / sweep / ablation blocks (headline only)")
     ap.add_argument("--profile", action="store_true",
                     help="after warm-up run ONE step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
-    from promptcache_b200.synthetic import CONFIGS, MODEL_DIMS, IdTokenizer, make_case
-    md = dict(MODEL_DIMS[CONFIGS[args.config]["model"]])
-    case = make_case(args.config, vocab=md["vocab_size"])
-    seg_lens = {"C1": [24] + [92] * 6 + [24], "C2": [24] + [400] * 5 + [24], "C3": [512] * 8}[args.config]
+    from promptcache_b200.synthetic import CONFIGS, MODEL_DIMS, make_case
+    c5_only = args.config == "C5"
+    flat_cfg = "C2" if c5_only else args.config
+    model_key = CONFIGS[flat_cfg]["model"]
+    md = dict(MODEL_DIMS[model_key])
+    if args.layers:
+        md["num_hidden_layers"] = args.layers
+    case = make_case(flat_cfg, vocab=md["vocab_size"])
+    seg_lens = SEG_LENS.get(flat_cfg)
     dims = dict(L=md["num_hidden_layers"], H=md["num_attention_heads"], hidden=md["hidden_size"],
-                inter=md["intermediate_size"], vocab=md["vocab_size"])
+                inter=md.get("intermediate_size", 4 * md["hidden_size"]), vocab=md["vocab_size"])
     if args.impl == "reference":
-        run_reference(args, case, dims, seg_lens)
+        if c5_only:
+            print(json.dumps({"impl": "reference", "unavailable": "C5 on host cores needs a 16384-token fp32 schema encode (34 GB of "
+                              "scores per layer); the reference arm runs C1-C4"}), flush=True)
+            return
+        run_reference(args, case, md, dims, seg_lens)
         return
 
     import torch.distributed as dist
@@ -304,79 +547,46 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from promptcache_b200 import CacheEngine, GenerationEngine, GenerationParameters, Prompt, _native as nat
-    from promptcache_b200 import build as pc_build
-    from promptcache_b200.model import Llama2, LlamaConfigLite, LlamaForCausalLM
-    from promptcache_b200.synthetic import flat_schema
+    from promptcache_b200 import _native as nat, build as pc_build, parallel
     if rank == 0:
         pc_build.build()
     if world > 1:
         dist.barrier()
     nat.load()
 
-    if args.layers:
-        md["num_hidden_layers"] = args.layers
-    torch.manual_seed(0)
-    model = LlamaForCausalLM(LlamaConfigLite(**md), device=dev)
-    lm = Llama2(CONFIGS[args.config]["model"], model=model, tokenizer=IdTokenizer(md["vocab_size"]))
-    max_ctx = ((case.n_cached + case.q_len + 256 + 127) // 128) * 128
-    eng = CacheEngine(max_ctx, lm)
-    eng.prompt_cache.retain_prefix = False  # every step splices every segment
-    from promptcache_b200 import parallel
-    if world > 1:
-        # rank 0 encodes the schema once; the segment store reaches the other GPUs over NCCL (NVLink)
-        eng.add_schema(case.schema_xml, no_cache=(rank != 0))
-        parallel.broadcast_schema(eng.schemas[case.name], src=0, device=dev)
-    else:
-        eng.add_schema(case.schema_xml)
-    # each rank serves its own prompt (same modules, its own suffix tokens)
-    if world > 1:
-        mine = flat_schema(case.name, seg_lens, case.q_len, md["vocab_size"], seed=1002 + 17 * rank)
-        prompt_xml = mine.prompt_xml
-    else:
-        prompt_xml = case.prompt_xml
-    prompt = Prompt(prompt_xml)
-    gen = GenerationEngine(lm)
-    params = GenerationParameters(temperature=0.0, max_new_tokens=1, stop_token_ids=[], stop_str=[])
-    tokens_per_step = case.n_cached + case.q_len
-
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident arm ("value"): ids already in HBM, no host sync inside the step -------------------
-    ids, pos, _, _ = eng.process(prompt)
-    ids_dev = torch.tensor([ids], device=dev)
-    pos_dev = torch.tensor([pos], device=dev)
-    cached, used, _, _, _, _ = eng.plan(prompt, collect_original=False)
-    seq_caches = [cached.get_cache_l1(s) for s in used]
-    max_pos = max(pos)
-    splice_ev = []
+    lm, md = build_lm(model_key, dev, args.layers)
+    model = lm.hf_model
+    if c5_only:  # C5 as the whole run: print its block as the line
+        blk = c5_block(lm, dev, world, rank)
+        if rank == 0:
+            print(json.dumps({"metric": "Llama-2-7B prefill tok/s, C5 batch (64 prompts x 8224 tokens) over the node", "value": blk["full_splice"]["tok_s"],
+                              "unit": "tok/s", "n_gpus": world, "higher_is_better": True, "scaling": "strong", "dtype": "f16",
+                              "data": "synthetic", "config": {"workload": blk["workload"]}, "c5": blk}), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
-    def device_step(record):
-        if record:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        eng.prompt_cache.update(seq_caches)
-        if record:
-            e1.record()
-            splice_ev.append((e0, e1))
-        kv = [(k.unsqueeze(0), v.unsqueeze(0)) for k, v in eng.prompt_cache.cache]
-        return lm(input_ids=ids_dev, position_ids=pos_dev, past_key_values=kv, use_cache=True, max_position=max_pos)
+    w = RequestStep(lm, case, dev, world, rank, seg_lens)
+    tokens_per_step = case.n_cached + w.q_len
 
     # The clock sampler (nvidia-smi -lms) is started BEFORE the warm-up: its start-up enumerates every GPU of the box
-    # and can hold the driver for tens of ms, which must not land in the 20-step timed region.  Only the samples
-    # taken from the start of the timed region on are reported.
+    # and can hold the driver for tens of ms, which must not land in the timed region.  Only the samples taken from
+    # the start of the timed region on are reported.
     sampler = ClockSampler(local)
     if rank == 0 and not args.profile:
         sampler.start()
     for _ in range(args.warmup):
-        device_step(False)
+        w.device_step()
     sync_all()
     if args.profile:
         torch.cuda.profiler.start()
-        device_step(False)
+        w.device_step()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
@@ -385,100 +595,157 @@ def main():
         while not sampler.lines and time.time() < deadline:
             time.sleep(0.02)
     sync_all()
-    device_step(False)  # one more untimed step after that wait, so that the timed region starts on a busy GPU
+    w.device_step()  # one more untimed step after that wait, so that the timed region starts on a busy GPU
     sync_all()
     sampler.mark()
     launches0 = nat.launch_count()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for _ in range(args.steps):
-        out = device_step(True)
-    t1.record()
-    sync_all()
-    dev_ms = t0.elapsed_time(t1)
-    if os.environ.get("PC_BENCH_DEBUG"):
-        print(f"[rank {rank}] device arm {dev_ms / args.steps:.3f} ms/step, splice {statistics.mean(a.elapsed_time(b) for a, b in splice_ev):.3f} ms, "
-              f"graphs {len(model._graphs)}", file=sys.stderr, flush=True)
+    ms_per_step = w.timed(lambda: w.device_step(True), args.steps, sync_all)
     launches = nat.launch_count() - launches0
-    splice_ms = statistics.mean(a.elapsed_time(b) for a, b in splice_ev)
+    splice_ms = statistics.mean(a.elapsed_time(b) for a, b in w.splice_ev)
 
     # ---- end-to-end arm: the public API with host inputs (token lists -> device) and the first token read back ---
-    def e2e_step():
-        i2, p2, cache_ms, cache = eng.process(prompt)
-        first = next(gen.generate(i2, p2, params, cache, stream_interval=1))
-        return first
-
     for _ in range(args.warmup):
-        e2e_step()
-    sync_all()
-    w0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        e2e_step()
-    e1.record()
-    sync_all()
-    e2e_ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+        w.e2e_step()
+    e2e_ms = w.timed(w.e2e_step, args.steps, sync_all)
+    n_clock_samples = len(sampler.lines)
 
     # ---- decode after the prefill (informative; the headline metric is TTFT): 33 greedy tokens through the public API
     decode_ms = None
     try:
+        from promptcache_b200 import GenerationParameters
         dparams = GenerationParameters(temperature=0.0, max_new_tokens=33, stop_token_ids=[], stop_str=[])
         for _ in range(2):  # first pass warms up (captures the decode graph of this KV buffer), second is reported
-            i2, p2, _, cache = eng.process(prompt)
-            outs = list(gen.generate(i2, p2, dparams, cache))  # default stream_interval (2): greedy tokens stay on the device between yields
+            i2, p2, _, cache = w.eng.process(w.prompt)
+            outs = list(w.gen.generate(i2, p2, dparams, cache))
         decode_ms = (outs[-1].response_time - outs[0].response_time) / 32.0
     except Exception:
         pass
 
-    times = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+    times = torch.tensor([ms_per_step, e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(times[0]), float(times[1])
+    ms_per_step, e2e_ms = float(times[0]), float(times[1])
+
+    # ---- in-step attribution by ablation (rank-local; same graph machinery, kernel families left out) ------------
+    ablation = None
+    llama_native = model_key.startswith("llama") and w.q_len <= model.linear_max_q and model.linear_impl == "native"
+    if not args.no_extras and llama_native and not args.layers:
+        try:
+            ablation = {}
+            for fam in ("attn", "linear", "norm"):
+                model.ablate = frozenset([fam])
+                for _ in range(3):
+                    w.device_step()
+                ablation[fam] = w.timed(w.device_step, 10, torch.cuda.synchronize)
+            model.ablate = frozenset()
+            for _ in range(2):
+                w.device_step()
+            ablation["full"] = w.timed(w.device_step, 10, torch.cuda.synchronize)
+        except Exception as ex:
+            ablation = {"error": str(ex)}
+        finally:
+            model.ablate = frozenset()
+
+    c5 = None
+    if not args.no_extras and model_key == "llama2-7b" and not args.layers:
+        try:
+            c5 = c5_block(lm, dev, world, rank)
+        except Exception as ex:
+            c5 = {"error": f"{type(ex).__name__}: {ex}"}
 
     if rank == 0:
+        clocks = sampler.stop(upto=n_clock_samples)
         peak, peak_kind, tflops_peak = load_peaks()
-        ms_per_step = dev_ms / args.steps
         L, Hkv, D = lm.get_cache_shape()
+        H = model.n_heads
         splice_bytes = 8.0 * L * Hkv * case.n_cached * D  # read + write of K and V, fp16
-        achieved = splice_bytes / (splice_ms * 1e-3) / 1e9
-        line = {"metric": METRIC, "value": world * tokens_per_step / (ms_per_step * 1e-3), "unit": "tok/s", "n_gpus": world,
+        attn_bytes = L * (4.0 * Hkv * (case.n_cached + w.q_len) * D + 4.0 * H * w.q_len * D)
+        wbytes = weight_bytes(md, model_key)
+        step_bytes = splice_bytes + attn_bytes + wbytes
+        sp_ach = splice_bytes / (splice_ms * 1e-3) / 1e9
+        line = {"metric": metric_name(args), "value": world * tokens_per_step / (ms_per_step * 1e-3), "unit": "tok/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "ttft_ms": ms_per_step,
+                "computed_tok_s": world * w.q_len / (ms_per_step * 1e-3),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
                 "config": config_dict(args, case),
-                "e2e": {"value": world * tokens_per_step / (e2e_ms / args.steps * 1e-3), "unit": "tok/s",
-                        "ttft_ms": e2e_ms / args.steps, "h2d_bytes_per_step": 2 * 8 * case.q_len, "d2h_bytes_per_step": 8,
+                "e2e": {"value": world * tokens_per_step / (e2e_ms * 1e-3), "unit": "tok/s", "ttft_ms": e2e_ms,
+                        "computed_tok_s": world * w.q_len / (e2e_ms * 1e-3),
+                        "h2d_bytes_per_step": 2 * 8 * w.q_len, "d2h_bytes_per_step": 8,
                         "note": "CacheEngine.process + GenerationEngine.generate(max_new_tokens=1): token/position id lists go "
                                 "host->device, the greedy token comes back; cached segments are HBM-resident by design"},
                 "gpu_launches": int(launches), "decode_ms_per_token": decode_ms,
-                "roofline": {"kernel": "splice_kernel (pc_splice_kv)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic("splice_kernel", args.config),
-                             "peak_kind": peak_kind + " (burst copy)",
-                             "algorithmic_bytes_per_launch": splice_bytes, "avg_launch_ms": splice_ms,
-                             "share_of_step": splice_ms / ms_per_step},
+                "roofline_step": {"bound": "hbm", "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                  "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_step": step_bytes,
+                                  "parts": {"weights": wbytes, "splice_read_write": splice_bytes, "attention_kv_q_o": attn_bytes},
+                                  "peak_kind": peak_kind + " (copy, read+write)",
+                                  "note": "whole step: every weight matrix once + splice read/write + K/V/Q/O of attention, over ms_per_step"},
+                "roofline_splice": {"kernel": "splice_kernel (pc_splice_kv)", "bound": "hbm", "achieved": sp_ach, "peak": peak,
+                                    "unit": "GB/s", "frac": sp_ach / peak, "traffic": load_traffic("splice_kernel", args.config),
+                                    "algorithmic_bytes_per_launch": splice_bytes, "avg_launch_ms": splice_ms,
+                                    "share_of_step": splice_ms / ms_per_step, "timed": "CUDA events around every launch of the timed region"},
                 "clocks": clocks}
-        try:
-            line["roofline_attention"] = attention_alone(nat, lm, case, dev, peak)
-        except Exception as ex:
-            line["roofline_attention"] = {"error": str(ex)}
-        try:
-            line["roofline_attention_tensor"] = attention_tensor_alone(nat, dev, tflops_peak)
-        except Exception as ex:
-            line["roofline_attention_tensor"] = {"error": str(ex)}
+        if world > 1:
+            line["segment_store_broadcast"] = w.broadcast
+        if ablation and "error" not in ablation:
+            full = ablation["full"]
+            n_lin = 4 * L + 1  # qkv, o, gate/up, down per layer + lm_head
+            lin_ms = max(full - ablation["linear"], 1e-6)
+            att_ms = max(full - ablation["attn"], 1e-6)
+            lin_ach = wbytes / (lin_ms * 1e-3) / 1e9
+            att_ach = attn_bytes / (att_ms * 1e-3) / 1e9
+            line["roofline"] = {"kernel": "linear_small_kernel (pc_linear_small: qkv+RoPE+append, o_proj, gate/up+SiLU, down_proj, lm_head) -- "
+                                          "the kernel that owns the step", "bound": "hbm", "achieved": lin_ach, "peak": peak,
+                                "unit": "GB/s", "frac": lin_ach / peak, "traffic": load_traffic("linear_small_kernel", args.config),
+                                "peak_kind": peak_kind + " (copy, read+write)", "launches_per_step": n_lin,
+                                "algorithmic_bytes_per_launch": wbytes / n_lin, "avg_launch_ms": lin_ms / n_lin,
+                                "in_step_ms": lin_ms, "share_of_step": lin_ms / full,
+                                "timed": "in the step: (full step) - (the same CUDA-graph step with the linear launches left out), "
+                                         "CUDA events over 10 steps each; includes the launches' programmatic overlap with their neighbours"}
+            line["roofline_attention"] = {"kernel": "attn_small_kernel (pc_prefill_attn)", "bound": "hbm", "achieved": att_ach, "peak": peak,
+                                          "unit": "GB/s", "frac": att_ach / peak, "traffic": load_traffic("attn_small_kernel", args.config),
+                                          "algorithmic_bytes_per_launch": attn_bytes / L, "avg_launch_ms": att_ms / L, "in_step_ms": att_ms,
+                                          "share_of_step": att_ms / full, "timed": "in the step, by ablation (see roofline.timed)"}
+            line["step_attribution_ms"] = {"full_step": full, "linears": lin_ms, "attention": att_ms, "norms": full - ablation["norm"],
+                                           "splice": splice_ms, "method": "T(full) - T(step without the family); families overlap "
+                                           "through PDL, so the parts need not add up to the step"}
+        else:
+            line["roofline"] = dict(line["roofline_splice"])
+            if ablation:
+                line["ablation_error"] = ablation["error"]
+        if not args.no_extras:
+            try:
+                alone = attention_point(nat, dev, H, Hkv, D, w.q_len, case.n_cached, peak, tflops_peak,
+                                        rounding=getattr(model, "rounding", None))
+                line.setdefault("roofline_attention", {})["alone"] = alone
+                line["roofline_attention_tensor"] = dict(attention_point(nat, dev, 32, 32, 128, 1024, 8192, peak, tflops_peak, launches=8),
+                                                         kernel="attn_pp_kernel (pc_prefill_attn, q=1024 over N=8192)", peak=tflops_peak,
+                                                         unit="TFLOP/s")
+                line["suffix_sweep"] = suffix_sweep(nat, dev, peak, tflops_peak)
+            except Exception as ex:
+                line["suffix_sweep"] = {"error": str(ex)}
+        if c5 is not None:
+            line["c5"] = c5
         if args.layers:
             line["invalid"] = f"debug run with {args.layers} layers"
-        if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            try:
-                ref = CpuReference(dims, case.n_cached, case.q_len, seg_lens, 2, threads)
-                ref.step()
-                r = min((ref.step() for _ in range(3)), key=lambda d: d["ttft_s"])
-                line["cpu_baseline"] = {"value": tokens_per_step / r["ttft_s"], "unit": "tok/s", "cores": threads, "kind": "port",
-                                        "ttft_ms": r["ttft_s"] * 1e3, "splice_ms": r["splice_s"] * 1e3,
-                                        "sample": "best of 3 after 1 warm-up; " + ref.describe(case.n_cached)}
-            except Exception as ex:  # never lose the GPU line to a host-side OOM
-                line["cpu_baseline"] = {"value": None, "unit": "tok/s", "cores": threads, "kind": "port", "sample": f"failed: {ex}"}
+    if world == 1 and rank == 0 and not args.no_extras and args.config == "C2" and not args.layers:
+        try:
+            del w
+            torch.cuda.empty_cache()
+            line["c4"] = c4_block(dev, max(5, args.steps // 2), 3)
+        except Exception as ex:
+            line["c4"] = {"error": f"{type(ex).__name__}: {ex}"}
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        try:
+            ref = make_cpu_reference(args, case, md, dims, seg_lens, threads, synthetic_segments=True)
+            ref.step()
+            r = min((ref.step() for _ in range(3)), key=lambda d: d["ttft_s"])
+            line["cpu_baseline"] = {"value": tokens_per_step / r["ttft_s"], "unit": "tok/s", "cores": threads, "kind": ref.kind,
+                                    "ttft_ms": r["ttft_s"] * 1e3, "cache_ms": r["cache_ms"],
+                                    "sample": "best of 3 after 1 warm-up; " + ref.describe()}
+        except Exception as ex:  # never lose the GPU line to a host-side OOM
+            line["cpu_baseline"] = {"value": None, "unit": "tok/s", "cores": threads, "kind": "unavailable", "sample": f"failed: {type(ex).__name__}: {ex}"}
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

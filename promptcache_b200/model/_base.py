@@ -43,6 +43,7 @@ class B200CausalLM(nn.Module):
         self.linear_tiled = os.environ.get("PC_LINEAR_TILED", "1") != "0"  # native linears stream pre-tiled weight copies
         # CUDA graphs of the whole single-sequence forward, keyed by (q_len, n_cached, KV buffer): the per-layer
         # launch sequence is fixed once those are, so a repeated request shape is replayed with one launch
+        self.ablate = frozenset()  # measurement only: kernel families left out of the step (see LlamaForCausalLM._layers_ablated)
         self.use_cuda_graphs = True
         self._graphs = {}
         self._graph_seen = {}
@@ -95,7 +96,7 @@ class B200CausalLM(nn.Module):
         """Every switch that changes the launch sequence of `_layers`; part of each graph key so that toggling one
         after a capture can never replay a stale sequence."""
         return (self.linear_impl, tuple(sorted(self.linear_native_ops)), self.linear_max_q, self.linear_partials,
-                self.linear_tiled, self.attn_impl)
+                self.linear_tiled, self.attn_impl, tuple(sorted(self.ablate)))
 
     def _note_seen(self, key) -> None:
         if len(self._graph_seen) >= 256:  # bounded: forked / short-lived buffers would otherwise grow it forever

@@ -124,6 +124,38 @@ class LlamaForCausalLM(B200CausalLM):
             self._tiled[key] = t if t is not None else False
         return t if t is not False else None
 
+    def _layers_ablated(self, x, h, pos, kv, q_rot, attn_out, act, ws, lws, pbuf_o, pbuf_d, n_dev):
+        """The native q <= linear_max_q step with the kernel families named in `self.ablate` left out ("linear", "attn",
+        "norm").  Results are meaningless; bench.py times it to attribute the step: cost(X) = T(full) - T(without X),
+        which includes the overlap X has with its neighbours (programmatic dependent launch) -- the in-step number."""
+        ab = self.ablate
+        q_len, H, Hkv, D, N = x.shape[0], self.n_heads, self.n_kv_heads, self.head_dim, kv.n_cached
+        if lws is None or pbuf_o is None or pbuf_d is None:
+            raise nat.NativeError("ablation runs need the native skinny-linear step (q_len <= linear_max_q)")
+        for l in range(self.n_layers):
+            if "norm" not in ab:
+                nat.add_rmsnorm(x, pbuf_d if l else None, self.ln1[l], h, self.eps)
+            if "linear" not in ab:
+                nat.linear_rope_append(h, self.wqkv[l], pos, self._cos, self._sin, q_rot, kv.k[l], kv.v[l], N, H, Hkv, lws,
+                                       w_tiled=self._wt(("qkv", l), self.wqkv[l], nat.PC_LIN_ROPE_APPEND))
+            if "attn" not in ab:
+                nat.attention(q_rot, kv.k[l], kv.v[l], attn_out, N, q_len, H, Hkv, D, self.scale, self.rounding, workspace=ws,
+                              decode=(q_len == 1), impl=self.attn_impl)
+            if "linear" not in ab:
+                nat.linear_partials(attn_out, self.wo[l], pbuf_o, lws, w_tiled=self._wt(("o", l), self.wo[l], nat.PC_LIN_PARTIALS))
+            if "norm" not in ab:
+                nat.add_rmsnorm(x, pbuf_o, self.ln2[l], h, self.eps)
+            if "linear" not in ab:
+                nat.linear_small(h, self.w_gate_up[l], act, lws, silu_mul=True,
+                                 w_tiled=self._wt(("gu", l), self.w_gate_up[l], nat.PC_LIN_SILU_MUL))
+                nat.linear_partials(act, self.w_down[l], pbuf_d, lws, w_tiled=self._wt(("down", l), self.w_down[l], nat.PC_LIN_PARTIALS))
+        if "norm" not in ab:
+            nat.add_rmsnorm(x, pbuf_d, self.norm, h, self.eps)
+        logits = torch.zeros(q_len, self.vocab_size, dtype=torch.float16, device=self.device)
+        if "linear" not in ab:
+            nat.linear_small(h, self.lm_head, logits, lws, w_tiled=self._wt(("lm_head", 0), self.lm_head, nat.PC_LIN_PLAIN))
+        return logits.float()
+
     # ---- forward (one sequence; batching, KV buffers and graph replay live in B200CausalLM) ---------------
     def _layers(self, ids: torch.Tensor, pos: torch.Tensor, kv, extra=(), n_dev=None) -> torch.Tensor:
         q_len = ids.shape[0]
@@ -155,6 +187,8 @@ class LlamaForCausalLM(B200CausalLM):
         which = self.linear_native_ops  # which linears run natively (A/B switch, PC_LINEAR_OPS)
         lin_qkv, lin_o, lin_gu, lin_down, lin_head = (lin and k in which for k in ("qkv", "o", "gu", "down", "head"))
         delta = None
+        if self.ablate:  # measurement only (bench.py: in-step cost of a kernel family = full step - step without it)
+            return self._layers_ablated(x, h, pos, kv, q_rot, attn_out, act, ws, lws, pbuf_o, pbuf_d, n_dev)
         for l in range(self.n_layers):
             nat.add_rmsnorm(x, delta, self.ln1[l], h, self.eps)          # x += mlp(l-1); h = norm(x)
             # n_dev: run-time cached length (decode graph); N is then only the sizing upper bound

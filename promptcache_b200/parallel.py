@@ -60,36 +60,88 @@ def max_over_ranks(value_ms: float, device=None) -> float:
     return float(t[0])
 
 
-def broadcast_schema(schema_cache, src: int = 0, device=None) -> None:
+def _default_device(device):
+    """NCCL moves CUDA tensors only and the splice needs HBM-resident segments: default to the current CUDA device
+    (gloo test rigs on CUDA-less hosts get "cpu")."""
+    if device is not None:
+        return torch.device(device)
+    if torch.cuda.is_available():
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def broadcast_schema(schema_cache, src: int = 0, device=None) -> dict:
     """Make every rank hold the segment store rank `src` encoded.
 
     `schema_cache` is a SchemaCache built with the same schema on every rank (`no_cache=True` on ranks other
     than `src`, so only `src` ran the scaffold forwards).  Segments are matched by (offset, length, token ids),
     which every rank derives identically from the schema, and moved with one broadcast per segment (each is a
-    single packed [L,2,Hkv,len,D] allocation)."""
+    single packed [L,2,Hkv,len,D] allocation; C5: 64 x 128 MiB).  Returns {"segments", "bytes"} of what was moved."""
     from .cache_engine import TokenSequenceCache
     if world() == 1:
-        return
+        return {"segments": 0, "bytes": 0}
+    device = _default_device(device if device is not None else getattr(schema_cache, "target_device", None))
     schema = schema_cache.schema
     seqs = []
     for path in schema_cache.scaffold_paths():
         for seq in schema.get_scaffold(path).select(path).all_token_sequences():
             if len(seq) > 0 and all(seq is not s for s in seqs):
                 seqs.append(seq)
-    # shape header from the source rank
+    # shape header from the source rank; an empty store is announced instead of raising before the collective
     meta: List[Any] = [None]
     if rank() == src:
-        first = next(iter(schema_cache.cache_l1.values()))
-        L, two, hkv, _, d = first.packed.shape
-        meta = [(int(L), int(hkv), int(d), str(first.packed.dtype).replace("torch.", ""))]
+        first = next(iter(schema_cache.cache_l1.values()), None)
+        if first is None:
+            meta = [("empty",)]
+        else:
+            L, two, hkv, _, d = first.packed.shape
+            meta = [(int(L), int(hkv), int(d), str(first.packed.dtype).replace("torch.", ""))]
     dist.broadcast_object_list(meta, src=src)
+    if meta[0][0] == "empty":
+        return {"segments": 0, "bytes": 0}
     L, hkv, d, dtype_name = meta[0]
     dtype = getattr(torch, dtype_name)
+    moved = 0
     for seq in seqs:
         if rank() == src:
             buf = schema_cache.cache_l1[id(seq)].packed
         else:
-            buf = torch.empty(L, 2, hkv, len(seq), d, dtype=dtype, device=device if device is not None else "cpu")
+            buf = torch.empty(L, 2, hkv, len(seq), d, dtype=dtype, device=device)
         dist.broadcast(buf, src=src)
+        moved += buf.numel() * buf.element_size()
         if rank() != src:
             schema_cache.cache_l1[id(seq)] = TokenSequenceCache(seq, buf)
+    return {"segments": len(seqs), "bytes": moved}
+
+
+class ServedPrompt:
+    """What `serve_batch` returns per prompt (in prompt order on every rank)."""
+
+    __slots__ = ("index", "rank", "text", "cache_ms", "prefill_ms", "n_cached", "q_len", "spliced_rows")
+
+    def __init__(self, **kw):
+        for k in self.__slots__:
+            setattr(self, k, kw.get(k))
+
+    @property
+    def ttft_ms(self) -> float:
+        return self.cache_ms + self.prefill_ms
+
+
+def serve_batch(cache_engine, gen_engine, prompts: Sequence, params, stream_interval: int = 2) -> List[ServedPrompt]:
+    """Serve a batch of independent prompts across the ranks of the process group: prompt b runs on rank b mod G
+    through the same public calls a single-GPU user makes (CacheEngine.process -> GenerationEngine.generate), the
+    results are all-gathered and returned in prompt order on every rank.  No data-path collective: the in-process
+    equivalent of the reference's one-OS-process-per-GPU dataset partition (eval_acc.py:240-262,
+    scripts/run_benchmarks.py:48-62)."""
+    lm = cache_engine.lm
+    full_ids = bool(getattr(lm, "use_full_position_ids", False))
+    mine = []
+    for b in shard_indices(len(prompts)):
+        ids, pos, cache_ms, cache = cache_engine.process(prompts[b], return_full_position_ids=full_ids)
+        outs = list(gen_engine.generate(ids, pos, params, cache, stream_interval=stream_interval, use_full_position_ids=full_ids))
+        mine.append(dict(index=b, rank=rank(), text=outs[-1].new_text if outs else "", cache_ms=float(cache_ms),
+                         prefill_ms=float(outs[0].elapsed_time) if outs else 0.0, n_cached=len(cache_engine.prompt_cache),
+                         q_len=len(ids), spliced_rows=int(cache_engine.prompt_cache.last_spliced_rows)))
+    merged = merge_sharded(gather_results(mine), len(prompts))
+    return [ServedPrompt(**m) for m in merged]

@@ -71,13 +71,14 @@ def union_schema(name: str, head: int, slots: int, slot_width: int, member_len: 
 
 def parameter_schema(name: str, vocab: int, seed: int) -> SyntheticCase:
     """C4 'travel-like': 5 segments, N=256, parameters `duration` (len 5) and `city` (len 10) filled with 2 and
-    3 tokens -> 5 interior-position suffix tokens + 16 trailing (examples/parameterized_prompts.xml:14,21)."""
+    3 tokens -> 5 interior-position suffix tokens + 16 trailing (examples/parameterized_prompts.xml:14,21).  The prompt
+    names `city` before `duration`, so the suffix ids arrive in argument order, not position order: non-monotone."""
     rng = random.Random(seed)
     w = lambda n: words(rng, n, vocab)
     schema = (f'<schema name="{name}"><module name="sys">{w(40)}</module>'
               f'<module name="plan">{w(60)}<parameter name="duration" length="5"/>{w(70)}'
               f'<parameter name="city" length="10"/>{w(50)}</module><module name="end">{w(36)}</module></schema>')
-    prompt = (f'<prompt schema="{name}"><sys/><plan duration="{w(2)}" city="{w(3)}"/><end/>{w(16)}</prompt>')
+    prompt = (f'<prompt schema="{name}"><sys/><plan city="{w(3)}" duration="{w(2)}"/><end/>{w(16)}</prompt>')
     return SyntheticCase(name, schema, prompt, 256, 21, 5)
 
 
@@ -107,6 +108,11 @@ MODEL_DIMS = {
                       num_attention_heads=32, num_key_value_heads=32, max_position_embeddings=4096, rms_norm_eps=1e-5),
     "llama2-13b": dict(vocab_size=32000, hidden_size=5120, intermediate_size=13824, num_hidden_layers=40,
                        num_attention_heads=40, num_key_value_heads=40, max_position_embeddings=4096, rms_norm_eps=1e-5),
+    # tiiuae/falcon-7b: multi_query, parallel_attn, rotary, no bias (== transformers FalconConfig() defaults)
+    "falcon-7b": dict(vocab_size=65024, hidden_size=4544, num_hidden_layers=32, num_attention_heads=71,
+                      layer_norm_epsilon=1e-5, max_position_embeddings=2048),
+    # mosaicml/mpt-7b-chat with the reference's max_seq_len override (model/__init__.py:266)
+    "mpt-7b": dict(vocab_size=50432, hidden_size=4096, num_hidden_layers=32, num_attention_heads=32, max_seq_len=8192),
 }
 
 

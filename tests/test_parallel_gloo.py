@@ -30,6 +30,34 @@ def _free_port():
         return s.getsockname()[1]
 
 
+class _Out:
+    def __init__(self, text, ms):
+        self.new_text, self.elapsed_time = text, ms
+
+
+class _StubCache:
+    last_spliced_rows = 0
+
+    def __len__(self):
+        return 7
+
+
+class _StubEngine:
+    """Duck-typed CacheEngine / GenerationEngine pair: serve_batch only touches the public calls."""
+
+    def __init__(self, lm):
+        self.lm, self.prompt_cache = lm, _StubCache()
+
+    def process(self, prompt, return_full_position_ids=False):
+        self.prompt_cache.last_spliced_rows = 10 * int(prompt[1:])
+        return [1, 2], [7, 8], 1.5, prompt
+
+
+class _StubGen:
+    def generate(self, ids, pos, params, cache, stream_interval=2, use_full_position_ids=False):
+        yield _Out(cache + "!", float(cache[1:]))
+
+
 def _worker(rank, world, port, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -45,7 +73,14 @@ def _worker(rank, world, port, ret):
                     t = torch.full((2, 2, 3, len(seq), 8), float(seq.offset), dtype=torch.float16)
                     t += torch.arange(len(seq)).view(1, 1, 1, -1, 1) / 16
                     sc.cache_l1[id(seq)] = TokenSequenceCache(seq, t)
-        parallel.broadcast_schema(sc, src=0)
+        moved = parallel.broadcast_schema(sc, src=0)
+        assert moved["segments"] == 4 and moved["bytes"] == sum(e.packed.numel() * 2 for e in sc.cache_l1.values())
+        # an empty store on the source is announced, not raised before the collective (no deadlock)
+        empty = SchemaCache(Schema(SCHEMA.replace('name="s"', 'name="e"'), lm), lm, no_cache=True, target_device="cpu")
+        assert parallel.broadcast_schema(empty, src=0) == {"segments": 0, "bytes": 0} and not empty.cache_l1
+        served = parallel.serve_batch(_StubEngine(lm), _StubGen(), [f"p{i}" for i in range(5)], params=None)
+        assert [(s.index, s.rank, s.text) for s in served] == [(i, i % world, f"p{i}!") for i in range(5)]
+        assert all(s.ttft_ms == 1.5 + s.index for s in served) and served[3].spliced_rows == 30
         store = sorted((e.token_sequence.offset, len(e), float(e.packed.sum())) for e in sc.cache_l1.values())
         mine = [f"r{rank}-p{i}" for i in parallel.shard_indices(5)]
         gathered = parallel.gather_results(mine)
