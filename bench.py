@@ -167,13 +167,16 @@ class RequestStep:
         self.seq_caches = [cached.get_cache_l1(s) for s in used if len(s) > 0]
         self.max_pos = max(pos)
         self.splice_ev = []
+        # virtual splice (the engine's default whenever the model's short-suffix attention can read the arena in place)
+        self.virtual = eng.virtual_splice and 0 < self.q_len <= getattr(lm.hf_model, "virtual_kv_max_q", lambda: 0)()
 
-    def device_step(self, record=False):
+    def device_step(self, record=False, virtual=None):
         """ids already in HBM, no host sync inside the step."""
+        virtual = self.virtual if virtual is None else virtual
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        self.eng.prompt_cache.update(self.seq_caches)
+        self.eng.prompt_cache.update(self.seq_caches, virtual=virtual)
         if record:
             e1.record()
             self.splice_ev.append((e0, e1))
@@ -444,7 +447,9 @@ class RealReference:
         self.synthetic_segments, self.case, self.layers = synthetic_segments, case, md["num_hidden_layers"]
 
     def step(self):
-        with torch.inference_mode():
+        import contextlib
+        # the reference prints "Prefill latency" on stdout (generation_engine.py:115); stdout carries the one JSON line only
+        with torch.inference_mode(), contextlib.redirect_stdout(sys.stderr):
             return self.run.step(invalidate=True)
 
     def describe(self):
@@ -601,7 +606,15 @@ def main():
     launches0 = nat.launch_count()
     ms_per_step = w.timed(lambda: w.device_step(True), args.steps, sync_all)
     launches = nat.launch_count() - launches0
+    # the same step with the reference's copy (PromptCache.update moves all N rows): the splice kernel's roofline, and
+    # what the virtual splice saves
+    w.splice_ev = []
+    for _ in range(3):
+        w.device_step(virtual=False)
+    ms_per_step_copied = w.timed(lambda: w.device_step(True, virtual=False), args.steps, sync_all)
     splice_ms = statistics.mean(a.elapsed_time(b) for a, b in w.splice_ev)
+    for _ in range(2):
+        w.device_step()
 
     # ---- end-to-end arm: the public API with host inputs (token lists -> device) and the first token read back ---
     for _ in range(args.warmup):
@@ -621,10 +634,10 @@ def main():
     except Exception:
         pass
 
-    times = torch.tensor([ms_per_step, e2e_ms], device=dev, dtype=torch.float64)
+    times = torch.tensor([ms_per_step, e2e_ms, ms_per_step_copied], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_per_step, e2e_ms = float(times[0]), float(times[1])
+    ms_per_step, e2e_ms, ms_per_step_copied = float(times[0]), float(times[1]), float(times[2])
 
     # ---- in-step attribution by ablation (rank-local; same graph machinery, kernel families left out) ------------
     ablation = None
@@ -661,11 +674,12 @@ def main():
         splice_bytes = 8.0 * L * Hkv * case.n_cached * D  # read + write of K and V, fp16
         attn_bytes = L * (4.0 * Hkv * (case.n_cached + w.q_len) * D + 4.0 * H * w.q_len * D)
         wbytes = weight_bytes(md, model_key)
-        step_bytes = splice_bytes + attn_bytes + wbytes
+        step_bytes = (0.0 if w.virtual else splice_bytes) + attn_bytes + wbytes
         sp_ach = splice_bytes / (splice_ms * 1e-3) / 1e9
         line = {"metric": metric_name(args), "value": world * tokens_per_step / (ms_per_step * 1e-3), "unit": "tok/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "ttft_ms": ms_per_step,
                 "computed_tok_s": world * w.q_len / (ms_per_step * 1e-3),
+                "virtual_splice": bool(w.virtual), "ms_per_step_with_copied_splice": ms_per_step_copied,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
                 "config": config_dict(args, case),
                 "e2e": {"value": world * tokens_per_step / (e2e_ms * 1e-3), "unit": "tok/s", "ttft_ms": e2e_ms,
@@ -676,13 +690,17 @@ def main():
                 "gpu_launches": int(launches), "decode_ms_per_token": decode_ms,
                 "roofline_step": {"bound": "hbm", "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                   "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_step": step_bytes,
-                                  "parts": {"weights": wbytes, "splice_read_write": splice_bytes, "attention_kv_q_o": attn_bytes},
+                                  "parts": {"weights": wbytes, "splice_read_write": 0.0 if w.virtual else splice_bytes,
+                                            "attention_kv_q_o": attn_bytes},
                                   "peak_kind": peak_kind + " (copy, read+write)",
-                                  "note": "whole step: every weight matrix once + splice read/write + K/V/Q/O of attention, over ms_per_step"},
+                                  "note": "whole step: every weight matrix once + K/V/Q/O of attention (+ splice read/write when the "
+                                          "cached rows are copied; with the virtual splice attention reads the segment arena in place), over ms_per_step"},
                 "roofline_splice": {"kernel": "splice_kernel (pc_splice_kv)", "bound": "hbm", "achieved": sp_ach, "peak": peak,
                                     "unit": "GB/s", "frac": sp_ach / peak, "traffic": load_traffic("splice_kernel", args.config),
                                     "algorithmic_bytes_per_launch": splice_bytes, "avg_launch_ms": splice_ms,
-                                    "share_of_step": splice_ms / ms_per_step, "timed": "CUDA events around every launch of the timed region"},
+                                    "share_of_step": splice_ms / ms_per_step_copied,
+                                    "timed": "CUDA events around every launch of a second timed region that runs the step with the "
+                                             "reference's copy (virtual splice off); the engine's own path launches no splice"},
                 "clocks": clocks}
         if world > 1:
             line["segment_store_broadcast"] = w.broadcast
@@ -706,7 +724,7 @@ def main():
                                           "algorithmic_bytes_per_launch": attn_bytes / L, "avg_launch_ms": att_ms / L, "in_step_ms": att_ms,
                                           "share_of_step": att_ms / full, "timed": "in the step, by ablation (see roofline.timed)"}
             line["step_attribution_ms"] = {"full_step": full, "linears": lin_ms, "attention": att_ms, "norms": full - ablation["norm"],
-                                           "splice": splice_ms, "method": "T(full) - T(step without the family); families overlap "
+                                           "splice": 0.0 if w.virtual else splice_ms, "method": "T(full) - T(step without the family); families overlap "
                                            "through PDL, so the parts need not add up to the step"}
         else:
             line["roofline"] = dict(line["roofline_splice"])

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PC_ABI_VERSION 3
+#define PC_ABI_VERSION 4
 
 enum {
   PC_OK = 0,
@@ -81,6 +81,12 @@ typedef struct pc_segment {
 
 int pc_splice_kv(const pc_segment* segs /*HOST*/, int n_segs, void* cache_dev, int n_layers,
                  int n_kv_heads, int head_dim, int max_ctx, int elem_bytes, void* stream);
+
+/* Same, for segments that live in a shared ARENA  arena[L][2][Hkv][arena_rows][D]  (all token sequences of a schema in one
+ * allocation; see "virtual splice" below): `segs[i].base` points at row `row0_i` of layer 0 / K / head 0 and consecutive
+ * (layer, K|V, head) runs are `src_run_rows[i]` rows apart in the source (== len for a packed segment). */
+int pc_splice_kv_strided(const pc_segment* segs /*HOST*/, const int64_t* src_run_rows /*HOST*/, int n_segs, void* cache_dev,
+                         int n_layers, int n_kv_heads, int head_dim, int max_ctx, int elem_bytes, void* stream);
 
 /* Reference layout.  The reference keeps one tensor per (segment, layer, K|V), each [Hkv][len][D]
  * contiguous, and one target per (layer, K|V), each [Hkv][max_ctx][D] (cache_engine.py:139-149).
@@ -158,6 +164,22 @@ typedef struct pc_attn_params {
                               * ZERO it once before first use (arrival counters; kernels     *
                               * leave them zeroed); one workspace per concurrent stream      */
   size_t workspace_bytes;
+  /* ---- virtual splice: the copy of PromptCache.update (cache_engine.py:135-151) is
+   * not made; the kernel reads the cached keys straight from the schema's segment ARENA through a per-request
+   * tile list.  With kv_tiles != NULL the first `kv_rows` of the n_cached keys are NOT read from k/v: they are the
+   * `kv_n_tiles` tiles listed in kv_tiles, each {first arena row, valid rows (1..128)} -- one tile never spans two
+   * segments -- read from kv_arena_k / kv_arena_v = [Hkv][kv_arena_rows][D] (this layer's K and V planes of the
+   * arena).  Rows [kv_rows, n_cached + q_len) of k/v (appended suffix / decode rows, in place as always) are read
+   * as before.  Short-suffix kernel only (head_dim 128, G*q_len <= 32, no ALiBi); the tile list is DEVICE memory
+   * that the caller may rewrite between launches (a captured CUDA graph serves every request with the same
+   * kv_n_tiles / kv_rows).  Cached keys are all visible to all query rows, so their order does not matter. */
+  const void* kv_arena_k;
+  const void* kv_arena_v;
+  const int32_t* kv_tiles;   /* device: int32[kv_n_tiles][2] */
+  int32_t kv_arena_rows;
+  int32_t kv_n_tiles;
+  int32_t kv_rows;
+  int32_t kv_reserved;
 } pc_attn_params;
 
 size_t pc_attn_workspace_bytes(int n_heads, int q_len, int head_dim);

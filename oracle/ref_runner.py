@@ -68,6 +68,8 @@ def build_reference_lm(arch: str, dims: Dict, tokenizer, dtype=torch.float32, de
     finally:
         torch.set_default_dtype(prev)
     model = model.eval()
+    if getattr(cfg, "tie_word_embeddings", False):
+        model.tie_weights()  # no_init_weights skipped post_init's tying: Falcon / MPT share lm_head with the embedding
     with torch.no_grad():
         if state_dict is not None:
             missing = model.load_state_dict({k: v.to(device=device, dtype=dtype) for k, v in state_dict.items()}, strict=False)

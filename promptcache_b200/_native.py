@@ -26,7 +26,7 @@ PC_ATTN_SIMT = 1
 PC_ATTN_TCGEN05 = 2
 PC_ATTN_GLOBAL_MERGE = 0x100
 
-EXPORTS = ("pc_version", "pc_last_error", "pc_device_info", "pc_splice_kv", "pc_splice_kv_tensors",
+EXPORTS = ("pc_version", "pc_last_error", "pc_device_info", "pc_splice_kv", "pc_splice_kv_strided", "pc_splice_kv_tensors",
            "pc_rope_append", "pc_rope_append_dyn", "pc_attn_workspace_bytes", "pc_prefill_attn", "pc_decode_attn", "pc_launch_count",
            "pc_add_rmsnorm", "pc_silu_mul", "pc_linear_workspace_bytes", "pc_linear_small",
            "pc_linear_tiled_bytes", "pc_linear_tile_weights", "pc_linear_partial_splits", "pc_add_rmsnorm_partials")
@@ -57,7 +57,9 @@ class pc_attn_params(C.Structure):
                 ("scale", C.c_float), ("rounding", C.c_int32),
                 ("alibi_slopes", C.c_void_p), ("key_pos", C.c_void_p),
                 ("alibi_max_pos", C.c_int32), ("impl", C.c_int32), ("n_cached_dev", C.c_void_p),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+                ("kv_arena_k", C.c_void_p), ("kv_arena_v", C.c_void_p), ("kv_tiles", C.c_void_p),
+                ("kv_arena_rows", C.c_int32), ("kv_n_tiles", C.c_int32), ("kv_rows", C.c_int32), ("kv_reserved", C.c_int32)]
 
 
 class pc_linear_params(C.Structure):
@@ -93,6 +95,9 @@ def load() -> C.CDLL:
     lib.pc_splice_kv.argtypes = [C.POINTER(pc_segment), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_void_p]
     lib.pc_splice_kv.restype = C.c_int
+    lib.pc_splice_kv_strided.argtypes = [C.POINTER(pc_segment), C.POINTER(C.c_int64), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, C.c_void_p]
+    lib.pc_splice_kv_strided.restype = C.c_int
     lib.pc_splice_kv_tensors.argtypes = [C.POINTER(pc_copy2d), C.c_int, C.c_void_p]
     lib.pc_splice_kv_tensors.restype = C.c_int
     lib.pc_rope_append.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
@@ -162,7 +167,8 @@ def launch_count() -> int:
 
 
 def splice_kv(segments: Sequence[tuple], cache: torch.Tensor) -> None:
-    """segments: (packed_segment_tensor[L,2,Hkv,len,D], dst_row) pairs; cache: [L,2,Hkv,max_ctx,D]."""
+    """segments: (segment tensor [L,2,Hkv,len,D], dst_row) pairs; cache: [L,2,Hkv,max_ctx,D].  A segment is either a
+    packed (contiguous) allocation or a row slice `arena[:, :, :, r0:r0+len, :]` of a schema's segment arena."""
     lib = load()
     _require_cuda(cache)
     if cache.dim() != 5 or cache.shape[1] != 2 or not cache.is_contiguous():
@@ -170,17 +176,29 @@ def splice_kv(segments: Sequence[tuple], cache: torch.Tensor) -> None:
     L, _, Hkv, max_ctx, D = cache.shape
     n = len(segments)
     arr = (pc_segment * max(n, 1))()
+    run_rows = (C.c_int64 * max(n, 1))()
+    strided = False
     for i, (seg, row) in enumerate(segments):
         _require_cuda(seg)
-        if seg.dim() != 5 or tuple(seg.shape[:3]) != (L, 2, Hkv) or seg.shape[4] != D or not seg.is_contiguous() \
-                or seg.dtype != cache.dtype:
+        if seg.dim() != 5 or tuple(seg.shape[:3]) != (L, 2, Hkv) or seg.shape[4] != D or seg.dtype != cache.dtype:
             raise NativeError(f"splice_kv: segment {i} has shape {tuple(seg.shape)}/{seg.dtype}, "
-                              f"expected [{L},2,{Hkv},len,{D}] {cache.dtype} contiguous")
+                              f"expected [{L},2,{Hkv},len,{D}] {cache.dtype}")
+        s0, s1, s2, s3, s4 = seg.stride()
+        ln = int(seg.shape[3])
+        if s4 != 1 or s3 != D or s2 % D != 0 or s2 < ln * D or s1 != Hkv * s2 or s0 != 2 * s1:
+            raise NativeError(f"splice_kv: segment {i} must be contiguous or a row slice of a [L,2,Hkv,R,D] arena "
+                              f"(strides {seg.stride()})")
         arr[i].base = seg.data_ptr()
-        arr[i].len = int(seg.shape[3])
+        arr[i].len = ln
         arr[i].dst_row = int(row)
-    _check(lib.pc_splice_kv(arr, n, cache.data_ptr(), L, Hkv, D, max_ctx, cache.element_size(), _stream()),
-           "pc_splice_kv")
+        run_rows[i] = s2 // D
+        strided |= run_rows[i] != ln
+    if strided:
+        _check(lib.pc_splice_kv_strided(arr, run_rows, n, cache.data_ptr(), L, Hkv, D, max_ctx, cache.element_size(), _stream()),
+               "pc_splice_kv_strided")
+    else:
+        _check(lib.pc_splice_kv(arr, n, cache.data_ptr(), L, Hkv, D, max_ctx, cache.element_size(), _stream()),
+               "pc_splice_kv")
 
 
 def splice_kv_tensors(copies: Sequence[tuple]) -> None:
@@ -260,8 +278,10 @@ def attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, out
               q_len: int, n_heads: int, n_kv_heads: int, head_dim: int, scale: float, rounding: int,
               workspace: Optional[torch.Tensor] = None, alibi_slopes: Optional[torch.Tensor] = None,
               key_pos: Optional[torch.Tensor] = None, alibi_max_pos: int = 0, impl: int = PC_ATTN_AUTO,
-              decode: bool = False, n_cached_dev: Optional[torch.Tensor] = None) -> None:
-    """q: [H,q,D] fp16; caches [Hkv,max_ctx,D] (row-contiguous views allowed); out: [q,H*D] fp16."""
+              decode: bool = False, n_cached_dev: Optional[torch.Tensor] = None, virtual: Optional[tuple] = None) -> None:
+    """q: [H,q,D] fp16; caches [Hkv,max_ctx,D] (row-contiguous views allowed); out: [q,H*D] fp16.
+    `virtual` = (arena_k [Hkv,R,D], arena_v [Hkv,R,D], tiles int32 [T,2] on the device, T, rows): the first `rows` cached
+    keys are read in place from the segment arena through the tile list instead of from k_cache/v_cache (virtual splice)."""
     lib = load()
     _require_cuda(q, k_cache, v_cache, out)
     if k_cache.stride(2) != 1 or k_cache.stride(1) != head_dim or k_cache.stride(0) != v_cache.stride(0):
@@ -287,6 +307,16 @@ def attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, out
         p.n_cached_dev = n_cached_dev.data_ptr()
     if workspace is not None:
         p.workspace, p.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    if virtual is not None:
+        ak, av, tiles, n_tiles, rows = virtual
+        _require_cuda(ak, av, tiles)
+        if ak.dtype != torch.float16 or ak.dim() != 3 or ak.shape != av.shape or ak.shape[0] != n_kv_heads or ak.shape[2] != head_dim \
+                or not ak.is_contiguous() or not av.is_contiguous():
+            raise NativeError("attention: arena planes must be contiguous fp16 [Hkv,R,D]")
+        if tiles.dtype != torch.int32 or not tiles.is_contiguous() or tiles.numel() < 2 * n_tiles:
+            raise NativeError("attention: the tile list must be a contiguous int32 [T,2] CUDA tensor")
+        p.kv_arena_k, p.kv_arena_v, p.kv_tiles = ak.data_ptr(), av.data_ptr(), tiles.data_ptr()
+        p.kv_arena_rows, p.kv_n_tiles, p.kv_rows = int(ak.shape[1]), int(n_tiles), int(rows)
     fn = lib.pc_decode_attn if decode else lib.pc_prefill_attn
     _check(fn(C.byref(p), _stream()), "pc_decode_attn" if decode else "pc_prefill_attn")
 

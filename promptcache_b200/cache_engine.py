@@ -23,7 +23,7 @@ from typing import Dict, List, Optional, Tuple, Union
 import torch
 
 from . import _native as nat
-from .model._kv import KVBuffer, PastKV
+from .model._kv import KVBuffer, PastKV, StaleKVError, VirtualKV
 from .prompt import ModuleRef, Prompt
 from .schema import Module, Path, Schema, TokenSequence, UnionModule
 
@@ -39,10 +39,36 @@ class SplicedKV(list):
     kv_buffer: Optional[KVBuffer] = None
     rows: int = 0
     epoch: int = 0  # of the buffer when process() handed the views out: a later process() makes them stale
+    virtual: Optional[VirtualKV] = None  # virtual splice: the rows the views show are copied in only when somebody looks
 
     def batched(self) -> PastKV:
         """The `[(k.unsqueeze(0), v.unsqueeze(0)) ...]` of generation_engine.py:101-102, materialised lazily."""
-        return PastKV(self.kv_buffer, self.rows, self.epoch)
+        return PastKV(self.kv_buffer, self.rows, self.epoch, virtual=self.virtual)
+
+    def _touch(self) -> None:
+        if self.virtual is not None and not self.virtual.done:
+            self.virtual.materialise()
+
+    # every way of reading the (K, V) views makes the rows real first; len() and batched() do not
+    def __getitem__(self, i):
+        self._touch()
+        return list.__getitem__(self, i)
+
+    def __iter__(self):
+        self._touch()
+        return list.__iter__(self)
+
+    def __reversed__(self):
+        self._touch()
+        return list.__reversed__(self)
+
+    def copy(self):
+        self._touch()
+        return list.copy(self)
+
+    def __add__(self, other):
+        self._touch()
+        return list.__add__(self, other)
 
 
 def pad_batch(batch_list: List[List[int]], pad_id: int) -> Tuple[List[List[int]], List[List[int]]]:
@@ -56,11 +82,20 @@ def pad_batch(batch_list: List[List[int]], pad_id: int) -> Tuple[List[List[int]]
 class TokenSequenceCache:
     """KV of one TokenSequence, resident in HBM as a single packed allocation."""
 
-    def __init__(self, seq: TokenSequence, packed: torch.Tensor):
-        if packed.dim() != 5 or packed.shape[1] != 2 or not packed.is_contiguous():
-            raise ValueError("packed segment must be a contiguous [L,2,Hkv,len,D] tensor")
+    def __init__(self, seq: TokenSequence, packed: torch.Tensor, arena: Optional[torch.Tensor] = None, row0: int = 0):
+        """`packed` is [L,2,Hkv,len,D]: a contiguous allocation of its own, or the row slice
+        `arena[:, :, :, row0:row0+len, :]` of the schema's segment arena (SchemaCache)."""
+        if packed.dim() != 5 or packed.shape[1] != 2:
+            raise ValueError("a segment must be a [L,2,Hkv,len,D] tensor")
+        if arena is None:
+            if not packed.is_contiguous():
+                raise ValueError("a stand-alone segment must be a contiguous [L,2,Hkv,len,D] tensor")
+            arena, row0 = packed, 0
+        elif packed.data_ptr() != arena[0, 0, 0, row0].data_ptr() or packed.stride() != arena.stride():
+            raise ValueError("segment is not a row slice of its arena")
         self.token_sequence = seq
         self.packed = packed
+        self.arena, self.row0 = arena, row0
         self.usage_counter = 0
 
     def inc_usage_counter(self) -> None:
@@ -106,10 +141,19 @@ class PromptCache:
         # new splice overwrote -- the reference's forward would hold a private torch.cat copy (llama2.py:361-364)
         self.kv = KVBuffer(self._bases_k, self._bases_v, max_ctx_length, storage=self.buffer)
         self._views: Dict[int, SplicedKV] = {}                          # spliced length -> the 2L views of that length
-        self.staged: List[TokenSequenceCache] = []
+        self.staged: List[TokenSequenceCache] = []    # the layout of rows [0, length), in row order
+        self._copied: List[TokenSequenceCache] = []   # the prefix of a layout the buffer physically holds
         self.length = 0
         self.retain_prefix = True
         self.last_spliced_rows = 0
+        # virtual splice: per-request tile list (int32 [T,2]: first arena row, valid rows), fixed device address so that a
+        # captured forward graph serves every request with the same tile / row counts
+        cap = max_ctx_length // 128 + 1024
+        # pinned staging slots, each guarded by the event of the copy that last read it (the host may run ahead of the GPU)
+        self._tile_slots = [[torch.zeros(cap, 2, dtype=torch.int32).pin_memory(), None] for _ in range(4)]
+        self._tile_slot = 0
+        self._tiles_dev = torch.zeros(cap, 2, dtype=torch.int32, device=device)
+        self.virtual: Optional[VirtualKV] = None
 
     @property
     def device_cache(self) -> KVCache:
@@ -118,31 +162,91 @@ class PromptCache:
     def invalidate(self) -> None:
         """Forget the staged layout so the next update() moves every segment."""
         self.staged = []
+        self._copied = []
         self.length = 0
+        self.virtual = None
         self.kv.rewritten(0)
 
     @torch.inference_mode()
-    def update(self, modules: List[TokenSequenceCache]) -> None:
+    def update(self, modules: List[TokenSequenceCache], virtual: bool = False) -> None:
+        """Lay out `modules` as the cached rows [0, N) (reference :116-156).
+
+        virtual=False: the rows are copied into the contiguous buffer now (one pc_splice_kv launch; with
+        `retain_prefix` only the segments behind the longest common prefix with what the buffer already holds).
+        virtual=True ("virtual splice"): nothing is copied.  When every segment lives in ONE arena the
+        request's tile list {first arena row, valid rows} goes to the device (one small pinned copy) and the short-suffix
+        attention kernel reads the segments in place; the copy is made later only if somebody asks for the contiguous
+        rows (`materialise`).  Either way rows >= N of the buffer receive the suffix / decode rows in place."""
         # most-used segments first (stable), as the reference lays them out (:121)
         ordered = sorted(modules, key=lambda e: e.usage_counter, reverse=True)
+        row = sum(len(m) for m in ordered)
+        if row > self.max_ctx_length:
+            raise ValueError(f"spliced prompt needs {row} rows but max_ctx_length is {self.max_ctx_length}")
+        # what the buffer physically holds stays valid only as far as the new layout agrees with it (the rows behind are
+        # about to receive another request's segments or appended tokens)
         kept = 0
         if self.retain_prefix:
-            for cur, prev in zip(ordered, self.staged):
+            for cur, prev in zip(ordered, self._copied):
                 if cur is not prev:
                     break
                 kept += 1
-        row = sum(len(m) for m in ordered[:kept])
-        plan = []
-        for m in ordered[kept:]:
-            plan.append((m.packed, row))
-            row += len(m)
-        if row > self.max_ctx_length:
-            raise ValueError(f"spliced prompt needs {row} rows but max_ctx_length is {self.max_ctx_length}")
-        nat.splice_kv(plan, self.buffer)
-        self.last_spliced_rows = sum(int(p.shape[3]) for p, _ in plan)
+        self._copied = self._copied[:kept]
         self.staged = ordered
         self.length = row
         self.kv.rewritten(row)  # rows >= `row` are scratch for the request being served; older pasts are stale now
+        self.virtual = None
+        self.last_spliced_rows = 0
+        if virtual and ordered and self._upload_tiles(ordered):
+            return
+        self.materialise()
+
+    def _upload_tiles(self, ordered: List[TokenSequenceCache]) -> bool:
+        arena = ordered[0].arena
+        if any(m.arena is not arena for m in ordered) or arena.device != self.buffer.device or arena.dtype != self.buffer.dtype \
+                or tuple(arena.shape[:3]) != tuple(self.buffer.shape[:3]) or arena.shape[4] != self.head_dim or not arena.is_contiguous():
+            return False  # segments from different allocations: the copy is made instead
+        tiles = []
+        for m in ordered:
+            n = len(m)
+            for r in range(0, n, 128):
+                tiles.append((m.row0 + r, min(128, n - r)))
+        if len(tiles) > self._tiles_dev.shape[0]:
+            return False
+        t = len(tiles)
+        slot = self._tile_slots[self._tile_slot]
+        self._tile_slot = (self._tile_slot + 1) % len(self._tile_slots)
+        if slot[1] is not None:
+            slot[1].synchronize()
+        slot[0][:t] = torch.tensor(tiles, dtype=torch.int32)
+        self._tiles_dev[:t].copy_(slot[0][:t], non_blocking=True)  # stream-ordered before the forward that reads it
+        if slot[1] is None:
+            slot[1] = torch.cuda.Event()
+        slot[1].record()
+        epoch = self.kv.epoch
+
+        def materialise():
+            if self.kv.epoch != epoch:
+                raise StaleKVError("the prompt cache was re-spliced after this cache was handed out")
+            self.materialise()
+
+        self.virtual = VirtualKV(arena, self._tiles_dev, t, self.length, materialise)
+        return True
+
+    @torch.inference_mode()
+    def materialise(self) -> None:
+        """Copy every staged segment the buffer does not hold yet (the splice proper)."""
+        kept = len(self._copied)
+        row = sum(len(m) for m in self.staged[:kept])
+        plan = []
+        for m in self.staged[kept:]:
+            plan.append((m.packed, row))
+            row += len(m)
+        if plan:
+            nat.splice_kv(plan, self.buffer)
+        self.last_spliced_rows += sum(int(p.shape[3]) for p, _ in plan)
+        self._copied = list(self.staged)
+        if self.virtual is not None:
+            self.virtual.done = True
 
     def __len__(self) -> int:
         return self.length
@@ -159,7 +263,7 @@ class PromptCache:
             master = SplicedKV((self.buffer[l, 0, :, :n, :], self.buffer[l, 1, :, :n, :]) for l in range(self.num_layers))
             self._views[n] = master
         out = SplicedKV(master)
-        out.kv_buffer, out.rows, out.epoch = self.kv, n, self.kv.epoch
+        out.kv_buffer, out.rows, out.epoch, out.virtual = self.kv, n, self.kv.epoch, self.virtual
         return out
 
 
@@ -172,8 +276,36 @@ class SchemaCache:
         self.cache_l1: Dict[int, TokenSequenceCache] = {}
         self.cache_l2: Dict[Tuple[int, int], Tuple[TokenSequenceCache, TokenSequenceCache]] = {}
         self.target_device = lm.device if target_device is None else target_device
+        self.arena: Optional[torch.Tensor] = None  # [L,2,Hkv,R,D]: every token sequence of the schema, one allocation
         if not no_cache:
             self._process(batch_size)
+
+    def layout(self):
+        """Encode plan + arena layout, derived from the schema alone (identical on every rank): the list of
+        (path, scaffold, token sequences to store) per scaffold path, the first arena row of every sequence, and the
+        total number of rows."""
+        plan, rows, r = [], {}, 0
+        for path in self.scaffold_paths():
+            scaffold = self.schema.get_scaffold(path)
+            target = [seq for seq in scaffold.select(path).all_token_sequences() if len(seq) > 0]
+            for seq in target:
+                if id(seq) not in rows:
+                    rows[id(seq)] = r
+                    r += len(seq)
+            plan.append((path, scaffold, target))
+        return plan, rows, r
+
+    def allocate_arena(self, total_rows: int) -> torch.Tensor:
+        L, hkv, d = self.lm.get_cache_shape()
+        self.arena = torch.empty(L, 2, hkv, max(total_rows, 1), d, dtype=torch.half, device=self.target_device)
+        return self.arena
+
+    def adopt(self, seq: TokenSequence, row0: int) -> TokenSequenceCache:
+        """Register rows [row0, row0+len) of the arena as the cache of `seq`."""
+        view = self.arena[:, :, :, row0:row0 + len(seq), :]
+        entry = TokenSequenceCache(seq, view, arena=self.arena, row0=row0)
+        self.cache_l1[id(seq)] = entry
+        return entry
 
     def scaffold_paths(self) -> List[Path]:
         """Default scaffold + one path per non-default union member, in the reference's order (:188-210)."""
@@ -215,13 +347,13 @@ class SchemaCache:
         token the path has to store -- prompt caching applied to its own encoder."""
         full_ids = not getattr(self.lm, "use_full_position_ids", False)  # MPT wants cached + new ids: keep it simple
         base_ids = base_pos = base_kv = None
-        for path in self.scaffold_paths():
-            scaffold = self.schema.get_scaffold(path)
+        plan, rows, total = self.layout()
+        self.allocate_arena(total)
+        for path, scaffold, target in plan:
             token_ids = scaffold.token_ids()
             position_ids = scaffold.position_ids()
             if len(token_ids) == 0:
                 continue
-            target = [seq for seq in scaffold.select(path).all_token_sequences() if len(seq) > 0]
             first = 0
             if self.reuse_prefix and full_ids and base_kv is not None and target:
                 common = 0
@@ -246,10 +378,10 @@ class SchemaCache:
             for seq in target:
                 st = position_ids.index(seq.offset)  # offsets and row order can differ (:275-279)
                 ed = st + len(seq)
-                ks = torch.stack([self.lm.store_k_hook(kv[l][0])[0, :, st:ed, :] for l in range(len(kv))])
-                vs = torch.stack([self.lm.store_v_hook(kv[l][1])[0, :, st:ed, :] for l in range(len(kv))])
-                packed = torch.stack([ks, vs], dim=1).to(device=self.target_device, dtype=torch.half).contiguous()
-                self.cache_l1[id(seq)] = TokenSequenceCache(seq, packed)
+                entry = self.adopt(seq, rows[id(seq)])  # straight into the schema's arena: no per-segment allocation
+                for l in range(len(kv)):
+                    entry.packed[l, 0].copy_(self.lm.store_k_hook(kv[l][0])[0, :, st:ed, :])
+                    entry.packed[l, 1].copy_(self.lm.store_v_hook(kv[l][1])[0, :, st:ed, :])
             del out, kv
         del base_kv
         gc.collect()
@@ -273,6 +405,7 @@ class CacheEngine:
         if hasattr(lm.hf_model, "ensure_rope"):
             lm.hf_model.ensure_rope(max_ctx_length)
         self._events = None
+        self.virtual_splice = True  # False: PromptCache.update always copies (the reference's behaviour)
         from .model import LanguageModel
         self._identity_hooks = all(getattr(getattr(lm, name, None), "__func__", None) is getattr(LanguageModel, name)
                                    for name in ("read_k_hook", "read_v_hook"))
@@ -377,7 +510,11 @@ class CacheEngine:
                 raise ValueError(f"token sequence at offset {seq.offset} of schema {prompt.schema} is not cached")
             entry.inc_usage_counter()
             seq_caches.append(entry)
-        self.prompt_cache.update(seq_caches)
+        # virtual splice when the model's short-suffix attention can read the segments in place (decided per request:
+        # the suffix length is known here); otherwise the rows are copied as the reference does
+        max_q = getattr(self.lm.hf_model, "virtual_kv_max_q", lambda: 0)()
+        virtual = self.virtual_splice and self._identity_hooks and not return_full_position_ids and 0 < len(input_ids) <= max_q
+        self.prompt_cache.update(seq_caches, virtual=virtual)
         cache = self.prompt_cache.cache
         end.record()
         end.synchronize()

@@ -60,6 +60,9 @@ struct SmallParams {
   float scale;
   unsigned long long* trace;  // PC_DEBUG builds: %globaltimer stamps of CTA 0 (PC_ATTN_TRACE_PTR), else nullptr
   bool global_merge;          // PC_ATTN_GLOBAL_MERGE: merge split-KV partials through the workspace, not the cluster
+  // virtual splice: the first v_rows keys are not in k/v but in n_vtiles tiles {arena row, valid rows} of the segment arena
+  const int2* vtiles;         // device; nullptr = everything is read from k/v
+  int n_vtiles, v_rows;
 };
 
 __device__ __forceinline__ unsigned long long gtime() {
@@ -146,12 +149,13 @@ __device__ __forceinline__ int reduced_column(int lane) {
 template <int NPAD, int ROUND, bool ALIBI, bool CLUSTER>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                  const __grid_constant__ CUtensorMap map_v, const SmallParams pin) {
+                  const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_ak,
+                  const __grid_constant__ CUtensorMap map_av, const SmallParams pin) {
   using C = SCfg<NPAD>;
   pdl_launch_dependents();  // programmatic dependent launch: see pc_common.cuh
   SmallParams p = pin;
   if (pin.n_cached_dev != nullptr) pdl_wait();  // the run-time length is written by the previous kernels
-  if (pin.n_cached_dev != nullptr) p.n_cached = max(0, min(__ldg(pin.n_cached_dev), pin.n_cached));
+  if (pin.n_cached_dev != nullptr) p.n_cached = max(pin.v_rows, min(__ldg(pin.n_cached_dev), pin.n_cached));
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   unsigned char* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -181,7 +185,11 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   const int cols_valid = G * p.q_len;  // <= NPAD
   const int split = blockIdx.x % pin.n_splits;
   const int hk = blockIdx.x / pin.n_splits;
-  const int tiles_total = (p.n_cached + p.q_len + BK - 1) / BK;
+  // Key order: [virtual tiles: cached segments read in place from the arena] [rows v_rows.. of k/v: rows appended by
+  // earlier forwards (n_tail of them, all visible), then the q_len new rows (causal)].  Without a tile list vt = 0.
+  const int vt = p.n_vtiles;
+  const int n_tail = p.n_cached - p.v_rows;
+  const int tiles_total = vt + (n_tail + p.q_len + BK - 1) / BK;
   // With a run-time N the grid was sized for an upper bound: only the first min(n_splits, tiles) splits work, the
   // other CTAs leave before touching any barrier, TMEM or the arrival counter.
   if (p.n_splits > tiles_total) p.n_splits = tiles_total;
@@ -243,18 +251,24 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         const int s = j % kStages;
         unsigned char* dk = sKV + (2 * s) * kTileBytes;
         unsigned char* dv = dk + kTileBytes;
-        const int key0 = (tile0 + j) * BK;
+        const int t = tile0 + j;
+        const bool virt = t < vt;
+        // a virtual tile may run past its segment into the next one's rows (masked by `valid`) or past the arena (zeros)
+        const int key0 = virt ? __ldg(&p.vtiles[t].x) : p.v_rows + (t - vt) * BK;
+        const CUtensorMap* mk = virt ? &map_ak : &map_k;
+        const CUtensorMap* mv = virt ? &map_av : &map_v;
         mbar_expect_tx(&k_full[s], kTileBytes);
-        for (int hf = 0; hf < 2; ++hf) tma_load_3d(dk + hf * 16384, &map_k, &k_full[s], hf * 64, key0, hk);
+        for (int hf = 0; hf < 2; ++hf) tma_load_3d(dk + hf * 16384, mk, &k_full[s], hf * 64, key0, hk);
         mbar_expect_tx(&v_full[s], kTileBytes);
-        for (int hf = 0; hf < 2; ++hf) tma_load_3d(dv + hf * 16384, &map_v, &v_full[s], hf * 64, key0, hk);
+        for (int hf = 0; hf < 2; ++hf) tma_load_3d(dv + hf * 16384, mv, &v_full[s], hf * 64, key0, hk);
       };
       // Programmatic dependent launch: this CTA may be running while the previous kernels of the step (the QKV
       // projection, RoPE + append) are still in flight.  Rows [0, n_cached) of this layer's K/V were written before
       // the forward began (splice, earlier forwards) and nothing inside a forward touches them, so tiles that lie
-      // entirely in them are streamed into the ring right away; Q and the tiles holding new rows wait.
+      // entirely in them are streamed into the ring right away; Q and the tiles holding new rows wait.  (Virtual tiles
+      // are cached rows by definition, and their tile list was uploaded before the forward began.)
       int pre = 0;
-      while (pre < T && pre < kStages && (tile0 + pre + 1) * BK <= p.n_cached) load_kv(pre++);
+      while (pre < T && pre < kStages && (tile0 + pre < vt || (tile0 + pre - vt + 1) * BK <= n_tail)) load_kv(pre++);
       pdl_wait();
       mbar_expect_tx(q_full, C::kQBytes);
       for (int hf = 0; hf < 2; ++hf) tma_load_3d(sQ + hf * (NPAD * 128), &map_q, q_full, hf * 64, 0, hk);
@@ -316,13 +330,15 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
     for (int j = 0; j < T; ++j) {
       const int b = j & 1;
+      const int tj = tile0 + j;
+      const int valid = tj < vt ? __ldg(&p.vtiles[tj].y) : BK;  // issued before the wait: off the critical path
       mbar_wait(&s_full[b], static_cast<uint32_t>((j >> 1) & 1));
       tc_fence_after();
       if (tid == 0 && j < 8) PC_TRACE(8 + 4 * j);  // S^T_j landed
       float x[NH];
       tmem_ld_n<NH>(tmem_base + lane_base + b * NPAD + c0, x);
       tmem_ld_wait();
-      const int key = (tile0 + j) * BK + kl;
+      const int key = p.v_rows + (tj - vt) * BK + kl;  // index among all keys (tail tiles; virtual tiles never use it)
       float kp = 0.f;
       if (ALIBI) kp = static_cast<float>(__ldg(p.key_pos + min(key, p.n_cached + p.q_len - 1)) - p.alibi_max_pos);
 #pragma unroll
@@ -334,7 +350,12 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         if (ALIBI) v += slopetab[c0 + i] * kp;
         x[i] = v * kLog2e;
       }
-      if ((tile0 + j + 1) * BK > p.n_cached) {  // tile touches the suffix: key n_cached+t is visible to row r iff t <= r
+      if (tj < vt) {  // virtual tile: rows past the segment's end belong to another segment (or are zero fill)
+        if (kl >= valid) {
+#pragma unroll
+          for (int i = 0; i < NH; ++i) x[i] = -INFINITY;
+        }
+      } else if ((tj - vt + 1) * BK > n_tail) {  // tile touches the suffix: key n_cached+t is visible to row r iff t <= r
         const int t = key - p.n_cached;
 #pragma unroll
         for (int i = 0; i < NH; ++i)
@@ -588,8 +609,8 @@ bool clusters_fit(int cluster_x, int clusters) {
 }
 
 template <int NPAD, int ROUND, bool ALIBI>
-int launch_small_one(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const SmallParams& sp, int grid,
-                     cudaStream_t st) {
+int launch_small_one(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mak,
+                     const CUtensorMap& mav, const SmallParams& sp, int grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     PC_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<NPAD, ROUND, ALIBI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -601,10 +622,10 @@ int launch_small_one(const CUtensorMap& mq, const CUtensorMap& mk, const CUtenso
   const bool want_cluster = sp.n_splits >= 2 && sp.n_splits <= 8 && !sp.global_merge;
   if (want_cluster && clusters_fit<NPAD, ROUND, ALIBI>(sp.n_splits, grid / sp.n_splits)) {
     PC_CHECK_CUDA(launch_pdl_cluster(attn_small_kernel<NPAD, ROUND, ALIBI, true>, sp.n_splits, dim3(grid), dim3(kThreads),
-                                     SCfg<NPAD>::kSmem, st, mq, mk, mv, sp));
+                                     SCfg<NPAD>::kSmem, st, mq, mk, mv, mak, mav, sp));
   } else {
     PC_CHECK_CUDA(launch_pdl(attn_small_kernel<NPAD, ROUND, ALIBI, false>, dim3(grid), dim3(kThreads), SCfg<NPAD>::kSmem, st, mq, mk,
-                             mv, sp));
+                             mv, mak, mav, sp));
   }
   count_launch();
   return PC_OK;
@@ -613,7 +634,17 @@ int launch_small_one(const CUtensorMap& mq, const CUtensorMap& mk, const CUtenso
 template <int NPAD>
 int launch_small_n(const pc_attn_params& p, cudaStream_t st) {
   const int G = p.n_heads / p.n_kv_heads;
-  const int tiles = (p.n_cached + p.q_len + BK - 1) / BK;  // with n_cached_dev: an upper bound
+  const bool virt = p.kv_tiles != nullptr && p.kv_n_tiles > 0;
+  if (virt) {
+    PC_REQUIRE(p.kv_arena_k && p.kv_arena_v && p.kv_arena_rows > 0 && p.kv_rows > 0 && p.kv_rows <= p.n_cached,
+               "attn(tcgen05-small): bad virtual-splice arguments (arena rows %d, kv_rows %d, n_cached %d)", p.kv_arena_rows,
+               p.kv_rows, p.n_cached);
+    PC_REQUIRE(p.alibi_slopes == nullptr, "attn(tcgen05-small): the virtual splice does not carry key positions (ALiBi)");
+    PC_REQUIRE((reinterpret_cast<uintptr_t>(p.kv_arena_k) | reinterpret_cast<uintptr_t>(p.kv_arena_v)) % 16 == 0,
+               "attn(tcgen05-small): arena planes must be 16B aligned");
+  }
+  const int v_rows = virt ? p.kv_rows : 0, n_vtiles = virt ? p.kv_n_tiles : 0;
+  const int tiles = n_vtiles + (p.n_cached - v_rows + p.q_len + BK - 1) / BK;  // with n_cached_dev: an upper bound
   int n_splits = sm_count() / p.n_kv_heads;
   if (const char* e = dbg_env("PC_ATTN_SPLITS")) n_splits = atoi(e);
   if (n_splits > tiles) n_splits = tiles;
@@ -651,6 +682,9 @@ int launch_small_n(const pc_attn_params& p, cudaStream_t st) {
   sp.scale = p.scale;
   sp.trace = nullptr;
   sp.global_merge = (p.impl & PC_ATTN_GLOBAL_MERGE) != 0;
+  sp.vtiles = virt ? reinterpret_cast<const int2*>(p.kv_tiles) : nullptr;
+  sp.n_vtiles = n_vtiles;
+  sp.v_rows = v_rows;
   if (const char* e = dbg_env("PC_ATTN_TRACE_PTR")) sp.trace = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
 
   const int rows_total = G * p.q_len;
@@ -660,11 +694,19 @@ int launch_small_n(const pc_attn_params& p, cudaStream_t st) {
   const long long kv_rows = p.n_cached_dev ? static_cast<long long>(p.max_ctx) : static_cast<long long>(p.n_cached) + p.q_len;
   if (int rc = make_tensor_map_3d(&mk, p.k, D, kv_rows, p.n_kv_heads, static_cast<long long>(p.max_ctx) * D, BK)) return rc;
   if (int rc = make_tensor_map_3d(&mv, p.v, D, kv_rows, p.n_kv_heads, static_cast<long long>(p.max_ctx) * D, BK)) return rc;
+  CUtensorMap mak = mk, mav = mv;  // unused without a tile list
+  if (virt) {
+    const long long ar = p.kv_arena_rows;
+    if (int rc = make_tensor_map_3d(&mak, p.kv_arena_k, D, ar, p.n_kv_heads, ar * D, BK)) return rc;
+    if (int rc = make_tensor_map_3d(&mav, p.kv_arena_v, D, ar, p.n_kv_heads, ar * D, BK)) return rc;
+  }
   const int grid = p.n_kv_heads * n_splits;
   const bool alibi = p.alibi_slopes != nullptr;
   if (p.rounding == 0)
-    return alibi ? launch_small_one<NPAD, 0, true>(mq, mk, mv, sp, grid, st) : launch_small_one<NPAD, 0, false>(mq, mk, mv, sp, grid, st);
-  return alibi ? launch_small_one<NPAD, 3, true>(mq, mk, mv, sp, grid, st) : launch_small_one<NPAD, 3, false>(mq, mk, mv, sp, grid, st);
+    return alibi ? launch_small_one<NPAD, 0, true>(mq, mk, mv, mak, mav, sp, grid, st)
+                 : launch_small_one<NPAD, 0, false>(mq, mk, mv, mak, mav, sp, grid, st);
+  return alibi ? launch_small_one<NPAD, 3, true>(mq, mk, mv, mak, mav, sp, grid, st)
+               : launch_small_one<NPAD, 3, false>(mq, mk, mv, mak, mav, sp, grid, st);
 }
 
 }  // namespace

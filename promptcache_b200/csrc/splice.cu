@@ -158,9 +158,8 @@ std::map<cudaStream_t, Staging> g_stages;
 
 }  // namespace
 
-PC_API int pc_splice_kv(const pc_segment* segs, int n_segs, void* cache_dev, int n_layers,
-                            int n_kv_heads, int head_dim, int max_ctx, int elem_bytes,
-                            void* stream) {
+static int splice_kv_impl(const pc_segment* segs, const int64_t* src_run_rows, int n_segs, void* cache_dev, int n_layers,
+                          int n_kv_heads, int head_dim, int max_ctx, int elem_bytes, void* stream) {
   PC_REQUIRE(n_segs >= 0, "pc_splice_kv: n_segs < 0");
   if (n_segs == 0) return PC_OK;
   PC_REQUIRE(segs && cache_dev, "pc_splice_kv: null pointer");
@@ -193,7 +192,7 @@ PC_API int pc_splice_kv(const pc_segment* segs, int n_segs, void* cache_dev, int
       d.src = static_cast<const char*>(s.base);
       d.dst = static_cast<char*>(cache_dev) + static_cast<long long>(s.dst_row) * row_bytes;
       d.run_bytes = static_cast<long long>(s.len) * row_bytes;
-      d.src_run_stride = d.run_bytes;
+      d.src_run_stride = src_run_rows ? static_cast<long long>(src_run_rows[base + i]) * row_bytes : d.run_bytes;
       d.dst_run_stride = static_cast<long long>(max_ctx) * row_bytes;
       d.n_runs = n_runs;
     }
@@ -203,6 +202,20 @@ PC_API int pc_splice_kv(const pc_segment* segs, int n_segs, void* cache_dev, int
     pc::count_launch();
   }
   return PC_OK;
+}
+
+PC_API int pc_splice_kv(const pc_segment* segs, int n_segs, void* cache_dev, int n_layers, int n_kv_heads, int head_dim,
+                        int max_ctx, int elem_bytes, void* stream) {
+  return splice_kv_impl(segs, nullptr, n_segs, cache_dev, n_layers, n_kv_heads, head_dim, max_ctx, elem_bytes, stream);
+}
+
+PC_API int pc_splice_kv_strided(const pc_segment* segs, const int64_t* src_run_rows, int n_segs, void* cache_dev, int n_layers,
+                                int n_kv_heads, int head_dim, int max_ctx, int elem_bytes, void* stream) {
+  PC_REQUIRE(n_segs <= 0 || src_run_rows != nullptr, "pc_splice_kv_strided: null src_run_rows");
+  for (int i = 0; i < n_segs; ++i)
+    PC_REQUIRE(src_run_rows[i] >= segs[i].len, "pc_splice_kv_strided: segment %d: run stride %lld rows < len %d", i,
+               static_cast<long long>(src_run_rows[i]), segs[i].len);
+  return splice_kv_impl(segs, src_run_rows, n_segs, cache_dev, n_layers, n_kv_heads, head_dim, max_ctx, elem_bytes, stream);
 }
 
 PC_API int pc_splice_kv_tensors(const pc_copy2d* copies, int n_copies, void* stream) {

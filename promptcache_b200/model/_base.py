@@ -92,6 +92,11 @@ class B200CausalLM(nn.Module):
 
     supports_dynamic_n = False    # _layers(..., n_dev=) reads the cached length on the device (decode graph)
 
+    def virtual_kv_max_q(self) -> int:
+        """Longest suffix whose attention can read cached segments in place from the schema arena (virtual splice);
+        0 = this model always needs the contiguous rows."""
+        return 0
+
     def _launch_shape_key(self):
         """Every switch that changes the launch sequence of `_layers`; part of each graph key so that toggling one
         after a capture can never replay a stale sequence."""
@@ -126,7 +131,7 @@ class B200CausalLM(nn.Module):
         """One-token decode through ONE captured graph per KV buffer: the cached length is a device scalar the
         kernels read at run time (pc_rope_append_dyn, pc_attn_params.n_cached_dev), so the same graph serves every
         step of every request on that buffer (reference loop: generation_engine.py:123-147)."""
-        key = ("decode", kv.buf.serial, kv.max_ctx) + self._launch_shape_key()
+        key = ("decode", kv.buf.serial, kv.max_ctx, kv.virtual.key() if kv.virtual is not None else None) + self._launch_shape_key()
         entry = self._graphs.get(key)
         if entry is None:
             if self._graph_seen.get(key, 0) < 1:  # first decode step on this buffer runs eagerly
@@ -156,6 +161,9 @@ class B200CausalLM(nn.Module):
         q_len = ids.shape[0]
         kv = resolve_kv(past, q_len, self.n_layers, self.n_kv_heads, self.head_dim, self.device)
         N = kv.n_cached
+        if kv.virtual is not None and not (0 < q_len <= self.virtual_kv_max_q()):
+            kv.virtual.materialise()  # this forward needs the contiguous rows: make the copy the engine skipped
+            kv.virtual = None
         if (q_len == 1 and N > 0 and self.use_cuda_graphs and self.supports_dynamic_n and not self.full_position_ids
                 and N + 1 < kv.max_ctx and not torch.cuda.is_current_stream_capturing()):
             logits = self._decode_replay(ids, pos, kv)
@@ -163,7 +171,8 @@ class B200CausalLM(nn.Module):
                 kv.wrote(N + 1)
                 return logits, (kv.views(N + 1) if use_cache else None)
         extra = self._graph_extra(max_position)
-        key = (q_len, N, kv.buf.serial, kv.max_ctx, pos.shape[0]) + self._launch_shape_key() + tuple(extra)
+        key = (q_len, N, kv.buf.serial, kv.max_ctx, pos.shape[0], kv.virtual.key() if kv.virtual is not None else None) \
+            + self._launch_shape_key() + tuple(extra)
         if self.use_cuda_graphs and N > 0 and q_len > 1 and not torch.cuda.is_current_stream_capturing():
             entry = self._graphs.get(key)
             if entry is None and self._graph_seen.get(key, 0) >= 1:

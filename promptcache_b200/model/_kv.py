@@ -78,18 +78,43 @@ def buffer_of(t: torch.Tensor) -> Optional[KVBuffer]:
     return ref() if ref is not None else None
 
 
+class VirtualKV:
+    """The cached rows [0, rows) of a KVBuffer that have NOT been copied into it ("virtual splice"):
+    they are read in place from the schema's segment arena [L,2,Hkv,R,D] through `tiles` (int32 [T,2] on the device:
+    first arena row, valid rows).  `materialise()` makes the copy after all, for consumers that need the contiguous rows
+    (long-suffix / ALiBi attention kernels, callers indexing the reference-shaped views)."""
+
+    __slots__ = ("arena", "tiles", "n_tiles", "rows", "_materialise", "done")
+
+    def __init__(self, arena: torch.Tensor, tiles: torch.Tensor, n_tiles: int, rows: int, materialise):
+        self.arena, self.tiles, self.n_tiles, self.rows = arena, tiles, n_tiles, rows
+        self._materialise, self.done = materialise, False
+
+    def materialise(self) -> None:
+        if not self.done:
+            self._materialise()
+            self.done = True
+
+    def key(self):
+        """What a captured CUDA graph bakes in (tensor maps over the arena, tile-list address, tile and row counts)."""
+        return (self.arena.data_ptr(), int(self.arena.shape[3]), self.tiles.data_ptr(), self.n_tiles, self.rows)
+
+    def planes(self, layer: int):
+        return (self.arena[layer, 0], self.arena[layer, 1], self.tiles, self.n_tiles, self.rows)
+
+
 class LayerKV:
     """What one forward works on: a buffer and the number of valid rows in front of the rows it will write."""
 
-    def __init__(self, buf: KVBuffer, n_cached: int):
-        self.buf, self.n_cached = buf, n_cached
+    def __init__(self, buf: KVBuffer, n_cached: int, virtual: Optional[VirtualKV] = None):
+        self.buf, self.n_cached, self.virtual = buf, n_cached, virtual
 
     k = property(lambda self: self.buf.k)
     v = property(lambda self: self.buf.v)
     max_ctx = property(lambda self: self.buf.max_ctx)
 
     def views(self, rows: int) -> "PastKV":
-        return PastKV(self.buf, rows)
+        return PastKV(self.buf, rows, virtual=self.virtual)
 
     def wrote(self, rows: int) -> None:
         self.buf.high = max(self.buf.high, rows)
@@ -100,9 +125,10 @@ class PastKV:
     [1, Hkv, rows, D] (llama2.py:366), but the views are only materialised when somebody indexes them.  Passing it
     back into the next forward is O(1): the buffer is recognised instead of re-validated tensor by tensor."""
 
-    def __init__(self, buf: KVBuffer, rows: int, epoch: Optional[int] = None):
+    def __init__(self, buf: KVBuffer, rows: int, epoch: Optional[int] = None, virtual: Optional[VirtualKV] = None):
         self.buf, self.rows = buf, rows
         self.epoch = buf.epoch if epoch is None else epoch
+        self.virtual = virtual  # leading rows still live in the segment arena only (see VirtualKV)
         self._views = {}
 
     def __len__(self) -> int:
@@ -114,6 +140,10 @@ class PastKV:
         if l < 0:
             l += len(self)
         if l not in self._views:
+            if self.virtual is not None:  # somebody wants the contiguous rows after all
+                if self.epoch != self.buf.epoch:
+                    raise StaleKVError("this past_key_values was handed out before the engine re-spliced its buffer")
+                self.virtual.materialise()
             k, v = self.buf.k[l], self.buf.v[l]
             self._views[l] = (k[:, :self.rows, :].unsqueeze(0), v[:, :self.rows, :].unsqueeze(0))
         return self._views[l]
@@ -164,9 +194,12 @@ def resolve_kv(past: Optional[Sequence[Tuple[torch.Tensor, torch.Tensor]]], q_le
         if own is not None:
             buf, rows = own
     if buf is not None:
+        virtual = past.virtual if isinstance(past, PastKV) else None
         if rows == buf.high and rows + q_len <= buf.max_ctx:
-            return LayerKV(buf, rows)                      # the tip of the sequence: append in place, O(1)
+            return LayerKV(buf, rows, virtual)             # the tip of the sequence: append in place, O(1)
         # somebody already appended behind these rows (or there is no room): continue on a private copy
+        if virtual is not None:
+            virtual.materialise()
         return _fork(lambda l: buf.k[l][:, :rows], lambda l: buf.v[l][:, :rows], rows, q_len, n_layers, n_kv_heads,
                      head_dim, device, headroom)
     if past is None or len(past) == 0 or past[0] is None:

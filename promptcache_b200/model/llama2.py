@@ -50,6 +50,9 @@ class LlamaForCausalLM(B200CausalLM):
     def supports_dynamic_n(self) -> bool:  # the short-suffix kernel reads N on the device (D=128, G <= 32)
         return self.head_dim == 128 and self.n_heads // self.n_kv_heads <= 32
 
+    def virtual_kv_max_q(self) -> int:  # the short-suffix kernel reads segments in place: D=128, G*q <= 32
+        return 32 // (self.n_heads // self.n_kv_heads) if self.head_dim == 128 else 0
+
     def __init__(self, config, device="cuda", dtype=torch.float16):
         super().__init__()
         self.config = config
@@ -139,8 +142,10 @@ class LlamaForCausalLM(B200CausalLM):
                 nat.linear_rope_append(h, self.wqkv[l], pos, self._cos, self._sin, q_rot, kv.k[l], kv.v[l], N, H, Hkv, lws,
                                        w_tiled=self._wt(("qkv", l), self.wqkv[l], nat.PC_LIN_ROPE_APPEND))
             if "attn" not in ab:
+                virt = kv.virtual
                 nat.attention(q_rot, kv.k[l], kv.v[l], attn_out, N, q_len, H, Hkv, D, self.scale, self.rounding, workspace=ws,
-                              decode=(q_len == 1), impl=self.attn_impl)
+                              decode=(q_len == 1), impl=self.attn_impl if virt is None else nat.PC_ATTN_TCGEN05,
+                              virtual=virt.planes(l) if virt is not None else None)
             if "linear" not in ab:
                 nat.linear_partials(attn_out, self.wo[l], pbuf_o, lws, w_tiled=self._wt(("o", l), self.wo[l], nat.PC_LIN_PARTIALS))
             if "norm" not in ab:
@@ -187,6 +192,7 @@ class LlamaForCausalLM(B200CausalLM):
         which = self.linear_native_ops  # which linears run natively (A/B switch, PC_LINEAR_OPS)
         lin_qkv, lin_o, lin_gu, lin_down, lin_head = (lin and k in which for k in ("qkv", "o", "gu", "down", "head"))
         delta = None
+        virt = kv.virtual  # cached rows still in the schema arena: attention reads them through the tile list
         if self.ablate:  # measurement only (bench.py: in-step cost of a kernel family = full step - step without it)
             return self._layers_ablated(x, h, pos, kv, q_rot, attn_out, act, ws, lws, pbuf_o, pbuf_d, n_dev)
         for l in range(self.n_layers):
@@ -202,7 +208,8 @@ class LlamaForCausalLM(B200CausalLM):
                                 self._sin, q_rot, kv.k[l], kv.v[l], N if n_dev is None else n_dev, H, Hkv, D)
             nat.attention(q_rot, kv.k[l], kv.v[l], attn_out, N if n_dev is None else kv.max_ctx - q_len, q_len, H, Hkv,
                           D, self.scale, self.rounding, workspace=ws, decode=(q_len == 1), n_cached_dev=n_dev,
-                          impl=self.attn_impl if n_dev is None else nat.PC_ATTN_TCGEN05)
+                          impl=self.attn_impl if (n_dev is None and virt is None) else nat.PC_ATTN_TCGEN05,
+                          virtual=virt.planes(l) if virt is not None else None)
             if lin_o and pbuf_o is not None:
                 nat.linear_partials(attn_out, self.wo[l], pbuf_o, lws, w_tiled=self._wt(("o", l), self.wo[l], nat.PC_LIN_PARTIALS))
                 delta = pbuf_o

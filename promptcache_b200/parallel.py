@@ -74,19 +74,17 @@ def broadcast_schema(schema_cache, src: int = 0, device=None) -> dict:
     """Make every rank hold the segment store rank `src` encoded.
 
     `schema_cache` is a SchemaCache built with the same schema on every rank (`no_cache=True` on ranks other
-    than `src`, so only `src` ran the scaffold forwards).  Segments are matched by (offset, length, token ids),
-    which every rank derives identically from the schema, and moved with one broadcast per segment (each is a
-    single packed [L,2,Hkv,len,D] allocation; C5: 64 x 128 MiB).  Returns {"segments", "bytes"} of what was moved."""
-    from .cache_engine import TokenSequenceCache
+    than `src`, so only `src` ran the scaffold forwards).  The store is ONE arena [L,2,Hkv,R,D] whose row layout every
+    rank derives identically from the schema (`SchemaCache.layout`), so it moves with a single ncclBroadcast (C5: 8 GiB)
+    and the receivers just register row slices.  Returns {"segments", "bytes"} of what was moved."""
     if world() == 1:
         return {"segments": 0, "bytes": 0}
     device = _default_device(device if device is not None else getattr(schema_cache, "target_device", None))
-    schema = schema_cache.schema
-    seqs = []
-    for path in schema_cache.scaffold_paths():
-        for seq in schema.get_scaffold(path).select(path).all_token_sequences():
-            if len(seq) > 0 and all(seq is not s for s in seqs):
-                seqs.append(seq)
+    plan, rows, total = schema_cache.layout()
+    seqs = {}
+    for _, _, target in plan:
+        for seq in target:
+            seqs.setdefault(id(seq), seq)
     # shape header from the source rank; an empty store is announced instead of raising before the collective
     meta: List[Any] = [None]
     if rank() == src:
@@ -94,24 +92,27 @@ def broadcast_schema(schema_cache, src: int = 0, device=None) -> dict:
         if first is None:
             meta = [("empty",)]
         else:
-            L, two, hkv, _, d = first.packed.shape
-            meta = [(int(L), int(hkv), int(d), str(first.packed.dtype).replace("torch.", ""))]
+            if schema_cache.arena is None:  # entries built one by one (tests, older stores): pack them into an arena first
+                L, _, hkv, _, d = first.packed.shape
+                arena = torch.empty(L, 2, hkv, max(total, 1), d, dtype=first.packed.dtype, device=first.packed.device)
+                old = dict(schema_cache.cache_l1)
+                schema_cache.arena = arena
+                for sid, seq in seqs.items():
+                    if sid in old:
+                        schema_cache.adopt(seq, rows[sid]).packed.copy_(old[sid].packed)
+            a = schema_cache.arena
+            meta = [(int(a.shape[0]), int(a.shape[2]), int(a.shape[4]), str(a.dtype).replace("torch.", ""), int(a.shape[3]))]
     dist.broadcast_object_list(meta, src=src)
     if meta[0][0] == "empty":
         return {"segments": 0, "bytes": 0}
-    L, hkv, d, dtype_name = meta[0]
-    dtype = getattr(torch, dtype_name)
-    moved = 0
-    for seq in seqs:
-        if rank() == src:
-            buf = schema_cache.cache_l1[id(seq)].packed
-        else:
-            buf = torch.empty(L, 2, hkv, len(seq), d, dtype=dtype, device=device)
-        dist.broadcast(buf, src=src)
-        moved += buf.numel() * buf.element_size()
-        if rank() != src:
-            schema_cache.cache_l1[id(seq)] = TokenSequenceCache(seq, buf)
-    return {"segments": len(seqs), "bytes": moved}
+    L, hkv, d, dtype_name, total_rows = meta[0]
+    if rank() != src:
+        schema_cache.arena = torch.empty(L, 2, hkv, total_rows, d, dtype=getattr(torch, dtype_name), device=device)
+    dist.broadcast(schema_cache.arena, src=src)
+    if rank() != src:
+        for sid, seq in seqs.items():
+            schema_cache.adopt(seq, rows[sid])
+    return {"segments": len(seqs), "bytes": schema_cache.arena.numel() * schema_cache.arena.element_size()}
 
 
 class ServedPrompt:
