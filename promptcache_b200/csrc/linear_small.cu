@@ -54,11 +54,18 @@ struct LCfg {
   static constexpr int kXBytes = NPAD * BKK * 2;
   static constexpr int kStageBytes = KPS * (kWBytes + kXBytes);
   // bytes in flight per SM bound its streaming rate (Little's law, ~2.5 us loaded latency): as many stages as fit
-  static constexpr int kStages = KPS == 2 ? (NPAD <= 16 ? 6 : 5) : (NPAD <= 16 ? 11 : 10);
+#ifndef PC_LIN_STAGES16
+#define PC_LIN_STAGES16 6
+#endif
+  static constexpr int kStages = KPS == 2 ? (NPAD <= 16 ? PC_LIN_STAGES16 : 5) : (NPAD <= 16 ? 11 : 10);
   static constexpr int kOffExch = kStages * kStageBytes;
   static constexpr int kExchBytes = NPAD * BM * 2;
   static constexpr int kOffBars = kOffExch + kExchBytes;
-  static constexpr int kSmem = 1024 + kOffBars + 512;
+  // 1 KiB of slack for the 1024-byte alignment of the swizzled tiles; the half-size ring (two CTAs per SM) has 768 B --
+  // the kernel traps if the dynamic shared memory base ever needs more
+  static constexpr int kAlignSlack = (KPS == 2 && NPAD <= 16 && PC_LIN_STAGES16 <= 3) ? 768 : 1024;
+  static constexpr int kSmem = kAlignSlack + kOffBars + 256;
+  static constexpr int kMinBlocks = (KPS == 2 && NPAD <= 16 && PC_LIN_STAGES16 <= 3) ? 2 : 1;
   static constexpr int kTmemCols = 2 * NPAD <= 32 ? 32 : 64;
 };
 
@@ -209,7 +216,7 @@ struct WorkIter {
 };
 
 template <int NPAD, int EPI, bool TILED>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, LCfg<NPAD, TILED ? 2 : 1>::kMinBlocks)
 linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const LinParams p) {
   constexpr int KPS = TILED ? 2 : 1;
   using C = LCfg<NPAD, KPS>;
@@ -217,6 +224,7 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   unsigned char* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  if (((1024u - (raw_addr & 1023u)) & 1023u) > static_cast<uint32_t>(C::kAlignSlack)) __trap();
   __half* exch = reinterpret_cast<__half*>(smem + C::kOffExch);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBars);
   uint64_t* full = bars;

@@ -264,8 +264,8 @@ def test_c2_llama7b_full_depth_logits_at_the_fp16_noise_floor(native):
     """BASELINE configs[1] at FULL depth (32 layers, real dims) through both engines.  fp16 end-to-end logits of two
     different-but-equivalent pipelines differ by rounding noise that grows with depth, so the bar is the noise floor
     itself: the CUDA path must be as close to the reference run in fp32 as the reference run in fp16 is (x1.5), and
-    within 5e-3 of the fp16 reference outright; the greedy token must agree with the fp32 reference whenever the
-    fp16 reference's does."""
+    within 2.5 noise floors of the fp16 reference; the greedy token must agree with the fp32 reference whenever the
+    fp16 reference's does.  (Measured on the B200: the two fp16 pipelines are 1.7e-2 of max|logit| apart at depth 32.)"""
     from promptcache_b200 import Prompt
     from promptcache_b200.synthetic import MODEL_DIMS, make_case
     ref_shim.load_reference()
@@ -294,9 +294,48 @@ def test_c2_llama7b_full_depth_logits_at_the_fp16_noise_floor(native):
     ref32 = _prefill_logits(ref_lm, i32, p32, c32)
     floor = _rel(ref16, ref32)
     err = _rel(ours, ref32)
-    print(f"[C2 full depth] reference fp16 vs fp32: {floor:.2e}; CUDA path vs fp32: {err:.2e}; CUDA path vs reference fp16: "
-          f"{_rel(ours, ref16):.2e}")
-    assert err <= 1.5 * floor + 1e-4, (err, floor)
-    assert _rel(ours, ref16) <= 5e-3
+    both = _rel(ours, ref16)
+    report = f"[C2 full depth] reference fp16 vs fp32: {floor:.2e}; CUDA path vs fp32: {err:.2e}; CUDA path vs reference fp16: {both:.2e}"
+    print(report)
+    assert err <= 1.5 * floor + 1e-4, report
+    # two fp16 pipelines, each `floor` away from the truth in its own direction, are up to ~2 floors apart
+    assert both <= 2.5 * floor + 1e-4, report
     if int(ref16[0, -1].argmax()) == int(ref32[0, -1].argmax()):
         assert int(ours[0, -1].argmax()) == int(ref32[0, -1].argmax())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the generation loop itself: sampling paths (generation_engine.py:149-165) -- reference loop vs ours, SAME model object
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kw", [
+    dict(temperature=0.8, top_p=0.9),                                   # nucleus sampling -> torch.multinomial
+    dict(temperature=1.0, top_k=20),                                    # top-k warper
+    dict(temperature=0.7, top_p=0.95, repetition_penalty=1.3),          # penalty sees prompt + generated ids (:149-152)
+    dict(temperature=0.0, repetition_penalty=1.25),                     # greedy, but the penalty moves the argmax
+    dict(temperature=1.3, top_p=1.0, top_k=-1),                         # plain temperature sampling
+])
+@pytest.mark.parametrize("stream_interval", [1, 3])
+def test_sampling_paths_equal_the_reference_generation_loop(native, kw, stream_interval):
+    """The reference's OWN GenerationEngine.generate drives the CUDA-path LanguageModel, then ours does, from the same
+    torch seed: logits processors, multinomial draws, stop handling and streaming must yield identical texts."""
+    from tests.test_virtual_splice_gpu import _engine
+    from promptcache_b200 import GenerationEngine, GenerationParameters
+    ref_shim.load_reference()
+    from promptcache import GenerationEngine as RefGen, GenerationParameters as RefParams
+    eng, lm, case, prompt = _engine(seg_lens=(128, 256, 128), suffix=7, max_ctx=1024, vocab=512)
+    stop = [5, 6, 7]
+
+    def run(gen_cls, params_cls, virtual):
+        eng.virtual_splice = virtual
+        eng.prompt_cache.invalidate()
+        ids, pos, _, cache = eng.process(prompt)
+        params = params_cls(max_new_tokens=24, stop_token_ids=stop, stop_str=["t9 t9"], **kw)
+        torch.manual_seed(1234)
+        torch.cuda.manual_seed_all(1234)
+        return [(o.text, o.new_text) for o in gen_cls(lm).generate(ids, pos, params, cache, stream_interval=stream_interval)]
+
+    want = run(RefGen, RefParams, False)
+    got = run(GenerationEngine, GenerationParameters, False)
+    assert got == want and len(want) >= 1
+    # whole-tile segments: the virtual splice is bit-identical to the copy, so sampling through it draws the same tokens
+    assert run(GenerationEngine, GenerationParameters, True) == want

@@ -97,8 +97,9 @@ def test_virtual_ragged_segments_match_copied_path_and_oracle(native, H, Hkv, le
     virt = _run(native, Q, Kh, Vh, N, q, H, Hkv, virtual=(AK, AV, tiles, nt, nv))
     ref = _oracle_llama(Q, K, V, N, q)
     assert _rel(virt, ref) <= 1e-3 and _rel(copied, ref) <= 1e-3
-    # different tile boundaries, same keys: the two kernels' outputs differ by fp32 summation order only
-    assert _rel(virt, copied) <= 5e-4
+    # different tile boundaries, same keys: the outputs differ by fp32 summation order, i.e. an fp16 ulp here and there
+    assert _rel(virt, copied) <= 1e-3
+    assert float((virt.float() - copied.float()).abs().mean() / copied.float().abs().mean()) <= 3e-4
     assert torch.isfinite(virt.float()).all()
 
 
@@ -115,7 +116,7 @@ def test_virtual_runtime_length_decode_graph_semantics(native):
         got = _run(native, Q, Kh, Vh, N, 1, H, Hkv, virtual=(AK, AV, tiles, nt, nv), n_dev=n_dev, n_upper=upper)
         want = _run(native, Q, Kh, Vh, N, 1, H, Hkv, virtual=(AK, AV, tiles, nt, nv))
         assert _rel(got, _oracle_llama(Q, K, V, N, 1)) <= 1e-3
-        assert _rel(got, want) <= 5e-4
+        assert _rel(got, want) <= 1e-3
 
 
 def test_virtual_rejects_what_it_cannot_serve(native):
@@ -172,6 +173,9 @@ def test_engine_serves_requests_without_a_splice_launch_and_materialises_on_dema
     assert pc.last_spliced_rows == n == case.n_cached
     # the copied path (what the reference does) gives the same logits within fp32 summation-order noise
     eng.virtual_splice = False
+    ids2, pos2, _, cache2 = eng.process(prompt)
+    assert eng.prompt_cache.virtual is None and eng.prompt_cache.last_spliced_rows == 0  # retained: the rows are already there
+    eng.prompt_cache.invalidate()
     ids2, pos2, _, cache2 = eng.process(prompt)
     assert eng.prompt_cache.virtual is None and eng.prompt_cache.last_spliced_rows == case.n_cached
     out_c = lm(input_ids=torch.tensor([ids2], device=DEV), position_ids=torch.tensor([pos2], device=DEV),
