@@ -152,6 +152,7 @@ class PromptCache:
         # pinned staging slots, each guarded by the event of the copy that last read it (the host may run ahead of the GPU)
         self._tile_slots = [[torch.zeros(cap, 2, dtype=torch.int32).pin_memory(), None] for _ in range(4)]
         self._tile_slot = 0
+        self._tiles_key, self._tiles_count = None, {}  # which layout the device tile list currently describes
         self._tiles_dev = torch.zeros(cap, 2, dtype=torch.int32, device=device)
         self.virtual: Optional[VirtualKV] = None
 
@@ -165,6 +166,7 @@ class PromptCache:
         self._copied = []
         self.length = 0
         self.virtual = None
+        self._tiles_key = None
         self.kv.rewritten(0)
 
     @torch.inference_mode()
@@ -205,23 +207,27 @@ class PromptCache:
         if any(m.arena is not arena for m in ordered) or arena.device != self.buffer.device or arena.dtype != self.buffer.dtype \
                 or tuple(arena.shape[:3]) != tuple(self.buffer.shape[:3]) or arena.shape[4] != self.head_dim or not arena.is_contiguous():
             return False  # segments from different allocations: the copy is made instead
-        tiles = []
-        for m in ordered:
-            n = len(m)
-            for r in range(0, n, 128):
-                tiles.append((m.row0 + r, min(128, n - r)))
-        if len(tiles) > self._tiles_dev.shape[0]:
-            return False
-        t = len(tiles)
-        slot = self._tile_slots[self._tile_slot]
-        self._tile_slot = (self._tile_slot + 1) % len(self._tile_slots)
-        if slot[1] is not None:
-            slot[1].synchronize()
-        slot[0][:t] = torch.tensor(tiles, dtype=torch.int32)
-        self._tiles_dev[:t].copy_(slot[0][:t], non_blocking=True)  # stream-ordered before the forward that reads it
-        if slot[1] is None:
-            slot[1] = torch.cuda.Event()
-        slot[1].record()
+        key = tuple(id(m) for m in ordered)
+        t = self._tiles_count.get(key) if key == self._tiles_key else None
+        if t is None:  # the device list holds another request's tiles: build this layout's list and upload it
+            tiles = []
+            for m in ordered:
+                n = len(m)
+                for r in range(0, n, 128):
+                    tiles.append((m.row0 + r, min(128, n - r)))
+            if len(tiles) > self._tiles_dev.shape[0]:
+                return False
+            t = len(tiles)
+            slot = self._tile_slots[self._tile_slot]
+            self._tile_slot = (self._tile_slot + 1) % len(self._tile_slots)
+            if slot[1] is not None:
+                slot[1].synchronize()
+            slot[0][:t] = torch.tensor(tiles, dtype=torch.int32)
+            self._tiles_dev[:t].copy_(slot[0][:t], non_blocking=True)  # stream-ordered before the forward that reads it
+            if slot[1] is None:
+                slot[1] = torch.cuda.Event()
+            slot[1].record()
+            self._tiles_key, self._tiles_count = key, {key: t}
         epoch = self.kv.epoch
 
         def materialise():

@@ -69,6 +69,7 @@ class GenerationEngine:
         self.lm = lm
         self.verbose = False
         self._events = None  # one (start, end) pair, reused: the loop is synchronous
+        self._pool = []      # timing events of the device-sampling loop
         self.device_sampling = True  # greedy decoding keeps the sampled token on the device between yields
 
     def _forward(self, ids: List[List[int]], pos: List[List[int]], past, device):
@@ -102,8 +103,11 @@ class GenerationEngine:
         position_offset = max(position_ids) + 1
         n_max = params.max_new_tokens
         # decode step i >= 1 runs at position position_offset + i (one position is skipped, reference :82,132)
-        pos_all = torch.arange(position_offset, position_offset + n_max + 1, device=device, dtype=torch.long).view(1, -1)
-        pool = [torch.cuda.Event(enable_timing=True) for _ in range(2 * (max(1, stream_interval) + 1))]
+        pos_all = None  # built at the first decode step: a one-token request (the TTFT measurement) never needs it
+        need = 2 * (max(1, stream_interval) + 1)
+        if len(self._pool) < need:  # timing events are reused across requests: the loop is synchronous at every yield
+            self._pool += [torch.cuda.Event(enable_timing=True) for _ in range(need - len(self._pool))]
+        pool = self._pool
         pending = []  # (token on the device, start event, end event) of the steps the host has not looked at yet
         past = tok_dev = None
         inference_time = response_time = 0.0
@@ -117,17 +121,21 @@ class GenerationEngine:
                 both = torch.tensor([list(token_ids), list(position_ids)], device=device, dtype=torch.long)
                 ids_t, pos_t, past_in, max_pos = both[0:1], both[1:2], cache, max(position_ids)
             else:
+                if pos_all is None:
+                    pos_all = torch.arange(position_offset, position_offset + n_max + 1, device=device, dtype=torch.long).view(1, -1)
                 ids_t, pos_t, past_in, max_pos = tok_dev.view(1, 1), pos_all[:, i:i + 1], past, position_offset + i
             start.record()
-            out = self.lm(input_ids=ids_t, position_ids=pos_t, past_key_values=past_in, use_cache=True, max_position=max_pos)
+            # the argmax below is taken before the next forward: a graph replay may return its static logits buffer
+            out = self.lm(input_ids=ids_t, position_ids=pos_t, past_key_values=past_in, use_cache=True, max_position=max_pos,
+                          static_logits_ok=True)
             end.record()
             past = out.past_key_values
             tok_dev = torch.argmax(out.logits[0, -1])
             pending.append((tok_dev, start, end))
             if not (i % stream_interval == 0 or i == n_max - 1):
                 continue  # the reference loop would not yield here (unless this token stops it: found at the next flush)
-            end.synchronize()
-            ids = torch.stack([p[0] for p in pending]).tolist()  # one device->host read for all pending steps
+            # one device->host read for all pending steps (it also waits for the last step's end event)
+            ids = [int(pending[0][0])] if len(pending) == 1 else torch.stack([p[0] for p in pending]).tolist()
             stopped = False
             for (_, s_ev, e_ev), tid in zip(pending, ids):
                 inference_time += s_ev.elapsed_time(e_ev)

@@ -127,7 +127,7 @@ class B200CausalLM(nn.Module):
         self._weights_changed()
         return out
 
-    def _decode_replay(self, ids, pos, kv):
+    def _decode_replay(self, ids, pos, kv, static_ok=False):
         """One-token decode through ONE captured graph per KV buffer: the cached length is a device scalar the
         kernels read at run time (pc_rope_append_dyn, pc_attn_params.n_cached_dev), so the same graph serves every
         step of every request on that buffer (reference loop: generation_engine.py:123-147)."""
@@ -155,9 +155,12 @@ class B200CausalLM(nn.Module):
         s_n.fill_(kv.n_cached)
         graph.replay()
         nat.note_replayed_launches(n_native)
-        return s_logits.clone()
+        return s_logits if static_ok else s_logits.clone()
 
-    def _forward_one(self, ids: torch.Tensor, pos: torch.Tensor, past, use_cache: bool, max_position: int):
+    def _forward_one(self, ids: torch.Tensor, pos: torch.Tensor, past, use_cache: bool, max_position: int,
+                     static_ok: bool = False):
+        """`static_ok`: the caller consumes the logits before the next forward, so a graph replay may hand back its
+        static output buffer instead of a copy (GenerationEngine's device-side greedy loop)."""
         q_len = ids.shape[0]
         kv = resolve_kv(past, q_len, self.n_layers, self.n_kv_heads, self.head_dim, self.device)
         N = kv.n_cached
@@ -166,7 +169,7 @@ class B200CausalLM(nn.Module):
             kv.virtual = None
         if (q_len == 1 and N > 0 and self.use_cuda_graphs and self.supports_dynamic_n and not self.full_position_ids
                 and N + 1 < kv.max_ctx and not torch.cuda.is_current_stream_capturing()):
-            logits = self._decode_replay(ids, pos, kv)
+            logits = self._decode_replay(ids, pos, kv, static_ok)
             if logits is not None:
                 kv.wrote(N + 1)
                 return logits, (kv.views(N + 1) if use_cache else None)
@@ -185,7 +188,7 @@ class B200CausalLM(nn.Module):
                 graph.replay()
                 nat.note_replayed_launches(n_native)
                 kv.wrote(N + q_len)
-                return s_logits.clone(), (kv.views(N + q_len) if use_cache else None)
+                return (s_logits if static_ok else s_logits.clone()), (kv.views(N + q_len) if use_cache else None)
         logits = self._layers(ids, pos, kv, extra)
         kv.wrote(N + q_len)
         return logits, (kv.views(N + q_len) if use_cache else None)
@@ -208,7 +211,7 @@ class B200CausalLM(nn.Module):
     def forward(self, input_ids: torch.Tensor = None, position_ids: Optional[torch.Tensor] = None,
                 past_key_values=None, attention_mask: Optional[torch.Tensor] = None, inputs_embeds=None, labels=None,
                 use_cache: Optional[bool] = None, output_attentions=None, output_hidden_states=None,
-                return_dict=None, max_position: Optional[int] = None, **_):
+                return_dict=None, max_position: Optional[int] = None, static_logits_ok: bool = False, **_):
         if input_ids is None:
             raise ValueError("promptcache_b200 models need input_ids")
         if not input_ids.is_cuda:
@@ -231,7 +234,7 @@ class B200CausalLM(nn.Module):
         self.ensure_rope(max_position + 1)
         if bsz == 1:
             logits, pkv = self._forward_one(input_ids[0], position_ids[0].contiguous(), past_key_values, use_cache,
-                                            max_position)
+                                            max_position, static_logits_ok)
             return CausalLMOutput(logits.unsqueeze(0), pkv)
         # batch > 1 (schema encoding with right padding, cache_engine.py:240-248): rows are independent
         if past_key_values:
