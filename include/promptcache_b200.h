@@ -250,6 +250,10 @@ typedef struct pc_linear_params {
   const void* w_tiled; /* optional: the same weights re-laid out by pc_linear_tile_weights (k % 128 == 0).  The kernel  *
                         * then streams them with one 32 KiB bulk copy per pipeline stage instead of 128-byte-row     *
                         * tensor-map boxes (an SM pulls ~2x more per second that way); `w` is still required.         */
+  const struct pc_linear_params* prefetch_next; /* optional HOST pointer: the pc_linear_small launch that follows on this      *
+                        * stream (only k, n_rows, epilogue, n_heads, n_kv_heads and w_tiled are read, during this call).     *
+                        * Each CTA, once its own weight loads are all in flight, asks L2 for the first pipeline stages the   *
+                        * CTAs of that launch will read, so its ring fills from L2 across the launch boundary.  A hint only. */
 } pc_linear_params;
 
 size_t pc_linear_workspace_bytes(void);

@@ -71,7 +71,7 @@ class pc_linear_params(C.Structure):
                 ("q_out", C.c_void_p), ("k_cache", C.c_void_p), ("v_cache", C.c_void_p),
                 ("dst_row0", C.c_int32), ("n_heads", C.c_int32), ("n_kv_heads", C.c_int32), ("reserved", C.c_int32),
                 ("dst_row0_dev", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
-                ("w_tiled", C.c_void_p)]
+                ("w_tiled", C.c_void_p), ("prefetch_next", C.c_void_p)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -369,8 +369,20 @@ def tile_weights(w: torch.Tensor, epilogue: int = PC_LIN_PLAIN) -> Optional[torc
     return out
 
 
+def linear_hint(w: torch.Tensor, epilogue: int, w_tiled: Optional[torch.Tensor], n_heads: int = 0, n_kv_heads: int = 0):
+    """Description of a pc_linear_small launch for `prefetch_next` of the launch before it (partition fields only).
+    None when that launch does not stream pre-tiled weights."""
+    if w_tiled is None:
+        return None
+    h = pc_linear_params()
+    h.k, h.n_rows, h.epilogue, h.n_heads, h.n_kv_heads = w.shape[1], w.shape[0], epilogue, n_heads, n_kv_heads
+    h.w_tiled = w_tiled.data_ptr()
+    h._keep = w_tiled
+    return h
+
+
 def _linear_params(x: torch.Tensor, w: torch.Tensor, workspace: torch.Tensor, epilogue: int,
-                   w_tiled: Optional[torch.Tensor] = None) -> pc_linear_params:
+                   w_tiled: Optional[torch.Tensor] = None, nxt=None) -> pc_linear_params:
     _require_cuda(x, w, workspace, w_tiled)
     if x.dim() != 2 or w.dim() != 2 or x.dtype != torch.float16 or w.dtype != torch.float16 or not x.is_contiguous() \
             or not w.is_contiguous() or x.shape[1] != w.shape[1]:
@@ -383,13 +395,15 @@ def _linear_params(x: torch.Tensor, w: torch.Tensor, workspace: torch.Tensor, ep
         if w_tiled.numel() * w_tiled.element_size() != int(load().pc_linear_tiled_bytes(w.shape[0], w.shape[1], epilogue)):
             raise NativeError("linear_small: w_tiled does not belong to this weight / epilogue")
         p.w_tiled = w_tiled.data_ptr()
+    if nxt is not None:
+        p.prefetch_next = C.addressof(nxt)
     return p
 
 
 def linear_small(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, workspace: torch.Tensor, silu_mul: bool = False,
-                 w_tiled: Optional[torch.Tensor] = None) -> None:
+                 w_tiled: Optional[torch.Tensor] = None, nxt=None) -> None:
     """out[q, n] = x[q, k] @ w[n, k]^T  (q <= 32), or with `silu_mul` out[q, n/2] = silu(x @ w[:n/2]^T) * (x @ w[n/2:]^T)."""
-    p = _linear_params(x, w, workspace, PC_LIN_SILU_MUL if silu_mul else PC_LIN_PLAIN, w_tiled)
+    p = _linear_params(x, w, workspace, PC_LIN_SILU_MUL if silu_mul else PC_LIN_PLAIN, w_tiled, nxt)
     _require_cuda(out)
     cols = w.shape[0] // 2 if silu_mul else w.shape[0]
     if out.dim() != 2 or out.dtype != torch.float16 or out.stride(1) != 1 or out.shape[0] != x.shape[0] or out.shape[1] != cols:
@@ -401,9 +415,9 @@ def linear_small(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, workspace:
 def linear_rope_append(x: torch.Tensor, wqkv: torch.Tensor, position_ids: Optional[torch.Tensor], cos: Optional[torch.Tensor],
                        sin: Optional[torch.Tensor], q_out: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor,
                        dst_row0, n_heads: int, n_kv_heads: int, workspace: torch.Tensor,
-                       w_tiled: Optional[torch.Tensor] = None) -> None:
+                       w_tiled: Optional[torch.Tensor] = None, nxt=None) -> None:
     """Fused QKV projection + RoPE at `position_ids` + in-place KV append (head_dim 128 only).  Arguments as rope_append."""
-    p = _linear_params(x, wqkv, workspace, PC_LIN_ROPE_APPEND, w_tiled)
+    p = _linear_params(x, wqkv, workspace, PC_LIN_ROPE_APPEND, w_tiled, nxt)
     _require_cuda(q_out, k_cache, v_cache)
     D = 128
     if k_cache.stride(2) != 1 or k_cache.stride(1) != D or k_cache.stride(0) != v_cache.stride(0) or not q_out.is_contiguous():
@@ -433,10 +447,10 @@ def linear_partial_splits(n_rows: int, k: int) -> int:
 
 
 def linear_partials(x: torch.Tensor, w: torch.Tensor, part: torch.Tensor, workspace: torch.Tensor,
-                    w_tiled: Optional[torch.Tensor] = None) -> int:
+                    w_tiled: Optional[torch.Tensor] = None, nxt=None) -> int:
     """part[s, q, n] (fp32) = split-K partials of x @ w^T, s < linear_partial_splits(n, k); the consumer adds them
     (add_rmsnorm(..., partials=part)).  Returns the number of splits written."""
-    p = _linear_params(x, w, workspace, PC_LIN_PARTIALS, w_tiled)
+    p = _linear_params(x, w, workspace, PC_LIN_PARTIALS, w_tiled, nxt)
     _require_cuda(part)
     splits = linear_partial_splits(w.shape[0], w.shape[1])
     if part.dtype != torch.float32 or not part.is_contiguous() or tuple(part.shape) != (splits, x.shape[0], w.shape[0]):

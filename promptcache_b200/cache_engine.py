@@ -342,19 +342,47 @@ class SchemaCache:
                        attention_mask=torch.ones(1, len(token_ids), device=device, dtype=torch.float16),
                        past_key_values=past, use_cache=True, **extra)
 
+    batch_token_budget = 4096  # tokens per batched member forward when `batch_size` leaves the choice to the engine
+
+    def _store(self, kv, position_ids: List[int], target, rows) -> None:
+        """Slice the per-TokenSequence segments out of a path's KV (row i holds scaffold token i) into the arena."""
+        for seq in target:
+            st = position_ids.index(seq.offset)  # offsets and row order can differ (:275-279)
+            ed = st + len(seq)
+            entry = self.adopt(seq, rows[id(seq)])  # straight into the schema's arena: no per-segment allocation
+            for l in range(len(kv)):
+                entry.packed[l, 0].copy_(self.lm.store_k_hook(kv[l][0])[0, :, st:ed, :])
+                entry.packed[l, 1].copy_(self.lm.store_v_hook(kv[l][1])[0, :, st:ed, :])
+
     @torch.inference_mode()
     def _process(self, batch_size: int = 1) -> None:
-        """One forward per scaffold path (reference :212-304).  `batch_size` is accepted for API compatibility;
-        right-padded batching gives the same per-path KV, so paths are encoded one at a time and sliced on the device.
+        """Encode every scaffold path and store its token sequences (reference :212-304).
 
-        The reference re-runs the WHOLE scaffold for every non-default union member.  Attention is causal, so the KV of
-        a member only depends on the tokens before it: with `reuse_prefix` the member's path is encoded as a cached
-        prefill over the longest token/position prefix it shares with the default scaffold, and stops at the last
-        token the path has to store -- prompt caching applied to its own encoder."""
+        The reference re-runs the WHOLE scaffold for every non-default union member, right-padded into batches of
+        `batch_size` paths (pad_batch, :228-248).  Attention is causal, so the KV of a member only depends on the tokens
+        before it: with `reuse_prefix` a member's path is encoded as a cached prefill over the longest token/position
+        prefix it shares with the default scaffold and stops at the last token the path has to store -- prompt caching
+        applied to its own encoder.  Those member prefills are BATCHED: the tokens of up to `batch_size`
+        members (or `batch_token_budget` tokens when batch_size is 1) go through the model's linears as one
+        concatenated sequence -- no padding -- and only RoPE+append / attention run per member, each over its own copy
+        of the shared prefix (`forward_many`)."""
         full_ids = not getattr(self.lm, "use_full_position_ids", False)  # MPT wants cached + new ids: keep it simple
+        many = getattr(self.lm.hf_model, "forward_many", None) if self.reuse_prefix and full_ids else None
         base_ids = base_pos = base_kv = None
         plan, rows, total = self.layout()
         self.allocate_arena(total)
+        batch: List[tuple] = []  # (token ids, position ids, first, hi, target) of member paths waiting for one forward
+
+        def flush():
+            if not batch:
+                return
+            dev = self.lm.device
+            items = [(torch.tensor(ids[first:hi], device=dev, dtype=torch.long), torch.tensor(pos[first:hi], device=dev, dtype=torch.long),
+                      [(k[:, :, :first], v[:, :, :first]) for k, v in base_kv]) for ids, pos, first, hi, _ in batch]
+            for (ids, pos, first, hi, target), kv in zip(batch, many(items, max_position=max(max(b[1]) for b in batch))):
+                self._store(kv, pos, target, rows)
+            batch.clear()
+
         for path, scaffold, target in plan:
             token_ids = scaffold.token_ids()
             position_ids = scaffold.position_ids()
@@ -371,6 +399,12 @@ class SchemaCache:
                 lo, hi = min(starts), max(st + len(seq) for st, seq in zip(starts, target))
                 first = min(common, lo)
                 if first > 0 and hi > first:
+                    if many is not None:
+                        batch.append((token_ids, position_ids, first, hi, target))
+                        limit = batch_size if batch_size > 1 else 1 << 30
+                        if len(batch) >= limit or sum(b[3] - b[2] for b in batch) >= self.batch_token_budget:
+                            flush()
+                        continue
                     past = [(k[:, :, :first].contiguous(), v[:, :, :first].contiguous()) for k, v in base_kv]
                     out = self._forward(token_ids[first:hi], position_ids[first:hi], past)
                 else:
@@ -381,14 +415,9 @@ class SchemaCache:
             kv = out.past_key_values  # rows [0, first) are the reused prefix, row i holds scaffold token i
             if base_kv is None:
                 base_ids, base_pos, base_kv = token_ids, position_ids, kv
-            for seq in target:
-                st = position_ids.index(seq.offset)  # offsets and row order can differ (:275-279)
-                ed = st + len(seq)
-                entry = self.adopt(seq, rows[id(seq)])  # straight into the schema's arena: no per-segment allocation
-                for l in range(len(kv)):
-                    entry.packed[l, 0].copy_(self.lm.store_k_hook(kv[l][0])[0, :, st:ed, :])
-                    entry.packed[l, 1].copy_(self.lm.store_v_hook(kv[l][1])[0, :, st:ed, :])
+            self._store(kv, position_ids, target, rows)
             del out, kv
+        flush()
         del base_kv
         gc.collect()
 

@@ -93,7 +93,26 @@ struct LinParams {
   int max_ctx, row0, n_heads, n_kv_heads;
   const int* row0_dev;
   unsigned long long* trace;  // debug: 8 %globaltimer stamps per CTA (PC_LIN_TRACE_PTR), else nullptr
+  // L2 prefetch of the NEXT linear's weight stream (pre-tiled): once this CTA has issued its last weight load it asks
+  // L2 for the first pf_units pipeline stages of the CTAs of the next launch (their partition is replayed here), so
+  // that the next kernel's ring fills from L2 instead of paying the HBM latency after every launch boundary
+  const unsigned char* pf_w;
+  long long pf_units_total;
+  int pf_kb, pf_grid, pf_whole, pf_splits, pf_units;
 };
+
+// units [u0, u1) of CTA c (same arithmetic as the kernel prologue; `splits` > 0 = PC_LIN_PARTIALS)
+__device__ __forceinline__ void cta_units(int c, int G, long long U, int KB, int splits, long long& u0, long long& u1) {
+  if (splits > 0) {
+    const int tile_c = c / splits, sp = c - tile_c * splits;
+    u0 = static_cast<long long>(tile_c) * KB + (static_cast<long long>(sp) * KB) / splits;
+    u1 = static_cast<long long>(tile_c) * KB + (static_cast<long long>(sp + 1) * KB) / splits;
+    return;
+  }
+  const int Gs = static_cast<int>(min(static_cast<long long>(G), U));
+  u0 = c < Gs ? (static_cast<long long>(c) * U) / Gs : 0;
+  u1 = c < Gs ? (static_cast<long long>(c + 1) * U) / Gs : 0;
+}
 
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
@@ -298,6 +317,23 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
           } else {
             tma_load_3d(dw, &map_w, &full[s], k0, row_a, 0);
             tma_load_3d(dw + kWBytes / 2, &map_w, &full[s], k0, row_a + p.second_half_off, 0);
+          }
+        }
+      }
+      if (p.pf_w != nullptr) {
+        // all of this CTA's weight loads are in flight: hand the memory system the head of the next launch's stream
+        constexpr uint32_t kUnitBytes = 2 * kWBytes;  // a pre-tiled pipeline stage (two k-blocks)
+        for (int c2 = c; c2 < p.pf_grid; c2 += G) {
+          long long n0, n1;
+          cta_units(c2, p.pf_grid, p.pf_units_total, p.pf_kb, p.pf_splits, n0, n1);
+          WorkIter nit(n0, n1, p.pf_kb, p.pf_whole, p.pf_grid, c2);
+          Seg ns;
+          int left = p.pf_units;
+          while (left > 0 && nit.next(ns)) {
+            const int n = min(ns.n, left);
+            for (int j = 0; j < n; ++j)
+              bulk_prefetch_l2(p.pf_w + (static_cast<long long>(ns.tile) * p.pf_kb + ns.kb0 + j) * kUnitBytes, kUnitBytes);
+            left -= n;
           }
         }
       }
@@ -641,6 +677,49 @@ PC_API int pc_linear_partial_splits(int n_rows, int k) {
   return s;
 }
 
+namespace pc {
+namespace {
+#ifndef PC_LIN_PREFETCH_UNITS
+#define PC_LIN_PREFETCH_UNITS 6
+#endif
+constexpr int kPrefetchUnits = PC_LIN_PREFETCH_UNITS;  // pipeline stages (32 KiB each) of the next launch asked from L2 per CTA
+
+// Grid / partition of one launch (see the header comment).  An SM that is fed 16 KiB per TMA instruction pulls
+// ~100 GB/s, so ~2/3 of the SMs saturate HBM.  When the tile count has a divisor in [sm/2, sm] every CTA gets WHOLE
+// tiles (no split-K, no cross-CTA reduction: the tail is a plain epilogue); otherwise all SMs share the (tile, k-block)
+// space evenly (stream-K, partial tiles reduced).  `units_total` comes in as n_tiles * units_per_tile.
+void choose_grid(int epilogue, int n_tiles, int units_per_tile, bool tiled, int splits, int* grid_out, int* whole_per_cta,
+                 long long* units_total) {
+  int grid = sm_count();
+  const int min_whole = tiled ? (sm_count() * 5) / 8 : sm_count();  // row-major tensor-map loads need every SM's TMA
+  for (int g = sm_count(); g >= min_whole; --g)
+    if (n_tiles % g == 0) {
+      grid = g;
+      break;
+    }
+  if (grid == sm_count() && n_tiles < sm_count()) {
+    // few tiles (o_proj, down_proj): a regular split-K, the same number of CTAs per tile, keeps the reduction groups small
+    const int per_tile = sm_count() / n_tiles;
+    if (per_tile >= 2 && per_tile * n_tiles >= (sm_count() * 3) / 4) grid = per_tile * n_tiles;
+  }
+  const char* hy = dbg_env("PC_LIN_HYBRID");
+  *whole_per_cta = 0;
+  if (epilogue == PC_LIN_PARTIALS) grid = n_tiles * splits;
+  else if (const char* e = dbg_env("PC_LIN_GRID")) grid = atoi(e);
+  else if (n_tiles > sm_count() && !(hy && hy[0] == '0')) {
+    // more tiles than SMs: whole tiles first-come per CTA, the remainder shared stream-K (and processed first)
+    grid = sm_count();
+    *whole_per_cta = n_tiles / grid;
+    *units_total = static_cast<long long>(n_tiles - *whole_per_cta * grid) * units_per_tile;
+  }
+  if (grid > sm_count()) grid = sm_count();
+  if (*whole_per_cta == 0 && grid > *units_total) grid = static_cast<int>(*units_total);
+  if (grid < 1) grid = 1;
+  *grid_out = grid;
+}
+}  // namespace
+}  // namespace pc
+
 PC_API size_t pc_linear_workspace_bytes(void) {
   return pc::kLinCounterBytes + static_cast<size_t>(pc::sm_count()) * 2 * 32 * pc::BM * sizeof(float);
 }
@@ -745,33 +824,32 @@ PC_API int pc_linear_small(const pc_linear_params* p, void* stream) {
   lp.trace = nullptr;
   if (const char* e = dbg_env("PC_LIN_TRACE_PTR")) lp.trace = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
 
-  // Grid: an SM that is fed 16 KiB per TMA instruction pulls ~100 GB/s, so ~2/3 of the SMs saturate HBM.  When the
-  // tile count has a divisor in [sm/2, sm] every CTA gets WHOLE tiles (no split-K, no cross-CTA reduction: the tail
-  // is a plain epilogue); otherwise all SMs share the (tile, k-block) space evenly (stream-K, partial tiles reduced).
-  int grid = sm_count();
-  const int min_whole = tiled ? (sm_count() * 5) / 8 : sm_count();  // row-major tensor-map loads need every SM's TMA
-  for (int g = sm_count(); g >= min_whole; --g)
-    if (n_tiles % g == 0) {
-      grid = g;
-      break;
+  int grid = 1;
+  choose_grid(p->epilogue, n_tiles, units_per_tile, tiled, lp.splits, &grid, &lp.whole_per_cta, &lp.units_total);
+  // optional hint: the launch that follows on this stream (see LinParams::pf_w)
+  lp.pf_w = nullptr;
+  if (const pc_linear_params* nx = p->prefetch_next) {
+    if (nx->w_tiled != nullptr && nx->k > 0 && nx->k % 128 == 0 && nx->n_rows > 0) {
+      int nt = 0;
+      switch (nx->epilogue) {
+        case PC_LIN_SILU_MUL: nt = (nx->n_rows / 2 + 63) / 64; break;
+        case PC_LIN_ROPE_APPEND: nt = nx->n_heads + 2 * nx->n_kv_heads; break;
+        default: nt = (nx->n_rows + BM - 1) / BM; break;
+      }
+      const int upt = nx->k / 128;
+      const int nsplits = nx->epilogue == PC_LIN_PARTIALS ? pc_linear_partial_splits(nx->n_rows, nx->k) : 0;
+      int ngrid = 1, nwhole = 0;
+      long long nunits = static_cast<long long>(nt) * upt;
+      choose_grid(nx->epilogue, nt, upt, true, nsplits, &ngrid, &nwhole, &nunits);
+      lp.pf_w = static_cast<const unsigned char*>(nx->w_tiled);
+      lp.pf_units_total = nunits;
+      lp.pf_kb = upt;
+      lp.pf_grid = ngrid;
+      lp.pf_whole = nwhole;
+      lp.pf_splits = nsplits;
+      lp.pf_units = kPrefetchUnits;
     }
-  if (grid == sm_count() && n_tiles < sm_count()) {
-    // few tiles (o_proj, down_proj): a regular split-K, the same number of CTAs per tile, keeps the reduction groups small
-    const int per_tile = sm_count() / n_tiles;
-    if (per_tile >= 2 && per_tile * n_tiles >= (sm_count() * 3) / 4) grid = per_tile * n_tiles;
   }
-  const char* hy = dbg_env("PC_LIN_HYBRID");
-  if (p->epilogue == PC_LIN_PARTIALS) grid = n_tiles * lp.splits;
-  else if (const char* e = dbg_env("PC_LIN_GRID")) grid = atoi(e);
-  else if (n_tiles > sm_count() && !(hy && hy[0] == '0')) {
-    // more tiles than SMs: whole tiles first-come per CTA, the remainder shared stream-K (and processed first)
-    grid = sm_count();
-    lp.whole_per_cta = n_tiles / grid;
-    lp.units_total = static_cast<long long>(n_tiles - lp.whole_per_cta * grid) * units_per_tile;
-  }
-  if (grid > sm_count()) grid = sm_count();
-  if (lp.whole_per_cta == 0 && grid > lp.units_total) grid = static_cast<int>(lp.units_total);
-  if (grid < 1) grid = 1;
   lp.w_one_box = (lp.second_half_off == 64) ? 1 : 0;
   if (const char* e = dbg_env("PC_LIN_ONEBOX")) lp.w_one_box = lp.w_one_box && atoi(e) != 0;
   CUtensorMap mw, mx;

@@ -167,6 +167,10 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
       "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// hint: bring [gsrc, gsrc + bytes) into L2 (no destination, no completion to wait for)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
                "r"(smem_u32(smem_src)), "r"(bytes)

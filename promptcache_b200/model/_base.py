@@ -41,6 +41,8 @@ class B200CausalLM(nn.Module):
         self.linear_max_q = min(32, int(os.environ.get("PC_LINEAR_MAX_Q", "16")))
         self.linear_partials = os.environ.get("PC_LINEAR_PARTIALS", "1") != "0"
         self.linear_tiled = os.environ.get("PC_LINEAR_TILED", "1") != "0"  # native linears stream pre-tiled weight copies
+        # each native linear asks L2 for the head of the next one's weight stream while its own tail drains
+        self.linear_prefetch = os.environ.get("PC_LINEAR_PREFETCH", "1") != "0"
         # CUDA graphs of the whole single-sequence forward, keyed by (q_len, n_cached, KV buffer): the per-layer
         # launch sequence is fixed once those are, so a repeated request shape is replayed with one launch
         self.ablate = frozenset()  # measurement only: kernel families left out of the step (see LlamaForCausalLM._layers_ablated)
@@ -101,7 +103,7 @@ class B200CausalLM(nn.Module):
         """Every switch that changes the launch sequence of `_layers`; part of each graph key so that toggling one
         after a capture can never replay a stale sequence."""
         return (self.linear_impl, tuple(sorted(self.linear_native_ops)), self.linear_max_q, self.linear_partials,
-                self.linear_tiled, self.attn_impl, tuple(sorted(self.ablate)))
+                self.linear_tiled, self.linear_prefetch, self.attn_impl, tuple(sorted(self.ablate)))
 
     def _note_seen(self, key) -> None:
         if len(self._graph_seen) >= 256:  # bounded: forked / short-lived buffers would otherwise grow it forever
@@ -111,9 +113,9 @@ class B200CausalLM(nn.Module):
     def _weights_changed(self) -> None:
         """Captured graphs and pre-tiled weight copies refer to the old parameter storage / values."""
         self._graphs.clear()
-        tiled = getattr(self, "_tiled", None)
-        if tiled is not None:
-            tiled.clear()
+        for cache in (getattr(self, "_tiled", None), getattr(self, "_hints", None)):
+            if cache is not None:
+                cache.clear()
 
     def _apply(self, fn, *args, **kwargs):  # .to() / .half() / .cuda()
         out = super()._apply(fn, *args, **kwargs)

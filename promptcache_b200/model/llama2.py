@@ -83,6 +83,7 @@ class LlamaForCausalLM(B200CausalLM):
         self.lm_head = w(c.vocab_size, hid)
         self._init_runtime()
         self._tiled = {}  # pre-tiled copies of the weights for pc_linear_small, built on first native use
+        self._hints = {}  # prefetch_next descriptions of the native linears
         self.rounding = nat.PC_ROUND_LLAMA
         self.scale = nat.softmax_scale(self.head_dim)
 
@@ -92,6 +93,7 @@ class LlamaForCausalLM(B200CausalLM):
         """Load a HuggingFace Llama state dict (model.layers.N.self_attn.q_proj.weight ...)."""
         g = lambda k: sd[k].to(self.embed_tokens.device, self.embed_tokens.dtype)
         self._tiled.clear()
+        self._hints.clear()
         self._graphs.clear()
         self.embed_tokens.copy_(g("model.embed_tokens.weight"))
         self.norm.copy_(g("model.norm.weight"))
@@ -161,6 +163,80 @@ class LlamaForCausalLM(B200CausalLM):
             nat.linear_small(h, self.lm_head, logits, lws, w_tiled=self._wt(("lm_head", 0), self.lm_head, nat.PC_LIN_PLAIN))
         return logits.float()
 
+    @torch.inference_mode()
+    def forward_many(self, items, max_position: Optional[int] = None):
+        """Cached prefill of SEVERAL independent sequences in one pass (schema encoding; the reference
+        pads whole scaffolds into a batch instead, cache_engine.py:228-248).  `items` = [(ids [n_b], position ids [n_b],
+        past_key_values or None)].  The tokens of all sequences run through the norms / projections / MLP as ONE
+        concatenated [sum n_b, hidden] matrix (no padding, one weight stream for all of them); RoPE + append and
+        attention run per sequence over that sequence's own KV buffer.  Returns the per-sequence past_key_values
+        (no logits: the encoder only stores KV)."""
+        from ._kv import resolve_kv
+        H, Hkv, D = self.n_heads, self.n_kv_heads, self.head_dim
+        lens = [int(ids.shape[0]) for ids, _, _ in items]
+        kvs = [resolve_kv(past, n, self.n_layers, Hkv, D, self.device) for (_, _, past), n in zip(items, lens)]
+        for kv in kvs:
+            if kv.virtual is not None:
+                kv.virtual.materialise()
+                kv.virtual = None
+        ids = torch.cat([i for i, _, _ in items])
+        pos = torch.cat([p for _, p, _ in items]).long().contiguous()
+        if max_position is None:
+            max_position = int(pos.max())
+        self.ensure_rope(max_position + 1)
+        T, inter = ids.shape[0], self.config.intermediate_size
+        x = F.embedding(ids, self.embed_tokens)
+        h = torch.empty_like(x)
+        attn_out = torch.empty(T, H * D, dtype=torch.float16, device=self.device)
+        act = torch.empty(T, inter, dtype=torch.float16, device=self.device)
+        q_rots = [torch.empty(H, n, D, dtype=torch.float16, device=self.device) for n in lens]
+        ws = self._workspace(max(lens))
+        delta = None
+        for l in range(self.n_layers):
+            nat.add_rmsnorm(x, delta, self.ln1[l], h, self.eps)
+            qkv = F.linear(h, self.wqkv[l])
+            off = 0
+            for kv, n, q_rot in zip(kvs, lens, q_rots):
+                rows = qkv[off:off + n]
+                nat.rope_append(rows[:, :H * D], rows[:, H * D:(H + Hkv) * D], rows[:, (H + Hkv) * D:], pos[off:off + n], self._cos,
+                                self._sin, q_rot, kv.k[l], kv.v[l], kv.n_cached, H, Hkv, D)
+                nat.attention(q_rot, kv.k[l], kv.v[l], attn_out[off:off + n], kv.n_cached, n, H, Hkv, D, self.scale, self.rounding,
+                              workspace=ws, impl=self.attn_impl, decode=False)
+                off += n
+            if l + 1 == self.n_layers:
+                break  # the last layer's K/V are stored: its output projection and MLP feed nothing the encoder keeps
+            delta = F.linear(attn_out, self.wo[l])
+            nat.add_rmsnorm(x, delta, self.ln2[l], h, self.eps)
+            nat.silu_mul(F.linear(h, self.w_gate_up[l]), act, inter)
+            delta = F.linear(act, self.w_down[l])
+        out = []
+        for kv, n in zip(kvs, lens):
+            kv.wrote(kv.n_cached + n)
+            out.append(kv.views(kv.n_cached + n))
+        return out
+
+    def _hint(self, name: str, l: int, partials: bool):
+        """`prefetch_next` description of the linear that follows (its CTAs' first weight stages are asked from L2 by
+        the tail of the current one); None when that linear is not a pre-tiled native launch."""
+        if not self.linear_prefetch or name not in self.linear_native_ops:
+            return None
+        key = (name, l, partials)
+        h = self._hints.get(key)
+        if h is None:
+            H, Hkv = self.n_heads, self.n_kv_heads
+            if name == "qkv":
+                h = nat.linear_hint(self.wqkv[l], nat.PC_LIN_ROPE_APPEND, self._wt(("qkv", l), self.wqkv[l], nat.PC_LIN_ROPE_APPEND), H, Hkv)
+            elif name == "gu":
+                h = nat.linear_hint(self.w_gate_up[l], nat.PC_LIN_SILU_MUL, self._wt(("gu", l), self.w_gate_up[l], nat.PC_LIN_SILU_MUL))
+            elif name == "head":
+                h = nat.linear_hint(self.lm_head, nat.PC_LIN_PLAIN, self._wt(("lm_head", 0), self.lm_head, nat.PC_LIN_PLAIN))
+            else:
+                w = self.wo[l] if name == "o" else self.w_down[l]
+                epi = nat.PC_LIN_PARTIALS if partials else nat.PC_LIN_PLAIN
+                h = nat.linear_hint(w, epi, self._wt((name, l), w, epi))
+            self._hints[key] = h if h is not None else False
+        return h if h is not False else None
+
     # ---- forward (one sequence; batching, KV buffers and graph replay live in B200CausalLM) ---------------
     def _layers(self, ids: torch.Tensor, pos: torch.Tensor, kv, extra=(), n_dev=None) -> torch.Tensor:
         q_len = ids.shape[0]
@@ -201,7 +277,8 @@ class LlamaForCausalLM(B200CausalLM):
             if lin_qkv:
                 nat.linear_rope_append(h, self.wqkv[l], pos, self._cos, self._sin, q_rot, kv.k[l], kv.v[l],
                                        N if n_dev is None else n_dev, H, Hkv, lws,
-                                       w_tiled=self._wt(("qkv", l), self.wqkv[l], nat.PC_LIN_ROPE_APPEND))
+                                       w_tiled=self._wt(("qkv", l), self.wqkv[l], nat.PC_LIN_ROPE_APPEND),
+                                       nxt=self._hint("o", l, pbuf_o is not None) if lin_o else None)
             else:
                 qkv = F.linear(h, self.wqkv[l])                          # [q, (H+2Hkv)*D]
                 nat.rope_append(qkv[:, :H * D], qkv[:, H * D:(H + Hkv) * D], qkv[:, (H + Hkv) * D:], pos, self._cos,
@@ -211,25 +288,33 @@ class LlamaForCausalLM(B200CausalLM):
                           impl=self.attn_impl if (n_dev is None and virt is None) else nat.PC_ATTN_TCGEN05,
                           virtual=virt.planes(l) if virt is not None else None)
             if lin_o and pbuf_o is not None:
-                nat.linear_partials(attn_out, self.wo[l], pbuf_o, lws, w_tiled=self._wt(("o", l), self.wo[l], nat.PC_LIN_PARTIALS))
+                nat.linear_partials(attn_out, self.wo[l], pbuf_o, lws, w_tiled=self._wt(("o", l), self.wo[l], nat.PC_LIN_PARTIALS),
+                                    nxt=self._hint("gu", l, False) if lin_gu else None)
                 delta = pbuf_o
             elif lin_o:
-                nat.linear_small(attn_out, self.wo[l], dbuf, lws, w_tiled=self._wt(("o", l), self.wo[l], nat.PC_LIN_PLAIN))
+                nat.linear_small(attn_out, self.wo[l], dbuf, lws, w_tiled=self._wt(("o", l), self.wo[l], nat.PC_LIN_PLAIN),
+                                 nxt=self._hint("gu", l, False) if lin_gu else None)
                 delta = dbuf
             else:
                 delta = F.linear(attn_out, self.wo[l])
             nat.add_rmsnorm(x, delta, self.ln2[l], h, self.eps)          # x += attn; h = norm(x)
             if lin_gu:
                 nat.linear_small(h, self.w_gate_up[l], act, lws, silu_mul=True,
-                                 w_tiled=self._wt(("gu", l), self.w_gate_up[l], nat.PC_LIN_SILU_MUL))
+                                 w_tiled=self._wt(("gu", l), self.w_gate_up[l], nat.PC_LIN_SILU_MUL),
+                                 nxt=self._hint("down", l, pbuf_d is not None) if lin_down else None)
             else:
                 gu = F.linear(h, self.w_gate_up[l])
                 nat.silu_mul(gu, act, inter)
             if lin_down and pbuf_d is not None:
-                nat.linear_partials(act, self.w_down[l], pbuf_d, lws, w_tiled=self._wt(("down", l), self.w_down[l], nat.PC_LIN_PARTIALS))
+                nxt_d = (self._hint("qkv", l + 1, False) if lin_qkv else None) if l + 1 < self.n_layers else \
+                    (self._hint("head", 0, False) if lin_head else None)
+                nat.linear_partials(act, self.w_down[l], pbuf_d, lws, w_tiled=self._wt(("down", l), self.w_down[l], nat.PC_LIN_PARTIALS),
+                                    nxt=nxt_d)
                 delta = pbuf_d
             elif lin_down:
-                nat.linear_small(act, self.w_down[l], dbuf, lws, w_tiled=self._wt(("down", l), self.w_down[l], nat.PC_LIN_PLAIN))
+                nxt_d = (self._hint("qkv", l + 1, False) if lin_qkv else None) if l + 1 < self.n_layers else \
+                    (self._hint("head", 0, False) if lin_head else None)
+                nat.linear_small(act, self.w_down[l], dbuf, lws, w_tiled=self._wt(("down", l), self.w_down[l], nat.PC_LIN_PLAIN), nxt=nxt_d)
                 delta = dbuf
             else:
                 delta = F.linear(act, self.w_down[l])
