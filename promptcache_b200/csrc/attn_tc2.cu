@@ -38,7 +38,17 @@ int launch_attn_combine(const float* part_o, const float* part_ml, void* out, in
 namespace {
 
 constexpr int BM = 128;
-constexpr int BN = 64;
+#ifndef PC_PP_BN
+#define PC_PP_BN 64
+#endif
+// Keys per K/V tile = N of the S MMA.  64 keys leave room for TWO S buffers inside a query tile's 128 TMEM columns, so
+// S_x(j+1) executes while softmax_x(j) runs.  128 keys (-DPC_PP_BN=128: one S buffer, P written back over it, FA-style
+// ping-pong between the two query tiles only, 2 K/V stages) halve the S MMA's shared-memory traffic per FLOP but
+// serialise each tile's S -> softmax -> PV chain: measured SLOWER on the B200 (q=1024 over N=8192: 667 vs 864 TFLOP/s;
+// without any softmax math 946 vs 1110), so 64 stays the default.  The softmax below handles both widths.
+constexpr int BN = PC_PP_BN;
+static_assert(BN == 64 || BN == 128, "PC_PP_BN must be 64 or 128");
+constexpr int kSBufs = 128 / BN;  // S buffers per query tile
 constexpr int kThreads = 352;  // WG0 (warps 0-3), WG1 (warps 4-7), TMA warp 8, MMA warps 9 (tile A) and 10 (tile B)
 constexpr int kMaxSplits = 32;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -49,7 +59,10 @@ struct Cfg2 {
   static constexpr int kQBytes = BM * D * 2;     // one query tile
   static constexpr int kTileBytes = BN * D * 2;  // one K or V tile
   static constexpr int kHalfStride = BN * 128;   // bytes between the two 64-column halves of a K/V tile (D=128)
-  static constexpr int kStages = 4;
+  // as many (K, V) stages as fit beside the two query tiles (D=128: 4 at 64 keys, 2 at 128 keys; D=64: 4)
+  static constexpr int kStagesFit = (220 * 1024 - 2 * kQBytes) / (2 * kTileBytes);
+  static constexpr int kStages = kStagesFit < 4 ? kStagesFit : 4;
+  static_assert(kStages >= 2, "the K/V ring needs two stages");
   static constexpr int kOffKV = 2 * kQBytes;     // Q_A, Q_B first
   static constexpr int kOffBars = kOffKV + kStages * 2 * kTileBytes;
   static constexpr int kSmem = 1024 + kOffBars + 256;
@@ -213,39 +226,40 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         mbar_wait(&k_full[j % C::kStages], static_cast<uint32_t>((j / C::kStages) & 1));
         tc_fence_after();
       };
-      auto issue_s = [&](int j) {  // S_x(j) = Q_x . K_j^T into S buffer (x, j&1); k_full(j) already waited
+      auto issue_s = [&](int j) {  // S_x(j) = Q_x . K_j^T into S buffer (x, j % kSBufs); k_full(j) already waited
         const uint64_t k_desc = k_desc0 + static_cast<uint64_t>(((j % C::kStages) * 2 * C::kTileBytes) >> 4);
-        const uint32_t d = tmem_sx + (j & 1) * BN;
+        const uint32_t d = tmem_sx + (j % kSBufs) * BN;
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)
           umma_ss(d, q_desc + static_cast<uint64_t>(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4),
                   k_desc + static_cast<uint64_t>(((kk >> 2) * C::kHalfStride + (kk & 3) * 32) >> 4), idesc_qk,
                   kk > 0 ? 1u : 0u);
-        tc_commit(&s_full[x * 2 + (j & 1)]);
+        tc_commit(&s_full[x * 2 + (j % kSBufs)]);
       };
       auto issue_pv = [&](int j) {  // O_x += P_x(j) . V_j
         const uint64_t v_desc = v_desc0 + static_cast<uint64_t>(((j % C::kStages) * 2 * C::kTileBytes) >> 4);
-        const uint32_t pa = tmem_sx + (j & 1) * BN;
+        const uint32_t pa = tmem_sx + (j % kSBufs) * BN;
 #pragma unroll
         for (int kk = 0; kk < BN / 16; ++kk)
           umma_ts(tmem_ox, pa + kk * 8, v_desc + static_cast<uint64_t>((kk * 2048) >> 4), idesc_pv,
                   (j > 0 || kk > 0) ? 1u : 0u);
-        tc_commit(&o_full[x * 2 + (j & 1)]);
+        tc_commit(&o_full[x * 2 + (j & 1)]);  // by tile parity (see o_full)
       };
       mbar_wait(q_full, 0);
-      for (int j = 0; j < 2 && j < Tx; ++j) {  // two S tiles in flight per query tile
+      for (int j = 0; j < kSBufs && j < Tx; ++j) {  // kSBufs S tiles in flight per query tile
         wait_k(j);
         issue_s(j);
       }
       for (int j = 0; j < Tx; ++j) {
         const int s = j % C::kStages;
+        const int jn = j + kSBufs;  // the S tile that reuses P_x(j)'s buffer
         // operands first (they landed long ago), so that nothing but the MMA issue follows the arrival of P_x(j)
         mbar_wait(&v_full[s], static_cast<uint32_t>((j / C::kStages) & 1));
-        if (j + 2 < Tx) mbar_wait(&k_full[(j + 2) % C::kStages], static_cast<uint32_t>(((j + 2) / C::kStages) & 1));
-        mbar_wait(&p_full[x * 2 + (j & 1)], static_cast<uint32_t>((j >> 1) & 1));
+        if (jn < Tx) mbar_wait(&k_full[jn % C::kStages], static_cast<uint32_t>((jn / C::kStages) & 1));
+        mbar_wait(&p_full[x * 2 + (j % kSBufs)], static_cast<uint32_t>((j / kSBufs) & 1));
         tc_fence_after();
         issue_pv(j);
-        if (j + 2 < Tx) issue_s(j + 2);  // S buffer (x, j&1) is free once PV_x(j) has been issued (in-order execution)
+        if (jn < Tx) issue_s(jn);  // the S buffer is free once PV_x(j) has been issued (in-order execution)
         tc_commit(&kv_empty[x * C::kStages + s]);  // this tile's MMAs on stage s have all been issued
       }
     }
@@ -274,20 +288,23 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     float m_run = -INFINITY, l_run = 0.f;  // m in the log2 domain
 
     if (warp_valid) {
+      constexpr int CH = 64;           // columns of S handled at a time (64 registers)
+      constexpr int kChunks = BN / CH;  // 1 at 64-key tiles, 2 at 128-key tiles
       for (int j = 0; j < Tx; ++j) {
-        const int b = j & 1;
+        const int b = j % kSBufs;
         const uint32_t tmem_s = tmem_sx + b * BN;
-        mbar_wait(&s_full[x * 2 + b], static_cast<uint32_t>((j >> 1) & 1));
+        mbar_wait(&s_full[x * 2 + b], static_cast<uint32_t>((j / kSBufs) & 1));
         tc_fence_after();
         const int key0 = (t0 + j) * BN;
         const bool need_mask = key0 + BN > vis_end;
 
 #if defined(PC_EXP_NO_SOFTMAX)  // experiment: MMA / barrier chain alone (P = garbage, no math)
         {
-          uint32_t z[BN / 2];
+          uint32_t z[32];
 #pragma unroll
-          for (int c = 0; c < BN / 2; ++c) z[c] = 0x3c003c00u;
-          tmem_st32(tmem_s, z);
+          for (int c = 0; c < 32; ++c) z[c] = 0x3c003c00u;
+#pragma unroll
+          for (int ck = 0; ck < kChunks; ++ck) tmem_st32(tmem_s + ck * 32, z);
           l_run += 1.f;
           tmem_st_wait();
           tc_fence_before();
@@ -295,25 +312,39 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           continue;
         }
 #endif
-        // ---- the whole 64-key row of S lives in registers: one TMEM read per tile ----
-        float sv[BN];
-        tmem_ld32(tmem_s, reinterpret_cast<uint32_t(&)[32]>(sv[0]));
-        tmem_ld32(tmem_s + 32, reinterpret_cast<uint32_t(&)[32]>(sv[32]));
-        tmem_ld_wait();
         const bool warp_mask = __any_sync(0xffffffffu, need_mask);  // warp-uniform: mask code only near the diagonal
+        // a 64-column chunk of the S row in registers (one TMEM read; with 128-key tiles each chunk is read in both passes)
+        float sv[CH];
+        auto load_chunk = [&](int ck) {
+          tmem_ld32(tmem_s + ck * CH, reinterpret_cast<uint32_t(&)[32]>(sv[0]));
+          tmem_ld32(tmem_s + ck * CH + 32, reinterpret_cast<uint32_t(&)[32]>(sv[32]));
+          tmem_ld_wait();
+        };
+        // the reference's transform of one raw score (ALiBi: natural-log domain incl. the key's bias)
+        auto alibi_score = [&](float t, int key) {
+          if (ROUND & PC_ROUND_QK) t = round_h(t);
+          t *= p.scale;
+          if (ROUND & PC_ROUND_SCALED) t = round_h(t);
+          return t + slope * static_cast<float>(__ldg(p.key_pos + min(key, p.n_cached + p.q_len - 1)) - p.alibi_max_pos);
+        };
 
         // ---- pass 1: row maximum (log2 domain) ----
-        float mt;
+        float mt = -INFINITY;
         if (!ALIBI) {
           // max over the RAW accumulators; the fp16-rounding + scale transform is monotone, so it commutes with max
           float raw_max = -INFINITY;
-          if (warp_mask) {
 #pragma unroll
-            for (int c = 0; c < BN; ++c)
-              if (key0 + c < vis_end) raw_max = fmaxf(raw_max, sv[c]);
-          } else {
+          for (int ck = 0; ck < kChunks; ++ck) {
+            load_chunk(ck);
+            const int kc = key0 + ck * CH;
+            if (warp_mask) {
 #pragma unroll
-            for (int c = 0; c < BN; c += 2) raw_max = fmaxf(raw_max, fmaxf(sv[c], sv[c + 1]));
+              for (int c = 0; c < CH; ++c)
+                if (kc + c < vis_end) raw_max = fmaxf(raw_max, sv[c]);
+            } else {
+#pragma unroll
+              for (int c = 0; c < CH; c += 2) raw_max = fmaxf(raw_max, fmaxf(sv[c], sv[c + 1]));
+            }
           }
           float t = raw_max;
           if (ROUND == PC_ROUND_LLAMA) {
@@ -327,18 +358,17 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           }
           mt = t * kLog2e;
         } else {
-          // ALiBi adds a per-key bias: transform every score once (kept in sv, natural-log domain), then take the max
-          mt = -INFINITY;
-          const int kmax = p.n_cached + p.q_len - 1;
+          // ALiBi adds a per-key bias: every score is transformed before the max (and again in pass 2 at 128-key tiles)
 #pragma unroll
-          for (int c = 0; c < BN; ++c) {
-            float t = sv[c];
-            if (ROUND & PC_ROUND_QK) t = round_h(t);
-            t *= p.scale;
-            if (ROUND & PC_ROUND_SCALED) t = round_h(t);
-            t += slope * static_cast<float>(__ldg(p.key_pos + min(key0 + c, kmax)) - p.alibi_max_pos);
-            sv[c] = t;
-            if (key0 + c < vis_end) mt = fmaxf(mt, t * kLog2e);
+          for (int ck = 0; ck < kChunks; ++ck) {
+            load_chunk(ck);
+            const int kc = key0 + ck * CH;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+              const float t = alibi_score(sv[c], kc + c);
+              if (kChunks == 1) sv[c] = t;  // single chunk: pass 2 reuses the transformed row
+              if (kc + c < vis_end) mt = fmaxf(mt, t * kLog2e);
+            }
           }
         }
 
@@ -351,7 +381,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           l_run *= alpha;
         }
         if (j > 0 && __any_sync(0xffffffffu, grow)) {
-          // PV_x(j-1) must have landed (S_x(j) was issued two tiles ahead, so this is not implied by s_full)
+          // PV_x(j-1) must have landed (with two S buffers S_x(j) was issued two tiles ahead: not implied by s_full)
           mbar_wait(&o_full[x * 2 + ((j - 1) & 1)], static_cast<uint32_t>(((j - 1) >> 1) & 1));
           tc_fence_after();
 #pragma unroll
@@ -366,52 +396,61 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
         const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
 
-        // ---- pass 2: P = 2^(score - m), written over S as packed fp16 (32 columns) ----
+        // ---- pass 2: P = 2^(score - m), written over S as packed fp16 (32 TMEM columns per 64 keys) ----
         float lt = 0.f;
-        uint32_t pk[BN / 2];
-        auto pass2 = [&](auto masked_tag) {
-          constexpr bool kMasked = decltype(masked_tag)::value;
 #pragma unroll
-          for (int c = 0; c < BN; c += 2) {
-            const float a = sv[c], b2 = sv[c + 1];
-            float ya, yb;
-            if (ALIBI) {
-              ya = fmaf(a, kLog2e, -m_use);
-              yb = fmaf(b2, kLog2e, -m_use);
-            } else if (ROUND == 0) {
-              ya = fmaf(a, scale_l2, -m_use);
-              yb = fmaf(b2, scale_l2, -m_use);
-            } else if (ROUND == PC_ROUND_LLAMA) {
-              // half(half(acc) * scale) in packed fp16: scale = s_hi + s_lo (both fp16), one fused rounding
-              const __half2 a16 = __floats2half2_rn(a, b2);
-              const float2 f = __half22float2(__hfma2(a16, scale_hi, __hmul2(a16, scale_lo)));
-              ya = fmaf(f.x, kLog2e, -m_use);
-              yb = fmaf(f.y, kLog2e, -m_use);
-            } else {
-              float ta = a, tb = b2;
-              if (ROUND & PC_ROUND_QK) round_h2(ta, tb);
-              ta *= p.scale;
-              tb *= p.scale;
-              if (ROUND & PC_ROUND_SCALED) round_h2(ta, tb);
-              ya = fmaf(ta, kLog2e, -m_use);
-              yb = fmaf(tb, kLog2e, -m_use);
-            }
-            if (kMasked) {
-              if (key0 + c >= vis_end) ya = -INFINITY;
-              if (key0 + c + 1 >= vis_end) yb = -INFINITY;
-            }
+        for (int ck = 0; ck < kChunks; ++ck) {
+          if (kChunks > 1) load_chunk(ck);  // (single chunk: sv still holds the row)
+          const int kc = key0 + ck * CH;
+          uint32_t pk[CH / 2];
+          auto pass2 = [&](auto masked_tag) {
+            constexpr bool kMasked = decltype(masked_tag)::value;
+#pragma unroll
+            for (int c = 0; c < CH; c += 2) {
+              const float a = sv[c], b2 = sv[c + 1];
+              float ya, yb;
+              if (ALIBI) {
+                const float ta = kChunks == 1 ? a : alibi_score(a, kc + c);
+                const float tb = kChunks == 1 ? b2 : alibi_score(b2, kc + c + 1);
+                ya = fmaf(ta, kLog2e, -m_use);
+                yb = fmaf(tb, kLog2e, -m_use);
+              } else if (ROUND == 0) {
+                ya = fmaf(a, scale_l2, -m_use);
+                yb = fmaf(b2, scale_l2, -m_use);
+              } else if (ROUND == PC_ROUND_LLAMA) {
+                // half(half(acc) * scale) in packed fp16: scale = s_hi + s_lo (both fp16), one fused rounding
+                const __half2 a16 = __floats2half2_rn(a, b2);
+                const float2 f = __half22float2(__hfma2(a16, scale_hi, __hmul2(a16, scale_lo)));
+                ya = fmaf(f.x, kLog2e, -m_use);
+                yb = fmaf(f.y, kLog2e, -m_use);
+              } else {
+                float ta = a, tb = b2;
+                if (ROUND & PC_ROUND_QK) round_h2(ta, tb);
+                ta *= p.scale;
+                tb *= p.scale;
+                if (ROUND & PC_ROUND_SCALED) round_h2(ta, tb);
+                ya = fmaf(ta, kLog2e, -m_use);
+                yb = fmaf(tb, kLog2e, -m_use);
+              }
+              if (kMasked) {
+                if (kc + c >= vis_end) ya = -INFINITY;
+                if (kc + c + 1 >= vis_end) yb = -INFINITY;
+              }
 #if defined(PC_EXP_NO_MUFU)  // experiment: how much of the time is the exponential?
-            const float p0 = ya * 1e-3f, p1 = yb * 1e-3f;
+              const float p0 = ya * 1e-3f, p1 = yb * 1e-3f;
 #else
-            const float p0 = ex2(ya), p1 = ex2(yb);
+              const float p0 = ex2(ya), p1 = ex2(yb);
 #endif
-            lt += p0 + p1;
-            pk[c >> 1] = pack_h2(p0, p1);
-          }
-        };
-        if (warp_mask) pass2(std::true_type{});
-        else pass2(std::false_type{});
-        tmem_st32(tmem_s, pk);
+              lt += p0 + p1;
+              pk[c >> 1] = pack_h2(p0, p1);
+            }
+          };
+          if (warp_mask) pass2(std::true_type{});
+          else pass2(std::false_type{});
+          // P chunk ck covers the first half of S chunk ck's columns and, for ck = 1, S columns 32-63: every S value
+          // that lands under it is already in registers or consumed
+          tmem_st32(tmem_s + ck * (CH / 2), pk);
+        }
         l_run += lt;
         tmem_st_wait();
         tc_fence_before();

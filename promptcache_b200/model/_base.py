@@ -41,8 +41,9 @@ class B200CausalLM(nn.Module):
         self.linear_max_q = min(32, int(os.environ.get("PC_LINEAR_MAX_Q", "16")))
         self.linear_partials = os.environ.get("PC_LINEAR_PARTIALS", "1") != "0"
         self.linear_tiled = os.environ.get("PC_LINEAR_TILED", "1") != "0"  # native linears stream pre-tiled weight copies
-        # each native linear asks L2 for the head of the next one's weight stream while its own tail drains
-        self.linear_prefetch = os.environ.get("PC_LINEAR_PREFETCH", "1") != "0"
+        # experiment, off: each native linear asks L2 for the head of the next one's weight stream while its own tail drains --
+        # measured SLOWER (3.43 vs 3.31 ms per C2 step, worse with more stages): the tail is bandwidth-contended, not idle
+        self.linear_prefetch = os.environ.get("PC_LINEAR_PREFETCH", "0") != "0"
         # CUDA graphs of the whole single-sequence forward, keyed by (q_len, n_cached, KV buffer): the per-layer
         # launch sequence is fixed once those are, so a repeated request shape is replayed with one launch
         self.ablate = frozenset()  # measurement only: kernel families left out of the step (see LlamaForCausalLM._layers_ablated)
