@@ -122,13 +122,21 @@ def build_lm(model_key, dev, layers=None):
     tok = IdTokenizer(md["vocab_size"])
     if model_key.startswith("falcon"):
         return Falcon(model_key, model=FalconForCausalLM(FalconConfigLite(**md), device=dev), tokenizer=tok), md
+    if model_key.startswith("mpt"):
+        from promptcache_b200.model import Mpt
+        from promptcache_b200.model.mpt import MptConfigLite, MptForCausalLM
+        cfg = MptConfigLite(d_model=md["hidden_size"], n_heads=md["num_attention_heads"], n_layers=md["num_hidden_layers"],
+                            vocab_size=md["vocab_size"], max_seq_len=md.get("max_seq_len", 8192))
+        return Mpt(model_key, model=MptForCausalLM(cfg, device=dev), tokenizer=tok), md
     return Llama2(model_key, model=LlamaForCausalLM(LlamaConfigLite(**md), device=dev), tokenizer=tok), md
 
 
 def weight_bytes(md, model_key):
     """fp16 bytes of every matrix one forward streams once (embedding rows excluded: q rows only)."""
     hid, L, V = md["hidden_size"], md["num_hidden_layers"], md["vocab_size"]
-    if model_key.startswith("falcon"):
+    if model_key.startswith("mpt"):
+        per = 12 * hid * hid
+    elif model_key.startswith("falcon"):
         D = hid // md["num_attention_heads"]
         per = (hid + 2 * D) * hid + hid * hid + 8 * hid * hid
     else:
@@ -159,7 +167,8 @@ class RequestStep:
         self.prompt = Prompt(prompt_xml)
         self.gen = GenerationEngine(lm)
         self.params = GenerationParameters(temperature=0.0, max_new_tokens=1, stop_token_ids=[], stop_str=[])
-        ids, pos, _, _ = eng.process(self.prompt)
+        self.full_ids = bool(getattr(lm, "use_full_position_ids", False))  # MPT: ids of the cached rows + the new tokens
+        ids, pos, _, _ = eng.process(self.prompt, return_full_position_ids=self.full_ids)
         self.q_len = len(ids)
         self.ids_dev = torch.tensor([ids], device=dev)
         self.pos_dev = torch.tensor([pos], device=dev)
@@ -185,8 +194,18 @@ class RequestStep:
 
     def e2e_step(self):
         """The public API with host inputs (token lists -> device) and the first token read back."""
-        i2, p2, _, cache = self.eng.process(self.prompt)
-        return next(self.gen.generate(i2, p2, self.params, cache, stream_interval=1))
+        i2, p2, _, cache = self.eng.process(self.prompt, return_full_position_ids=self.full_ids)
+        return next(self.gen.generate(i2, p2, self.params, cache, stream_interval=1, use_full_position_ids=self.full_ids))
+
+    def decode_ms_per_token(self, n_tokens=17):
+        """Greedy decode after the prefill through the public API; first pass warms up (graph capture), second is reported."""
+        from promptcache_b200 import GenerationParameters
+        dparams = GenerationParameters(temperature=0.0, max_new_tokens=n_tokens, stop_token_ids=[], stop_str=[])
+        outs = []
+        for _ in range(2):
+            i2, p2, _, cache = self.eng.process(self.prompt, return_full_position_ids=self.full_ids)
+            outs = list(self.gen.generate(i2, p2, dparams, cache, use_full_position_ids=self.full_ids))
+        return (outs[-1].response_time - outs[0].response_time) / (n_tokens - 1)
 
     def timed(self, fn, steps, sync_all):
         sync_all()
@@ -203,6 +222,8 @@ def timed_broadcast(schema_cache, dev):
     """NCCL broadcast of the encoded segment store from rank 0, device-timed, max over ranks."""
     import torch.distributed as dist
     from promptcache_b200 import parallel
+    warm = torch.zeros(1024, device=dev)
+    dist.broadcast(warm, src=0)  # the first collective of a process group sets up the NCCL communicator (~100 ms): not timed
     dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -214,7 +235,8 @@ def timed_broadcast(schema_cache, dev):
     gbs = moved["bytes"] / (ms * 1e-3) / 1e9 if ms > 0 else None
     return {"bytes": moved["bytes"], "segments": moved["segments"], "ms": ms, "GB/s": gbs, "peer_peak_GB/s": NVLINK_PEER_GBS,
             "frac_of_peer_peak": (gbs / NVLINK_PEER_GBS) if gbs else None,
-            "note": "one ncclBroadcast per packed segment, rank 0 -> all; includes the object broadcast of the shape header"}
+            "note": "ONE ncclBroadcast of the schema's segment arena [L,2,Hkv,R,D], rank 0 -> all, device-timed, max over ranks; "
+                    "includes the object broadcast of the shape header"}
 
 
 def c5_block(lm, dev, world, rank, batch=64, pool=64, picks=32, seg_len=256, suffix=32):
@@ -247,7 +269,8 @@ def c5_block(lm, dev, world, rank, batch=64, pool=64, picks=32, seg_len=256, suf
         torch.cuda.synchronize()
 
     out = {}
-    for mode, retain in (("full_splice", False), ("retained_prefix", True)):
+    for mode, virtual, retain in (("virtual_splice", True, False), ("copied_splice", False, False), ("copied_retained_prefix", False, True)):
+        eng.virtual_splice = virtual
         eng.prompt_cache.retain_prefix = retain
         for m in eng.schemas["pool"].cache_l1.values():
             m.usage_counter = 0
@@ -274,19 +297,23 @@ def c5_block(lm, dev, world, rank, batch=64, pool=64, picks=32, seg_len=256, suf
     L, Hkv, D = lm.get_cache_shape()
     res = {"workload": f"C5: {batch} prompts x ({picks} of a {pool}-segment pool x {seg_len} tokens = {n_cached} cached + {suffix} suffix), "
                        f"prompt b -> rank b mod {world}; public API (process + generate(1)), max over ranks",
-           "n_gpus": world, "pool_bytes": 4.0 * L * Hkv * D * pool * seg_len, "encode_s_rank0": encode_s, "broadcast": bc, **out,
-           "note": "retained_prefix: usage-ordered layout + retained common prefix (cache_engine.py:121-131) on; "
-                   "full_splice: every request moves all 8192 rows (8 GiB of HBM traffic)"}
+           "n_gpus": world, "pool_bytes": 4.0 * L * Hkv * D * pool * seg_len, "encode_s_rank0": encode_s, "broadcast": bc,
+           "tok_s": out["virtual_splice"]["tok_s"], "ttft_ms_max": out["virtual_splice"]["ttft_ms_max"], **out,
+           "note": "virtual_splice (engine default): attention reads the pool's arena through the request's tile list, nothing is "
+                   "copied; copied_splice: every request moves all 8192 rows (8 GiB of HBM traffic, the reference's PromptCache.update); "
+                   "copied_retained_prefix: the copy with the usage-ordered layout + retained common prefix (cache_engine.py:121-131)"}
     del eng
     return res
 
 
-def c4_block(dev, steps, warmup):
-    """BASELINE configs[3]: Falcon-7B at real dims (H=71, Hkv=1, D=64, hidden 4544, 32 layers), parameterized schema:
-    5 segments = 256 cached tokens, 21-token suffix of which 5 sit at interior parameter slots (non-monotone ids)."""
+def family_block(model_key, cfg_name, dev, steps, warmup):
+    """Another model family on the same engine, one request per step.  C4 = BASELINE configs[3]: Falcon-7B at real dims
+    (H=71, Hkv=1, D=64, hidden 4544, 32 layers), parameterized schema: 5 segments = 256 cached tokens, 21-token suffix of
+    which 5 sit at interior parameter slots (non-monotone ids).  MPT-7B (ALiBi at key ids, full position ids) is run on
+    the C2 schema shape."""
     from promptcache_b200.synthetic import make_case
-    lm, md = build_lm("falcon-7b", dev)
-    case = make_case("C4", vocab=md["vocab_size"])
+    lm, md = build_lm(model_key, dev)
+    case = make_case(cfg_name, vocab=md["vocab_size"])
     w = RequestStep(lm, case, dev, 1, 0)
     sync = torch.cuda.synchronize
     for _ in range(warmup):
@@ -295,16 +322,20 @@ def c4_block(dev, steps, warmup):
     for _ in range(warmup):
         w.e2e_step()
     e2e_ms = w.timed(w.e2e_step, steps, sync)
-    tokens = case.n_cached + w.q_len
-    wb = weight_bytes(md, "falcon-7b")
+    tokens = case.n_cached + case.q_len
+    wb = weight_bytes(md, model_key)
     peak, _, _ = load_peaks()
-    res = {"workload": f"C4: falcon-7b, {case.n_segments} cached segments = {case.n_cached} tokens, {w.q_len}-token suffix "
-                       f"(position ids {w.pos_dev[0, :6].tolist()}..., non-monotone), one request per step",
-           "ttft_ms": dev_ms, "tok_s": tokens / (dev_ms * 1e-3), "computed_tok_s": w.q_len / (dev_ms * 1e-3),
-           "e2e_ttft_ms": e2e_ms, "e2e_tok_s": tokens / (e2e_ms * 1e-3),
+    try:
+        decode_ms = w.decode_ms_per_token()
+    except Exception as ex:
+        decode_ms = f"failed: {type(ex).__name__}: {ex}"
+    res = {"workload": f"{cfg_name}: {model_key}, {case.n_segments} cached segments = {case.n_cached} tokens, {case.q_len}-token suffix "
+                       f"(suffix position ids {w.pos_dev[0, -case.q_len:][:6].tolist()}...), one request per step",
+           "ttft_ms": dev_ms, "tok_s": tokens / (dev_ms * 1e-3), "computed_tok_s": case.q_len / (dev_ms * 1e-3),
+           "e2e_ttft_ms": e2e_ms, "e2e_tok_s": tokens / (e2e_ms * 1e-3), "decode_ms_per_token": decode_ms,
            "splice_ms": statistics.mean(a.elapsed_time(b) for a, b in w.splice_ev),
            "roofline_step": {"bound": "hbm", "algorithmic_bytes": wb, "achieved": wb / (dev_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                             "frac": wb / (dev_ms * 1e-3) / 1e9 / peak, "note": "weights only (14.4 GB); linears are cuBLAS for Falcon"}}
+                             "frac": wb / (dev_ms * 1e-3) / 1e9 / peak, "note": "weights only; the linears of this family are cuBLAS"}}
     del w, lm
     torch.cuda.empty_cache()
     return res
@@ -496,7 +527,7 @@ def run_reference(args, case, md, dims, seg_lens):
 
 def metric_name(args):
     from promptcache_b200.synthetic import CONFIGS
-    model = {"llama2-7b": "Llama-2-7B", "llama2-13b": "Llama-2-13B", "falcon-7b": "Falcon-7B"}[CONFIGS[args.config]["model"]]
+    model = {"llama2-7b": "Llama-2-7B", "llama2-13b": "Llama-2-13B", "falcon-7b": "Falcon-7B", "mpt-7b": "MPT-7B"}[CONFIGS[args.config]["model"]]
     return f"{model} prefill tok/s (served prompt tokens / TTFT; TTFT = ms_per_step)"
 
 
@@ -569,7 +600,7 @@ def main():
     if c5_only:  # C5 as the whole run: print its block as the line
         blk = c5_block(lm, dev, world, rank)
         if rank == 0:
-            print(json.dumps({"metric": "Llama-2-7B prefill tok/s, C5 batch (64 prompts x 8224 tokens) over the node", "value": blk["full_splice"]["tok_s"],
+            print(json.dumps({"metric": "Llama-2-7B prefill tok/s, C5 batch (64 prompts x 8224 tokens) over the node", "value": blk["tok_s"],
                               "unit": "tok/s", "n_gpus": world, "higher_is_better": True, "scaling": "strong", "dtype": "f16",
                               "data": "synthetic", "config": {"workload": blk["workload"]}, "c5": blk}), flush=True)
         if world > 1:
@@ -590,8 +621,13 @@ def main():
         w.device_step()
     sync_all()
     if args.profile:
+        copied = os.environ.get("PC_BENCH_PROFILE_COPIED") == "1"  # profile the step WITH the reference's copy (splice kernel)
+        if copied:
+            for _ in range(3):
+                w.device_step(virtual=False)
+            torch.cuda.synchronize()
         torch.cuda.profiler.start()
-        w.device_step()
+        w.device_step(virtual=False if copied else None)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
@@ -749,9 +785,13 @@ def main():
         try:
             del w
             torch.cuda.empty_cache()
-            line["c4"] = c4_block(dev, max(5, args.steps // 2), 3)
+            line["c4"] = family_block("falcon-7b", "C4", dev, max(5, args.steps // 2), 3)
         except Exception as ex:
             line["c4"] = {"error": f"{type(ex).__name__}: {ex}"}
+        try:
+            line["mpt"] = family_block("mpt-7b", "C2", dev, max(5, args.steps // 2), 3)
+        except Exception as ex:
+            line["mpt"] = {"error": f"{type(ex).__name__}: {ex}"}
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         try:
