@@ -196,6 +196,12 @@ int pc_decode_attn(const pc_attn_params* p, void* stream);
 int pc_add_rmsnorm(void* x, const void* delta, const void* weight, void* h_out, int rows, int hidden,
                    float eps, void* stream);
 int pc_silu_mul(const void* gate_up, void* out, int rows, int inter, int64_t row_stride, void* stream);
+/* LayerNorm families (Falcon, MPT): x[rows][hidden] = half(x + half(d1 + d2)) written back (d1 / d2 may be NULL: no add), then
+ * h_out = half(((x - mean) * rstd) * weight + bias) with fp32 statistics -- F.layer_norm on fp16 input; bias may be NULL.
+ *   Falcon  x + (mlp_out += attn_out), next input_layernorm   falcon.py:781,796-810
+ *   MPT     x + attn_out -> norm_2 ; x + ffn_out -> norm_1    mpt.py:220-222,246-268 */
+int pc_add_layernorm(void* x, const void* d1, const void* d2, const void* weight, const void* bias, void* h_out, int rows,
+                     int hidden, float eps, void* stream);
 /* pc_add_rmsnorm whose delta is the sum of `n_splits` fp32 partials [split][rows][hidden] (PC_LIN_PARTIALS output),
  * added in split order and rounded to fp16 once before the fp16 residual add. */
 int pc_add_rmsnorm_partials(void* x, const void* delta_partials, int n_splits, const void* weight, void* h_out, int rows,

@@ -28,7 +28,7 @@ PC_ATTN_GLOBAL_MERGE = 0x100
 
 EXPORTS = ("pc_version", "pc_last_error", "pc_device_info", "pc_splice_kv", "pc_splice_kv_strided", "pc_splice_kv_tensors",
            "pc_rope_append", "pc_rope_append_dyn", "pc_attn_workspace_bytes", "pc_prefill_attn", "pc_decode_attn", "pc_launch_count",
-           "pc_add_rmsnorm", "pc_silu_mul", "pc_linear_workspace_bytes", "pc_linear_small",
+           "pc_add_rmsnorm", "pc_add_layernorm", "pc_silu_mul", "pc_linear_workspace_bytes", "pc_linear_small",
            "pc_linear_tiled_bytes", "pc_linear_tile_weights", "pc_linear_partial_splits", "pc_add_rmsnorm_partials")
 PC_LIN_PLAIN = 0
 PC_LIN_SILU_MUL = 1
@@ -117,6 +117,9 @@ def load() -> C.CDLL:
     lib.pc_launch_count.restype = C.c_int64
     lib.pc_add_rmsnorm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]
     lib.pc_add_rmsnorm.restype = C.c_int
+    lib.pc_add_layernorm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float,
+                                     C.c_void_p]
+    lib.pc_add_layernorm.restype = C.c_int
     lib.pc_silu_mul.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]
     lib.pc_silu_mul.restype = C.c_int
     lib.pc_linear_workspace_bytes.argtypes = []
@@ -339,6 +342,19 @@ def add_rmsnorm(x: torch.Tensor, delta: Optional[torch.Tensor], weight: torch.Te
     rows, hidden = x.shape
     _check(load().pc_add_rmsnorm(x.data_ptr(), delta.data_ptr() if delta is not None else None, weight.data_ptr(),
                                  h_out.data_ptr(), rows, hidden, float(eps), _stream()), "pc_add_rmsnorm")
+
+
+def add_layernorm(x: torch.Tensor, d1: Optional[torch.Tensor], d2: Optional[torch.Tensor], weight: torch.Tensor,
+                  bias: Optional[torch.Tensor], h_out: torch.Tensor, eps: float) -> None:
+    """x[rows,hidden] = half(x + half(d1 + d2)) in place (either delta may be None), h_out = LayerNorm(x) * weight + bias."""
+    _require_cuda(x, weight, h_out, d1, d2, bias)
+    for t in (x, h_out, d1, d2):
+        if t is not None and (not t.is_contiguous() or t.dtype != torch.float16 or t.shape != x.shape):
+            raise NativeError("add_layernorm: x / deltas / h_out must be contiguous fp16 tensors of one shape")
+    rows, hidden = x.shape
+    _check(load().pc_add_layernorm(x.data_ptr(), d1.data_ptr() if d1 is not None else None, d2.data_ptr() if d2 is not None else None,
+                                   weight.data_ptr(), bias.data_ptr() if bias is not None else None, h_out.data_ptr(), rows, hidden,
+                                   float(eps), _stream()), "pc_add_layernorm")
 
 
 def silu_mul(gate_up: torch.Tensor, out: torch.Tensor, inter: int) -> None:

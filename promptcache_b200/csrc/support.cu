@@ -89,6 +89,89 @@ add_rmsnorm_kernel(__half* __restrict__ x, const __half* __restrict__ delta, con
   }
 }
 
+// x = half(x + half(d1 + d2)) (d2 optional; d1 optional), then LayerNorm over the row: fp32 mean / variance of the fp16
+// values, (x - mean) * rstd * weight + bias evaluated in fp32 and rounded once -- the arithmetic of F.layer_norm on fp16
+// input.  Falcon: x + (mlp_out += attn_out) then the next block's input_layernorm (falcon.py:796-810, :781);
+// MPT: x + attn_out -> norm_2, x + ffn -> next norm_1 (mpt.py:246-268), bias == nullptr (mpt.py:220-222).
+__global__ void __launch_bounds__(kNormThreads)
+add_layernorm_kernel(__half* __restrict__ x, const __half* __restrict__ d1, const __half* __restrict__ d2,
+                     const __half* __restrict__ weight, const __half* __restrict__ bias, __half* __restrict__ h_out, int hidden,
+                     float eps) {
+  __shared__ float red[2][kNormThreads / 32];
+  pc::pdl_launch_dependents();
+  pc::pdl_wait();
+  const int row = blockIdx.x;
+  const long long off = static_cast<long long>(row) * hidden;
+  __half* xr = x + off;
+  __half* hr = h_out + off;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = threadIdx.x * 8; i < hidden; i += kNormThreads * 8) {
+    uint4 xv = *reinterpret_cast<const uint4*>(xr + i);
+    __half2* xh = reinterpret_cast<__half2*>(&xv);
+    if (d1) {
+      uint4 av = *reinterpret_cast<const uint4*>(d1 + off + i);
+      __half2* ah = reinterpret_cast<__half2*>(&av);
+      if (d2) {
+        const uint4 bv = *reinterpret_cast<const uint4*>(d2 + off + i);
+        const __half2* bh = reinterpret_cast<const __half2*>(&bv);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ah[k] = __hadd2_rn(ah[k], bh[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) xh[k] = __hadd2_rn(xh[k], ah[k]);
+      *reinterpret_cast<uint4*>(xr + i) = xv;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(xh[k]);
+      s1 += f.x + f.y;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = s1;
+  __syncthreads();
+  float t1 = 0.f;
+#pragma unroll
+  for (int w = 0; w < kNormThreads / 32; ++w) t1 += red[0][w];
+  const float mean = t1 / static_cast<float>(hidden);
+  // second pass over the row (this thread's own stores: L1 hits) for the centred sum of squares -- no cancellation
+  for (int i = threadIdx.x * 8; i < hidden; i += kNormThreads * 8) {
+    const uint4 xv = *reinterpret_cast<const uint4*>(xr + i);
+    const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(xh[k]);
+      s2 = fmaf(f.x - mean, f.x - mean, s2);
+      s2 = fmaf(f.y - mean, f.y - mean, s2);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  if ((threadIdx.x & 31) == 0) red[1][threadIdx.x >> 5] = s2;
+  __syncthreads();
+  float t2 = 0.f;
+#pragma unroll
+  for (int w = 0; w < kNormThreads / 32; ++w) t2 += red[1][w];
+  const float var = t2 / static_cast<float>(hidden);
+  const float rstd = rsqrtf(var + eps);
+  for (int i = threadIdx.x * 8; i < hidden; i += kNormThreads * 8) {
+    uint4 xv = *reinterpret_cast<const uint4*>(xr + i);
+    const uint4 wv = *reinterpret_cast<const uint4*>(weight + i);
+    uint4 bv = make_uint4(0u, 0u, 0u, 0u);
+    if (bias) bv = *reinterpret_cast<const uint4*>(bias + i);
+    __half2* xh = reinterpret_cast<__half2*>(&xv);
+    const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+    const __half2* bh = reinterpret_cast<const __half2*>(&bv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(xh[k]);
+      const float2 w = __half22float2(wh[k]);
+      const float2 b = __half22float2(bh[k]);
+      xh[k] = __floats2half2_rn(fmaf((f.x - mean) * rstd, w.x, b.x), fmaf((f.y - mean) * rstd, w.y, b.y));
+    }
+    *reinterpret_cast<uint4*>(hr + i) = xv;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 silu_mul_kernel(const __half* __restrict__ gate_up, __half* __restrict__ out, int inter, long long row_stride) {
   pc::pdl_launch_dependents();
@@ -140,6 +223,23 @@ PC_API int pc_add_rmsnorm_partials(void* x, const void* delta_partials, int n_sp
                                static_cast<__half*>(x), static_cast<const __half*>(nullptr), static_cast<const __half*>(weight),
                                static_cast<__half*>(h_out), hidden, eps, static_cast<const float*>(delta_partials), n_splits,
                                static_cast<long long>(rows) * hidden));
+  pc::count_launch();
+  return PC_OK;
+}
+
+PC_API int pc_add_layernorm(void* x, const void* d1, const void* d2, const void* weight, const void* bias, void* h_out, int rows,
+                            int hidden, float eps, void* stream) {
+  if (rows == 0) return PC_OK;
+  PC_REQUIRE(x && weight && h_out, "pc_add_layernorm: null tensor");
+  PC_REQUIRE(d1 != nullptr || d2 == nullptr, "pc_add_layernorm: d2 without d1");
+  PC_REQUIRE(rows > 0 && hidden > 0 && hidden % 8 == 0, "pc_add_layernorm: hidden %d must be a positive multiple of 8", hidden);
+  const uintptr_t align = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(d1) | reinterpret_cast<uintptr_t>(d2) |
+                          reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(h_out);
+  PC_REQUIRE(align % 16 == 0, "pc_add_layernorm: tensors must be 16B aligned");
+  PC_CHECK_CUDA(pc::launch_pdl(add_layernorm_kernel, dim3(rows), dim3(kNormThreads), 0, static_cast<cudaStream_t>(stream),
+                               static_cast<__half*>(x), static_cast<const __half*>(d1), static_cast<const __half*>(d2),
+                               static_cast<const __half*>(weight), static_cast<const __half*>(bias), static_cast<__half*>(h_out),
+                               hidden, eps));
   pc::count_launch();
   return PC_OK;
 }

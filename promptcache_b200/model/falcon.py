@@ -105,11 +105,14 @@ class FalconForCausalLM(B200CausalLM):
         N = kv.n_cached
         hid = self.config.hidden_size
         x = F.embedding(ids, self.word_embeddings)
+        ln = torch.empty_like(x)
         q_rot = torch.empty(H, q_len, D, dtype=torch.float16, device=self.device)
         ctx = torch.empty(q_len, H * D, dtype=torch.float16, device=self.device)
         ws = self._workspace(q_len)
+        attn = mlp = None
         for l in range(self.n_layers):
-            ln = F.layer_norm(x, (hid,), self.ln_w[l], self.ln_b[l], self.eps)        # input_layernorm (falcon.py:781)
+            # x = x + (mlp += attn) of the previous block (falcon.py:807-810) and this block's input_layernorm (:781): one launch
+            nat.add_layernorm(x, mlp, attn, self.ln_w[l], self.ln_b[l], ln, self.eps)
             qkv = F.linear(ln, self.wqkv[l])                                          # [q, (H+2)*D]: q heads | k | v (:385-388)
             nat.rope_append(qkv[:, :H * D], qkv[:, H * D:(H + 1) * D], qkv[:, (H + 1) * D:], pos, self._cos, self._sin,
                             q_rot, kv.k[l], kv.v[l], N, H, 1, D)
@@ -117,7 +120,5 @@ class FalconForCausalLM(B200CausalLM):
                           impl=self.attn_impl, decode=(q_len == 1))
             attn = F.linear(ctx, self.wdense[l])                                      # :493
             mlp = F.linear(F.gelu(F.linear(ln, self.w_h4h[l])), self.w_4hh[l])        # parallel MLP on the same norm (:796-805)
-            mlp += attn                                                               # :807-808
-            x = mlp + x                                                               # dropout_add (:810)
-        x = F.layer_norm(x, (hid,), self.lnf_w, self.lnf_b, self.eps)
-        return F.linear(x, self.word_embeddings).float()
+        nat.add_layernorm(x, mlp, attn, self.lnf_w, self.lnf_b, ln, self.eps)          # last block's residual adds + ln_f
+        return F.linear(ln, self.word_embeddings).float()

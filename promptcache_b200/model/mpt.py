@@ -118,19 +118,21 @@ class MptForCausalLM(B200CausalLM):
         max_pos = int(extra[0])
         key_pos = pos.to(torch.int32)  # ids of all N+q keys: cached rows in buffer order, then the new tokens
         x = F.embedding(ids, self.wte)
+        ln = torch.empty_like(x)
         q_out = torch.empty(H, q_len, D, dtype=torch.float16, device=self.device)
         ctx = torch.empty(q_len, H * D, dtype=torch.float16, device=self.device)
         ws = self._workspace(q_len)
+        ffn = None
         for l in range(self.n_layers):
-            ln = F.layer_norm(x, (hid,), self.norm1[l], None, self.eps)                     # norm_1, bias dropped (mpt.py:220-222)
+            # x += ffn of the previous block (:208) and norm_1, bias dropped (mpt.py:220-222): one launch
+            nat.add_layernorm(x, ffn, None, self.norm1[l], None, ln, self.eps)
             qkv = F.linear(ln, self.wqkv[l])                                                # chunk(3): q | k | v (:142-143)
             nat.rope_append(qkv[:, :hid], qkv[:, hid:2 * hid], qkv[:, 2 * hid:], None, None, None, q_out, kv.k[l], kv.v[l],
                             N, H, H, D)                                                     # no rotary: transpose + append (:148-151)
             nat.attention(q_out, kv.k[l], kv.v[l], ctx, N, q_len, H, H, D, self.scale, self.rounding, workspace=ws,
                           alibi_slopes=self.slopes, key_pos=key_pos, alibi_max_pos=max_pos, impl=self.attn_impl,
                           decode=(q_len == 1))                                              # :156-185
-            x = F.linear(ctx, self.wo[l]) + x                                               # :251
-            ln = F.layer_norm(x, (hid,), self.norm2[l], None, self.eps)
-            x = F.linear(F.gelu(F.linear(ln, self.w_up[l])), self.w_down[l]) + x            # MptMLP (:200-208)
-        x = F.layer_norm(x, (hid,), self.norm_f, None, self.eps)
-        return F.linear(x, self.wte).float()
+            nat.add_layernorm(x, F.linear(ctx, self.wo[l]), None, self.norm2[l], None, ln, self.eps)   # x += attn (:251); norm_2
+            ffn = F.linear(F.gelu(F.linear(ln, self.w_up[l])), self.w_down[l])              # MptMLP (:200-208)
+        nat.add_layernorm(x, ffn, None, self.norm_f, None, ln, self.eps)
+        return F.linear(ln, self.wte).float()

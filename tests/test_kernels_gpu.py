@@ -365,3 +365,30 @@ def test_attention_cluster_merge_with_runtime_length_and_surplus_ranks(native, m
             res[flag] = out
         assert torch.equal(res["1"], res["0"])
         assert _rel(res["1"], _oracle_llama(Q, K, V, N, q)) <= 1e-3
+
+
+# ------------------------------------------------------------------ fused residual + LayerNorm (Falcon / MPT)
+@pytest.mark.parametrize("rows,hidden,two,bias", [(21, 4544, True, True), (16, 4096, False, False), (1, 4544, True, True),
+                                                  (300, 512, False, True), (7, 4096, True, False)])
+def test_add_layernorm_matches_eager_reference_arithmetic(native, rows, hidden, two, bias):
+    """x + (mlp += attn) then F.layer_norm, as falcon.py:781,796-810 / mpt.py:246-268 evaluate them in fp16."""
+    g = torch.Generator(device="cpu").manual_seed(rows + hidden)
+    x = (torch.randn(rows, hidden, generator=g) * 2 + 0.3).half().to(DEV)
+    d1 = torch.randn(rows, hidden, generator=g).half().to(DEV)
+    d2 = torch.randn(rows, hidden, generator=g).half().to(DEV) if two else None
+    w = (1 + 0.1 * torch.randn(hidden, generator=g)).half().to(DEV)
+    b = (0.1 * torch.randn(hidden, generator=g)).half().to(DEV) if bias else None
+    t = d1.clone()
+    if two:
+        t += d2                      # mlp_output += attention_output
+    want_x = x + t                   # residual + out
+    want_h = torch.nn.functional.layer_norm(want_x, (hidden,), w, b, 1e-5)
+    got_x, got_h = x.clone(), torch.empty_like(x)
+    native.add_layernorm(got_x, d1, d2, w, b, got_h, 1e-5)
+    torch.cuda.synchronize()
+    assert torch.equal(got_x, want_x)
+    assert _rel(got_h, want_h) <= 1e-3
+    # no deltas: a plain LayerNorm
+    h2 = torch.empty_like(x)
+    native.add_layernorm(got_x, None, None, w, b, h2, 1e-5)
+    assert torch.equal(h2, got_h)
