@@ -157,9 +157,9 @@ typedef struct pc_attn_params {
   const int32_t* key_pos;    /* [n_cached+q_len] or NULL (required with alibi_slopes)        */
   int32_t alibi_max_pos;     /* max(position_ids) (mpt.py:522)                               */
   int32_t impl;              /* PC_ATTN_*                                                    */
-  const int32_t* n_cached_dev; /* optional: N is read from the device at run time (graph-replayable decode /  *
-                              * short suffixes, head_dim 128, G*q_len <= 32 only); `n_cached` is then an    *
-                              * upper bound used for sizing, all max_ctx rows of k/v must hold finite values */
+  const int32_t* n_cached_dev; /* optional: N is read from the device at run time (graph-replayable decode);  *
+                              * `n_cached` is then an upper bound used for sizing, and all max_ctx rows of   *
+                              * k/v must hold finite values (tcgen05 kernels only)                           */
   void* workspace;           /* split-KV scratch, >= pc_attn_workspace_bytes(...) or NULL;   *
                               * ZERO it once before first use (arrival counters; kernels     *
                               * leave them zeroed); one workspace per concurrent stream      */

@@ -92,9 +92,8 @@ static int attn_dispatch(const pc_attn_params* p, void* stream, const char* who)
     return launch_attn_small(*p, st);
   }
   if (p->n_cached_dev != nullptr) {
-    if (impl != PC_ATTN_TCGEN05 || !attn_small_supported(*p))
-      return set_error(PC_ERR_UNSUPPORTED, "%s: n_cached_dev needs the short-suffix tcgen05 kernel (head_dim 128, G*q <= 32)", who);
-    return launch_attn_small(*p, st);
+    if (impl != PC_ATTN_TCGEN05) return set_error(PC_ERR_UNSUPPORTED, "%s: n_cached_dev needs the tcgen05 kernels", who);
+    return attn_small_supported(*p) ? launch_attn_small(*p, st) : launch_attn_pp(*p, st);
   }
   if (impl == PC_ATTN_SIMT) return launch_attn_simt(*p, st);
   if (impl == PC_ATTN_TCGEN05) {

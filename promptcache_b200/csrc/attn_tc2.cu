@@ -76,6 +76,7 @@ struct PpParams {
   float* part_ml;
   const float* alibi_slopes;
   const int* key_pos;
+  const int* n_cached_dev;  // optional run-time N (graph-replayable decode): n_cached is then the sizing upper bound
   int n_heads, n_kv_heads, n_cached, q_len, n_splits, m_pairs, alibi_max_pos;
   float scale;
 };
@@ -109,8 +110,12 @@ __device__ __forceinline__ int tile_kv_end(int row_lo, int rows_total, int q_len
 template <int D, int ROUND, bool ALIBI>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-               const __grid_constant__ CUtensorMap map_v, const PpParams p) {
+               const __grid_constant__ CUtensorMap map_v, const PpParams pin) {
   using C = Cfg2<D>;
+  PpParams p = pin;
+  // run-time cached length: the grid, the split count and the tensor maps were sized for the upper bound; splits that end
+  // up without tiles publish an empty partial (m = -inf, l = 0), rows past N + q are masked by the causal bound
+  if (pin.n_cached_dev != nullptr) p.n_cached = max(0, min(__ldg(pin.n_cached_dev), pin.n_cached));
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   unsigned char* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -551,7 +556,8 @@ int launch_pp_d(const pc_attn_params& p, cudaStream_t st) {
   }
   CUtensorMap mq, mk, mv;
   if (int rc = make_tensor_map_3d(&mq, p.q, D, rows_total, p.n_kv_heads, static_cast<long long>(rows_total) * D, BM)) return rc;
-  const long long kv_rows = static_cast<long long>(p.n_cached) + p.q_len;
+  // run-time N: the maps cover the whole buffer (rows past N+q are masked; they must hold finite values)
+  const long long kv_rows = p.n_cached_dev ? static_cast<long long>(p.max_ctx) : static_cast<long long>(p.n_cached) + p.q_len;
   if (int rc = make_tensor_map_3d(&mk, p.k, D, kv_rows, p.n_kv_heads, static_cast<long long>(p.max_ctx) * D, BN)) return rc;
   if (int rc = make_tensor_map_3d(&mv, p.v, D, kv_rows, p.n_kv_heads, static_cast<long long>(p.max_ctx) * D, BN)) return rc;
   PpParams pp;
@@ -560,6 +566,7 @@ int launch_pp_d(const pc_attn_params& p, cudaStream_t st) {
   pp.part_ml = part_ml;
   pp.alibi_slopes = p.alibi_slopes;
   pp.key_pos = p.key_pos;
+  pp.n_cached_dev = p.n_cached_dev;
   pp.n_heads = p.n_heads;
   pp.n_kv_heads = p.n_kv_heads;
   pp.n_cached = p.n_cached;

@@ -99,7 +99,9 @@ class FalconForCausalLM(B200CausalLM):
         model.load_hf_state_dict(hf.state_dict())
         return model
 
-    def _layers(self, ids: torch.Tensor, pos: torch.Tensor, kv, extra=()) -> torch.Tensor:
+    supports_dynamic_n = True  # decode graph: pc_rope_append_dyn + attention with a run-time cached length
+
+    def _layers(self, ids: torch.Tensor, pos: torch.Tensor, kv, extra=(), n_dev=None) -> torch.Tensor:
         q_len = ids.shape[0]
         H, D = self.n_heads, self.head_dim
         N = kv.n_cached
@@ -114,10 +116,12 @@ class FalconForCausalLM(B200CausalLM):
             # x = x + (mlp += attn) of the previous block (falcon.py:807-810) and this block's input_layernorm (:781): one launch
             nat.add_layernorm(x, mlp, attn, self.ln_w[l], self.ln_b[l], ln, self.eps)
             qkv = F.linear(ln, self.wqkv[l])                                          # [q, (H+2)*D]: q heads | k | v (:385-388)
+            # n_dev: run-time cached length (decode graph); N is then only the sizing upper bound
             nat.rope_append(qkv[:, :H * D], qkv[:, H * D:(H + 1) * D], qkv[:, (H + 1) * D:], pos, self._cos, self._sin,
-                            q_rot, kv.k[l], kv.v[l], N, H, 1, D)
-            nat.attention(q_rot, kv.k[l], kv.v[l], ctx, N, q_len, H, 1, D, self.scale, self.rounding, workspace=ws,
-                          impl=self.attn_impl, decode=(q_len == 1))
+                            q_rot, kv.k[l], kv.v[l], N if n_dev is None else n_dev, H, 1, D)
+            nat.attention(q_rot, kv.k[l], kv.v[l], ctx, N if n_dev is None else kv.max_ctx - q_len, q_len, H, 1, D, self.scale,
+                          self.rounding, workspace=ws, impl=self.attn_impl if n_dev is None else nat.PC_ATTN_TCGEN05,
+                          decode=(q_len == 1), n_cached_dev=n_dev)
             attn = F.linear(ctx, self.wdense[l])                                      # :493
             mlp = F.linear(F.gelu(F.linear(ln, self.w_h4h[l])), self.w_4hh[l])        # parallel MLP on the same norm (:796-805)
         nat.add_layernorm(x, mlp, attn, self.lnf_w, self.lnf_b, ln, self.eps)          # last block's residual adds + ln_f

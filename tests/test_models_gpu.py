@@ -125,3 +125,56 @@ def test_mpt_engine_full_ids_generate(native, gold):
     ids, pos, _, cache = eng.process(Prompt(xml), return_full_position_ids=True)
     outs = list(GenerationEngine(lm).generate(ids, pos, params, cache, stream_interval=1, use_full_position_ids=True))
     assert len(outs) == 3
+
+
+def test_falcon_decode_graph_with_runtime_length_equals_eager_decode(native, gold):
+    """Falcon decode replays ONE captured graph per KV buffer (run-time cached length in pc_rope_append_dyn and in the
+    long-suffix attention kernel, MQA fold of 71 heads -> here 2): same greedy tokens as the eager step-by-step loop."""
+    from promptcache_b200 import CacheEngine, GenerationEngine, GenerationParameters, Prompt
+    from promptcache_b200.model import Falcon
+    g = gold["falcon"]
+    lm = Falcon("tiny-falcon", model=_falcon(g), tokenizer=WordTokenizer(128))
+    assert lm.hf_model.supports_dynamic_n
+    eng = CacheEngine(256, lm)
+    eng.add_schema('<schema name="s"><module name="a">' + " ".join(f"w{i}" for i in range(70)) + '</module><module name="b">'
+                   + " ".join(f"v{i}" for i in range(45)) + "</module></schema>")
+    xml = '<prompt schema="s"><a/><b/>and then what</prompt>'
+    params = GenerationParameters(temperature=0.0, max_new_tokens=12, stop_token_ids=[], stop_str=[])
+
+    def run(graphs, device_sampling):
+        lm.hf_model.use_cuda_graphs = graphs
+        gen = GenerationEngine(lm)
+        gen.device_sampling = device_sampling
+        texts = []
+        for _ in range(2):  # the second request replays the decode graph captured during the first
+            ids, pos, _, cache = eng.process(Prompt(xml))
+            texts.append([o.new_text for o in gen.generate(ids, pos, params, cache, stream_interval=1)][-1])
+        return texts
+
+    eager = run(False, False)
+    replay = run(True, True)
+    assert eager[0] == eager[1] == replay[0] == replay[1] and len(eager[0].split()) == 12
+    assert any(k[0] == "decode" for k in lm.hf_model._graphs), "the decode step was not captured"
+
+
+@pytest.mark.parametrize("H,Hkv,D,q,N", [(71, 1, 64, 1, 300), (71, 1, 64, 1, 2100), (8, 2, 128, 40, 700), (71, 1, 64, 21, 256)])
+def test_long_suffix_kernel_runtime_length(native, H, Hkv, D, q, N):
+    """pc_prefill_attn with n_cached_dev on the ping-pong kernel: grid / maps sized for the upper bound, N read on device."""
+    g = torch.Generator(device="cpu").manual_seed(N + q)
+    max_ctx = 4096
+    Q = torch.randn(H, q, D, generator=g).half().to(DEV)
+    K = torch.zeros(Hkv, max_ctx, D, dtype=torch.half, device=DEV)
+    V = torch.zeros_like(K)
+    K[:, :N + q] = torch.randn(Hkv, N + q, D, generator=g).half().to(DEV)
+    V[:, :N + q] = torch.randn(Hkv, N + q, D, generator=g).half().to(DEV)
+    ws = torch.zeros(native.attn_workspace_bytes(H, q, D), dtype=torch.uint8, device=DEV)
+    rounding = native.PC_ROUND_FALCON if D == 64 else native.PC_ROUND_LLAMA
+    want = torch.empty(q, H * D, dtype=torch.half, device=DEV)
+    native.attention(Q, K, V, want, N, q, H, Hkv, D, native.softmax_scale(D), rounding, workspace=ws, impl=native.PC_ATTN_TCGEN05)
+    got = torch.full_like(want, float("nan"))
+    n_dev = torch.tensor([N], dtype=torch.int32, device=DEV)
+    native.attention(Q, K, V, got, max_ctx - q, q, H, Hkv, D, native.softmax_scale(D), rounding, workspace=ws,
+                     impl=native.PC_ATTN_TCGEN05, n_cached_dev=n_dev)
+    torch.cuda.synchronize()
+    assert torch.isfinite(got.float()).all()
+    assert _rel(got, want) <= 1e-3  # different split boundaries: fp32 summation order only
