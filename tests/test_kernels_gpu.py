@@ -310,10 +310,10 @@ def test_attention_runtime_length_equals_host_length(native):
                          n_cached_dev=n_dev, impl=native.PC_ATTN_TCGEN05)
         assert _rel(b, _oracle_llama(Q, K, V, N, q)) <= 1e-3
         assert float((a.float() - b.float()).abs().max()) <= 2e-3  # split partition may differ (sized for the upper bound)
-    with pytest.raises(native.NativeError):  # long suffixes have no run-time-length path
+    with pytest.raises(native.NativeError):  # the CUDA-core cross-check kernel has no run-time-length path
         Q, K, V = _attn_case(H, Hkv, D, 200, 100, seed=1)
         native.attention(Q, K, V, torch.empty(200, H * D, dtype=torch.half, device=DEV), 100, 200, H, Hkv, D, 0.1, 3, workspace=ws,
-                         n_cached_dev=torch.tensor([100], dtype=torch.int32, device=DEV))
+                         n_cached_dev=torch.tensor([100], dtype=torch.int32, device=DEV), impl=native.PC_ATTN_SIMT)
 
 
 @pytest.mark.parametrize("H,Hkv,q,N", [
