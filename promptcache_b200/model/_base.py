@@ -50,6 +50,7 @@ class B200CausalLM(nn.Module):
         self.use_cuda_graphs = True
         self._graphs = {}
         self._graph_seen = {}
+        self._decode_pos_len = {}
         self.max_graphs = 8
 
     @property
@@ -142,7 +143,12 @@ class B200CausalLM(nn.Module):
                 return None
             if len(self._graphs) >= self.max_graphs:
                 self._graphs.pop(next(iter(self._graphs)))
-            s_ids, s_pos = ids.clone(), pos.clone()
+            s_ids = ids.clone()
+            if self.full_position_ids:  # ids of every key: a max_ctx-long static buffer, filled up to N+1 per step
+                s_pos = torch.zeros(kv.max_ctx, dtype=pos.dtype, device=self.device)
+                s_pos[:pos.shape[0]].copy_(pos)
+            else:
+                s_pos = pos.clone()
             s_n = torch.full((1,), kv.n_cached, dtype=torch.int32, device=self.device)
             self._layers(s_ids, s_pos, kv, (), n_dev=s_n)  # warm-up; rewrites row n_cached with the same values
             torch.cuda.synchronize()
@@ -154,7 +160,14 @@ class B200CausalLM(nn.Module):
             self._graphs[key] = entry
         graph, s_ids, s_pos, s_n, s_logits, n_native = entry
         s_ids.copy_(ids, non_blocking=True)
-        s_pos.copy_(pos, non_blocking=True)
+        if self.full_position_ids:
+            n = pos.shape[0]
+            if n < self._decode_pos_len.get(key, 0):  # a shorter sequence than the last one on this buffer: clear stale ids
+                s_pos[n:].zero_()
+            self._decode_pos_len[key] = n
+            s_pos[:n].copy_(pos, non_blocking=True)
+        else:
+            s_pos.copy_(pos, non_blocking=True)
         s_n.fill_(kv.n_cached)
         graph.replay()
         nat.note_replayed_launches(n_native)
@@ -170,7 +183,7 @@ class B200CausalLM(nn.Module):
         if kv.virtual is not None and not (0 < q_len <= self.virtual_kv_max_q()):
             kv.virtual.materialise()  # this forward needs the contiguous rows: make the copy the engine skipped
             kv.virtual = None
-        if (q_len == 1 and N > 0 and self.use_cuda_graphs and self.supports_dynamic_n and not self.full_position_ids
+        if (q_len == 1 and N > 0 and self.use_cuda_graphs and self.supports_dynamic_n
                 and N + 1 < kv.max_ctx and not torch.cuda.is_current_stream_capturing()):
             logits = self._decode_replay(ids, pos, kv, static_ok)
             if logits is not None:

@@ -108,15 +108,17 @@ class MptForCausalLM(B200CausalLM):
         model.load_hf_state_dict(hf.state_dict())
         return model
 
-    def _graph_extra(self, pos_host_max: int):
-        return (int(pos_host_max),)  # alibi_max_pos is a kernel parameter
+    supports_dynamic_n = True  # decode graph: the key ids live in a max_ctx-long static buffer, N is read on the device
 
-    def _layers(self, ids: torch.Tensor, pos: torch.Tensor, kv, extra=()) -> torch.Tensor:
+    def _layers(self, ids: torch.Tensor, pos: torch.Tensor, kv, extra=(), n_dev=None) -> torch.Tensor:
         q_len = ids.shape[0]
         H, D, hid = self.n_heads, self.head_dim, self.hidden
         N = kv.n_cached
-        max_pos = int(extra[0])
-        key_pos = pos.to(torch.int32)  # ids of all N+q keys: cached rows in buffer order, then the new tokens
+        # ids of all N+q keys (cached rows in buffer order, then the new tokens), relative to max(position_ids)
+        # (mpt.py:522: the table is built for max(position_ids)+1 positions), computed on the device so that neither a
+        # host value nor a kernel parameter changes from step to step; with n_dev `pos` is the max_ctx-long static buffer
+        # (zeros behind the live ids, which never exceed the maximum)
+        key_pos = (pos - pos.max()).to(torch.int32)
         x = F.embedding(ids, self.wte)
         ln = torch.empty_like(x)
         q_out = torch.empty(H, q_len, D, dtype=torch.float16, device=self.device)
@@ -128,10 +130,11 @@ class MptForCausalLM(B200CausalLM):
             nat.add_layernorm(x, ffn, None, self.norm1[l], None, ln, self.eps)
             qkv = F.linear(ln, self.wqkv[l])                                                # chunk(3): q | k | v (:142-143)
             nat.rope_append(qkv[:, :hid], qkv[:, hid:2 * hid], qkv[:, 2 * hid:], None, None, None, q_out, kv.k[l], kv.v[l],
-                            N, H, H, D)                                                     # no rotary: transpose + append (:148-151)
-            nat.attention(q_out, kv.k[l], kv.v[l], ctx, N, q_len, H, H, D, self.scale, self.rounding, workspace=ws,
-                          alibi_slopes=self.slopes, key_pos=key_pos, alibi_max_pos=max_pos, impl=self.attn_impl,
-                          decode=(q_len == 1))                                              # :156-185
+                            N if n_dev is None else n_dev, H, H, D)                         # no rotary: transpose + append (:148-151)
+            nat.attention(q_out, kv.k[l], kv.v[l], ctx, N if n_dev is None else kv.max_ctx - q_len, q_len, H, H, D, self.scale,
+                          self.rounding, workspace=ws, alibi_slopes=self.slopes, key_pos=key_pos, alibi_max_pos=0,
+                          impl=self.attn_impl if n_dev is None else nat.PC_ATTN_TCGEN05, decode=(q_len == 1),
+                          n_cached_dev=n_dev)                                               # :156-185
             nat.add_layernorm(x, F.linear(ctx, self.wo[l]), None, self.norm2[l], None, ln, self.eps)   # x += attn (:251); norm_2
             ffn = F.linear(F.gelu(F.linear(ln, self.w_up[l])), self.w_down[l])              # MptMLP (:200-208)
         nat.add_layernorm(x, ffn, None, self.norm_f, None, ln, self.eps)

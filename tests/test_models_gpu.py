@@ -178,3 +178,32 @@ def test_long_suffix_kernel_runtime_length(native, H, Hkv, D, q, N):
     torch.cuda.synchronize()
     assert torch.isfinite(got.float()).all()
     assert _rel(got, want) <= 1e-3  # different split boundaries: fp32 summation order only
+
+
+@pytest.mark.parametrize("head_dim", [64, 128])  # 64: long-suffix kernel with ALiBi; 128: short-suffix kernel with ALiBi
+def test_mpt_decode_graph_with_full_position_ids_equals_eager_decode(native, head_dim):
+    """MPT decode replays one captured graph per KV buffer although every step carries the ids of ALL keys: they live in a
+    max_ctx-long static buffer, max(position_ids) is taken on the device, the cached length is a device scalar."""
+    from promptcache_b200 import CacheEngine, GenerationEngine, GenerationParameters, Prompt
+    from promptcache_b200.model import Mpt
+    from promptcache_b200.model.mpt import MptConfigLite, MptForCausalLM
+    torch.manual_seed(7)
+    model = MptForCausalLM(MptConfigLite(d_model=2 * head_dim, n_heads=2, n_layers=2, vocab_size=128), device=DEV)
+    lm = Mpt("tiny-mpt", model=model, tokenizer=WordTokenizer(128))
+    eng = CacheEngine(512, lm)
+    eng.add_schema('<schema name="s"><module name="a">' + " ".join(f"w{i}" for i in range(150)) + '</module><union><module name="b1">'
+                   + " ".join(f"v{i}" for i in range(45)) + '</module><module name="b2">x y z</module></union></schema>')
+    params = GenerationParameters(temperature=0.0, max_new_tokens=10, stop_token_ids=[], stop_str=[])
+
+    def run(graphs, xml):
+        model.use_cuda_graphs = graphs
+        gen = GenerationEngine(lm)
+        ids, pos, _, cache = eng.process(Prompt(xml), return_full_position_ids=True)
+        return [o.new_text for o in gen.generate(ids, pos, params, cache, stream_interval=1, use_full_position_ids=True)][-1]
+
+    long_xml = '<prompt schema="s"><a/><b1/>and then what</prompt>'
+    short_xml = '<prompt schema="s"><b2/>tell me</prompt>'  # a much shorter sequence on the same buffer: stale ids must not leak
+    eager = [run(False, long_xml), run(False, short_xml), run(False, long_xml)]
+    replay = [run(True, long_xml), run(True, short_xml), run(True, long_xml)]
+    assert eager == replay and len(eager[0].split()) == 10
+    assert any(k[0] == "decode" for k in model._graphs)
