@@ -202,6 +202,10 @@ int pc_silu_mul(const void* gate_up, void* out, int rows, int inter, int64_t row
  *   MPT     x + attn_out -> norm_2 ; x + ffn_out -> norm_1    mpt.py:220-222,246-268 */
 int pc_add_layernorm(void* x, const void* d1, const void* d2, const void* weight, const void* bias, void* h_out, int rows,
                      int hidden, float eps, void* stream);
+/* Same with the single delta given as `n_splits` fp32 split-K partials [split][rows][hidden] (PC_LIN_PARTIALS output),
+ * added in split order and rounded to fp16 once before the residual add. */
+int pc_add_layernorm_partials(void* x, const void* delta_partials, int n_splits, const void* weight, const void* bias,
+                              void* h_out, int rows, int hidden, float eps, void* stream);
 /* pc_add_rmsnorm whose delta is the sum of `n_splits` fp32 partials [split][rows][hidden] (PC_LIN_PARTIALS output),
  * added in split order and rounded to fp16 once before the fp16 residual add. */
 int pc_add_rmsnorm_partials(void* x, const void* delta_partials, int n_splits, const void* weight, void* h_out, int rows,
@@ -230,6 +234,7 @@ int pc_add_rmsnorm_partials(void* x, const void* delta_partials, int n_splits, c
  * (out_stride == n_rows); the consumer adds the splits in order and rounds once -- pc_add_rmsnorm_partials does that
  * for the o_proj / down_proj outputs, whose only consumer is the residual add (llama2.py:636,644).  No workspace use. */
 #define PC_LIN_PARTIALS 3
+#define PC_LIN_ACT_GELU 1
 
 typedef struct pc_linear_params {
   const void* x;
@@ -249,7 +254,7 @@ typedef struct pc_linear_params {
   int32_t dst_row0;
   int32_t n_heads;
   int32_t n_kv_heads;
-  int32_t reserved;
+  int32_t activation; /* PLAIN only: 0, or PC_LIN_ACT_GELU = exact GELU of the fp16-rounded output (MPT / Falcon MLP) */
   const int32_t* dst_row0_dev;
   void* workspace;
   size_t workspace_bytes;

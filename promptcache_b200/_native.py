@@ -28,7 +28,7 @@ PC_ATTN_GLOBAL_MERGE = 0x100
 
 EXPORTS = ("pc_version", "pc_last_error", "pc_device_info", "pc_splice_kv", "pc_splice_kv_strided", "pc_splice_kv_tensors",
            "pc_rope_append", "pc_rope_append_dyn", "pc_attn_workspace_bytes", "pc_prefill_attn", "pc_decode_attn", "pc_launch_count",
-           "pc_add_rmsnorm", "pc_add_layernorm", "pc_silu_mul", "pc_linear_workspace_bytes", "pc_linear_small",
+           "pc_add_rmsnorm", "pc_add_layernorm", "pc_add_layernorm_partials", "pc_silu_mul", "pc_linear_workspace_bytes", "pc_linear_small",
            "pc_linear_tiled_bytes", "pc_linear_tile_weights", "pc_linear_partial_splits", "pc_add_rmsnorm_partials")
 PC_LIN_PLAIN = 0
 PC_LIN_SILU_MUL = 1
@@ -69,7 +69,7 @@ class pc_linear_params(C.Structure):
                 ("position_ids", C.c_void_p), ("cos", C.c_void_p), ("sin", C.c_void_p),
                 ("table_rows", C.c_int32), ("max_ctx", C.c_int32),
                 ("q_out", C.c_void_p), ("k_cache", C.c_void_p), ("v_cache", C.c_void_p),
-                ("dst_row0", C.c_int32), ("n_heads", C.c_int32), ("n_kv_heads", C.c_int32), ("reserved", C.c_int32),
+                ("dst_row0", C.c_int32), ("n_heads", C.c_int32), ("n_kv_heads", C.c_int32), ("activation", C.c_int32),
                 ("dst_row0_dev", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
                 ("w_tiled", C.c_void_p), ("prefetch_next", C.c_void_p)]
 
@@ -120,6 +120,9 @@ def load() -> C.CDLL:
     lib.pc_add_layernorm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float,
                                      C.c_void_p]
     lib.pc_add_layernorm.restype = C.c_int
+    lib.pc_add_layernorm_partials.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                              C.c_float, C.c_void_p]
+    lib.pc_add_layernorm_partials.restype = C.c_int
     lib.pc_silu_mul.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]
     lib.pc_silu_mul.restype = C.c_int
     lib.pc_linear_workspace_bytes.argtypes = []
@@ -346,8 +349,18 @@ def add_rmsnorm(x: torch.Tensor, delta: Optional[torch.Tensor], weight: torch.Te
 
 def add_layernorm(x: torch.Tensor, d1: Optional[torch.Tensor], d2: Optional[torch.Tensor], weight: torch.Tensor,
                   bias: Optional[torch.Tensor], h_out: torch.Tensor, eps: float) -> None:
-    """x[rows,hidden] = half(x + half(d1 + d2)) in place (either delta may be None), h_out = LayerNorm(x) * weight + bias."""
+    """x[rows,hidden] = half(x + half(d1 + d2)) in place (either delta may be None), h_out = LayerNorm(x) * weight + bias.
+    An fp32 3-D `d1` is a stack of split-K partials [splits, rows, hidden] (linear_partials)."""
     _require_cuda(x, weight, h_out, d1, d2, bias)
+    if d1 is not None and d1.dtype == torch.float32:
+        rows, hidden = x.shape
+        if d2 is not None or d1.dim() != 3 or tuple(d1.shape[1:]) != (rows, hidden) or not (d1.is_contiguous() and x.is_contiguous()
+                                                                                          and h_out.is_contiguous()):
+            raise NativeError("add_layernorm: partials must be a contiguous fp32 [splits, rows, hidden] stack (and d2 None)")
+        _check(load().pc_add_layernorm_partials(x.data_ptr(), d1.data_ptr(), d1.shape[0], weight.data_ptr(),
+                                                bias.data_ptr() if bias is not None else None, h_out.data_ptr(), rows, hidden, float(eps),
+                                                _stream()), "pc_add_layernorm_partials")
+        return
     for t in (x, h_out, d1, d2):
         if t is not None and (not t.is_contiguous() or t.dtype != torch.float16 or t.shape != x.shape):
             raise NativeError("add_layernorm: x / deltas / h_out must be contiguous fp16 tensors of one shape")
@@ -417,9 +430,14 @@ def _linear_params(x: torch.Tensor, w: torch.Tensor, workspace: torch.Tensor, ep
 
 
 def linear_small(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, workspace: torch.Tensor, silu_mul: bool = False,
-                 w_tiled: Optional[torch.Tensor] = None, nxt=None) -> None:
-    """out[q, n] = x[q, k] @ w[n, k]^T  (q <= 32), or with `silu_mul` out[q, n/2] = silu(x @ w[:n/2]^T) * (x @ w[n/2:]^T)."""
+                 w_tiled: Optional[torch.Tensor] = None, nxt=None, gelu: bool = False) -> None:
+    """out[q, n] = x[q, k] @ w[n, k]^T  (q <= 32), or with `silu_mul` out[q, n/2] = silu(x @ w[:n/2]^T) * (x @ w[n/2:]^T);
+    `gelu`: exact GELU of the fp16-rounded product (the MLP activation of MPT / Falcon fused into the up projection)."""
     p = _linear_params(x, w, workspace, PC_LIN_SILU_MUL if silu_mul else PC_LIN_PLAIN, w_tiled, nxt)
+    if gelu:
+        if silu_mul:
+            raise NativeError("linear_small: gelu and silu_mul are exclusive")
+        p.activation = 1
     _require_cuda(out)
     cols = w.shape[0] // 2 if silu_mul else w.shape[0]
     if out.dim() != 2 or out.dtype != torch.float16 or out.stride(1) != 1 or out.shape[0] != x.shape[0] or out.shape[1] != cols:

@@ -96,6 +96,7 @@ struct LinParams {
   // L2 prefetch of the NEXT linear's weight stream (pre-tiled): once this CTA has issued its last weight load it asks
   // L2 for the first pf_units pipeline stages of the CTAs of the next launch (their partition is replayed here), so
   // that the next kernel's ring fills from L2 instead of paying the HBM latency after every launch boundary
+  int act;               // PLAIN: 1 = exact GELU applied to the fp16-rounded output (mpt.py:200-208 / falcon MLP)
   const unsigned char* pf_w;
   long long pf_units_total;
   int pf_kb, pf_grid, pf_whole, pf_splits, pf_units;
@@ -480,6 +481,14 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
         if constexpr (EPI == PC_LIN_PLAIN || EPI == PC_LIN_PARTIALS) {
           const int col = tile * BM + f;
           if (col < p.n_out) {
+            if (EPI == PC_LIN_PLAIN && p.act == 1) {
+              // nn.GELU() on the fp16 output of the projection: 0.5 x (1 + erf(x / sqrt 2)) in fp32, rounded once
+#pragma unroll
+              for (int t = 0; t < NPAD; ++t) {
+                const float xg = __half2float(__float2half_rn(v[t]));
+                v[t] = 0.5f * xg * (1.f + erff(xg * 0.70710678118654752440f));
+              }
+            }
 #pragma unroll
             for (int t = 0; t < NPAD; ++t)
               if (t < p.q_len) p.out[t * p.out_stride + col] = __float2half_rn(v[t]);
@@ -821,6 +830,9 @@ PC_API int pc_linear_small(const pc_linear_params* p, void* stream) {
   lp.row0_dev = p->dst_row0_dev;
   lp.n_heads = p->n_heads;
   lp.n_kv_heads = p->n_kv_heads;
+  lp.act = (p->epilogue == PC_LIN_PLAIN && p->activation == PC_LIN_ACT_GELU) ? 1 : 0;
+  PC_REQUIRE(p->activation == 0 || (p->epilogue == PC_LIN_PLAIN && p->activation == PC_LIN_ACT_GELU),
+             "pc_linear_small: activation %d (only PC_LIN_ACT_GELU with PC_LIN_PLAIN)", p->activation);
   lp.trace = nullptr;
   if (const char* e = dbg_env("PC_LIN_TRACE_PTR")) lp.trace = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
 

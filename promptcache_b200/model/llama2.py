@@ -82,7 +82,6 @@ class LlamaForCausalLM(B200CausalLM):
         self.norm = ones()
         self.lm_head = w(c.vocab_size, hid)
         self._init_runtime()
-        self._tiled = {}  # pre-tiled copies of the weights for pc_linear_small, built on first native use
         self._hints = {}  # prefetch_next descriptions of the native linears
         self.rounding = nat.PC_ROUND_LLAMA
         self.scale = nat.softmax_scale(self.head_dim)
@@ -119,15 +118,6 @@ class LlamaForCausalLM(B200CausalLM):
         model = cls(cfg, device=device)
         model.load_hf_state_dict(hf.state_dict())
         return model
-
-    def _wt(self, key, w: torch.Tensor, epilogue: int):
-        """Pre-tiled copy of a weight (pc_linear_tile_weights): doubles the memory of the matrices it is used for, and
-        lets one SM stream ~1.5x more bytes per second than 128-byte-row tensor-map boxes do."""
-        t = self._tiled.get(key)
-        if t is None:
-            t = nat.tile_weights(w, epilogue) if self.linear_tiled else None
-            self._tiled[key] = t if t is not None else False
-        return t if t is not False else None
 
     def _layers_ablated(self, x, h, pos, kv, q_rot, attn_out, act, ws, lws, pbuf_o, pbuf_d, n_dev):
         """The native q <= linear_max_q step with the kernel families named in `self.ablate` left out ("linear", "attn",

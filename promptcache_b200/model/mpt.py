@@ -124,18 +124,42 @@ class MptForCausalLM(B200CausalLM):
         q_out = torch.empty(H, q_len, D, dtype=torch.float16, device=self.device)
         ctx = torch.empty(q_len, H * D, dtype=torch.float16, device=self.device)
         ws = self._workspace(q_len)
+        nd = N if n_dev is None else n_dev  # run-time cached length (decode graph); N is then only the sizing upper bound
+        # few tokens: the projections / MLP are weight streams -> pc_linear_small (no-rotary append in the QKV epilogue, GELU in the
+        # up projection's, out_proj / down_proj as split-K partials the next add+LayerNorm reduces); otherwise cuBLAS
+        lin = self.linear_impl == "native" and q_len <= self.linear_max_q and D == 128 and hid % 128 == 0
+        if lin:
+            lws = self._linear_workspace()
+            act = torch.empty(q_len, self.inter, dtype=torch.float16, device=self.device)
+            pbuf_o = torch.empty(nat.linear_partial_splits(hid, hid), q_len, hid, dtype=torch.float32, device=self.device)
+            pbuf_d = torch.empty(nat.linear_partial_splits(hid, self.inter), q_len, hid, dtype=torch.float32, device=self.device)
         ffn = None
         for l in range(self.n_layers):
             # x += ffn of the previous block (:208) and norm_1, bias dropped (mpt.py:220-222): one launch
             nat.add_layernorm(x, ffn, None, self.norm1[l], None, ln, self.eps)
-            qkv = F.linear(ln, self.wqkv[l])                                                # chunk(3): q | k | v (:142-143)
-            nat.rope_append(qkv[:, :hid], qkv[:, hid:2 * hid], qkv[:, 2 * hid:], None, None, None, q_out, kv.k[l], kv.v[l],
-                            N if n_dev is None else n_dev, H, H, D)                         # no rotary: transpose + append (:148-151)
+            if lin:
+                nat.linear_rope_append(ln, self.wqkv[l], None, None, None, q_out, kv.k[l], kv.v[l], nd, H, H, lws,
+                                       w_tiled=self._wt(("qkv", l), self.wqkv[l], nat.PC_LIN_ROPE_APPEND))  # q | k | v heads, no rotary
+            else:
+                qkv = F.linear(ln, self.wqkv[l])                                            # chunk(3): q | k | v (:142-143)
+                nat.rope_append(qkv[:, :hid], qkv[:, hid:2 * hid], qkv[:, 2 * hid:], None, None, None, q_out, kv.k[l], kv.v[l],
+                                nd, H, H, D)                                                # no rotary: transpose + append (:148-151)
             nat.attention(q_out, kv.k[l], kv.v[l], ctx, N if n_dev is None else kv.max_ctx - q_len, q_len, H, H, D, self.scale,
                           self.rounding, workspace=ws, alibi_slopes=self.slopes, key_pos=key_pos, alibi_max_pos=0,
                           impl=self.attn_impl if n_dev is None else nat.PC_ATTN_TCGEN05, decode=(q_len == 1),
                           n_cached_dev=n_dev)                                               # :156-185
-            nat.add_layernorm(x, F.linear(ctx, self.wo[l]), None, self.norm2[l], None, ln, self.eps)   # x += attn (:251); norm_2
-            ffn = F.linear(F.gelu(F.linear(ln, self.w_up[l])), self.w_down[l])              # MptMLP (:200-208)
+            if lin:
+                nat.linear_partials(ctx, self.wo[l], pbuf_o, lws, w_tiled=self._wt(("o", l), self.wo[l], nat.PC_LIN_PARTIALS))
+                nat.add_layernorm(x, pbuf_o, None, self.norm2[l], None, ln, self.eps)       # x += attn (:251); norm_2
+                nat.linear_small(ln, self.w_up[l], act, lws, gelu=True, w_tiled=self._wt(("up", l), self.w_up[l], nat.PC_LIN_PLAIN))
+                nat.linear_partials(act, self.w_down[l], pbuf_d, lws, w_tiled=self._wt(("down", l), self.w_down[l], nat.PC_LIN_PARTIALS))
+                ffn = pbuf_d                                                                # MptMLP (:200-208)
+            else:
+                nat.add_layernorm(x, F.linear(ctx, self.wo[l]), None, self.norm2[l], None, ln, self.eps)
+                ffn = F.linear(F.gelu(F.linear(ln, self.w_up[l])), self.w_down[l])
         nat.add_layernorm(x, ffn, None, self.norm_f, None, ln, self.eps)
+        if lin:
+            logits = torch.empty(q_len, self.vocab_size, dtype=torch.float16, device=self.device)
+            nat.linear_small(ln, self.wte, logits, lws, w_tiled=self._wt(("lm_head", 0), self.wte, nat.PC_LIN_PLAIN))
+            return logits.float()
         return F.linear(ln, self.wte).float()

@@ -209,3 +209,41 @@ def test_model_native_linears_match_cublas_linears(native):
     assert a[2] >= 2 * 7 and b[2] >= 2 * 5  # native: 7 launches of this library per layer; cuBLAS path: 5 (+4 library GEMMs)
     for other in res["native"][1:]:  # eager, then captured and replayed
         assert torch.equal(other[0], a[0]) and torch.equal(other[1], a[1])
+
+
+@pytest.mark.parametrize("q,k,n", [(16, 4096, 16384), (1, 512, 2048), (9, 4096, 640)])
+def test_gelu_epilogue_equals_gelu_of_the_fp16_projection(native, q, k, n):
+    """PLAIN + PC_LIN_ACT_GELU: nn.GELU() of the fp16-rounded projection (mpt.py:200-208), on integer-valued inputs so the
+    projection itself is exact."""
+    g = torch.Generator(device="cpu").manual_seed(q + k + n)
+    x = torch.randint(-2, 3, (q, k), generator=g).half().to(DEV)
+    w = (torch.randint(-2, 3, (n, k), generator=g).float() / 64).half().to(DEV)
+    ws = native.linear_workspace(DEV)
+    want = torch.nn.functional.gelu((x.double() @ w.double().t()).half())
+    for tiled in (False, True):
+        wt = native.tile_weights(w, native.PC_LIN_PLAIN) if tiled else None
+        out = torch.empty(q, n, dtype=torch.half, device=DEV)
+        native.linear_small(x, w, out, ws, gelu=True, w_tiled=wt)
+        torch.cuda.synchronize()
+        assert float((out.float() - want.float()).abs().max()) <= 2e-3 * float(want.float().abs().max())
+        assert float((out != want).float().mean()) < 1e-3  # erf implementations agree to the last bit almost everywhere
+
+
+def test_add_layernorm_partials_equal_linear_then_add_layernorm(native):
+    g = torch.Generator(device="cpu").manual_seed(3)
+    q, k, n = 12, 4096, 4096
+    x_in = torch.randint(-2, 3, (q, k), generator=g).half().to(DEV)
+    w = (torch.randint(-2, 3, (n, k), generator=g).float() / 64).half().to(DEV)
+    res = torch.randn(q, n, generator=g).half().to(DEV)
+    lw = (1 + 0.1 * torch.randn(n, generator=g)).half().to(DEV)
+    ws = native.linear_workspace(DEV)
+    part = torch.empty(native.linear_partial_splits(n, k), q, n, dtype=torch.float32, device=DEV)
+    native.linear_partials(x_in, w, part, ws, w_tiled=native.tile_weights(w, native.PC_LIN_PARTIALS))
+    a_x, a_h = res.clone(), torch.empty_like(res)
+    native.add_layernorm(a_x, part, None, lw, None, a_h, 1e-5)
+    out = torch.empty(q, n, dtype=torch.half, device=DEV)
+    native.linear_small(x_in, w, out, ws)
+    b_x, b_h = res.clone(), torch.empty_like(res)
+    native.add_layernorm(b_x, out, None, lw, None, b_h, 1e-5)
+    torch.cuda.synchronize()
+    assert torch.equal(a_x, b_x) and torch.equal(a_h, b_h)

@@ -207,3 +207,35 @@ def test_mpt_decode_graph_with_full_position_ids_equals_eager_decode(native, hea
     replay = [run(True, long_xml), run(True, short_xml), run(True, long_xml)]
     assert eager == replay and len(eager[0].split()) == 10
     assert any(k[0] == "decode" for k in model._graphs)
+
+
+def test_mpt_native_linears_match_cublas_step_and_oracle(native):
+    """MPT block on the weight-streaming kernels (no-rotary append in the QKV epilogue, GELU in the up projection's,
+    split-K partials reduced by the fused add+LayerNorm) vs the cuBLAS step vs the oracle's eager forward."""
+    from promptcache_b200.model.mpt import MptConfigLite, MptForCausalLM
+    torch.manual_seed(11)
+    model = MptForCausalLM(MptConfigLite(d_model=512, n_heads=4, n_layers=3, vocab_size=640), device=DEV)
+    g = torch.Generator().manual_seed(5)
+    pre_ids = torch.randint(3, 640, (1, 300), generator=g).to(DEV)
+    pre_pos = torch.arange(300, device=DEV).unsqueeze(0)
+    suf_ids = torch.randint(3, 640, (1, 9), generator=g).to(DEV)
+    full_pos = torch.cat([pre_pos, torch.arange(340, 349, device=DEV).unsqueeze(0)], dim=1)
+    outs = {}
+    for impl in ("native", "cublas"):
+        model.linear_impl = impl
+        past = model(pre_ids, pre_pos, use_cache=True).past_key_values
+        launches0 = native.launch_count()
+        outs[impl] = model(suf_ids, full_pos, past_key_values=past, use_cache=True).logits
+        outs[impl + "_launches"] = native.launch_count() - launches0
+    assert _rel(outs["native"], outs["cublas"]) <= 2e-3
+    assert outs["native_launches"] > outs["cublas_launches"]  # the linears went through the C ABI
+    sd = {"transformer.wte.weight": model.wte, "transformer.norm_f.weight": model.norm_f}
+    for l in range(3):
+        p = f"transformer.blocks.{l}."
+        sd.update({p + "norm_1.weight": model.norm1[l], p + "norm_2.weight": model.norm2[l], p + "attn.Wqkv.weight": model.wqkv[l],
+                   p + "attn.out_proj.weight": model.wo[l], p + "ffn.up_proj.weight": model.w_up[l], p + "ffn.down_proj.weight": model.w_down[l]})
+    sd = {k: v.detach() for k, v in sd.items()}
+    cfg = dict(n_layers=3, n_heads=4, eps=1e-5)
+    r1, rp = O.mpt_forward(sd, cfg, pre_ids, pre_pos)
+    r2, _ = O.mpt_forward(sd, cfg, suf_ids, full_pos, rp)
+    assert _rel(outs["native"], r2) <= 3e-3
