@@ -1,3 +1,4 @@
+# NOTE: needs a debug build of the library: PC_NVCC_EXTRA=-DPC_DEBUG python tools/debug_attn.py  (product builds compile the env / trace hooks out)
 import os, sys, math, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from promptcache_b200 import _native as nat

@@ -1,4 +1,5 @@
 """Is the spread of CTA finish times in a saturating weight stream tied to the SM (systematic) or random?"""
+# NOTE: needs a debug build of the library: PC_NVCC_EXTRA=-DPC_DEBUG python tools/smid_probe.py  (product builds compile the env / trace hooks out)
 import os, sys, torch
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

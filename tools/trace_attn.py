@@ -1,4 +1,5 @@
 """Debug: %globaltimer stamps of CTA 0 of the short-suffix attention kernel (PC_ATTN_TRACE_PTR)."""
+# NOTE: needs a debug build of the library: PC_NVCC_EXTRA=-DPC_DEBUG python tools/trace_attn.py  (product builds compile the env / trace hooks out)
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from promptcache_b200 import _native as nat

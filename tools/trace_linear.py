@@ -1,4 +1,5 @@
 """Debug: per-CTA %globaltimer stamps of pc_linear_small (PC_LIN_TRACE_PTR) -> where a launch spends its time."""
+# NOTE: needs a debug build of the library: PC_NVCC_EXTRA=-DPC_DEBUG python tools/trace_linear.py  (product builds compile the env / trace hooks out)
 import os, sys, torch
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
