@@ -222,8 +222,12 @@ def timed_broadcast(schema_cache, dev):
     """NCCL broadcast of the encoded segment store from rank 0, device-timed, max over ranks."""
     import torch.distributed as dist
     from promptcache_b200 import parallel
-    warm = torch.zeros(1024, device=dev)
-    dist.broadcast(warm, src=0)  # the first collective of a process group sets up the NCCL communicator (~100 ms): not timed
+    # the first collectives of a process group set up the NCCL communicator and, for large messages, its channels / buffers
+    # (~50-100 ms): warm both up, untimed
+    warm = torch.zeros(32 << 20, dtype=torch.half, device=dev)
+    for _ in range(2):
+        dist.broadcast(warm, src=0)
+    del warm
     dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

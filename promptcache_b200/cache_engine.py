@@ -207,7 +207,7 @@ class PromptCache:
         if any(m.arena is not arena for m in ordered) or arena.device != self.buffer.device or arena.dtype != self.buffer.dtype \
                 or tuple(arena.shape[:3]) != tuple(self.buffer.shape[:3]) or arena.shape[4] != self.head_dim or not arena.is_contiguous():
             return False  # segments from different allocations: the copy is made instead
-        key = tuple(id(m) for m in ordered)
+        key = (arena.data_ptr(),) + tuple((m.row0, len(m)) for m in ordered)  # what the tile list is a function of
         t = self._tiles_count.get(key) if key == self._tiles_key else None
         if t is None:  # the device list holds another request's tiles: build this layout's list and upload it
             tiles = []
