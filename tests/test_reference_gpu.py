@@ -339,3 +339,49 @@ def test_sampling_paths_equal_the_reference_generation_loop(native, kw, stream_i
     assert got == want and len(want) >= 1
     # whole-tile segments: the virtual splice is bit-identical to the copy, so sampling through it draws the same tokens
     assert run(GenerationEngine, GenerationParameters, True) == want
+
+
+def test_full_position_ids_describe_the_rows_even_when_usage_counters_reorder_the_layout(native):
+    """Documented deviation: `return_full_position_ids` (MPT's ALiBi needs the id of every cached row,
+    cache_engine.py:517-519).  The reference returns the ids in VISIT order while `PromptCache.update` lays the rows out in
+    USAGE order (:121) -- once a module is hotter than the ones visited before it, its ids no longer describe its rows.
+    Here the ids follow the buffer.  Both engines run on the GPU; the reference's own buffer is the witness."""
+    from oracle import ref_runner
+    from promptcache_b200 import CacheEngine, Prompt
+    from promptcache_b200.model import Llama2, LlamaConfigLite, LlamaForCausalLM
+    from promptcache_b200.synthetic import IdTokenizer
+    ref_shim.load_reference()
+    from promptcache import CacheEngine as RefEngine, Prompt as RefPrompt
+    dims = dict(vocab_size=256, hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
+                num_key_value_heads=2, max_position_embeddings=256, rms_norm_eps=1e-5)
+    tok = IdTokenizer(256)
+    ref_lm = ref_runner.build_reference_lm("llama", dims, tok, dtype=torch.float16, device=DEV, seed=3)
+    model = LlamaForCausalLM(LlamaConfigLite(**dims), device=DEV)
+    model.load_hf_state_dict(ref_lm.hf_model.state_dict())
+    lm = Llama2("tiny", model=model, tokenizer=tok)
+    schema = ('<schema name="s"><module name="a">t10 t11 t12</module><module name="b">t20 t21 t22 t23 t24</module>'
+              '<module name="c">t30 t31</module></schema>')
+    ref_eng, eng = RefEngine(64, ref_lm, target_device=DEV), CacheEngine(64, lm)
+    ref_eng.add_schema(schema)
+    eng.add_schema(schema)
+    hot, full = '<prompt schema="s"><b/>t50</prompt>', '<prompt schema="s"><a/><b/><c/>t50 t51</prompt>'
+    for e, P in ((ref_eng, RefPrompt), (eng, Prompt)):
+        for _ in range(2):
+            e.process(P(hot), return_full_position_ids=True)  # module b becomes the most used one
+    r_ids, r_pos, _, r_cache = ref_eng.process(RefPrompt(full), return_full_position_ids=True)
+    ids, pos, _, cache = eng.process(Prompt(full), return_full_position_ids=True)
+    assert list(ids) == list(r_ids) and sorted(pos) == sorted(r_pos) and len(pos) == 10 + 2
+    # our ids follow the buffer: b (offset 3, hottest) first, then the visit order of the rest
+    layout = [(m.token_sequence.offset, len(m)) for m in eng.prompt_cache.staged]
+    assert layout[0] == (3, 5)
+    want = [o + i for o, n in layout for i in range(n)]
+    assert pos[:10] == want
+    row = 0
+    for m in eng.prompt_cache.staged:  # and the rows really are those segments
+        assert torch.equal(cache[0][0][:, row:row + len(m)], m.cache[0][0])
+        row += len(m)
+    # the reference: rows in usage order (b first) ...
+    b_entry = next(m for m in ref_eng.prompt_cache.staged if m.token_sequence.offset == 3)
+    assert torch.equal(r_cache[0][0][:, :5].cpu(), b_entry.cache[0][0].cpu().to(r_cache[0][0].dtype))
+    # ... but ids in visit order: the ids it hands to MPT for rows 0-4 are not b's ids
+    assert r_pos[:10] != want and r_pos[:5] != [3, 4, 5, 6, 7]
