@@ -207,14 +207,22 @@ class PromptCache:
         if any(m.arena is not arena for m in ordered) or arena.device != self.buffer.device or arena.dtype != self.buffer.dtype \
                 or tuple(arena.shape[:3]) != tuple(self.buffer.shape[:3]) or arena.shape[4] != self.head_dim or not arena.is_contiguous():
             return False  # segments from different allocations: the copy is made instead
-        key = (arena.data_ptr(),) + tuple((m.row0, len(m)) for m in ordered)  # what the tile list is a function of
+        # Cached keys are visible to every query row, so their ORDER is irrelevant to attention: the tile list walks the
+        # used segments in arena order and lets a tile run across segments that are neighbours in the arena (C2: the seven
+        # segments of the schema are one contiguous run of 2048 rows = 16 tiles instead of 22 partly empty ones).
+        runs: List[List[int]] = []
+        for r0, n in sorted((m.row0, len(m)) for m in ordered):
+            if runs and runs[-1][0] + runs[-1][1] == r0:
+                runs[-1][1] += n
+            else:
+                runs.append([r0, n])
+        key = (arena.data_ptr(),) + tuple(map(tuple, runs))  # what the tile list is a function of
         t = self._tiles_count.get(key) if key == self._tiles_key else None
         if t is None:  # the device list holds another request's tiles: build this layout's list and upload it
             tiles = []
-            for m in ordered:
-                n = len(m)
+            for r0, n in runs:
                 for r in range(0, n, 128):
-                    tiles.append((m.row0 + r, min(128, n - r)))
+                    tiles.append((r0 + r, min(128, n - r)))
             if len(tiles) > self._tiles_dev.shape[0]:
                 return False
             t = len(tiles)
