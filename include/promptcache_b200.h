@@ -202,10 +202,11 @@ int pc_silu_mul(const void* gate_up, void* out, int rows, int inter, int64_t row
  *   MPT     x + attn_out -> norm_2 ; x + ffn_out -> norm_1    mpt.py:220-222,246-268 */
 int pc_add_layernorm(void* x, const void* d1, const void* d2, const void* weight, const void* bias, void* h_out, int rows,
                      int hidden, float eps, void* stream);
-/* Same with the single delta given as `n_splits` fp32 split-K partials [split][rows][hidden] (PC_LIN_PARTIALS output),
- * added in split order and rounded to fp16 once before the residual add. */
-int pc_add_layernorm_partials(void* x, const void* delta_partials, int n_splits, const void* weight, const void* bias,
-                              void* h_out, int rows, int hidden, float eps, void* stream);
+/* Same with the deltas given as fp32 split-K partials [split][rows][hidden] (PC_LIN_PARTIALS output): each stack is added in
+ * split order and rounded to fp16 once (= the fp16 output of its linear), then x = half(x + half(d1 + d2)).  The second
+ * stack is optional (NULL, 0): MPT has one delta per norm, Falcon's parallel block two (attention dense + MLP). */
+int pc_add_layernorm_partials(void* x, const void* delta_partials, int n_splits, const void* delta2_partials, int n_splits2,
+                              const void* weight, const void* bias, void* h_out, int rows, int hidden, float eps, void* stream);
 /* pc_add_rmsnorm whose delta is the sum of `n_splits` fp32 partials [split][rows][hidden] (PC_LIN_PARTIALS output),
  * added in split order and rounded to fp16 once before the fp16 residual add. */
 int pc_add_rmsnorm_partials(void* x, const void* delta_partials, int n_splits, const void* weight, void* h_out, int rows,
@@ -221,7 +222,7 @@ int pc_add_rmsnorm_partials(void* x, const void* delta_partials, int n_splits, c
  * (split-K partials included, added in a fixed order: results are deterministic), one rounding to fp16.
  *   PLAIN        out[t][r] = half(sum)                                        out: [q_len][out_stride]
  *   SILU_MUL     w = [gate rows (n_rows/2); up rows (n_rows/2)];  out[t][i] = half(silu_f32(half(gate_i))) * half(up_i)
- *   ROPE_APPEND  w = [q heads; k heads; v heads] of head_dim 128; the fp16 projections get the same treatment as
+ *   ROPE_APPEND  w = [q heads; k heads; v heads] of head_dim 128 or 64; the fp16 projections get the same treatment as
  *                pc_rope_append (bit-identical to it on the same fp16 inputs): rotated Q -> q_out[H][q_len][128],
  *                rotated K and V -> rows [dst_row0, dst_row0+q_len) of k_cache/v_cache[Hkv][max_ctx][128];
  *                cos == NULL skips the rotation; dst_row0_dev != NULL reads the row on the device.
@@ -265,6 +266,8 @@ typedef struct pc_linear_params {
                         * stream (only k, n_rows, epilogue, n_heads, n_kv_heads and w_tiled are read, during this call).     *
                         * Each CTA, once its own weight loads are all in flight, asks L2 for the first pipeline stages the   *
                         * CTAs of that launch will read, so its ring fills from L2 across the launch boundary.  A hint only. */
+  int32_t head_dim;    /* ROPE_APPEND: 128 (0 means 128) or 64 (Falcon: two heads per 128-row tile, tables [T][64])          */
+  int32_t reserved;
 } pc_linear_params;
 
 size_t pc_linear_workspace_bytes(void);
@@ -272,6 +275,7 @@ int pc_linear_partial_splits(int n_rows, int k);
 int pc_linear_small(const pc_linear_params* p, void* stream);
 /* One-off re-layout of w[n_rows][k] for `epilogue` into pc_linear_tiled_bytes(n_rows, k, epilogue) bytes at w_tiled:
  * the [tile][k-block] sequence of 16 KiB shared-memory images (128 rows x 64 columns, 128B-swizzled) the kernel consumes. */
+/* k must be a multiple of 64; an odd number of 64-column blocks is padded with one block of zeros in the copy. */
 size_t pc_linear_tiled_bytes(int n_rows, int k, int epilogue);
 int pc_linear_tile_weights(const void* w, int n_rows, int k, int epilogue, void* w_tiled, void* stream);
 

@@ -71,7 +71,7 @@ class pc_linear_params(C.Structure):
                 ("q_out", C.c_void_p), ("k_cache", C.c_void_p), ("v_cache", C.c_void_p),
                 ("dst_row0", C.c_int32), ("n_heads", C.c_int32), ("n_kv_heads", C.c_int32), ("activation", C.c_int32),
                 ("dst_row0_dev", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
-                ("w_tiled", C.c_void_p), ("prefetch_next", C.c_void_p)]
+                ("w_tiled", C.c_void_p), ("prefetch_next", C.c_void_p), ("head_dim", C.c_int32), ("reserved", C.c_int32)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -120,8 +120,8 @@ def load() -> C.CDLL:
     lib.pc_add_layernorm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float,
                                      C.c_void_p]
     lib.pc_add_layernorm.restype = C.c_int
-    lib.pc_add_layernorm_partials.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
-                                              C.c_float, C.c_void_p]
+    lib.pc_add_layernorm_partials.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_int, C.c_int, C.c_float, C.c_void_p]
     lib.pc_add_layernorm_partials.restype = C.c_int
     lib.pc_silu_mul.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]
     lib.pc_silu_mul.restype = C.c_int
@@ -350,14 +350,17 @@ def add_rmsnorm(x: torch.Tensor, delta: Optional[torch.Tensor], weight: torch.Te
 def add_layernorm(x: torch.Tensor, d1: Optional[torch.Tensor], d2: Optional[torch.Tensor], weight: torch.Tensor,
                   bias: Optional[torch.Tensor], h_out: torch.Tensor, eps: float) -> None:
     """x[rows,hidden] = half(x + half(d1 + d2)) in place (either delta may be None), h_out = LayerNorm(x) * weight + bias.
-    An fp32 3-D `d1` is a stack of split-K partials [splits, rows, hidden] (linear_partials)."""
+    fp32 3-D deltas are stacks of split-K partials [splits, rows, hidden] (linear_partials); both or only d1."""
     _require_cuda(x, weight, h_out, d1, d2, bias)
     if d1 is not None and d1.dtype == torch.float32:
         rows, hidden = x.shape
-        if d2 is not None or d1.dim() != 3 or tuple(d1.shape[1:]) != (rows, hidden) or not (d1.is_contiguous() and x.is_contiguous()
-                                                                                          and h_out.is_contiguous()):
-            raise NativeError("add_layernorm: partials must be a contiguous fp32 [splits, rows, hidden] stack (and d2 None)")
-        _check(load().pc_add_layernorm_partials(x.data_ptr(), d1.data_ptr(), d1.shape[0], weight.data_ptr(),
+        for t in (d1, d2):
+            if t is not None and (t.dtype != torch.float32 or t.dim() != 3 or tuple(t.shape[1:]) != (rows, hidden) or not t.is_contiguous()):
+                raise NativeError("add_layernorm: partials must be contiguous fp32 [splits, rows, hidden] stacks")
+        if not (x.is_contiguous() and h_out.is_contiguous()):
+            raise NativeError("add_layernorm: x / h_out must be contiguous")
+        _check(load().pc_add_layernorm_partials(x.data_ptr(), d1.data_ptr(), d1.shape[0], d2.data_ptr() if d2 is not None else None,
+                                                d2.shape[0] if d2 is not None else 0, weight.data_ptr(),
                                                 bias.data_ptr() if bias is not None else None, h_out.data_ptr(), rows, hidden, float(eps),
                                                 _stream()), "pc_add_layernorm_partials")
         return
@@ -385,7 +388,7 @@ def linear_workspace(device) -> torch.Tensor:
 
 
 def tile_weights(w: torch.Tensor, epilogue: int = PC_LIN_PLAIN) -> Optional[torch.Tensor]:
-    """Pre-tiled copy of an nn.Linear weight for pc_linear_small (None when k is not a multiple of 128)."""
+    """Pre-tiled copy of an nn.Linear weight for pc_linear_small (None when k is not a multiple of 64)."""
     _require_cuda(w)
     if w.dim() != 2 or w.dtype != torch.float16 or not w.is_contiguous():
         raise NativeError("tile_weights: w must be a contiguous fp16 [n, k] tensor")
@@ -449,17 +452,18 @@ def linear_small(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, workspace:
 def linear_rope_append(x: torch.Tensor, wqkv: torch.Tensor, position_ids: Optional[torch.Tensor], cos: Optional[torch.Tensor],
                        sin: Optional[torch.Tensor], q_out: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor,
                        dst_row0, n_heads: int, n_kv_heads: int, workspace: torch.Tensor,
-                       w_tiled: Optional[torch.Tensor] = None, nxt=None) -> None:
-    """Fused QKV projection + RoPE at `position_ids` + in-place KV append (head_dim 128 only).  Arguments as rope_append."""
+                       w_tiled: Optional[torch.Tensor] = None, nxt=None, head_dim: int = 128) -> None:
+    """Fused QKV projection + RoPE at `position_ids` + in-place KV append (head_dim 128 or 64).  Arguments as rope_append."""
     p = _linear_params(x, wqkv, workspace, PC_LIN_ROPE_APPEND, w_tiled, nxt)
     _require_cuda(q_out, k_cache, v_cache)
-    D = 128
+    D = int(head_dim)
+    p.head_dim = D
     if k_cache.stride(2) != 1 or k_cache.stride(1) != D or k_cache.stride(0) != v_cache.stride(0) or not q_out.is_contiguous():
-        raise NativeError("linear_rope_append: caches must be [Hkv,max_ctx,128] with contiguous rows, q_out contiguous")
+        raise NativeError("linear_rope_append: caches must be [Hkv,max_ctx,D] with contiguous rows, q_out contiguous")
     if cos is not None:
         if cos.dtype != torch.float16 or sin.dtype != torch.float16 or not cos.is_contiguous() or not sin.is_contiguous() \
                 or cos.shape[1] != D:
-            raise NativeError("linear_rope_append: cos/sin must be contiguous fp16 [T,128] tables")
+            raise NativeError("linear_rope_append: cos/sin must be contiguous fp16 [T,D] tables")
         if position_ids.dtype != torch.int64 or not position_ids.is_contiguous():
             raise NativeError("linear_rope_append: position_ids must be a contiguous int64 tensor")
         p.cos, p.sin, p.table_rows, p.position_ids = cos.data_ptr(), sin.data_ptr(), cos.shape[0], position_ids.data_ptr()

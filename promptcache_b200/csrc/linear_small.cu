@@ -91,6 +91,7 @@ struct LinParams {
   __half* k_cache;
   __half* v_cache;
   int max_ctx, row0, n_heads, n_kv_heads;
+  int head_dim;          // ROPE_APPEND: 128 (one head per tile) or 64 (two heads per tile: Falcon)
   const int* row0_dev;
   unsigned long long* trace;  // debug: 8 %globaltimer stamps per CTA (PC_LIN_TRACE_PTR), else nullptr
   // L2 prefetch of the NEXT linear's weight stream (pre-tiled): once this CTA has issued its last weight load it asks
@@ -513,17 +514,18 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
           }
           named_bar_sync(1, kEpiThreads);
         } else {
-          // one tile == one head of 128: [0,H) query heads, [H,H+Hkv) key heads, then value heads
+          // a tile holds 128 / D heads: [0,H) query heads, [H,H+Hkv) key heads, then value heads (rows past them: padding)
 #pragma unroll
           for (int t = 0; t < NPAD; ++t) exch[t * BM + f] = __float2half_rn(v[t]);
           named_bar_sync(1, kEpiThreads);
-          const int H = p.n_heads, Hkv = p.n_kv_heads;
-          const bool rotate = (tile < H + Hkv) && p.cos != nullptr;
+          const int H = p.n_heads, Hkv = p.n_kv_heads, HD = p.head_dim;
+          const int head = (tile * BM + f) / HD, d = f & (HD - 1);
+          const bool rotate = (head < H + Hkv) && p.cos != nullptr;
           __half* dst;
-          if (tile < H) dst = p.q_out + static_cast<long long>(tile) * p.q_len * BM + f;
-          else if (tile < H + Hkv) dst = p.k_cache + (static_cast<long long>(tile - H) * p.max_ctx + row0) * BM + f;
-          else dst = p.v_cache + (static_cast<long long>(tile - H - Hkv) * p.max_ctx + row0) * BM + f;
-          if (tile < H + 2 * Hkv) {
+          if (head < H) dst = p.q_out + static_cast<long long>(head) * p.q_len * HD + d;
+          else if (head < H + Hkv) dst = p.k_cache + (static_cast<long long>(head - H) * p.max_ctx + row0) * HD + d;
+          else dst = p.v_cache + (static_cast<long long>(head - H - Hkv) * p.max_ctx + row0) * HD + d;
+          if (head < H + 2 * Hkv) {
             if (rotate) {
               // all table gathers first (independent loads in flight together), then the arithmetic
               __half cs[NPAD], sn[NPAD];
@@ -532,22 +534,23 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
                 long long pos = t < p.q_len ? __ldg(p.pos + t) : 0;
                 if (pos < 0) pos = 0;
                 if (pos >= p.table_rows) pos = p.table_rows - 1;
-                cs[t] = __ldg(p.cos + pos * BM + f);
-                sn[t] = __ldg(p.sin + pos * BM + f);
+                cs[t] = __ldg(p.cos + pos * HD + d);
+                sn[t] = __ldg(p.sin + pos * HD + d);
               }
+              const int half_d = HD >> 1;
 #pragma unroll
               for (int t = 0; t < NPAD; ++t) {
                 if (t < p.q_len) {
                   const __half x = exch[t * BM + f];
-                  const __half partner = exch[t * BM + (f ^ 64)];
-                  const __half rot = f < 64 ? __hneg(partner) : partner;  // rotate_half(x) = cat(-x2, x1)
-                  dst[t * BM] = __hadd_rn(__hmul_rn(x, cs[t]), __hmul_rn(rot, sn[t]));
+                  const __half partner = exch[t * BM + (f ^ half_d)];
+                  const __half rot = d < half_d ? __hneg(partner) : partner;  // rotate_half(x) = cat(-x2, x1)
+                  dst[t * HD] = __hadd_rn(__hmul_rn(x, cs[t]), __hmul_rn(rot, sn[t]));
                 }
               }
             } else {
 #pragma unroll
               for (int t = 0; t < NPAD; ++t)
-                if (t < p.q_len) dst[t * BM] = exch[t * BM + f];
+                if (t < p.q_len) dst[t * HD] = exch[t * BM + f];
             }
           }
           named_bar_sync(1, kEpiThreads);
@@ -645,22 +648,26 @@ int tile_geometry(int n_rows, int epilogue, TileGeom* g) {
 }  // namespace
 }  // namespace pc
 
+// k-blocks of the pre-tiled copy: a pipeline stage is two k-blocks, so an odd count (Falcon: k = 4544 = 71 blocks) is padded
+// with one block of zeros (the tensor-map load that produces the copy reads zeros past k; so do the X loads of the kernel)
+static inline int tiled_k_blocks(int k) { return ((k / pc::BKK) + 1) & ~1; }
+
 PC_API size_t pc_linear_tiled_bytes(int n_rows, int k, int epilogue) {
   pc::TileGeom g;
-  if (n_rows <= 0 || k <= 0 || k % 128 != 0 || pc::tile_geometry(n_rows, epilogue, &g) != PC_OK) return 0;
-  return static_cast<size_t>(g.n_tiles) * (k / pc::BKK) * pc::kWBytes;
+  if (n_rows <= 0 || k <= 0 || k % pc::BKK != 0 || pc::tile_geometry(n_rows, epilogue, &g) != PC_OK) return 0;
+  return static_cast<size_t>(g.n_tiles) * tiled_k_blocks(k) * pc::kWBytes;
 }
 
 PC_API int pc_linear_tile_weights(const void* w, int n_rows, int k, int epilogue, void* w_tiled, void* stream) {
   using namespace pc;
   PC_REQUIRE(w && w_tiled, "pc_linear_tile_weights: null pointer");
-  PC_REQUIRE(n_rows > 0 && k > 0 && k % 128 == 0, "pc_linear_tile_weights: k %d must be a positive multiple of 128", k);
+  PC_REQUIRE(n_rows > 0 && k > 0 && k % BKK == 0, "pc_linear_tile_weights: k %d must be a positive multiple of 64", k);
   PC_REQUIRE((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(w_tiled)) % 16 == 0, "pc_linear_tile_weights: 16B alignment");
   TileGeom g;
   if (int rc = tile_geometry(n_rows, epilogue, &g)) return rc;
   CUtensorMap mw;
   if (int rc = make_tensor_map_3d(&mw, w, k, n_rows, 1, static_cast<long long>(n_rows) * k, 64)) return rc;
-  const int kb_total = k / BKK;
+  const int kb_total = tiled_k_blocks(k);
   const long long units = static_cast<long long>(g.n_tiles) * kb_total;
   static bool configured = false;
   if (!configured) {
@@ -752,9 +759,8 @@ PC_API int pc_linear_small(const pc_linear_params* p, void* stream) {
              p->workspace_bytes, pc_linear_workspace_bytes());
   LinParams lp{};
   lp.q_len = p->q_len;
-  lp.kb_total = p->k / BKK;
   const bool tiled = p->w_tiled != nullptr;
-  PC_REQUIRE(!tiled || p->k % 128 == 0, "pc_linear_small: pre-tiled weights need k %% 128 == 0 (k = %d)", p->k);
+  lp.kb_total = tiled ? tiled_k_blocks(p->k) : p->k / BKK;
   PC_REQUIRE(!tiled || reinterpret_cast<uintptr_t>(p->w_tiled) % 16 == 0, "pc_linear_small: w_tiled must be 16B aligned");
   int n_tiles = 0;
   switch (p->epilogue) {
@@ -786,20 +792,24 @@ PC_API int pc_linear_small(const pc_linear_params* p, void* stream) {
       PC_REQUIRE(inter % 64 == 0, "pc_linear_small(silu_mul): intermediate size %d must be a multiple of 64", inter);
       break;
     }
-    case PC_LIN_ROPE_APPEND:
-      PC_REQUIRE(p->n_heads > 0 && p->n_kv_heads > 0 && p->n_rows == (p->n_heads + 2 * p->n_kv_heads) * BM,
-                 "pc_linear_small(rope_append): n_rows %d must be (H + 2 Hkv) * 128", p->n_rows);
+    case PC_LIN_ROPE_APPEND: {
+      const int hd = p->head_dim == 0 ? 128 : p->head_dim;
+      PC_REQUIRE(hd == 64 || hd == 128, "pc_linear_small(rope_append): head_dim %d must be 64 or 128", hd);
+      PC_REQUIRE(p->n_heads > 0 && p->n_kv_heads > 0 && p->n_rows == (p->n_heads + 2 * p->n_kv_heads) * hd,
+                 "pc_linear_small(rope_append): n_rows %d must be (H + 2 Hkv) * head_dim", p->n_rows);
+      lp.head_dim = hd;
       PC_REQUIRE(p->q_out && p->k_cache && p->v_cache, "pc_linear_small(rope_append): null q_out / cache");
       PC_REQUIRE((p->cos == nullptr) == (p->sin == nullptr), "pc_linear_small(rope_append): cos/sin must both be set");
       PC_REQUIRE(p->cos == nullptr || (p->position_ids != nullptr && p->table_rows > 0),
                  "pc_linear_small(rope_append): rotary needs position ids and a table");
       PC_REQUIRE(p->dst_row0 >= 0 && static_cast<long long>(p->dst_row0) + p->q_len <= p->max_ctx,
                  "pc_linear_small(rope_append): rows [%d,%d) exceed max_ctx %d", p->dst_row0, p->dst_row0 + p->q_len, p->max_ctx);
-      n_tiles = p->n_heads + 2 * p->n_kv_heads;
+      n_tiles = (p->n_rows + BM - 1) / BM;
       lp.n_out = p->n_rows;
       lp.tile_row_stride = BM;
       lp.second_half_off = 64;
       break;
+    }
     default:
       return set_error(PC_ERR_INVALID, "pc_linear_small: unknown epilogue %d", p->epilogue);
   }
@@ -844,14 +854,13 @@ PC_API int pc_linear_small(const pc_linear_params* p, void* stream) {
   // optional hint: the launch that follows on this stream (see LinParams::pf_w)
   lp.pf_w = nullptr;
   if (const pc_linear_params* nx = p->prefetch_next) {
-    if (nx->w_tiled != nullptr && nx->k > 0 && nx->k % 128 == 0 && nx->n_rows > 0) {
+    if (nx->w_tiled != nullptr && nx->k > 0 && nx->k % BKK == 0 && nx->n_rows > 0) {
       int nt = 0;
       switch (nx->epilogue) {
         case PC_LIN_SILU_MUL: nt = (nx->n_rows / 2 + 63) / 64; break;
-        case PC_LIN_ROPE_APPEND: nt = nx->n_heads + 2 * nx->n_kv_heads; break;
         default: nt = (nx->n_rows + BM - 1) / BM; break;
       }
-      const int upt = nx->k / 128;
+      const int upt = tiled_k_blocks(nx->k) / 2;
       const int nsplits = nx->epilogue == PC_LIN_PARTIALS ? pc_linear_partial_splits(nx->n_rows, nx->k) : 0;
       int ngrid = 1, nwhole = 0;
       long long nunits = static_cast<long long>(nt) * upt;

@@ -96,7 +96,8 @@ add_rmsnorm_kernel(__half* __restrict__ x, const __half* __restrict__ delta, con
 __global__ void __launch_bounds__(kNormThreads)
 add_layernorm_kernel(__half* __restrict__ x, const __half* __restrict__ d1, const __half* __restrict__ d2,
                      const __half* __restrict__ weight, const __half* __restrict__ bias, __half* __restrict__ h_out, int hidden,
-                     float eps, const float* __restrict__ part, int n_splits, long long split_stride) {
+                     float eps, const float* __restrict__ part, int n_splits, const float* __restrict__ part2, int n_splits2,
+                     long long split_stride) {
   __shared__ float red[2][kNormThreads / 32];
   pc::pdl_launch_dependents();
   pc::pdl_wait();
@@ -117,8 +118,23 @@ add_layernorm_kernel(__half* __restrict__ x, const __half* __restrict__ d1, cons
         acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
         acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
       }
+      __half2 dsum[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) xh[k] = __hadd2_rn(xh[k], __floats2half2_rn(acc[2 * k], acc[2 * k + 1]));
+      for (int k = 0; k < 4; ++k) dsum[k] = __floats2half2_rn(acc[2 * k], acc[2 * k + 1]);
+      if (part2) {  // a second delta, also as partials (Falcon: mlp_out += attn_out, each the fp16 output of its own linear)
+        float acc2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const float* pr2 = part2 + off + i;
+        for (int sp = 0; sp < n_splits2; ++sp) {
+          const float4 a = __ldcg(reinterpret_cast<const float4*>(pr2 + sp * split_stride));
+          const float4 b = __ldcg(reinterpret_cast<const float4*>(pr2 + sp * split_stride) + 1);
+          acc2[0] += a.x; acc2[1] += a.y; acc2[2] += a.z; acc2[3] += a.w;
+          acc2[4] += b.x; acc2[5] += b.y; acc2[6] += b.z; acc2[7] += b.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dsum[k] = __hadd2_rn(dsum[k], __floats2half2_rn(acc2[2 * k], acc2[2 * k + 1]));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) xh[k] = __hadd2_rn(xh[k], dsum[k]);
       *reinterpret_cast<uint4*>(xr + i) = xv;
     } else if (d1) {
       uint4 av = *reinterpret_cast<const uint4*>(d1 + off + i);
@@ -251,23 +267,25 @@ PC_API int pc_add_layernorm(void* x, const void* d1, const void* d2, const void*
   PC_CHECK_CUDA(pc::launch_pdl(add_layernorm_kernel, dim3(rows), dim3(kNormThreads), 0, static_cast<cudaStream_t>(stream),
                                static_cast<__half*>(x), static_cast<const __half*>(d1), static_cast<const __half*>(d2),
                                static_cast<const __half*>(weight), static_cast<const __half*>(bias), static_cast<__half*>(h_out),
-                               hidden, eps, static_cast<const float*>(nullptr), 0, 0LL));
+                               hidden, eps, static_cast<const float*>(nullptr), 0, static_cast<const float*>(nullptr), 0, 0LL));
   pc::count_launch();
   return PC_OK;
 }
 
-PC_API int pc_add_layernorm_partials(void* x, const void* delta_partials, int n_splits, const void* weight, const void* bias,
-                                     void* h_out, int rows, int hidden, float eps, void* stream) {
+PC_API int pc_add_layernorm_partials(void* x, const void* delta_partials, int n_splits, const void* delta2_partials, int n_splits2,
+                                     const void* weight, const void* bias, void* h_out, int rows, int hidden, float eps, void* stream) {
   if (rows == 0) return PC_OK;
   PC_REQUIRE(x && weight && h_out && delta_partials, "pc_add_layernorm_partials: null tensor");
   PC_REQUIRE(rows > 0 && hidden > 0 && hidden % 8 == 0 && n_splits >= 1, "pc_add_layernorm_partials: bad shape");
+  PC_REQUIRE((delta2_partials == nullptr) == (n_splits2 == 0), "pc_add_layernorm_partials: second stack and its split count disagree");
   const uintptr_t align = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(delta_partials) | reinterpret_cast<uintptr_t>(weight) |
-                          reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(h_out);
+                          reinterpret_cast<uintptr_t>(delta2_partials) | reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(h_out);
   PC_REQUIRE(align % 16 == 0, "pc_add_layernorm_partials: tensors must be 16B aligned");
   PC_CHECK_CUDA(pc::launch_pdl(add_layernorm_kernel, dim3(rows), dim3(kNormThreads), 0, static_cast<cudaStream_t>(stream),
                                static_cast<__half*>(x), static_cast<const __half*>(nullptr), static_cast<const __half*>(nullptr),
                                static_cast<const __half*>(weight), static_cast<const __half*>(bias), static_cast<__half*>(h_out),
-                               hidden, eps, static_cast<const float*>(delta_partials), n_splits, static_cast<long long>(rows) * hidden));
+                               hidden, eps, static_cast<const float*>(delta_partials), n_splits,
+                               static_cast<const float*>(delta2_partials), n_splits2, static_cast<long long>(rows) * hidden));
   pc::count_launch();
   return PC_OK;
 }

@@ -9,6 +9,8 @@ Only the 7B layout is supported: multi_query, parallel_attn, no alibi, old decod
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -70,6 +72,10 @@ class FalconForCausalLM(B200CausalLM):
         self.w_4hh = nn.ParameterList([w(hid, 4 * hid) for _ in range(self.n_layers)])
         self.lnf_w, self.lnf_b = vec(1.0), vec(0.0)
         self._init_runtime()
+        # native skinny linears up to this many tokens (the kernel takes up to 32 token columns).  Measured on C4 (B200):
+        # decode 3.34 ms/token native vs 3.19 cuBLAS, 21-token prefill 3.65 vs 3.29 ms -- Falcon's shapes (37 / 36 row tiles,
+        # K = 71 k-blocks) partition worse than Llama's, so the default stays cuBLAS (0); tests switch it on.
+        self.linear_max_q_falcon = min(32, int(os.environ.get("PC_LINEAR_MAX_Q_FALCON", "0")))
         self.rounding = nat.PC_ROUND_FALCON
         self.scale = nat.softmax_scale(self.head_dim)
 
@@ -101,6 +107,9 @@ class FalconForCausalLM(B200CausalLM):
 
     supports_dynamic_n = True  # decode graph: pc_rope_append_dyn + attention with a run-time cached length
 
+    def _launch_shape_key(self):
+        return super()._launch_shape_key() + (self.linear_max_q_falcon,)
+
     def _layers(self, ids: torch.Tensor, pos: torch.Tensor, kv, extra=(), n_dev=None) -> torch.Tensor:
         q_len = ids.shape[0]
         H, D = self.n_heads, self.head_dim
@@ -111,18 +120,42 @@ class FalconForCausalLM(B200CausalLM):
         q_rot = torch.empty(H, q_len, D, dtype=torch.float16, device=self.device)
         ctx = torch.empty(q_len, H * D, dtype=torch.float16, device=self.device)
         ws = self._workspace(q_len)
+        nd = N if n_dev is None else n_dev  # run-time cached length (decode graph); N is then only the sizing upper bound
+        # few tokens: the block's four matrices are weight streams -> pc_linear_small (RoPE at head_dim 64 + MQA append in the
+        # fused QKV epilogue, GELU in h_to_4h's, dense / 4h_to_h as split-K partials that the next add+LayerNorm reduces);
+        # the pre-tiled copies pad K = 4544 (71 blocks of 64) with one block of zeros.  Longer suffixes: cuBLAS.
+        lin = self.linear_impl == "native" and q_len <= self.linear_max_q_falcon and D in (64, 128) and hid % 64 == 0 and not self.has_bias
+        if lin:
+            lws = self._linear_workspace()
+            act = torch.empty(q_len, 4 * hid, dtype=torch.float16, device=self.device)
+            pbuf_a = torch.empty(nat.linear_partial_splits(hid, hid), q_len, hid, dtype=torch.float32, device=self.device)
+            pbuf_m = torch.empty(nat.linear_partial_splits(hid, 4 * hid), q_len, hid, dtype=torch.float32, device=self.device)
         attn = mlp = None
         for l in range(self.n_layers):
             # x = x + (mlp += attn) of the previous block (falcon.py:807-810) and this block's input_layernorm (:781): one launch
             nat.add_layernorm(x, mlp, attn, self.ln_w[l], self.ln_b[l], ln, self.eps)
-            qkv = F.linear(ln, self.wqkv[l])                                          # [q, (H+2)*D]: q heads | k | v (:385-388)
-            # n_dev: run-time cached length (decode graph); N is then only the sizing upper bound
-            nat.rope_append(qkv[:, :H * D], qkv[:, H * D:(H + 1) * D], qkv[:, (H + 1) * D:], pos, self._cos, self._sin,
-                            q_rot, kv.k[l], kv.v[l], N if n_dev is None else n_dev, H, 1, D)
+            if lin:
+                nat.linear_rope_append(ln, self.wqkv[l], pos, self._cos, self._sin, q_rot, kv.k[l], kv.v[l], nd, H, 1, lws,
+                                       w_tiled=self._wt(("qkv", l), self.wqkv[l], nat.PC_LIN_ROPE_APPEND), head_dim=D)
+            else:
+                qkv = F.linear(ln, self.wqkv[l])                                      # [q, (H+2)*D]: q heads | k | v (:385-388)
+                nat.rope_append(qkv[:, :H * D], qkv[:, H * D:(H + 1) * D], qkv[:, (H + 1) * D:], pos, self._cos, self._sin,
+                                q_rot, kv.k[l], kv.v[l], nd, H, 1, D)
             nat.attention(q_rot, kv.k[l], kv.v[l], ctx, N if n_dev is None else kv.max_ctx - q_len, q_len, H, 1, D, self.scale,
                           self.rounding, workspace=ws, impl=self.attn_impl if n_dev is None else nat.PC_ATTN_TCGEN05,
                           decode=(q_len == 1), n_cached_dev=n_dev)
-            attn = F.linear(ctx, self.wdense[l])                                      # :493
-            mlp = F.linear(F.gelu(F.linear(ln, self.w_h4h[l])), self.w_4hh[l])        # parallel MLP on the same norm (:796-805)
+            if lin:
+                nat.linear_partials(ctx, self.wdense[l], pbuf_a, lws, w_tiled=self._wt(("dense", l), self.wdense[l], nat.PC_LIN_PARTIALS))
+                nat.linear_small(ln, self.w_h4h[l], act, lws, gelu=True, w_tiled=self._wt(("h4h", l), self.w_h4h[l], nat.PC_LIN_PLAIN))
+                nat.linear_partials(act, self.w_4hh[l], pbuf_m, lws, w_tiled=self._wt(("4hh", l), self.w_4hh[l], nat.PC_LIN_PARTIALS))
+                attn, mlp = pbuf_a, pbuf_m
+            else:
+                attn = F.linear(ctx, self.wdense[l])                                  # :493
+                mlp = F.linear(F.gelu(F.linear(ln, self.w_h4h[l])), self.w_4hh[l])    # parallel MLP on the same norm (:796-805)
         nat.add_layernorm(x, mlp, attn, self.lnf_w, self.lnf_b, ln, self.eps)          # last block's residual adds + ln_f
+        if lin:
+            logits = torch.empty(q_len, self.vocab_size, dtype=torch.float16, device=self.device)
+            nat.linear_small(ln, self.word_embeddings, logits, lws,
+                             w_tiled=self._wt(("lm_head", 0), self.word_embeddings, nat.PC_LIN_PLAIN))
+            return logits.float()
         return F.linear(ln, self.word_embeddings).float()

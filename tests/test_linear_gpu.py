@@ -45,7 +45,7 @@ def _tiled(native, w, epi, tiled):
         return None
     wt = native.tile_weights(w, epi)
     if wt is None:
-        pytest.skip("k is not a multiple of 128: no pre-tiled layout")
+        pytest.skip("k is not a multiple of 64: no pre-tiled layout")
     return wt
 
 
@@ -102,15 +102,19 @@ def test_linear_silu_mul(native, q, k, inter, tiled):
     assert torch.allclose(out.float(), ref.float(), rtol=2e-3, atol=1e-6)
 
 
-@pytest.mark.parametrize("q,H,Hkv,k,row0,rotary", [
-    (16, 32, 32, 4096, 2048, True),   # C2
-    (1, 32, 32, 4096, 777, True),     # decode
-    (32, 8, 2, 512, 5, True),         # GQA, NPAD 32
-    (9, 4, 4, 256, 0, False),         # MPT: no rotation, plain append
+@pytest.mark.parametrize("q,H,Hkv,k,row0,rotary,D", [
+    (16, 32, 32, 4096, 2048, True, 128),   # C2
+    (1, 32, 32, 4096, 777, True, 128),     # decode
+    (32, 8, 2, 512, 5, True, 128),         # GQA, NPAD 32
+    (9, 4, 4, 256, 0, False, 128),         # MPT: no rotation, plain append
+    (16, 71, 1, 4544, 256, True, 64),      # Falcon-7B: head_dim 64 (two heads per tile, last tile half padding), 71 k-blocks
+    (1, 71, 1, 4544, 1999, True, 64),      # Falcon decode
+    (21, 6, 2, 320, 7, True, 64),          # D=64 GQA, 5 k-blocks, NPAD 32
+    (5, 3, 1, 192, 0, False, 64),          # D=64 without rotation, 5 heads = 2.5 tiles
 ])
 @pytest.mark.parametrize("tiled", [False, True])
-def test_linear_rope_append_bit_exact_vs_unfused(native, q, H, Hkv, k, row0, rotary, tiled):
-    D, max_ctx = 128, row0 + q + 3
+def test_linear_rope_append_bit_exact_vs_unfused(native, q, H, Hkv, k, row0, rotary, D, tiled):
+    max_ctx = row0 + q + 3
     x = _ints((q, k), -4, 4, 0.25, seed=5)
     w = _ints(((H + 2 * Hkv) * D, k), -2, 2, 1.0 / 32, seed=6)
     g = torch.Generator(device="cpu").manual_seed(7)
@@ -126,7 +130,7 @@ def test_linear_rope_append_bit_exact_vs_unfused(native, q, H, Hkv, k, row0, rot
 
     q1, k1, v1 = fresh()
     native.linear_rope_append(x, w, pos if rotary else None, cos if rotary else None, sin if rotary else None, q1, k1, v1,
-                              row0, H, Hkv, ws, w_tiled=wt)
+                              row0, H, Hkv, ws, w_tiled=wt, head_dim=D)
     qkv = _exact_linear(x, w)
     q2, k2, v2 = fresh()
     native.rope_append(qkv[:, :H * D], qkv[:, H * D:(H + Hkv) * D], qkv[:, (H + Hkv) * D:], pos if rotary else None,
@@ -137,7 +141,7 @@ def test_linear_rope_append_bit_exact_vs_unfused(native, q, H, Hkv, k, row0, rot
     q3, k3, v3 = fresh()
     row_dev = torch.tensor([row0], dtype=torch.int32, device=DEV)
     native.linear_rope_append(x, w, pos if rotary else None, cos if rotary else None, sin if rotary else None, q3, k3, v3,
-                              row_dev, H, Hkv, ws, w_tiled=wt)
+                              row_dev, H, Hkv, ws, w_tiled=wt, head_dim=D)
     torch.cuda.synchronize()
     assert torch.equal(q3, q2) and torch.equal(k3, k2) and torch.equal(v3, v2)
 
@@ -245,5 +249,30 @@ def test_add_layernorm_partials_equal_linear_then_add_layernorm(native):
     native.linear_small(x_in, w, out, ws)
     b_x, b_h = res.clone(), torch.empty_like(res)
     native.add_layernorm(b_x, out, None, lw, None, b_h, 1e-5)
+    torch.cuda.synchronize()
+    assert torch.equal(a_x, b_x) and torch.equal(a_h, b_h)
+
+
+def test_add_layernorm_two_partial_stacks_equal_two_fp16_deltas(native):
+    """Falcon's parallel block: x + (mlp += attn) with both deltas as split-K partial stacks == the same add with the
+    fp16 outputs of the two linears (falcon.py:796-810), bit for bit on integer-valued inputs; K = 4544 (71 k-blocks)."""
+    g = torch.Generator(device="cpu").manual_seed(9)
+    q, hid = 13, 4544
+    ctx = torch.randint(-2, 3, (q, hid), generator=g).half().to(DEV)
+    act = torch.randint(-2, 3, (q, 4 * hid), generator=g).half().to(DEV)
+    wd = (torch.randint(-2, 3, (hid, hid), generator=g).float() / 64).half().to(DEV)
+    w4 = (torch.randint(-2, 3, (hid, 4 * hid), generator=g).float() / 64).half().to(DEV)
+    res = torch.randn(q, hid, generator=g).half().to(DEV)
+    lw = (1 + 0.1 * torch.randn(hid, generator=g)).half().to(DEV)
+    lb = (0.1 * torch.randn(hid, generator=g)).half().to(DEV)
+    ws = native.linear_workspace(DEV)
+    pa = torch.empty(native.linear_partial_splits(hid, hid), q, hid, dtype=torch.float32, device=DEV)
+    pm = torch.empty(native.linear_partial_splits(hid, 4 * hid), q, hid, dtype=torch.float32, device=DEV)
+    native.linear_partials(ctx, wd, pa, ws, w_tiled=native.tile_weights(wd, native.PC_LIN_PARTIALS))
+    native.linear_partials(act, w4, pm, ws, w_tiled=native.tile_weights(w4, native.PC_LIN_PARTIALS))
+    a_x, a_h = res.clone(), torch.empty_like(res)
+    native.add_layernorm(a_x, pm, pa, lw, lb, a_h, 1e-5)
+    b_x, b_h = res.clone(), torch.empty_like(res)
+    native.add_layernorm(b_x, _exact_linear(act, w4), _exact_linear(ctx, wd), lw, lb, b_h, 1e-5)
     torch.cuda.synchronize()
     assert torch.equal(a_x, b_x) and torch.equal(a_h, b_h)

@@ -239,3 +239,49 @@ def test_mpt_native_linears_match_cublas_step_and_oracle(native):
     r1, rp = O.mpt_forward(sd, cfg, pre_ids, pre_pos)
     r2, _ = O.mpt_forward(sd, cfg, suf_ids, full_pos, rp)
     assert _rel(outs["native"], r2) <= 3e-3
+
+
+def test_falcon_native_linears_match_cublas_step_and_oracle(native):
+    """Falcon-7B dims (H=71, D=64, hidden 4544 = 71 k-blocks, padded to 72 in the pre-tiled copies), 2 layers: the block on
+    the weight-streaming kernels (RoPE at head_dim 64 + MQA append in the QKV epilogue, GELU in h_to_4h's, dense / 4h_to_h
+    partials reduced together by the fused add+LayerNorm, tied lm_head) vs the cuBLAS step vs the oracle's eager forward;
+    then one decode step each way."""
+    from promptcache_b200.model.falcon import FalconConfigLite, FalconForCausalLM
+    torch.manual_seed(13)
+    model = FalconForCausalLM(FalconConfigLite(vocab_size=1000, num_hidden_layers=2), device=DEV)
+    for l in range(2):  # non-trivial norms
+        model.ln_w[l].copy_(1 + 0.1 * torch.randn(4544, device=DEV))
+        model.ln_b[l].copy_(0.1 * torch.randn(4544, device=DEV))
+    g = torch.Generator().manual_seed(5)
+    pre_ids = torch.randint(3, 1000, (1, 300), generator=g).to(DEV)
+    pre_pos = torch.arange(300, device=DEV).unsqueeze(0)
+    suf_ids = torch.randint(3, 1000, (1, 9), generator=g).to(DEV)
+    suf_pos = torch.tensor([[340, 341, 350, 351, 352, 310, 311, 353, 354]], device=DEV)  # parameter slots: non-monotone ids
+    dec_ids, dec_pos = torch.randint(3, 1000, (1, 1), generator=g).to(DEV), torch.tensor([[355]], device=DEV)
+    outs = {}
+    model.linear_max_q_falcon = 16
+    for impl in ("native", "cublas"):
+        model.linear_impl = impl
+        past = model(input_ids=pre_ids, position_ids=pre_pos, use_cache=True).past_key_values
+        launches0 = native.launch_count()
+        o = model(input_ids=suf_ids, position_ids=suf_pos, past_key_values=past, use_cache=True)
+        outs[impl + "_launches"] = native.launch_count() - launches0
+        outs[impl] = o.logits.clone()
+        outs[impl + "_k"] = o.past_key_values[1][0][..., 300:, :].clone()
+        outs[impl + "_dec"] = model(input_ids=dec_ids, position_ids=dec_pos, past_key_values=o.past_key_values, use_cache=True).logits.clone()
+    assert _rel(outs["native"], outs["cublas"]) <= 2e-3
+    assert _rel(outs["native_k"], outs["cublas_k"]) <= 2e-3
+    assert _rel(outs["native_dec"], outs["cublas_dec"]) <= 2e-3
+    assert outs["native_launches"] >= outs["cublas_launches"] + 2 * 3  # qkv replaces rope_append; dense, h_to_4h, 4h_to_h, lm_head
+    sd = {"transformer.word_embeddings.weight": model.word_embeddings, "transformer.ln_f.weight": model.lnf_w,
+          "transformer.ln_f.bias": model.lnf_b}
+    for l in range(2):
+        p = f"transformer.h.{l}."
+        sd.update({p + "input_layernorm.weight": model.ln_w[l], p + "input_layernorm.bias": model.ln_b[l],
+                   p + "self_attention.query_key_value.weight": model.wqkv[l], p + "self_attention.dense.weight": model.wdense[l],
+                   p + "mlp.dense_h_to_4h.weight": model.w_h4h[l], p + "mlp.dense_4h_to_h.weight": model.w_4hh[l]})
+    sd = {k: v.detach() for k, v in sd.items()}
+    cfg = dict(n_layers=2, n_heads=71, eps=1e-5, theta=10000.0)
+    r1, rp = O.falcon_forward(sd, cfg, pre_ids, pre_pos, cos=model._cos, sin=model._sin)
+    r2, _ = O.falcon_forward(sd, cfg, suf_ids, suf_pos, rp, cos=model._cos, sin=model._sin)
+    assert _rel(outs["native"], r2) <= 3e-3
