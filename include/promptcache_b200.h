@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PC_ABI_VERSION 4
+#define PC_ABI_VERSION 5
 
 enum {
   PC_OK = 0,
@@ -278,6 +278,37 @@ int pc_linear_small(const pc_linear_params* p, void* stream);
 /* k must be a multiple of 64; an odd number of 64-column blocks is padded with one block of zeros in the copy. */
 size_t pc_linear_tiled_bytes(int n_rows, int k, int epilogue);
 int pc_linear_tile_weights(const void* w, int n_rows, int k, int epilogue, void* w_tiled, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * A chain of pc_linear_small launches and the norms between them as ONE persistent launch (one CTA per SM): the weight
+ * stream of op k+1 starts while op k's epilogue, the grid barrier and the norm still run, so the launch-boundary dead
+ * time of ~7 kernels per decoder layer is paid once.  Llama-2 (llama2.py:623-648):
+ *   o_proj (PARTIALS) -> x += attn; h = RMSNorm(x) -> gate/up + SiLU*up -> down_proj (PARTIALS) -> x += mlp; h = RMSNorm(x)
+ *   -> q/k/v projections + RoPE + KV append of the NEXT layer (or lm_head)
+ * Ops run in order; `dep` names the earlier op of the chain whose output this op reads (-1: only kernels launched before
+ * the chain).  Because every CTA finishes op j before op j+1, waiting for op `dep` covers all ops <= dep.  All linears
+ * need pre-tiled weights and share q_len; norms take their deltas as split-K partial stacks (or none) and produce exactly
+ * what pc_add_rmsnorm_partials / pc_add_layernorm_partials produce.  workspace: the pc_linear_small workspace (zeroed once). */
+#define PC_CHAIN_LINEAR 0
+#define PC_CHAIN_ADD_RMSNORM 1
+#define PC_CHAIN_ADD_LAYERNORM 2
+#define PC_CHAIN_MAX_OPS 8
+typedef struct pc_chain_op {
+  int32_t kind;
+  int32_t dep;
+  pc_linear_params lin;  /* PC_CHAIN_LINEAR (workspace / workspace_bytes / prefetch_next are ignored) */
+  /* norms: x[rows][hidden] = half(x + half(sum part1) (+ half(sum part2))) in place; h_out = norm(x) * weight (+ bias) */
+  void* x;
+  const void* part1;     /* fp32 [n_splits1][rows][hidden] or NULL */
+  const void* part2;     /* LayerNorm only (Falcon's parallel block), or NULL */
+  const void* weight;
+  const void* bias;      /* LayerNorm only, or NULL */
+  void* h_out;
+  int32_t n_splits1, n_splits2, rows, hidden;
+  float eps;
+  int32_t reserved;
+} pc_chain_op;
+int pc_linear_chain(const pc_chain_op* ops, int n_ops, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 int64_t pc_launch_count(void);

@@ -5,6 +5,7 @@ If the shared library is missing or a call fails, a `NativeError` is raised -- l
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import math
 import os
@@ -29,7 +30,11 @@ PC_ATTN_GLOBAL_MERGE = 0x100
 EXPORTS = ("pc_version", "pc_last_error", "pc_device_info", "pc_splice_kv", "pc_splice_kv_strided", "pc_splice_kv_tensors",
            "pc_rope_append", "pc_rope_append_dyn", "pc_attn_workspace_bytes", "pc_prefill_attn", "pc_decode_attn", "pc_launch_count",
            "pc_add_rmsnorm", "pc_add_layernorm", "pc_add_layernorm_partials", "pc_silu_mul", "pc_linear_workspace_bytes", "pc_linear_small",
-           "pc_linear_tiled_bytes", "pc_linear_tile_weights", "pc_linear_partial_splits", "pc_add_rmsnorm_partials")
+           "pc_linear_tiled_bytes", "pc_linear_tile_weights", "pc_linear_partial_splits", "pc_add_rmsnorm_partials", "pc_linear_chain")
+PC_CHAIN_LINEAR = 0
+PC_CHAIN_ADD_RMSNORM = 1
+PC_CHAIN_ADD_LAYERNORM = 2
+PC_CHAIN_MAX_OPS = 8
 PC_LIN_PLAIN = 0
 PC_LIN_SILU_MUL = 1
 PC_LIN_ROPE_APPEND = 2
@@ -72,6 +77,13 @@ class pc_linear_params(C.Structure):
                 ("dst_row0", C.c_int32), ("n_heads", C.c_int32), ("n_kv_heads", C.c_int32), ("activation", C.c_int32),
                 ("dst_row0_dev", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
                 ("w_tiled", C.c_void_p), ("prefetch_next", C.c_void_p), ("head_dim", C.c_int32), ("reserved", C.c_int32)]
+
+
+class pc_chain_op(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("dep", C.c_int32), ("lin", pc_linear_params),
+                ("x", C.c_void_p), ("part1", C.c_void_p), ("part2", C.c_void_p), ("weight", C.c_void_p), ("bias", C.c_void_p),
+                ("h_out", C.c_void_p), ("n_splits1", C.c_int32), ("n_splits2", C.c_int32), ("rows", C.c_int32), ("hidden", C.c_int32),
+                ("eps", C.c_float), ("reserved", C.c_int32)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -123,6 +135,8 @@ def load() -> C.CDLL:
     lib.pc_add_layernorm_partials.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.c_int, C.c_int, C.c_float, C.c_void_p]
     lib.pc_add_layernorm_partials.restype = C.c_int
+    lib.pc_linear_chain.argtypes = [C.POINTER(pc_chain_op), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.pc_linear_chain.restype = C.c_int
     lib.pc_silu_mul.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]
     lib.pc_silu_mul.restype = C.c_int
     lib.pc_linear_workspace_bytes.argtypes = []
@@ -149,6 +163,12 @@ def _check(rc: int, what: str) -> None:
 
 
 def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _stream_flush() -> int:
+    """Stream handle for a launch that cannot be part of a chain: what the chain has recorded goes out first."""
+    chain_flush()
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -200,10 +220,10 @@ def splice_kv(segments: Sequence[tuple], cache: torch.Tensor) -> None:
         run_rows[i] = s2 // D
         strided |= run_rows[i] != ln
     if strided:
-        _check(lib.pc_splice_kv_strided(arr, run_rows, n, cache.data_ptr(), L, Hkv, D, max_ctx, cache.element_size(), _stream()),
+        _check(lib.pc_splice_kv_strided(arr, run_rows, n, cache.data_ptr(), L, Hkv, D, max_ctx, cache.element_size(), _stream_flush()),
                "pc_splice_kv_strided")
     else:
-        _check(lib.pc_splice_kv(arr, n, cache.data_ptr(), L, Hkv, D, max_ctx, cache.element_size(), _stream()),
+        _check(lib.pc_splice_kv(arr, n, cache.data_ptr(), L, Hkv, D, max_ctx, cache.element_size(), _stream_flush()),
                "pc_splice_kv")
 
 
@@ -226,7 +246,7 @@ def splice_kv_tensors(copies: Sequence[tuple]) -> None:
         arr[i].dst_run_stride = dst.stride(0) * es
         arr[i].run_bytes = ln * D * es
         arr[i].n_runs = Hkv
-    _check(lib.pc_splice_kv_tensors(arr, n, _stream()), "pc_splice_kv_tensors")
+    _check(lib.pc_splice_kv_tensors(arr, n, _stream_flush()), "pc_splice_kv_tensors")
 
 
 def rope_append(q_in: torch.Tensor, k_in: torch.Tensor, v_in: torch.Tensor, position_ids: Optional[torch.Tensor],
@@ -261,14 +281,14 @@ def rope_append(q_in: torch.Tensor, k_in: torch.Tensor, v_in: torch.Tensor, posi
                                       cos.data_ptr() if cos is not None else None,
                                       sin.data_ptr() if sin is not None else None, table_rows, q_out.data_ptr(),
                                       k_cache.data_ptr(), v_cache.data_ptr(), max_ctx, dst_row0.data_ptr(), n_heads,
-                                      n_kv_heads, head_dim, q_len, _stream()), "pc_rope_append_dyn")
+                                      n_kv_heads, head_dim, q_len, _stream_flush()), "pc_rope_append_dyn")
         return
     _check(lib.pc_rope_append(q_in.data_ptr(), k_in.data_ptr(), v_in.data_ptr(), q_in.stride(0), k_in.stride(0),
                               v_in.stride(0), position_ids.data_ptr() if position_ids is not None else None,
                               cos.data_ptr() if cos is not None else None,
                               sin.data_ptr() if sin is not None else None, table_rows, q_out.data_ptr(),
                               k_cache.data_ptr(), v_cache.data_ptr(), max_ctx, int(dst_row0), n_heads, n_kv_heads,
-                              head_dim, q_len, _stream()), "pc_rope_append")
+                              head_dim, q_len, _stream_flush()), "pc_rope_append")
 
 
 def attn_workspace_bytes(n_heads: int, q_len: int, head_dim: int) -> int:
@@ -324,7 +344,92 @@ def attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, out
         p.kv_arena_k, p.kv_arena_v, p.kv_tiles = ak.data_ptr(), av.data_ptr(), tiles.data_ptr()
         p.kv_arena_rows, p.kv_n_tiles, p.kv_rows = int(ak.shape[1]), int(n_tiles), int(rows)
     fn = lib.pc_decode_attn if decode else lib.pc_prefill_attn
-    _check(fn(C.byref(p), _stream()), "pc_decode_attn" if decode else "pc_prefill_attn")
+    _check(fn(C.byref(p), _stream_flush()), "pc_decode_attn" if decode else "pc_prefill_attn")
+
+
+# ---- chains: several linears / norms as ONE persistent launch (pc_linear_chain) -----------------------------------
+class _Chain:
+    """Ops recorded inside `with chain(workspace):`.  Dependencies are derived from the tensors: an op depends on the
+    latest earlier op that writes something it reads (RAW) or reads / writes something it writes (WAR / WAW)."""
+
+    def __init__(self, workspace: torch.Tensor):
+        self.workspace = workspace
+        self.ops = []  # (pc_chain_op, reads, writes, keep-alive)
+
+    def add(self, op: pc_chain_op, reads, writes, keep) -> None:
+        reads = {t.data_ptr() for t in reads if t is not None}
+        writes = {t.data_ptr() for t in writes if t is not None}
+        if len(self.ops) == PC_CHAIN_MAX_OPS:
+            self.flush()
+        dep = -1
+        for i, (_, r, w, _) in enumerate(self.ops):
+            if (w & reads) or (r & writes) or (w & writes):
+                dep = i
+        op.dep = dep
+        self.ops.append((op, reads, writes, keep))
+
+    def flush(self) -> None:
+        if not self.ops:
+            return
+        arr = (pc_chain_op * len(self.ops))(*[o[0] for o in self.ops])
+        n = len(self.ops)
+        self.ops = []
+        ws = self.workspace
+        _check(load().pc_linear_chain(arr, n, ws.data_ptr(), ws.numel() * ws.element_size(), _stream()), "pc_linear_chain")
+
+
+_chain: Optional[_Chain] = None
+
+
+@contextlib.contextmanager
+def chain(workspace: torch.Tensor):
+    """Inside the block linear_small / linear_partials / linear_rope_append (pre-tiled weights) and add_rmsnorm /
+    add_layernorm (partial-stack or no deltas) are recorded instead of launched; the block's end launches them as one
+    pc_linear_chain (several, if more than PC_CHAIN_MAX_OPS were recorded).  Anything else that is called in between
+    flushes the recorded ops first, so stream order is what the program order says."""
+    global _chain
+    if _chain is not None:
+        raise NativeError("chain: already recording")
+    _require_cuda(workspace)
+    ch = _Chain(workspace)
+    _chain = ch
+    try:
+        yield ch
+    except BaseException:
+        _chain = None
+        raise
+    _chain = None
+    ch.flush()
+
+
+def chain_flush() -> None:
+    """Launch what the active chain has recorded so far (no-op outside a chain block)."""
+    if _chain is not None:
+        _chain.flush()
+
+
+def _emit_linear(p: pc_linear_params, reads, writes) -> None:
+    if _chain is not None and p.w_tiled:
+        op = pc_chain_op()
+        op.kind = PC_CHAIN_LINEAR
+        op.lin = p
+        _chain.add(op, reads, writes, (reads, writes))
+        return
+    chain_flush()
+    _check(load().pc_linear_small(C.byref(p), _stream()), "pc_linear_small")
+
+
+def _emit_norm(kind: int, x, part1, part2, weight, bias, h_out, eps) -> None:
+    op = pc_chain_op()
+    op.kind = kind
+    op.x, op.weight, op.h_out = x.data_ptr(), weight.data_ptr(), h_out.data_ptr()
+    op.bias = bias.data_ptr() if bias is not None else None
+    op.part1 = part1.data_ptr() if part1 is not None else None
+    op.part2 = part2.data_ptr() if part2 is not None else None
+    op.n_splits1 = part1.shape[0] if part1 is not None else 0
+    op.n_splits2 = part2.shape[0] if part2 is not None else 0
+    op.rows, op.hidden, op.eps = x.shape[0], x.shape[1], float(eps)
+    _chain.add(op, (x, part1, part2), (x, h_out), (x, part1, part2, weight, bias, h_out))
 
 
 def add_rmsnorm(x: torch.Tensor, delta: Optional[torch.Tensor], weight: torch.Tensor, h_out: torch.Tensor,
@@ -337,14 +442,18 @@ def add_rmsnorm(x: torch.Tensor, delta: Optional[torch.Tensor], weight: torch.Te
         if not (x.is_contiguous() and h_out.is_contiguous() and delta.is_contiguous()) or x.dtype != torch.float16 \
                 or delta.dim() != 3 or tuple(delta.shape[1:]) != (rows, hidden):
             raise NativeError("add_rmsnorm: partials must be contiguous fp32 [splits, rows, hidden]")
+        if _chain is not None:
+            return _emit_norm(PC_CHAIN_ADD_RMSNORM, x, delta, None, weight, None, h_out, eps)
         _check(load().pc_add_rmsnorm_partials(x.data_ptr(), delta.data_ptr(), delta.shape[0], weight.data_ptr(), h_out.data_ptr(),
-                                              rows, hidden, float(eps), _stream()), "pc_add_rmsnorm_partials")
+                                              rows, hidden, float(eps), _stream_flush()), "pc_add_rmsnorm_partials")
         return
     if not (x.is_contiguous() and h_out.is_contiguous() and (delta is None or delta.is_contiguous())) or x.dtype != torch.float16:
         raise NativeError("add_rmsnorm: tensors must be contiguous fp16")
+    if _chain is not None and delta is None:
+        return _emit_norm(PC_CHAIN_ADD_RMSNORM, x, None, None, weight, None, h_out, eps)
     rows, hidden = x.shape
     _check(load().pc_add_rmsnorm(x.data_ptr(), delta.data_ptr() if delta is not None else None, weight.data_ptr(),
-                                 h_out.data_ptr(), rows, hidden, float(eps), _stream()), "pc_add_rmsnorm")
+                                 h_out.data_ptr(), rows, hidden, float(eps), _stream_flush()), "pc_add_rmsnorm")
 
 
 def add_layernorm(x: torch.Tensor, d1: Optional[torch.Tensor], d2: Optional[torch.Tensor], weight: torch.Tensor,
@@ -359,18 +468,22 @@ def add_layernorm(x: torch.Tensor, d1: Optional[torch.Tensor], d2: Optional[torc
                 raise NativeError("add_layernorm: partials must be contiguous fp32 [splits, rows, hidden] stacks")
         if not (x.is_contiguous() and h_out.is_contiguous()):
             raise NativeError("add_layernorm: x / h_out must be contiguous")
+        if _chain is not None:
+            return _emit_norm(PC_CHAIN_ADD_LAYERNORM, x, d1, d2, weight, bias, h_out, eps)
         _check(load().pc_add_layernorm_partials(x.data_ptr(), d1.data_ptr(), d1.shape[0], d2.data_ptr() if d2 is not None else None,
                                                 d2.shape[0] if d2 is not None else 0, weight.data_ptr(),
                                                 bias.data_ptr() if bias is not None else None, h_out.data_ptr(), rows, hidden, float(eps),
-                                                _stream()), "pc_add_layernorm_partials")
+                                                _stream_flush()), "pc_add_layernorm_partials")
         return
     for t in (x, h_out, d1, d2):
         if t is not None and (not t.is_contiguous() or t.dtype != torch.float16 or t.shape != x.shape):
             raise NativeError("add_layernorm: x / deltas / h_out must be contiguous fp16 tensors of one shape")
+    if _chain is not None and d1 is None and d2 is None:
+        return _emit_norm(PC_CHAIN_ADD_LAYERNORM, x, None, None, weight, bias, h_out, eps)
     rows, hidden = x.shape
     _check(load().pc_add_layernorm(x.data_ptr(), d1.data_ptr() if d1 is not None else None, d2.data_ptr() if d2 is not None else None,
                                    weight.data_ptr(), bias.data_ptr() if bias is not None else None, h_out.data_ptr(), rows, hidden,
-                                   float(eps), _stream()), "pc_add_layernorm")
+                                   float(eps), _stream_flush()), "pc_add_layernorm")
 
 
 def silu_mul(gate_up: torch.Tensor, out: torch.Tensor, inter: int) -> None:
@@ -378,7 +491,7 @@ def silu_mul(gate_up: torch.Tensor, out: torch.Tensor, inter: int) -> None:
     _require_cuda(gate_up, out)
     if gate_up.stride(1) != 1 or not out.is_contiguous() or gate_up.dtype != torch.float16:
         raise NativeError("silu_mul: tensors must be fp16 with contiguous rows")
-    _check(load().pc_silu_mul(gate_up.data_ptr(), out.data_ptr(), gate_up.shape[0], inter, gate_up.stride(0), _stream()),
+    _check(load().pc_silu_mul(gate_up.data_ptr(), out.data_ptr(), gate_up.shape[0], inter, gate_up.stride(0), _stream_flush()),
            "pc_silu_mul")
 
 
@@ -446,7 +559,7 @@ def linear_small(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, workspace:
     if out.dim() != 2 or out.dtype != torch.float16 or out.stride(1) != 1 or out.shape[0] != x.shape[0] or out.shape[1] != cols:
         raise NativeError(f"linear_small: out {tuple(out.shape)} must be fp16 [{x.shape[0]},{cols}] with contiguous rows")
     p.out, p.out_stride = out.data_ptr(), out.stride(0)
-    _check(load().pc_linear_small(C.byref(p), _stream()), "pc_linear_small")
+    _emit_linear(p, (x,), (out,))
 
 
 def linear_rope_append(x: torch.Tensor, wqkv: torch.Tensor, position_ids: Optional[torch.Tensor], cos: Optional[torch.Tensor],
@@ -476,7 +589,7 @@ def linear_rope_append(x: torch.Tensor, wqkv: torch.Tensor, position_ids: Option
         p.dst_row0, p.dst_row0_dev = 0, dst_row0.data_ptr()
     else:
         p.dst_row0 = int(dst_row0)
-    _check(load().pc_linear_small(C.byref(p), _stream()), "pc_linear_small")
+    _emit_linear(p, (x, position_ids, dst_row0 if isinstance(dst_row0, torch.Tensor) else None), (q_out, k_cache, v_cache))
 
 
 
@@ -494,5 +607,5 @@ def linear_partials(x: torch.Tensor, w: torch.Tensor, part: torch.Tensor, worksp
     if part.dtype != torch.float32 or not part.is_contiguous() or tuple(part.shape) != (splits, x.shape[0], w.shape[0]):
         raise NativeError(f"linear_partials: part {tuple(part.shape)} must be contiguous fp32 [{splits},{x.shape[0]},{w.shape[0]}]")
     p.out, p.out_stride = part.data_ptr(), w.shape[0]
-    _check(load().pc_linear_small(C.byref(p), _stream()), "pc_linear_small")
+    _emit_linear(p, (x,), (part,))
     return splits

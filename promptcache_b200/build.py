@@ -15,8 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpromptcache_b200.so")
 STAMP = os.path.join(HERE, ".libpromptcache_b200.stamp")
-SOURCES = ["api.cu", "splice.cu", "rope_append.cu", "attn_simt.cu", "attn_combine.cu", "attn_tc_small.cu", "attn_tc2.cu", "support.cu", "linear_small.cu"]
-HEADERS = [os.path.join(CSRC, "pc_common.cuh"), os.path.join(HERE, "..", "include", "promptcache_b200.h")]
+SOURCES = ["api.cu", "splice.cu", "rope_append.cu", "attn_simt.cu", "attn_combine.cu", "attn_tc_small.cu", "attn_tc2.cu", "support.cu", "linear_small.cu", "linear_chain.cu"]
+HEADERS = [os.path.join(CSRC, "pc_common.cuh"), os.path.join(CSRC, "linear_common.cuh"), os.path.join(HERE, "..", "include", "promptcache_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

@@ -26,216 +26,11 @@
 // * epilogues: plain fp16 store; half(silu(gate)) * up (llama2.py:241) with gate and up rows of the same
 //   features in one tile; RoPE at explicit position ids + in-place KV append with the reference's three fp16
 //   roundings (llama2.py:195-210,357-364) when a tile is one head (D = 128).
-#include <cuda.h>
-#include <math.h>
-#include <stdlib.h>
-
-#include "pc_common.cuh"
+#include "linear_common.cuh"
 
 namespace pc {
-
-int make_tensor_map_3d(CUtensorMap* map, const void* base, int D, long long rows, int heads, long long head_stride,
-                       int box_rows);
-
+namespace lin {
 namespace {
-
-constexpr int BM = 128;                 // out-features per tile (MMA M)
-constexpr int BKK = 64;                 // k per stage: one 128-byte swizzled row
-constexpr int kWBytes = BM * BKK * 2;   // 16 KiB
-constexpr int kEpiThreads = 128;
-constexpr int kThreads = 64 + kEpiThreads + 32;  // W-TMA warp + MMA warp + 4 epilogue warps + X-TMA warp
-constexpr size_t kLinCounterBytes = 16384;  // 4096 tile arrival counters
-constexpr int kMaxTiles = 4096;
-
-// KPS = k-blocks per pipeline stage: 1 with tensor-map loads of the row-major weight, 2 with pre-tiled weights (one
-// 32 KiB bulk copy per stage).
-template <int NPAD, int KPS>
-struct LCfg {
-  static constexpr int kXBytes = NPAD * BKK * 2;
-  static constexpr int kStageBytes = KPS * (kWBytes + kXBytes);
-  // bytes in flight per SM bound its streaming rate (Little's law, ~2.5 us loaded latency): as many stages as fit
-#ifndef PC_LIN_STAGES16
-#define PC_LIN_STAGES16 6
-#endif
-  static constexpr int kStages = KPS == 2 ? (NPAD <= 16 ? PC_LIN_STAGES16 : 5) : (NPAD <= 16 ? 11 : 10);
-  static constexpr int kOffExch = kStages * kStageBytes;
-  static constexpr int kExchBytes = NPAD * BM * 2;
-  static constexpr int kOffBars = kOffExch + kExchBytes;
-  // 1 KiB of slack for the 1024-byte alignment of the swizzled tiles; the half-size ring (two CTAs per SM) has 768 B --
-  // the kernel traps if the dynamic shared memory base ever needs more
-  static constexpr int kAlignSlack = (KPS == 2 && NPAD <= 16 && PC_LIN_STAGES16 <= 3) ? 768 : 1024;
-  static constexpr int kSmem = kAlignSlack + kOffBars + 256;
-  static constexpr int kMinBlocks = (KPS == 2 && NPAD <= 16 && PC_LIN_STAGES16 <= 3) ? 2 : 1;
-  static constexpr int kTmemCols = 2 * NPAD <= 32 ? 32 : 64;
-};
-
-struct LinParams {
-  __half* out;
-  long long out_stride;
-  float* slots;
-  int* counters;
-  int n_out;             // valid output columns (PLAIN: weight rows; SILU: inter)
-  int q_len, kb_total, tile_row_stride, second_half_off;
-  int w_one_box;         // the weight tile is 128 consecutive rows: one TMA box instead of two
-  const unsigned char* w_tiled;  // TILED: weights re-laid out as [tile][k-block] 16 KiB shared-memory images
-  int whole_per_cta;     // tiles [0, whole_per_cta * grid) are processed whole, the rest is the stream-K region
-  int splits;            // PARTIALS: regular split-K, CTA = (tile, split); fp32 partials go to part_out[split][t][col]
-  float* part_out;
-  long long units_total;
-  // RoPE + append epilogue
-  const long long* pos;
-  const __half* cos;
-  const __half* sin;
-  int table_rows;
-  __half* q_out;
-  __half* k_cache;
-  __half* v_cache;
-  int max_ctx, row0, n_heads, n_kv_heads;
-  int head_dim;          // ROPE_APPEND: 128 (one head per tile) or 64 (two heads per tile: Falcon)
-  const int* row0_dev;
-  unsigned long long* trace;  // debug: 8 %globaltimer stamps per CTA (PC_LIN_TRACE_PTR), else nullptr
-  // L2 prefetch of the NEXT linear's weight stream (pre-tiled): once this CTA has issued its last weight load it asks
-  // L2 for the first pf_units pipeline stages of the CTAs of the next launch (their partition is replayed here), so
-  // that the next kernel's ring fills from L2 instead of paying the HBM latency after every launch boundary
-  int act;               // PLAIN: 1 = exact GELU applied to the fp16-rounded output (mpt.py:200-208 / falcon MLP)
-  const unsigned char* pf_w;
-  long long pf_units_total;
-  int pf_kb, pf_grid, pf_whole, pf_splits, pf_units;
-};
-
-// units [u0, u1) of CTA c (same arithmetic as the kernel prologue; `splits` > 0 = PC_LIN_PARTIALS)
-__device__ __forceinline__ void cta_units(int c, int G, long long U, int KB, int splits, long long& u0, long long& u1) {
-  if (splits > 0) {
-    const int tile_c = c / splits, sp = c - tile_c * splits;
-    u0 = static_cast<long long>(tile_c) * KB + (static_cast<long long>(sp) * KB) / splits;
-    u1 = static_cast<long long>(tile_c) * KB + (static_cast<long long>(sp + 1) * KB) / splits;
-    return;
-  }
-  const int Gs = static_cast<int>(min(static_cast<long long>(G), U));
-  u0 = c < Gs ? (static_cast<long long>(c) * U) / Gs : 0;
-  u1 = c < Gs ? (static_cast<long long>(c + 1) * U) / Gs : 0;
-}
-
-__device__ __forceinline__ unsigned long long gtime() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-#ifdef PC_DEBUG
-#define LIN_TRACE(slot)                                                 \
-  do {                                                                  \
-    if (p.trace != nullptr) p.trace[blockIdx.x * 8 + (slot)] = gtime(); \
-  } while (0)
-#else
-#define LIN_TRACE(slot) do { } while (0)
-#endif
-
-__device__ __forceinline__ void named_bar_sync(int id, int n) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
-}
-
-// CTA whose unit range [c*U/G, (c+1)*U/G) holds unit u.
-__device__ __forceinline__ int cta_of_unit(long long u, long long U, int G) {
-  int c = static_cast<int>(((u + 1) * G + U - 1) / U) - 1;
-  if (c < 0) c = 0;
-  if (c > G - 1) c = G - 1;
-  while (c + 1 < G && (static_cast<long long>(c + 1) * U) / G <= u) ++c;
-  while (c > 0 && (static_cast<long long>(c) * U) / G > u) --c;
-  return c;
-}
-
-template <int N>
-__device__ __forceinline__ void tmem_ld_acc(uint32_t addr, float (&v)[N]) {
-  if constexpr (N == 16) tmem_ld16(addr, reinterpret_cast<uint32_t(&)[16]>(v));
-  else tmem_ld32(addr, reinterpret_cast<uint32_t(&)[32]>(v));
-}
-
-// One CTA's share of the (tile, k-block) space, cut at tile boundaries.  Segments that cover only part of a
-// tile's K ("partial": at most the first and the last of the range) are visited FIRST, whole tiles last: the
-// cross-CTA reduction of a partial (publish -> arrival counter -> slot reads) then overlaps the streaming of the
-// whole tiles instead of sitting in the kernel's tail.
-struct Seg {
-  int tile, kb0, n;
-  int rel;  // tile index inside the stream-K region (what the split bookkeeping counts in), -1 for a whole tile of phase 2
-};
-struct SegIter {
-  long long u0, u1;
-  int KB, t_first, t_last, phase, cur;
-  bool first_partial, last_partial;
-  __device__ SegIter(long long u0_, long long u1_, int KB_) : u0(u0_), u1(u1_), KB(KB_) {
-    if (u0 >= u1) {  // empty range
-      t_first = t_last = 0;
-      first_partial = last_partial = false;
-      phase = 2;
-      cur = 1;
-      return;
-    }
-    t_first = static_cast<int>(u0 / KB);
-    t_last = static_cast<int>((u1 - 1) / KB);
-    const long long first_end = min(u1, static_cast<long long>(t_first + 1) * KB);
-    first_partial = (u0 != static_cast<long long>(t_first) * KB) || (first_end - u0 != KB);
-    last_partial = (t_last > t_first) && (u1 != static_cast<long long>(t_last + 1) * KB);
-    phase = 0;
-    cur = first_partial ? t_first + 1 : t_first;
-  }
-  __device__ bool next(Seg& s) {
-    if (phase == 0) {
-      phase = 1;
-      if (last_partial) {
-        s.tile = t_last;
-        s.kb0 = 0;
-        s.n = static_cast<int>(u1 - static_cast<long long>(t_last) * KB);
-        return true;
-      }
-    }
-    if (phase == 1) {
-      phase = 2;
-      if (first_partial) {
-        s.tile = t_first;
-        s.kb0 = static_cast<int>(u0 - static_cast<long long>(t_first) * KB);
-        s.n = static_cast<int>(min(u1, static_cast<long long>(t_first + 1) * KB) - u0);
-        return true;
-      }
-    }
-    const int end = last_partial ? t_last - 1 : t_last;
-    if (cur <= end) {
-      s.tile = cur++;
-      s.kb0 = 0;
-      s.n = KB;
-      return true;
-    }
-    return false;
-  }
-};
-
-// A CTA's whole work list.  With more tiles than CTAs (gate/up, lm_head) the tiles [0, W*G) are dealt out WHOLE, W per
-// CTA, and only the remaining n_tiles - W*G tiles are shared stream-K fashion -- and those come first, so that their
-// cross-CTA reduction overlaps the streaming of the whole tiles and the kernel ends with a plain epilogue.
-struct WorkIter {
-  SegIter it;
-  int W, G, c, KB, rem_tile0, r;
-  __device__ WorkIter(long long u0, long long u1, int KB_, int W_, int G_, int c_) : it(u0, u1, KB_), W(W_), G(G_), c(c_), KB(KB_) {
-    rem_tile0 = W * G;
-    r = 0;
-  }
-  __device__ bool next(Seg& s) {
-    if (it.next(s)) {
-      s.rel = s.tile;
-      s.tile += rem_tile0;
-      return true;
-    }
-    if (r < W) {
-      s.tile = c + r * G;
-      s.rel = -1;
-      s.kb0 = 0;
-      s.n = KB;
-      ++r;
-      return true;
-    }
-    return false;
-  }
-};
-
 template <int NPAD, int EPI, bool TILED>
 __global__ void __launch_bounds__(kThreads, LCfg<NPAD, TILED ? 2 : 1>::kMinBlocks)
 linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const LinParams p) {
@@ -257,17 +52,9 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KB = p.kb_total / KPS;  // pipeline stages (units) per tile
-  const long long U = p.units_total;
-  const int G = gridDim.x, c = blockIdx.x;
-  // the stream-K region is shared by the first Gs CTAs (all of them unless it holds fewer units than there are CTAs)
-  const int Gs = static_cast<int>(min(static_cast<long long>(G), U));
-  long long u0 = c < Gs ? (static_cast<long long>(c) * U) / Gs : 0;
-  long long u1 = c < Gs ? (static_cast<long long>(c + 1) * U) / Gs : 0;
-  if constexpr (EPI == PC_LIN_PARTIALS) {  // regular split-K: every tile is cut into `splits` equal K ranges
-    const int tile_c = c / p.splits, sp = c - tile_c * p.splits;
-    u0 = static_cast<long long>(tile_c) * KB + (static_cast<long long>(sp) * KB) / p.splits;
-    u1 = static_cast<long long>(tile_c) * KB + (static_cast<long long>(sp + 1) * KB) / p.splits;
-  }
+  const int G = p.grid, c = blockIdx.x;
+  long long u0, u1;
+  lin_cta_range(p, EPI, c, KB, u0, u1);
   if (tid == 0) LIN_TRACE(0);
   if (tid == 0 && p.trace != nullptr) {  // slot 7: the SM this CTA runs on
     unsigned smid;
@@ -409,7 +196,6 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
     const int t_first = it.it.t_first;
     Seg sg;
     while (it.next(sg)) {
-      const int tile = sg.tile;
       const int buf = seg & 1;
       mbar_wait(&acc_full[buf], static_cast<uint32_t>((seg >> 1) & 1));
       tc_fence_after();
@@ -419,143 +205,7 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&acc_empty[buf]);
-      bool finalize = true;
-      if constexpr (EPI == PC_LIN_PARTIALS) {
-        // no cross-CTA reduction here: the consumer (pc_add_rmsnorm_partials) adds the splits in a fixed order
-        finalize = false;
-        const int col = tile * BM + f;
-        float* po = p.part_out + static_cast<long long>(c - (c / p.splits) * p.splits) * p.q_len * p.n_out + col;
-        if (col < p.n_out) {
-#pragma unroll
-          for (int t = 0; t < NPAD; ++t)
-            if (t < p.q_len) po[static_cast<long long>(t) * p.n_out] = v[t];
-        }
-      } else if (sg.n != KB) {
-        // partial K range: park the fp32 partial; the last CTA to arrive at this tile adds them up
-        const int rel = sg.rel;  // tile index inside the stream-K region
-        const int slot = (rel == t_first) ? 0 : 1;
-        float* sp = p.slots + (static_cast<size_t>(c) * 2 + slot) * NPAD * BM;
-#pragma unroll
-        for (int t = 0; t < NPAD; ++t)
-          if (t < p.q_len) __stcg(sp + t * BM + f, v[t]);
-        named_bar_sync(1, kEpiThreads);  // orders every thread's stores before thread 0's gpu-scope fence + arrival
-        if (et == 0) {
-          const int c_first = cta_of_unit(static_cast<long long>(rel) * KB, U, Gs);
-          const int c_last = cta_of_unit(static_cast<long long>(rel) * KB + KB - 1, U, Gs);
-          __threadfence();
-          const int old = atomicAdd(p.counters + tile, 1);
-          const int last = (old == c_last - c_first) ? 1 : 0;
-          if (last) p.counters[tile] = 0;  // self-cleaning for the next launch
-          __threadfence();
-          flag[0] = last;
-          flag[1] = c_first;
-          flag[2] = c_last;
-          LIN_TRACE(5);
-        }
-        named_bar_sync(1, kEpiThreads);
-        finalize = flag[0] != 0;
-        if (finalize) {
-          const int c_first = flag[1], c_last = flag[2];
-#pragma unroll
-          for (int t = 0; t < NPAD; ++t) v[t] = 0.f;
-          constexpr int CH = NPAD <= 16 ? 4 : 2;  // contributors whose loads are in flight together
-          for (int cc = c_first; cc <= c_last; cc += CH) {
-            float tmp[CH][NPAD];
-#pragma unroll
-            for (int j = 0; j < CH; ++j) {
-              const int ccj = min(cc + j, c_last);
-              const long long cu0 = (static_cast<long long>(ccj) * U) / Gs;
-              const int slot_c = (cu0 / KB == sg.rel) ? 0 : 1;
-              const float* rp = p.slots + (static_cast<size_t>(ccj) * 2 + slot_c) * NPAD * BM;
-#pragma unroll
-              for (int t = 0; t < NPAD; ++t) tmp[j][t] = (cc + j <= c_last && t < p.q_len) ? __ldcg(rp + t * BM + f) : 0.f;
-            }
-#pragma unroll
-            for (int j = 0; j < CH; ++j) {  // fixed order: deterministic sums
-#pragma unroll
-              for (int t = 0; t < NPAD; ++t) v[t] += tmp[j][t];
-            }
-          }
-        }
-      }
-      if (finalize) {
-        if constexpr (EPI == PC_LIN_PLAIN || EPI == PC_LIN_PARTIALS) {
-          const int col = tile * BM + f;
-          if (col < p.n_out) {
-            if (EPI == PC_LIN_PLAIN && p.act == 1) {
-              // nn.GELU() on the fp16 output of the projection: 0.5 x (1 + erf(x / sqrt 2)) in fp32, rounded once
-#pragma unroll
-              for (int t = 0; t < NPAD; ++t) {
-                const float xg = __half2float(__float2half_rn(v[t]));
-                v[t] = 0.5f * xg * (1.f + erff(xg * 0.70710678118654752440f));
-              }
-            }
-#pragma unroll
-            for (int t = 0; t < NPAD; ++t)
-              if (t < p.q_len) p.out[t * p.out_stride + col] = __float2half_rn(v[t]);
-          }
-        } else if constexpr (EPI == PC_LIN_SILU_MUL) {
-          // rows [0,64) of the tile are gate features, rows [64,128) the up features of the same columns
-          if (f >= 64) {
-#pragma unroll
-            for (int t = 0; t < NPAD; ++t) exch[t * 64 + (f - 64)] = __float2half_rn(v[t]);
-          }
-          named_bar_sync(1, kEpiThreads);
-          const int col = tile * 64 + f;
-          if (f < 64 && col < p.n_out) {
-#pragma unroll
-            for (int t = 0; t < NPAD; ++t) {
-              if (t < p.q_len) {
-                const float g = __half2float(__float2half_rn(v[t]));  // gate_proj output is fp16
-                const float s = g / (1.f + expf(-g));
-                p.out[t * p.out_stride + col] = __hmul_rn(__float2half_rn(s), exch[t * 64 + f]);
-              }
-            }
-          }
-          named_bar_sync(1, kEpiThreads);
-        } else {
-          // a tile holds 128 / D heads: [0,H) query heads, [H,H+Hkv) key heads, then value heads (rows past them: padding)
-#pragma unroll
-          for (int t = 0; t < NPAD; ++t) exch[t * BM + f] = __float2half_rn(v[t]);
-          named_bar_sync(1, kEpiThreads);
-          const int H = p.n_heads, Hkv = p.n_kv_heads, HD = p.head_dim;
-          const int head = (tile * BM + f) / HD, d = f & (HD - 1);
-          const bool rotate = (head < H + Hkv) && p.cos != nullptr;
-          __half* dst;
-          if (head < H) dst = p.q_out + static_cast<long long>(head) * p.q_len * HD + d;
-          else if (head < H + Hkv) dst = p.k_cache + (static_cast<long long>(head - H) * p.max_ctx + row0) * HD + d;
-          else dst = p.v_cache + (static_cast<long long>(head - H - Hkv) * p.max_ctx + row0) * HD + d;
-          if (head < H + 2 * Hkv) {
-            if (rotate) {
-              // all table gathers first (independent loads in flight together), then the arithmetic
-              __half cs[NPAD], sn[NPAD];
-#pragma unroll
-              for (int t = 0; t < NPAD; ++t) {
-                long long pos = t < p.q_len ? __ldg(p.pos + t) : 0;
-                if (pos < 0) pos = 0;
-                if (pos >= p.table_rows) pos = p.table_rows - 1;
-                cs[t] = __ldg(p.cos + pos * HD + d);
-                sn[t] = __ldg(p.sin + pos * HD + d);
-              }
-              const int half_d = HD >> 1;
-#pragma unroll
-              for (int t = 0; t < NPAD; ++t) {
-                if (t < p.q_len) {
-                  const __half x = exch[t * BM + f];
-                  const __half partner = exch[t * BM + (f ^ half_d)];
-                  const __half rot = d < half_d ? __hneg(partner) : partner;  // rotate_half(x) = cat(-x2, x1)
-                  dst[t * HD] = __hadd_rn(__hmul_rn(x, cs[t]), __hmul_rn(rot, sn[t]));
-                }
-              }
-            } else {
-#pragma unroll
-              for (int t = 0; t < NPAD; ++t)
-                if (t < p.q_len) dst[t * HD] = exch[t * BM + f];
-            }
-          }
-          named_bar_sync(1, kEpiThreads);
-        }
-      }
+      lin_epilogue<NPAD, EPI>(p, sg, v, c, KB, t_first, exch, flag, f, et, row0);
       ++seg;
     }
     if (et == 0) LIN_TRACE(6);
@@ -646,20 +296,23 @@ int tile_geometry(int n_rows, int epilogue, TileGeom* g) {
 }
 
 }  // namespace
+}  // namespace lin
 }  // namespace pc
 
 // k-blocks of the pre-tiled copy: a pipeline stage is two k-blocks, so an odd count (Falcon: k = 4544 = 71 blocks) is padded
 // with one block of zeros (the tensor-map load that produces the copy reads zeros past k; so do the X loads of the kernel)
-static inline int tiled_k_blocks(int k) { return ((k / pc::BKK) + 1) & ~1; }
+int pc::lin::tiled_k_blocks(int k) { return ((k / BKK) + 1) & ~1; }
+using pc::lin::tiled_k_blocks;
 
 PC_API size_t pc_linear_tiled_bytes(int n_rows, int k, int epilogue) {
-  pc::TileGeom g;
-  if (n_rows <= 0 || k <= 0 || k % pc::BKK != 0 || pc::tile_geometry(n_rows, epilogue, &g) != PC_OK) return 0;
-  return static_cast<size_t>(g.n_tiles) * tiled_k_blocks(k) * pc::kWBytes;
+  pc::lin::TileGeom g;
+  if (n_rows <= 0 || k <= 0 || k % pc::lin::BKK != 0 || pc::lin::tile_geometry(n_rows, epilogue, &g) != PC_OK) return 0;
+  return static_cast<size_t>(g.n_tiles) * tiled_k_blocks(k) * pc::lin::kWBytes;
 }
 
 PC_API int pc_linear_tile_weights(const void* w, int n_rows, int k, int epilogue, void* w_tiled, void* stream) {
   using namespace pc;
+  using namespace pc::lin;
   PC_REQUIRE(w && w_tiled, "pc_linear_tile_weights: null pointer");
   PC_REQUIRE(n_rows > 0 && k > 0 && k % BKK == 0, "pc_linear_tile_weights: k %d must be a positive multiple of 64", k);
   PC_REQUIRE((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(w_tiled)) % 16 == 0, "pc_linear_tile_weights: 16B alignment");
@@ -685,7 +338,7 @@ PC_API int pc_linear_tile_weights(const void* w, int n_rows, int k, int epilogue
 
 PC_API int pc_linear_partial_splits(int n_rows, int k) {
   if (n_rows <= 0 || k <= 0) return 0;
-  const int n_tiles = (n_rows + pc::BM - 1) / pc::BM;
+  const int n_tiles = (n_rows + pc::lin::BM - 1) / pc::lin::BM;
   int s = pc::sm_count() / n_tiles;  // as many CTAs per row tile as fit at once ...
   if (s > 8) s = 8;
   if (s > k / 128) s = k / 128;      // ... with at least one pipeline stage (128 columns) each
@@ -694,6 +347,7 @@ PC_API int pc_linear_partial_splits(int n_rows, int k) {
 }
 
 namespace pc {
+namespace lin {
 namespace {
 #ifndef PC_LIN_PREFETCH_UNITS
 #define PC_LIN_PREFETCH_UNITS 6
@@ -737,16 +391,18 @@ void choose_grid(int epilogue, int n_tiles, int units_per_tile, bool tiled, int 
   *grid_out = grid;
 }
 }  // namespace
+}  // namespace lin
 }  // namespace pc
 
+// [tile arrival counters][stream-K slots][chain barrier counters (linear_chain.cu)]
 PC_API size_t pc_linear_workspace_bytes(void) {
-  return pc::kLinCounterBytes + static_cast<size_t>(pc::sm_count()) * 2 * 32 * pc::BM * sizeof(float);
+  return pc::lin::kLinCounterBytes + static_cast<size_t>(pc::sm_count()) * 2 * 32 * pc::lin::BM * sizeof(float) + pc::lin::kChainBarBytes;
 }
 
-PC_API int pc_linear_small(const pc_linear_params* p, void* stream) {
+int pc::lin::prepare_linear(const pc_linear_params* p, LinLaunch* out) {
   using namespace pc;
+  using namespace pc::lin;
   if (!p) return set_error(PC_ERR_INVALID, "pc_linear_small: null params");
-  if (p->q_len == 0) return PC_OK;
   PC_REQUIRE(p->x && p->w && p->workspace, "pc_linear_small: null tensor / workspace");
   PC_REQUIRE(p->q_len > 0 && p->q_len <= 32, "pc_linear_small: q_len %d must be in [1,32]", p->q_len);
   PC_REQUIRE(p->k > 0 && p->k % BKK == 0, "pc_linear_small: k %d must be a positive multiple of 64", p->k);
@@ -757,7 +413,8 @@ PC_API int pc_linear_small(const pc_linear_params* p, void* stream) {
              "pc_linear_small: x / w / workspace must be 16B aligned");
   PC_REQUIRE(p->workspace_bytes >= pc_linear_workspace_bytes(), "pc_linear_small: workspace of %zu bytes, need %zu",
              p->workspace_bytes, pc_linear_workspace_bytes());
-  LinParams lp{};
+  LinParams& lp = out->lp;
+  lp = LinParams{};
   lp.q_len = p->q_len;
   const bool tiled = p->w_tiled != nullptr;
   lp.kb_total = tiled ? tiled_k_blocks(p->k) : p->k / BKK;
@@ -876,13 +533,32 @@ PC_API int pc_linear_small(const pc_linear_params* p, void* stream) {
   }
   lp.w_one_box = (lp.second_half_off == 64) ? 1 : 0;
   if (const char* e = dbg_env("PC_LIN_ONEBOX")) lp.w_one_box = lp.w_one_box && atoi(e) != 0;
-  CUtensorMap mw, mx;
+  lp.grid = grid;
+  CUtensorMap& mw = out->map_w;
+  CUtensorMap& mx = out->map_x;
   if (int rc = make_tensor_map_3d(&mw, p->w, p->k, p->n_rows, 1, static_cast<long long>(p->n_rows) * p->k, lp.w_one_box ? 128 : 64))
     return rc;
   const int npad = p->q_len <= 16 ? 16 : 32;
   // rows >= q_len of the X box read as zeros
   if (int rc = make_tensor_map_3d(&mx, p->x, p->k, p->q_len, 1, static_cast<long long>(p->q_len) * p->x_stride, npad)) return rc;
+  out->grid = grid;
+  out->npad = npad;
+  out->epilogue = p->epilogue;
+  out->tiled = tiled;
+  return PC_OK;
+}
+
+PC_API int pc_linear_small(const pc_linear_params* p, void* stream) {
+  using namespace pc;
+  using namespace pc::lin;
+  if (!p) return set_error(PC_ERR_INVALID, "pc_linear_small: null params");
+  if (p->q_len == 0) return PC_OK;
+  LinLaunch L;
+  if (int rc = prepare_linear(p, &L)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (tiled) return npad == 16 ? launch_lin_n<16, true>(p->epilogue, mw, mx, lp, grid, st) : launch_lin_n<32, true>(p->epilogue, mw, mx, lp, grid, st);
-  return npad == 16 ? launch_lin_n<16, false>(p->epilogue, mw, mx, lp, grid, st) : launch_lin_n<32, false>(p->epilogue, mw, mx, lp, grid, st);
+  if (L.tiled)
+    return L.npad == 16 ? launch_lin_n<16, true>(L.epilogue, L.map_w, L.map_x, L.lp, L.grid, st)
+                        : launch_lin_n<32, true>(L.epilogue, L.map_w, L.map_x, L.lp, L.grid, st);
+  return L.npad == 16 ? launch_lin_n<16, false>(L.epilogue, L.map_w, L.map_x, L.lp, L.grid, st)
+                      : launch_lin_n<32, false>(L.epilogue, L.map_w, L.map_x, L.lp, L.grid, st);
 }

@@ -44,6 +44,11 @@ class B200CausalLM(nn.Module):
         # experiment, off: each native linear asks L2 for the head of the next one's weight stream while its own tail drains --
         # measured SLOWER (3.43 vs 3.31 ms per C2 step, worse with more stages): the tail is bandwidth-contended, not idle
         self.linear_prefetch = os.environ.get("PC_LINEAR_PREFETCH", "0") != "0"
+        # experiment, off: the linears and norms between two attention launches as ONE persistent launch (pc_linear_chain, grid
+        # barriers between the ops).  Measured SLOWER: 106 vs 87 us per Llama-2-7B layer (4.22 vs 3.30 ms per C2 step) -- each
+        # of the 5 grid barriers + 2 in-kernel norms of a layer is a chain of L2 round trips under a saturated memory system,
+        # ~33 us of consumer stalls per layer against the ring's 4.3 us of run-ahead
+        self.linear_chain = os.environ.get("PC_LINEAR_CHAIN", "0") != "0"
         # CUDA graphs of the whole single-sequence forward, keyed by (q_len, n_cached, KV buffer): the per-layer
         # launch sequence is fixed once those are, so a repeated request shape is replayed with one launch
         self.ablate = frozenset()  # measurement only: kernel families left out of the step (see LlamaForCausalLM._layers_ablated)
@@ -115,7 +120,7 @@ class B200CausalLM(nn.Module):
         """Every switch that changes the launch sequence of `_layers`; part of each graph key so that toggling one
         after a capture can never replay a stale sequence."""
         return (self.linear_impl, tuple(sorted(self.linear_native_ops)), self.linear_max_q, self.linear_partials,
-                self.linear_tiled, self.linear_prefetch, self.attn_impl, tuple(sorted(self.ablate)))
+                self.linear_tiled, self.linear_prefetch, self.linear_chain, self.attn_impl, tuple(sorted(self.ablate)))
 
     def _note_seen(self, key) -> None:
         if len(self._graph_seen) >= 256:  # bounded: forked / short-lived buffers would otherwise grow it forever

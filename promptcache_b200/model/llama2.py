@@ -8,6 +8,8 @@ called through the C ABI; projections, norms and the MLP stay torch/cuBLAS (SURV
 """
 from __future__ import annotations
 
+import contextlib
+
 from typing import Optional
 
 import torch
@@ -261,56 +263,62 @@ class LlamaForCausalLM(B200CausalLM):
         virt = kv.virtual  # cached rows still in the schema arena: attention reads them through the tile list
         if self.ablate:  # measurement only (bench.py: in-step cost of a kernel family = full step - step without it)
             return self._layers_ablated(x, h, pos, kv, q_rot, attn_out, act, ws, lws, pbuf_o, pbuf_d, n_dev)
-        for l in range(self.n_layers):
-            nat.add_rmsnorm(x, delta, self.ln1[l], h, self.eps)          # x += mlp(l-1); h = norm(x)
-            # n_dev: run-time cached length (decode graph); N is then only the sizing upper bound
-            if lin_qkv:
-                nat.linear_rope_append(h, self.wqkv[l], pos, self._cos, self._sin, q_rot, kv.k[l], kv.v[l],
-                                       N if n_dev is None else n_dev, H, Hkv, lws,
-                                       w_tiled=self._wt(("qkv", l), self.wqkv[l], nat.PC_LIN_ROPE_APPEND),
-                                       nxt=self._hint("o", l, pbuf_o is not None) if lin_o else None)
-            else:
-                qkv = F.linear(h, self.wqkv[l])                          # [q, (H+2Hkv)*D]
-                nat.rope_append(qkv[:, :H * D], qkv[:, H * D:(H + Hkv) * D], qkv[:, (H + Hkv) * D:], pos, self._cos,
-                                self._sin, q_rot, kv.k[l], kv.v[l], N if n_dev is None else n_dev, H, Hkv, D)
-            nat.attention(q_rot, kv.k[l], kv.v[l], attn_out, N if n_dev is None else kv.max_ctx - q_len, q_len, H, Hkv,
-                          D, self.scale, self.rounding, workspace=ws, decode=(q_len == 1), n_cached_dev=n_dev,
-                          impl=self.attn_impl if (n_dev is None and virt is None) else nat.PC_ATTN_TCGEN05,
-                          virtual=virt.planes(l) if virt is not None else None)
-            if lin_o and pbuf_o is not None:
-                nat.linear_partials(attn_out, self.wo[l], pbuf_o, lws, w_tiled=self._wt(("o", l), self.wo[l], nat.PC_LIN_PARTIALS),
-                                    nxt=self._hint("gu", l, False) if lin_gu else None)
-                delta = pbuf_o
-            elif lin_o:
-                nat.linear_small(attn_out, self.wo[l], dbuf, lws, w_tiled=self._wt(("o", l), self.wo[l], nat.PC_LIN_PLAIN),
-                                 nxt=self._hint("gu", l, False) if lin_gu else None)
-                delta = dbuf
-            else:
-                delta = F.linear(attn_out, self.wo[l])
-            nat.add_rmsnorm(x, delta, self.ln2[l], h, self.eps)          # x += attn; h = norm(x)
-            if lin_gu:
-                nat.linear_small(h, self.w_gate_up[l], act, lws, silu_mul=True,
-                                 w_tiled=self._wt(("gu", l), self.w_gate_up[l], nat.PC_LIN_SILU_MUL),
-                                 nxt=self._hint("down", l, pbuf_d is not None) if lin_down else None)
-            else:
-                gu = F.linear(h, self.w_gate_up[l])
-                nat.silu_mul(gu, act, inter)
-            if lin_down and pbuf_d is not None:
-                nxt_d = (self._hint("qkv", l + 1, False) if lin_qkv else None) if l + 1 < self.n_layers else \
-                    (self._hint("head", 0, False) if lin_head else None)
-                nat.linear_partials(act, self.w_down[l], pbuf_d, lws, w_tiled=self._wt(("down", l), self.w_down[l], nat.PC_LIN_PARTIALS),
-                                    nxt=nxt_d)
-                delta = pbuf_d
-            elif lin_down:
-                nxt_d = (self._hint("qkv", l + 1, False) if lin_qkv else None) if l + 1 < self.n_layers else \
-                    (self._hint("head", 0, False) if lin_head else None)
-                nat.linear_small(act, self.w_down[l], dbuf, lws, w_tiled=self._wt(("down", l), self.w_down[l], nat.PC_LIN_PLAIN), nxt=nxt_d)
-                delta = dbuf
-            else:
-                delta = F.linear(act, self.w_down[l])
-        nat.add_rmsnorm(x, delta, self.norm, h, self.eps)
+        # chain mode: everything between two attention launches (o_proj, norm, gate/up, down, norm, next QKV) is recorded and
+        # goes out as ONE persistent launch when the next non-chainable call (attention) or the end of the block flushes it
+        chained = lin and self.linear_chain and self.linear_tiled and pbuf_o is not None and pbuf_d is not None \
+            and lin_qkv and lin_o and lin_gu and lin_down and lin_head and not self.linear_prefetch
+        with (nat.chain(lws) if chained else contextlib.nullcontext()):
+            for l in range(self.n_layers):
+                nat.add_rmsnorm(x, delta, self.ln1[l], h, self.eps)          # x += mlp(l-1); h = norm(x)
+                # n_dev: run-time cached length (decode graph); N is then only the sizing upper bound
+                if lin_qkv:
+                    nat.linear_rope_append(h, self.wqkv[l], pos, self._cos, self._sin, q_rot, kv.k[l], kv.v[l],
+                                           N if n_dev is None else n_dev, H, Hkv, lws,
+                                           w_tiled=self._wt(("qkv", l), self.wqkv[l], nat.PC_LIN_ROPE_APPEND),
+                                           nxt=self._hint("o", l, pbuf_o is not None) if lin_o else None)
+                else:
+                    qkv = F.linear(h, self.wqkv[l])                          # [q, (H+2Hkv)*D]
+                    nat.rope_append(qkv[:, :H * D], qkv[:, H * D:(H + Hkv) * D], qkv[:, (H + Hkv) * D:], pos, self._cos,
+                                    self._sin, q_rot, kv.k[l], kv.v[l], N if n_dev is None else n_dev, H, Hkv, D)
+                nat.attention(q_rot, kv.k[l], kv.v[l], attn_out, N if n_dev is None else kv.max_ctx - q_len, q_len, H, Hkv,
+                              D, self.scale, self.rounding, workspace=ws, decode=(q_len == 1), n_cached_dev=n_dev,
+                              impl=self.attn_impl if (n_dev is None and virt is None) else nat.PC_ATTN_TCGEN05,
+                              virtual=virt.planes(l) if virt is not None else None)
+                if lin_o and pbuf_o is not None:
+                    nat.linear_partials(attn_out, self.wo[l], pbuf_o, lws, w_tiled=self._wt(("o", l), self.wo[l], nat.PC_LIN_PARTIALS),
+                                        nxt=self._hint("gu", l, False) if lin_gu else None)
+                    delta = pbuf_o
+                elif lin_o:
+                    nat.linear_small(attn_out, self.wo[l], dbuf, lws, w_tiled=self._wt(("o", l), self.wo[l], nat.PC_LIN_PLAIN),
+                                     nxt=self._hint("gu", l, False) if lin_gu else None)
+                    delta = dbuf
+                else:
+                    delta = F.linear(attn_out, self.wo[l])
+                nat.add_rmsnorm(x, delta, self.ln2[l], h, self.eps)          # x += attn; h = norm(x)
+                if lin_gu:
+                    nat.linear_small(h, self.w_gate_up[l], act, lws, silu_mul=True,
+                                     w_tiled=self._wt(("gu", l), self.w_gate_up[l], nat.PC_LIN_SILU_MUL),
+                                     nxt=self._hint("down", l, pbuf_d is not None) if lin_down else None)
+                else:
+                    gu = F.linear(h, self.w_gate_up[l])
+                    nat.silu_mul(gu, act, inter)
+                if lin_down and pbuf_d is not None:
+                    nxt_d = (self._hint("qkv", l + 1, False) if lin_qkv else None) if l + 1 < self.n_layers else \
+                        (self._hint("head", 0, False) if lin_head else None)
+                    nat.linear_partials(act, self.w_down[l], pbuf_d, lws, w_tiled=self._wt(("down", l), self.w_down[l], nat.PC_LIN_PARTIALS),
+                                        nxt=nxt_d)
+                    delta = pbuf_d
+                elif lin_down:
+                    nxt_d = (self._hint("qkv", l + 1, False) if lin_qkv else None) if l + 1 < self.n_layers else \
+                        (self._hint("head", 0, False) if lin_head else None)
+                    nat.linear_small(act, self.w_down[l], dbuf, lws, w_tiled=self._wt(("down", l), self.w_down[l], nat.PC_LIN_PLAIN), nxt=nxt_d)
+                    delta = dbuf
+                else:
+                    delta = F.linear(act, self.w_down[l])
+            nat.add_rmsnorm(x, delta, self.norm, h, self.eps)
+            if lin_head:
+                logits = torch.empty(q_len, self.vocab_size, dtype=torch.float16, device=self.device)
+                nat.linear_small(h, self.lm_head, logits, lws, w_tiled=self._wt(("lm_head", 0), self.lm_head, nat.PC_LIN_PLAIN))
         if lin_head:
-            logits = torch.empty(q_len, self.vocab_size, dtype=torch.float16, device=self.device)
-            nat.linear_small(h, self.lm_head, logits, lws, w_tiled=self._wt(("lm_head", 0), self.lm_head, nat.PC_LIN_PLAIN))
             return logits.float()
         return F.linear(h, self.lm_head).float()

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol(native):
     assert declared == set(native.EXPORTS), declared ^ set(native.EXPORTS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.pc_version() == 4
+    assert lib.pc_version() == 5
     assert lib.pc_launch_count() >= 0
 
 
@@ -30,17 +30,19 @@ def test_struct_layout_matches_header(native):
     assert ctypes.sizeof(native.pc_segment) == 16
     assert ctypes.sizeof(native.pc_copy2d) == 48
     assert ctypes.sizeof(native.pc_attn_params) == 152
+    assert ctypes.sizeof(native.pc_linear_params) == 176 and ctypes.sizeof(native.pc_chain_op) == 256
     import subprocess, tempfile, textwrap
     src = textwrap.dedent('''
         #include <stdio.h>
         #include "promptcache_b200.h"
-        int main(void){ printf("%zu %zu %zu\\n", sizeof(pc_segment), sizeof(pc_copy2d), sizeof(pc_attn_params)); return 0; }
+        int main(void){ printf("%zu %zu %zu %zu %zu\\n", sizeof(pc_segment), sizeof(pc_copy2d), sizeof(pc_attn_params),
+                                 sizeof(pc_linear_params), sizeof(pc_chain_op)); return 0; }
     ''')
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(src)
         subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")], check=True)
         out = subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.split()
-    assert [int(x) for x in out] == [16, 48, 152]
+    assert [int(x) for x in out] == [16, 48, 152, 176, 256]
 
 
 def test_argument_validation_needs_no_gpu(native):
@@ -58,6 +60,9 @@ def test_argument_validation_needs_no_gpu(native):
     assert lib.pc_prefill_attn(ctypes.byref(p), None) == 0                      # q_len == 0: nothing to do
     p.q_len = 2
     assert lib.pc_decode_attn(ctypes.byref(p), None) == -1                      # decode is q_len == 1
+    ops = (native.pc_chain_op * 2)()
+    assert lib.pc_linear_chain(ops, 0, None, 0, None) == -1                     # an empty chain
+    assert lib.pc_linear_chain(ops, 9, None, 0, None) == -1                     # more than PC_CHAIN_MAX_OPS
 
 
 def test_product_has_no_oracle_or_cpu_path():

@@ -213,6 +213,15 @@ def test_model_native_linears_match_cublas_linears(native):
     assert a[2] >= 2 * 7 and b[2] >= 2 * 5  # native: 7 launches of this library per layer; cuBLAS path: 5 (+4 library GEMMs)
     for other in res["native"][1:]:  # eager, then captured and replayed
         assert torch.equal(other[0], a[0]) and torch.equal(other[1], a[1])
+    # the same step with everything between two attention launches chained into one persistent launch (experiment switch)
+    model.linear_impl, model.linear_chain = "native", True
+    before = native.launch_count()
+    ids, pos, _, cache = eng.process(Prompt(case.prompt_xml))
+    out = lm(input_ids=torch.tensor([ids], device=DEV), position_ids=torch.tensor([pos], device=DEV),
+             past_key_values=[(k.unsqueeze(0), v.unsqueeze(0)) for k, v in cache], use_cache=True)
+    torch.cuda.synchronize()
+    assert native.launch_count() - before <= 2 * 2 + 2  # per layer: one chain + one attention
+    assert float((out.logits - a[0]).abs().max()) < 2e-3 * scale
 
 
 @pytest.mark.parametrize("q,k,n", [(16, 4096, 16384), (1, 512, 2048), (9, 4096, 640)])
@@ -276,3 +285,57 @@ def test_add_layernorm_two_partial_stacks_equal_two_fp16_deltas(native):
     native.add_layernorm(b_x, _exact_linear(act, w4), _exact_linear(ctx, wd), lw, lb, b_h, 1e-5)
     torch.cuda.synchronize()
     assert torch.equal(a_x, b_x) and torch.equal(a_h, b_h)
+
+
+@pytest.mark.parametrize("q,hid,inter,H", [(9, 512, 1024, 4), (16, 4096, 11008, 32), (1, 4096, 11008, 32), (23, 1024, 2816, 8)])
+def test_linear_chain_equals_the_launches_it_replaces(native, q, hid, inter, H):
+    """pc_linear_chain (ONE persistent launch: o_proj partials -> add+RMSNorm -> gate/up+SiLU -> down partials -> add+RMSNorm ->
+    QKV+RoPE+append) against the same six ops launched one by one: the linears' outputs are bit-identical given identical
+    inputs, the norms differ only by the summation order of the row statistics (128 vs 512 threads)."""
+    D, row0, max_ctx = 128, 40, 96
+    g = torch.Generator(device="cpu").manual_seed(q + hid)
+    rnd = lambda *s, scale=1.0: (torch.randn(*s, generator=g) * scale).half().to(DEV)
+    attn_out, x0 = rnd(q, hid), rnd(q, hid)
+    wo, wgu, wd, wqkv = rnd(hid, hid, scale=0.03), rnd(2 * inter, hid, scale=0.03), rnd(hid, inter, scale=0.03), rnd(3 * hid, hid, scale=0.03)
+    n1, n2 = (1 + 0.1 * torch.randn(hid, generator=g)).half().to(DEV), (1 + 0.1 * torch.randn(hid, generator=g)).half().to(DEV)
+    pos = torch.randint(0, 2048, (q,), generator=g).to(DEV)
+    cos, sin = O.rope_tables(D, 2048, dtype=torch.float16)
+    cos, sin = cos.contiguous().to(DEV), sin.contiguous().to(DEV)
+    ws = native.linear_workspace(DEV)
+    t_o, t_gu = native.tile_weights(wo, native.PC_LIN_PARTIALS), native.tile_weights(wgu, native.PC_LIN_SILU_MUL)
+    t_d, t_qkv = native.tile_weights(wd, native.PC_LIN_PARTIALS), native.tile_weights(wqkv, native.PC_LIN_ROPE_APPEND)
+
+    def run(chained):
+        x, h = x0.clone(), torch.zeros(q, hid, dtype=torch.half, device=DEV)
+        act = torch.zeros(q, inter, dtype=torch.half, device=DEV)
+        p_o = torch.zeros(native.linear_partial_splits(hid, hid), q, hid, dtype=torch.float32, device=DEV)
+        p_d = torch.zeros(native.linear_partial_splits(hid, inter), q, hid, dtype=torch.float32, device=DEV)
+        qo = torch.zeros(H, q, D, dtype=torch.half, device=DEV)
+        kc, vc = torch.zeros(H, max_ctx, D, dtype=torch.half, device=DEV), torch.zeros(H, max_ctx, D, dtype=torch.half, device=DEV)
+        import contextlib
+        before = native.launch_count()
+        with (native.chain(ws) if chained else contextlib.nullcontext()):
+            native.linear_partials(attn_out, wo, p_o, ws, w_tiled=t_o)
+            native.add_rmsnorm(x, p_o, n1, h, 1e-5)
+            native.linear_small(h, wgu, act, ws, silu_mul=True, w_tiled=t_gu)
+            native.linear_partials(act, wd, p_d, ws, w_tiled=t_d)
+            native.add_rmsnorm(x, p_d, n2, h, 1e-5)
+            native.linear_rope_append(h, wqkv, pos, cos, sin, qo, kc, vc, row0, H, H, ws, w_tiled=t_qkv)
+        torch.cuda.synchronize()
+        return dict(x=x, h=h, act=act, p_o=p_o, p_d=p_d, q=qo, k=kc, v=vc), native.launch_count() - before
+
+    a, n_a = run(False)
+    for rep in range(3):  # the chain leaves its barrier counters zeroed: replays give the same bits
+        b, n_b = run(True)
+        assert (n_a, n_b) == (6, 1)
+        assert torch.equal(a["p_o"], b["p_o"])  # same inputs, same partition: same bits
+        rel = lambda u, v: float((u.float() - v.float()).abs().max() / v.float().abs().max().clamp_min(1e-9))
+        for name in ("x", "h", "act", "q", "k", "v"):
+            assert rel(b[name], a[name]) <= 2e-3, (name, rel(b[name], a[name]))
+        assert rel(b["p_d"].sum(0), a["p_d"].sum(0)) <= 2e-3
+        if rep:
+            assert all(torch.equal(b[k], prev[k]) for k in b)
+        prev = b
+    assert int(ws.view(torch.int32).abs().max()) == 0 or int(ws[:16384].view(torch.int32).abs().max()) == 0
+    bars = ws[-256:].view(torch.int32)
+    assert int(bars.abs().max()) == 0  # grid-barrier counters are left zeroed
