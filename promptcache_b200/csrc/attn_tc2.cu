@@ -52,6 +52,16 @@ constexpr int kSBufs = 128 / BN;  // S buffers per query tile
 constexpr int kThreads = 352;  // WG0 (warps 0-3), WG1 (warps 4-7), TMA warp 8, MMA warps 9 (tile A) and 10 (tile B)
 constexpr int kMaxSplits = 32;
 constexpr float kLog2e = 1.4426950408889634f;
+// Packed-fp16 exponentials in pass 2 (non-ALiBi): the softmax warps share their SM sub-partition's 4 MUFU lanes with the
+// other query tile's warpgroup, and at one fp32 ex2 per score the MUFU pipe is busy exactly as long as the tensor pipe
+// (8192 ex2 per 64-key tile and query tile = 512 cycles; the tile's MMAs: 512 cycles at D = 128, 256 at D = 64).
+// ex2.approx.f16x2 halves that; P is rounded to fp16 for the P.V MMA anyway, and the row sum is taken from the same rounded
+// values.  The running maximum is kept fp16-representable so that (score*log2e - m) is formed by one fp16 FMA per pair.
+// Measured (B200, -DPC_PP_EX2_H2=1): q=1024 over N=8192 871 -> 888 TFLOP/s, Falcon MQA q=256 unchanged, and the llama-rounding
+// parity case at q=1024 leaves the 1e-3 bar -- the softmax warps are bound by instruction issue, not by the MUFU pipe.  Off.
+#ifndef PC_PP_EX2_H2
+#define PC_PP_EX2_H2 0
+#endif
 constexpr float kRescaleThreshold = 8.0f;
 
 template <int D>
@@ -84,6 +94,12 @@ struct PpParams {
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// two exponentials per MUFU operation: 2^x of a packed fp16 pair, result packed fp16 (max relative error 2^-9.9)
+__device__ __forceinline__ uint32_t ex2_h2(uint32_t x) {
+  uint32_t y;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
   return y;
 }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
@@ -378,6 +394,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
 
         // ---- running maximum, lazy rescale of O ----
+        if (PC_PP_EX2_H2 && !ALIBI) mt = round_h(mt);  // fp16-representable maximum (a common shift of the row: cancels in p / l)
         const float m_new = fmaxf(m_run, mt);
         const bool grow = (m_new - m_run) > kRescaleThreshold;  // first finite max: +inf; both -inf: NaN -> false
         const float alpha = grow ? ex2(m_run - m_new) : 1.f;
@@ -410,6 +427,34 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           uint32_t pk[CH / 2];
           auto pass2 = [&](auto masked_tag) {
             constexpr bool kMasked = decltype(masked_tag)::value;
+            if constexpr (PC_PP_EX2_H2 && !ALIBI && (ROUND == 0 || ROUND == PC_ROUND_LLAMA)) {
+              const __half2 neg_m = __float2half2_rn(-m_use);  // exact: m is fp16-representable
+              const __half2 l2e_hi = __float2half2_rn(kLog2e);
+              const __half2 l2e_lo = __float2half2_rn(kLog2e - __half2float(__float2half_rn(kLog2e)));
+              const __half2 ninf = __float2half2_rn(-INFINITY);
+#pragma unroll
+              for (int c = 0; c < CH; c += 2) {
+                __half2 y;
+                if (ROUND == PC_ROUND_LLAMA) {
+                  // half(half(acc) * scale), then (t * log2e - m) with log2e = hi + lo: the first FMA is exact up to its one
+                  // rounding at |y| (small where p matters), the second adds the t * lo correction
+                  const __half2 a16 = __floats2half2_rn(sv[c], sv[c + 1]);
+                  const __half2 t = __hfma2(a16, scale_hi, __hmul2(a16, scale_lo));
+                  y = __hfma2(t, l2e_lo, __hfma2(t, l2e_hi, neg_m));
+                } else {
+                  y = __floats2half2_rn(fmaf(sv[c], scale_l2, -m_use), fmaf(sv[c + 1], scale_l2, -m_use));
+                }
+                if (kMasked) {
+                  if (kc + c >= vis_end) y = __halves2half2(__low2half(ninf), __high2half(y));
+                  if (kc + c + 1 >= vis_end) y = __halves2half2(__low2half(y), __low2half(ninf));
+                }
+                const uint32_t pr = ex2_h2(*reinterpret_cast<const uint32_t*>(&y));
+                const float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&pr));
+                lt += pf.x + pf.y;
+                pk[c >> 1] = pr;
+              }
+              return;
+            }
 #pragma unroll
             for (int c = 0; c < CH; c += 2) {
               const float a = sv[c], b2 = sv[c + 1];

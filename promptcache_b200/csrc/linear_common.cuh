@@ -45,6 +45,13 @@ struct LCfg {
   static constexpr int kTmemCols = 2 * NPAD <= 32 ? 32 : 64;
 };
 
+// Table-driven (SM-weighted) stream-K boundaries: experiment only (tools/sm_weights_probe.py), compiled in with -DPC_LIN_BOUNDS.
+#ifdef PC_LIN_BOUNDS
+#define PC_LIN_HAS_BOUNDS(p) ((p).bounds != nullptr)
+#else
+#define PC_LIN_HAS_BOUNDS(p) false
+#endif
+
 struct LinParams {
   __half* out;
   long long out_stride;
@@ -55,6 +62,9 @@ struct LinParams {
   int w_one_box;         // the weight tile is 128 consecutive rows: one TMA box instead of two
   const unsigned char* w_tiled;  // TILED: weights re-laid out as [tile][k-block] 16 KiB shared-memory images
   int grid;              // CTAs this linear is partitioned over (== gridDim.x of a single-linear launch)
+  // optional: unit boundaries of the stream-K region per partition index, [grid + 1] entries (bounds[0] = 0, bounds[grid] =
+  // units_total) instead of the uniform split -- a partition weighted by how fast each SM streams (see sm_weights)
+  const long long* bounds;
   int whole_per_cta;     // tiles [0, whole_per_cta * grid) are processed whole, the rest is the stream-K region
   int splits;            // PARTIALS: regular split-K, CTA = (tile, split); fp32 partials go to part_out[split][t][col]
   float* part_out;
@@ -214,6 +224,17 @@ struct WorkIter {
 };
 
 
+// CTA whose range of the table-driven partition holds unit u: the last i with bounds[i] <= u.
+__device__ __forceinline__ int cta_of_unit_bounds(const long long* b, int G, long long u) {
+  int lo = 0, hi = G - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(b + mid) <= u) lo = mid;
+    else hi = mid - 1;
+  }
+  return lo;
+}
+
 // This CTA's unit range [u0, u1) of the linear `p` (stream-K region or regular split-K; empty when c >= p.grid).
 __device__ __forceinline__ void lin_cta_range(const LinParams& p, int epi, int c, int KB, long long& u0, long long& u1) {
   if (c >= p.grid) {
@@ -224,6 +245,11 @@ __device__ __forceinline__ void lin_cta_range(const LinParams& p, int epi, int c
     const int tile_c = c / p.splits, sp = c - tile_c * p.splits;
     u0 = static_cast<long long>(tile_c) * KB + (static_cast<long long>(sp) * KB) / p.splits;
     u1 = static_cast<long long>(tile_c) * KB + (static_cast<long long>(sp + 1) * KB) / p.splits;
+    return;
+  }
+  if (PC_LIN_HAS_BOUNDS(p)) {
+    u0 = __ldg(p.bounds + c);
+    u1 = __ldg(p.bounds + c + 1);
     return;
   }
   // the stream-K region is shared by the first Gs CTAs (all of them unless it holds fewer units than there are CTAs)
@@ -263,13 +289,21 @@ __device__ __forceinline__ void lin_epilogue(const LinParams& p, const Seg& sg, 
       if (t < p.q_len) __stcg(sp + t * BM + f, v[t]);
     named_bar_sync(1, kEpiThreads);  // orders every thread's stores before thread 0's gpu-scope fence + arrival
     if (et == 0) {
-      const int c_first = cta_of_unit(static_cast<long long>(rel) * KB, U, Gs);
-      const int c_last = cta_of_unit(static_cast<long long>(rel) * KB + KB - 1, U, Gs);
+      const long long tu0 = static_cast<long long>(rel) * KB;
+      const int c_first = PC_LIN_HAS_BOUNDS(p) ? cta_of_unit_bounds(p.bounds, p.grid, tu0) : cta_of_unit(tu0, U, Gs);
+      const int c_last = PC_LIN_HAS_BOUNDS(p) ? cta_of_unit_bounds(p.bounds, p.grid, tu0 + KB - 1) : cta_of_unit(tu0 + KB - 1, U, Gs);
+      // one acq_rel RMW instead of fence.sc + atomic + fence.sc: the release half publishes the parked partial (ordered
+      // before it by the bar.sync above), the acquire half makes the other contributors' partials visible to the reduction
+      int old;
+#ifdef PC_LIN_SC_FENCES
       __threadfence();
-      const int old = atomicAdd(p.counters + tile, 1);
+      old = atomicAdd(p.counters + tile, 1);
+      __threadfence();
+#else
+      asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(old) : "l"(p.counters + tile) : "memory");
+#endif
       const int last = (old == c_last - c_first) ? 1 : 0;
-      if (last) p.counters[tile] = 0;  // self-cleaning for the next launch
-      __threadfence();
+      if (last) p.counters[tile] = 0;  // self-cleaning for the next launch (ordered by the kernel boundary)
       flag[0] = last;
       flag[1] = c_first;
       flag[2] = c_last;
@@ -286,7 +320,7 @@ __device__ __forceinline__ void lin_epilogue(const LinParams& p, const Seg& sg, 
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
           const int ccj = min(cc + j, c_last);
-          const long long cu0 = (static_cast<long long>(ccj) * U) / Gs;
+          const long long cu0 = PC_LIN_HAS_BOUNDS(p) ? __ldg(p.bounds + ccj) : (static_cast<long long>(ccj) * U) / Gs;
           const int slot_c = (cu0 / KB == sg.rel) ? 0 : 1;
           const float* rp = p.slots + (static_cast<size_t>(ccj) * 2 + slot_c) * NPAD * BM;
 #pragma unroll

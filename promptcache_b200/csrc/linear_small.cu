@@ -52,7 +52,15 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KB = p.kb_total / KPS;  // pipeline stages (units) per tile
-  const int G = p.grid, c = blockIdx.x;
+  const int G = p.grid;
+  int c = blockIdx.x;
+#if defined(PC_DEBUG) && defined(PC_LIN_BOUNDS)
+  if (p.bounds != nullptr) {  // experiment (PC_LIN_BOUNDS_PTR): partition index = the SM this CTA runs on; needs grid == #SMs on an idle GPU
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    c = static_cast<int>(smid);
+  }
+#endif
   long long u0, u1;
   lin_cta_range(p, EPI, c, KB, u0, u1);
   if (tid == 0) LIN_TRACE(0);
@@ -206,6 +214,7 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
       tc_fence_before();
       mbar_arrive(&acc_empty[buf]);
       lin_epilogue<NPAD, EPI>(p, sg, v, c, KB, t_first, exch, flag, f, et, row0);
+      if (et == 0 && sg.n != KB) LIN_TRACE(5);  // end of a partial segment's epilogue (incl. the cross-CTA reduction if last)
       ++seg;
     }
     if (et == 0) LIN_TRACE(6);
@@ -505,6 +514,7 @@ int pc::lin::prepare_linear(const pc_linear_params* p, LinLaunch* out) {
              "pc_linear_small: activation %d (only PC_LIN_ACT_GELU with PC_LIN_PLAIN)", p->activation);
   lp.trace = nullptr;
   if (const char* e = dbg_env("PC_LIN_TRACE_PTR")) lp.trace = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
+  lp.bounds = nullptr;
 
   int grid = 1;
   choose_grid(p->epilogue, n_tiles, units_per_tile, tiled, lp.splits, &grid, &lp.whole_per_cta, &lp.units_total);
@@ -531,6 +541,8 @@ int pc::lin::prepare_linear(const pc_linear_params* p, LinLaunch* out) {
       lp.pf_units = kPrefetchUnits;
     }
   }
+  if (const char* e = dbg_env("PC_LIN_BOUNDS_PTR"))  // experiment: weighted stream-K boundaries, only for full-grid non-split launches
+    if (p->epilogue != PC_LIN_PARTIALS && grid == sm_count()) lp.bounds = reinterpret_cast<const long long*>(strtoull(e, nullptr, 0));
   lp.w_one_box = (lp.second_half_off == 64) ? 1 : 0;
   if (const char* e = dbg_env("PC_LIN_ONEBOX")) lp.w_one_box = lp.w_one_box && atoi(e) != 0;
   lp.grid = grid;
