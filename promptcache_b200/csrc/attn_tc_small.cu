@@ -462,11 +462,11 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       // thread's partial stores before thread 0's gpu-scope fence + arrival (fence cumulativity).
       named_bar_sync(1, kSoftmaxThreads);
       if (tid == 0) {
-        __threadfence();
-        const int old = atomicAdd(p.counters + hk, 1);
+        // one acq_rel RMW: releases this CTA's partials (ordered before it by the bar.sync), acquires the other splits'
+        int old;
+        asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(old) : "l"(p.counters + hk) : "memory");
         const int last = (old == p.n_splits - 1) ? 1 : 0;
-        if (last) p.counters[hk] = 0;  // self-cleaning for the next launch
-        __threadfence();
+        if (last) p.counters[hk] = 0;  // self-cleaning for the next launch (ordered by the kernel boundary)
         *flag = last;
       }
       named_bar_sync(1, kSoftmaxThreads);
