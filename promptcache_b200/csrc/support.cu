@@ -20,12 +20,17 @@ add_rmsnorm_kernel(__half* __restrict__ x, const __half* __restrict__ delta, con
                    long long split_stride) {
   __shared__ float red[kNormThreads / 32];
   pc::pdl_launch_dependents();  // the following GEMM may start streaming its weights now
+  // the norm weight is static: its (first) chunk is fetched before the wait, off the dependent part of the kernel
+  const int i0 = threadIdx.x * 8;
+  uint4 w0 = make_uint4(0u, 0u, 0u, 0u);
+  if (i0 < hidden) w0 = __ldg(reinterpret_cast<const uint4*>(weight + i0));
   pc::pdl_wait();               // x / delta come from the previous kernel
   const int row = blockIdx.x;
   __half* xr = x + static_cast<long long>(row) * hidden;
   const __half* dr = delta ? delta + static_cast<long long>(row) * hidden : nullptr;
   __half* hr = h_out + static_cast<long long>(row) * hidden;
   float ss = 0.f;
+  uint4 x0 = make_uint4(0u, 0u, 0u, 0u);
   // pass 1: residual add (written back) + sum of squares; 8 halfs per thread per step
   for (int i = threadIdx.x * 8; i < hidden; i += kNormThreads * 8) {
     uint4 xv = *reinterpret_cast<const uint4*>(xr + i);
@@ -66,6 +71,7 @@ add_rmsnorm_kernel(__half* __restrict__ x, const __half* __restrict__ delta, con
       ss = fmaf(f.x, f.x, ss);
       ss = fmaf(f.y, f.y, ss);
     }
+    if (i == i0) x0 = xv;  // the first chunk stays in registers for pass 2
   }
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
@@ -76,8 +82,8 @@ add_rmsnorm_kernel(__half* __restrict__ x, const __half* __restrict__ delta, con
   const float inv = rsqrtf(tot / static_cast<float>(hidden) + eps);
   // pass 2: normalise (fp32) -> fp16 -> * weight (fp16)
   for (int i = threadIdx.x * 8; i < hidden; i += kNormThreads * 8) {
-    uint4 xv = *reinterpret_cast<const uint4*>(xr + i);
-    uint4 wv = *reinterpret_cast<const uint4*>(weight + i);
+    uint4 xv = i == i0 ? x0 : *reinterpret_cast<const uint4*>(xr + i);
+    uint4 wv = i == i0 ? w0 : *reinterpret_cast<const uint4*>(weight + i);
     __half2* xh = reinterpret_cast<__half2*>(&xv);
     const __half2* wh = reinterpret_cast<const __half2*>(&wv);
 #pragma unroll
@@ -100,6 +106,13 @@ add_layernorm_kernel(__half* __restrict__ x, const __half* __restrict__ d1, cons
                      long long split_stride) {
   __shared__ float red[2][kNormThreads / 32];
   pc::pdl_launch_dependents();
+  // static norm weight / bias: the (first) chunk is fetched before the wait
+  const int i0 = threadIdx.x * 8;
+  uint4 w0 = make_uint4(0u, 0u, 0u, 0u), b0 = make_uint4(0u, 0u, 0u, 0u), x0 = make_uint4(0u, 0u, 0u, 0u);
+  if (i0 < hidden) {
+    w0 = __ldg(reinterpret_cast<const uint4*>(weight + i0));
+    if (bias) b0 = __ldg(reinterpret_cast<const uint4*>(bias + i0));
+  }
   pc::pdl_wait();
   const int row = blockIdx.x;
   const long long off = static_cast<long long>(row) * hidden;
@@ -154,6 +167,7 @@ add_layernorm_kernel(__half* __restrict__ x, const __half* __restrict__ d1, cons
       const float2 f = __half22float2(xh[k]);
       s1 += f.x + f.y;
     }
+    if (i == i0) x0 = xv;  // the first chunk stays in registers for the next two passes
   }
   for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
   if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = s1;
@@ -164,7 +178,7 @@ add_layernorm_kernel(__half* __restrict__ x, const __half* __restrict__ d1, cons
   const float mean = t1 / static_cast<float>(hidden);
   // second pass over the row (this thread's own stores: L1 hits) for the centred sum of squares -- no cancellation
   for (int i = threadIdx.x * 8; i < hidden; i += kNormThreads * 8) {
-    const uint4 xv = *reinterpret_cast<const uint4*>(xr + i);
+    const uint4 xv = i == i0 ? x0 : *reinterpret_cast<const uint4*>(xr + i);
     const __half2* xh = reinterpret_cast<const __half2*>(&xv);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -182,10 +196,10 @@ add_layernorm_kernel(__half* __restrict__ x, const __half* __restrict__ d1, cons
   const float var = t2 / static_cast<float>(hidden);
   const float rstd = rsqrtf(var + eps);
   for (int i = threadIdx.x * 8; i < hidden; i += kNormThreads * 8) {
-    uint4 xv = *reinterpret_cast<const uint4*>(xr + i);
-    const uint4 wv = *reinterpret_cast<const uint4*>(weight + i);
-    uint4 bv = make_uint4(0u, 0u, 0u, 0u);
-    if (bias) bv = *reinterpret_cast<const uint4*>(bias + i);
+    uint4 xv = i == i0 ? x0 : *reinterpret_cast<const uint4*>(xr + i);
+    const uint4 wv = i == i0 ? w0 : *reinterpret_cast<const uint4*>(weight + i);
+    uint4 bv = b0;
+    if (i != i0) bv = bias ? *reinterpret_cast<const uint4*>(bias + i) : make_uint4(0u, 0u, 0u, 0u);
     __half2* xh = reinterpret_cast<__half2*>(&xv);
     const __half2* wh = reinterpret_cast<const __half2*>(&wv);
     const __half2* bh = reinterpret_cast<const __half2*>(&bv);
