@@ -22,6 +22,11 @@ __global__ void __launch_bounds__(D) attn_combine_kernel(const float* __restrict
                                                          __half* __restrict__ out, int n_heads, int q_len,
                                                          int n_splits) {
   const int r = blockIdx.x, h = blockIdx.y, d = threadIdx.x;
+#ifndef PC_PP_NO_PDL
+  // launched programmatically behind the attention kernel (hides its launch latency); it does NOT trigger its own dependents
+  // early: a register-heavy dependent waiting on the SMs would leave this many-CTA grid a fraction of its occupancy
+  pdl_wait();  // the partials come from the attention kernel launched just before
+#endif
   float m_star = -INFINITY;
   for (int s = 0; s < n_splits; ++s)
     m_star = fmaxf(m_star, part_ml[((static_cast<long long>(s) * n_heads + h) * q_len + r) * 2]);
@@ -78,11 +83,20 @@ int make_tensor_map_3d(CUtensorMap* map, const void* base, int D, long long rows
 int launch_attn_combine(const float* part_o, const float* part_ml, void* out, int n_heads, int q_len, int n_splits,
                         int head_dim, cudaStream_t st) {
   dim3 cgrid(q_len, n_heads);
+#ifdef PC_PP_NO_PDL
   if (head_dim == 128)
     attn_combine_kernel<128><<<cgrid, 128, 0, st>>>(part_o, part_ml, static_cast<__half*>(out), n_heads, q_len, n_splits);
   else
     attn_combine_kernel<64><<<cgrid, 64, 0, st>>>(part_o, part_ml, static_cast<__half*>(out), n_heads, q_len, n_splits);
   PC_CHECK_CUDA(cudaGetLastError());
+#else
+  if (head_dim == 128)
+    PC_CHECK_CUDA(launch_pdl(attn_combine_kernel<128>, cgrid, dim3(128), 0, st, part_o, part_ml, static_cast<__half*>(out), n_heads,
+                             q_len, n_splits));
+  else
+    PC_CHECK_CUDA(launch_pdl(attn_combine_kernel<64>, cgrid, dim3(64), 0, st, part_o, part_ml, static_cast<__half*>(out), n_heads,
+                             q_len, n_splits));
+#endif
   count_launch();
   return PC_OK;
 }

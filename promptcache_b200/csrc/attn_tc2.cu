@@ -129,9 +129,12 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                const __grid_constant__ CUtensorMap map_v, const PpParams pin) {
   using C = Cfg2<D>;
   PpParams p = pin;
+
   // run-time cached length: the grid, the split count and the tensor maps were sized for the upper bound; splits that end
-  // up without tiles publish an empty partial (m = -inf, l = 0), rows past N + q are masked by the causal bound
-  if (pin.n_cached_dev != nullptr) p.n_cached = max(0, min(__ldg(pin.n_cached_dev), pin.n_cached));
+  // up without tiles publish an empty partial (m = -inf, l = 0), rows past N + q are masked by the causal bound.  The value
+  // is written by an earlier kernel of the stream: this variant waits for its predecessors first, the static one after its
+  // barriers / TMEM / descriptors are set up (below).
+  // (both are done after the set-up below: the run-time length is written by an earlier kernel of the stream)
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   unsigned char* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -152,6 +155,44 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = p.n_heads / p.n_kv_heads;
   const int rows_total = G * p.q_len;
+
+  // valid 32-row warps of the two query tiles (static: needed for the barrier counts; kept in scalars -- arrays defined
+  // before the inline-asm wait below would be forced into local memory by its memory clobber)
+  const int mp_static = p.m_pairs - 1 - (static_cast<int>(blockIdx.x) / p.n_splits) / p.n_kv_heads;
+  const int rl0 = mp_static * 2 * BM, rl1 = rl0 + BM;
+  const int vw0 = rl0 < rows_total ? (min(BM, rows_total - rl0) + 31) / 32 : 0;
+  const int vw1 = rl1 < rows_total ? (min(BM, rows_total - rl1) + 31) / 32 : 0;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_v);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+      mbar_init(&kv_empty[C::kStages + s], 1);
+    }
+    for (int x = 0; x < 2; ++x) {
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&s_full[x * 2 + b], 1);
+        mbar_init(&p_full[x * 2 + b], max(32 * (x ? vw1 : vw0), 1));
+        mbar_init(&o_full[x * 2 + b], 1);
+      }
+    }
+    mbar_fence_init();
+  }
+  if (warp == 9) tmem_alloc<C::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // everything below reads what earlier kernels wrote (Q, the appended K/V rows, the run-time length) or writes what they read
+#ifndef PC_PP_NO_PDL
+  pdl_wait();
+#endif
+  if (pin.n_cached_dev != nullptr) p.n_cached = max(0, min(__ldg(pin.n_cached_dev), pin.n_cached));
 
   // Block order = longest work first: the causal extent grows with the row-pair index, so the last pairs of
   // every head are dispatched first and the short ones fill the tail of the grid.
@@ -177,31 +218,6 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 #pragma unroll
   for (int x = 0; x < 2; ++x) valid_warps[x] = row_lo[x] < rows_total ? (min(BM, rows_total - row_lo[x]) + 31) / 32 : 0;
 
-  if (warp == 8 && lane == 0) {
-    tma_prefetch_desc(&map_q);
-    tma_prefetch_desc(&map_k);
-    tma_prefetch_desc(&map_v);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < C::kStages; ++s) {
-      mbar_init(&k_full[s], 1);
-      mbar_init(&v_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-      mbar_init(&kv_empty[C::kStages + s], 1);
-    }
-    for (int x = 0; x < 2; ++x) {
-      for (int b = 0; b < 2; ++b) {
-        mbar_init(&s_full[x * 2 + b], 1);
-        mbar_init(&p_full[x * 2 + b], max(32 * valid_warps[x], 1));
-        mbar_init(&o_full[x * 2 + b], 1);
-      }
-    }
-    mbar_fence_init();
-  }
-  if (warp == 9) tmem_alloc<C::kTmemCols>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 8) {
     // ===================== TMA producer =====================
@@ -230,6 +246,12 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           tma_load_3d(dv + hf * C::kHalfStride, &map_v, &v_full[s], hf * 64, key0, hk);
       }
     }
+#ifndef PC_PP_NO_PDL
+    // Programmatic launch of the dependents (the combine kernel, the next projection) once this CTA's last loads are out:
+    // late enough that their CTAs do not sit on the SMs for the whole kernel (with the trigger at the top the 18 k-CTA
+    // combine grid of the Falcon MQA shape cost 6.5 us), early enough to hide their launch latency.
+    if (lane == 0) pdl_launch_dependents();
+#endif
   } else if (warp == 9 || warp == 10) {
     // ===================== MMA issuers: warp 9 drives query tile A, warp 10 tile B =====================
     const int x = warp - 9;
@@ -569,8 +591,12 @@ int launch_pp_one(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMa
                                        Cfg2<D>::kSmem));
     configured = true;
   }
+#ifndef PC_PP_NO_PDL
+  PC_CHECK_CUDA(launch_pdl(attn_pp_kernel<D, ROUND, ALIBI>, dim3(grid), dim3(kThreads), Cfg2<D>::kSmem, st, mq, mk, mv, pp));
+#else
   attn_pp_kernel<D, ROUND, ALIBI><<<grid, kThreads, Cfg2<D>::kSmem, st>>>(mq, mk, mv, pp);
   PC_CHECK_CUDA(cudaGetLastError());
+#endif
   count_launch();
   return PC_OK;
 }
@@ -583,6 +609,13 @@ int launch_pp_d(const pc_attn_params& p, cudaStream_t st) {
   const int tiles = (p.n_cached + p.q_len + BN - 1) / BN;
   const int base = p.n_kv_heads * m_pairs;
   int n_splits = sm_count() / base;
+  // at least three 64-key tiles per split: below that the per-CTA prologue and the combine pass over the partials cost more
+  // than the extra CTAs bring (Falcon MQA q=16 over N=2048: 29 splits 22.4 us, 11 splits 13.4 us; decode at N=2048: 32 splits
+  // 11.3 us, 11 splits 9.1 us; C4's N=277: 5 splits + combine 9.9 us, one split 9.0 us)
+  // (a single row pair -- decode -- has a cheap combine and nothing else to fill the SMs with: at least 4 splits there)
+  int by_tiles = tiles / 3;
+  if (m_pairs == 1 && by_tiles < 4) by_tiles = tiles < 4 ? tiles : 4;
+  if (n_splits > by_tiles) n_splits = by_tiles;
   if (const char* e = dbg_env("PC_ATTN_SPLITS")) n_splits = atoi(e);
   if (n_splits > tiles) n_splits = tiles;
   if (n_splits > kMaxSplits) n_splits = kMaxSplits;
