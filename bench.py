@@ -185,7 +185,7 @@ class RequestStep:
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        self.eng.prompt_cache.update(self.seq_caches, virtual=virtual)
+        self.eng.prompt_cache.update(self.seq_caches, virtual=virtual, slot_rows=self.full_ids)
         if record:
             e1.record()
             self.splice_ev.append((e0, e1))

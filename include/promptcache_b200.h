@@ -154,7 +154,9 @@ typedef struct pc_attn_params {
   float scale;               /* multiplies the raw score (1/sqrt(D))                         */
   int32_t rounding;          /* PC_ROUND_* flags                                             */
   const float* alibi_slopes; /* [H] or NULL                                                  */
-  const int32_t* key_pos;    /* [n_cached+q_len] or NULL (required with alibi_slopes)        */
+  const int32_t* key_pos;    /* [n_cached+q_len] or NULL (required with alibi_slopes); with kv_tiles the table is in TILE  *
+                              * order: [kv_n_tiles][128] slots of the virtual tiles, then the n_cached-kv_rows+q_len rows     *
+                              * behind them                                                                                    */
   int32_t alibi_max_pos;     /* max(position_ids) (mpt.py:522)                               */
   int32_t impl;              /* PC_ATTN_*                                                    */
   const int32_t* n_cached_dev; /* optional: N is read from the device at run time (graph-replayable decode);  *

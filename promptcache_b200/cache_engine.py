@@ -154,6 +154,10 @@ class PromptCache:
         self._tile_slot = 0
         self._tiles_key, self._tiles_count = None, {}  # which layout the device tile list currently describes
         self._tiles_dev = torch.zeros(cap, 2, dtype=torch.int32, device=device)
+        # buffer row of every tile slot (built only for models that carry per-key position ids: MPT's ALiBi)
+        self._slot_rows_dev: Optional[torch.Tensor] = None
+        self._slot_rows_pin: Optional[torch.Tensor] = None
+        self._slots_key = None
         self.virtual: Optional[VirtualKV] = None
 
     @property
@@ -167,10 +171,11 @@ class PromptCache:
         self.length = 0
         self.virtual = None
         self._tiles_key = None
+        self._slots_key = None
         self.kv.rewritten(0)
 
     @torch.inference_mode()
-    def update(self, modules: List[TokenSequenceCache], virtual: bool = False) -> None:
+    def update(self, modules: List[TokenSequenceCache], virtual: bool = False, slot_rows: bool = False) -> None:
         """Lay out `modules` as the cached rows [0, N) (reference :116-156).
 
         virtual=False: the rows are copied into the contiguous buffer now (one pc_splice_kv launch; with
@@ -198,11 +203,11 @@ class PromptCache:
         self.kv.rewritten(row)  # rows >= `row` are scratch for the request being served; older pasts are stale now
         self.virtual = None
         self.last_spliced_rows = 0
-        if virtual and ordered and self._upload_tiles(ordered):
+        if virtual and ordered and self._upload_tiles(ordered, slot_rows):
             return
         self.materialise()
 
-    def _upload_tiles(self, ordered: List[TokenSequenceCache]) -> bool:
+    def _upload_tiles(self, ordered: List[TokenSequenceCache], want_slot_rows: bool = False) -> bool:
         arena = ordered[0].arena
         if any(m.arena is not arena for m in ordered) or arena.device != self.buffer.device or arena.dtype != self.buffer.dtype \
                 or tuple(arena.shape[:3]) != tuple(self.buffer.shape[:3]) or arena.shape[4] != self.head_dim or not arena.is_contiguous():
@@ -236,6 +241,35 @@ class PromptCache:
                 slot[1] = torch.cuda.Event()
             slot[1].record()
             self._tiles_key, self._tiles_count = key, {key: t}
+        slot_rows = None
+        if want_slot_rows:
+            # the buffer row each tile slot would occupy after the copy: full position ids come in buffer order (usage-ordered
+            # segments), the kernel walks the keys in tile (arena) order
+            skey = key + tuple((m.row0, len(m)) for m in ordered)
+            if self._slot_rows_dev is None:
+                cap = self._tiles_dev.shape[0] * 128
+                self._slot_rows_dev = torch.zeros(cap, dtype=torch.int64, device=self.buffer.device)
+                self._slot_rows_pin = torch.zeros(cap, dtype=torch.int64).pin_memory()
+            if skey != self._slots_key:
+                import numpy as np
+                starts = np.array([m.row0 for m in ordered], dtype=np.int64)
+                lens = np.array([len(m) for m in ordered], dtype=np.int64)
+                offs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+                order = np.argsort(starts)
+                starts, lens, offs = starts[order], lens[order], offs[order]
+                table = np.zeros(t * 128, dtype=np.int64)
+                ti = 0
+                for r0, n in runs:
+                    for r in range(0, n, 128):
+                        rows = np.arange(r0 + r, r0 + r + min(128, n - r), dtype=np.int64)
+                        seg = np.searchsorted(starts, rows, side="right") - 1
+                        table[ti * 128: ti * 128 + rows.shape[0]] = offs[seg] + rows - starts[seg]
+                        ti += 1
+                torch.cuda.current_stream().synchronize()  # the pinned table may still be read by the previous upload
+                self._slot_rows_pin[:t * 128] = torch.from_numpy(table)
+                self._slot_rows_dev[:t * 128].copy_(self._slot_rows_pin[:t * 128], non_blocking=True)
+                self._slots_key = skey
+            slot_rows = self._slot_rows_dev[:t * 128]
         epoch = self.kv.epoch
 
         def materialise():
@@ -243,7 +277,7 @@ class PromptCache:
                 raise StaleKVError("the prompt cache was re-spliced after this cache was handed out")
             self.materialise()
 
-        self.virtual = VirtualKV(arena, self._tiles_dev, t, self.length, materialise)
+        self.virtual = VirtualKV(arena, self._tiles_dev, t, self.length, materialise, slot_rows)
         return True
 
     @torch.inference_mode()
@@ -556,8 +590,12 @@ class CacheEngine:
         # virtual splice when the model's short-suffix attention can read the segments in place (decided per request:
         # the suffix length is known here); otherwise the rows are copied as the reference does
         max_q = getattr(self.lm.hf_model, "virtual_kv_max_q", lambda: 0)()
-        virtual = self.virtual_splice and self._identity_hooks and not return_full_position_ids and 0 < len(input_ids) <= max_q
-        self.prompt_cache.update(seq_caches, virtual=virtual)
+        # models that take the ids of ALL keys (MPT's ALiBi) can read the segments in place too: they get the tile-slot -> buffer
+        # row table and put their ids in tile order themselves
+        full_ok = bool(getattr(self.lm.hf_model, "virtual_kv_full_ids", False))
+        virtual = self.virtual_splice and self._identity_hooks and (full_ok or not return_full_position_ids) \
+            and 0 < len(input_ids) <= max_q
+        self.prompt_cache.update(seq_caches, virtual=virtual, slot_rows=bool(return_full_position_ids and full_ok))
         cache = self.prompt_cache.cache
         end.record()
         end.synchronize()

@@ -86,9 +86,9 @@ static int attn_dispatch(const pc_attn_params* p, void* stream, const char* who)
     else impl = PC_ATTN_TCGEN05;
   }
   if (p->kv_tiles != nullptr && p->kv_n_tiles > 0) {
-    if (impl != PC_ATTN_TCGEN05 || !attn_small_supported(*p) || p->alibi_slopes != nullptr)
+    if (impl != PC_ATTN_TCGEN05 || !attn_small_supported(*p))
       return set_error(PC_ERR_UNSUPPORTED, "%s: the virtual splice (kv_tiles) needs the short-suffix tcgen05 kernel "
-                       "(head_dim 128, G*q <= 32, no ALiBi); materialise the cache with pc_splice_kv instead", who);
+                       "(head_dim 128, G*q <= 32); materialise the cache with pc_splice_kv instead", who);
     return launch_attn_small(*p, st);
   }
   if (p->n_cached_dev != nullptr) {

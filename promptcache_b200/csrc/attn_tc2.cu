@@ -613,9 +613,12 @@ int launch_pp_d(const pc_attn_params& p, cudaStream_t st) {
   // than the extra CTAs bring (Falcon MQA q=16 over N=2048: 29 splits 22.4 us, 11 splits 13.4 us; decode at N=2048: 32 splits
   // 11.3 us, 11 splits 9.1 us; C4's N=277: 5 splits + combine 9.9 us, one split 9.0 us)
   // (a single row pair -- decode -- has a cheap combine and nothing else to fill the SMs with: at least 4 splits there)
-  int by_tiles = tiles / 3;
-  if (m_pairs == 1 && by_tiles < 4) by_tiles = tiles < 4 ? tiles : 4;
-  if (n_splits > by_tiles) n_splits = by_tiles;
+  // Applied to folded heads (G > 1: MQA / GQA, where few row pairs meet many SMs); G = 1 keeps one tile per split as the floor.
+  if (G > 1) {
+    int by_tiles = tiles / 3;
+    if (m_pairs == 1 && by_tiles < 4) by_tiles = tiles < 4 ? tiles : 4;
+    if (n_splits > by_tiles) n_splits = by_tiles;
+  }
   if (const char* e = dbg_env("PC_ATTN_SPLITS")) n_splits = atoi(e);
   if (n_splits > tiles) n_splits = tiles;
   if (n_splits > kMaxSplits) n_splits = kMaxSplits;

@@ -340,7 +340,12 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       tmem_ld_wait();
       const int key = p.v_rows + (tj - vt) * BK + kl;  // index among all keys (tail tiles; virtual tiles never use it)
       float kp = 0.f;
-      if (ALIBI) kp = static_cast<float>(__ldg(p.key_pos + min(key, p.n_cached + p.q_len - 1)) - p.alibi_max_pos);
+      if (ALIBI) {
+        // key ids: by key index; with a tile list the table is laid out in TILE order instead -- 128 slots per virtual tile,
+        // then the appended rows -- so that slot tj * 128 + kl serves virtual and tail tiles alike
+        const int kidx = vt > 0 ? min(tj * BK + kl, vt * BK + n_tail + p.q_len - 1) : min(key, p.n_cached + p.q_len - 1);
+        kp = static_cast<float>(__ldg(p.key_pos + kidx) - p.alibi_max_pos);
+      }
 #pragma unroll
       for (int i = 0; i < NH; ++i) {
         float v = x[i];
@@ -639,7 +644,6 @@ int launch_small_n(const pc_attn_params& p, cudaStream_t st) {
     PC_REQUIRE(p.kv_arena_k && p.kv_arena_v && p.kv_arena_rows > 0 && p.kv_rows > 0 && p.kv_rows <= p.n_cached,
                "attn(tcgen05-small): bad virtual-splice arguments (arena rows %d, kv_rows %d, n_cached %d)", p.kv_arena_rows,
                p.kv_rows, p.n_cached);
-    PC_REQUIRE(p.alibi_slopes == nullptr, "attn(tcgen05-small): the virtual splice does not carry key positions (ALiBi)");
     PC_REQUIRE((reinterpret_cast<uintptr_t>(p.kv_arena_k) | reinterpret_cast<uintptr_t>(p.kv_arena_v)) % 16 == 0,
                "attn(tcgen05-small): arena planes must be 16B aligned");
   }

@@ -116,6 +116,12 @@ class B200CausalLM(nn.Module):
         0 = this model always needs the contiguous rows."""
         return 0
 
+    virtual_kv_full_ids = False   # the model takes position ids of ALL keys and can put them in tile order (MPT)
+
+    def _virtual_ok(self, virt, q_len: int) -> bool:
+        """Can this forward read the cached rows in place (else they are copied first)?"""
+        return 0 < q_len <= self.virtual_kv_max_q()
+
     def _launch_shape_key(self):
         """Every switch that changes the launch sequence of `_layers`; part of each graph key so that toggling one
         after a capture can never replay a stale sequence."""
@@ -195,7 +201,7 @@ class B200CausalLM(nn.Module):
         q_len = ids.shape[0]
         kv = resolve_kv(past, q_len, self.n_layers, self.n_kv_heads, self.head_dim, self.device)
         N = kv.n_cached
-        if kv.virtual is not None and not (0 < q_len <= self.virtual_kv_max_q()):
+        if kv.virtual is not None and not self._virtual_ok(kv.virtual, q_len):
             kv.virtual.materialise()  # this forward needs the contiguous rows: make the copy the engine skipped
             kv.virtual = None
         if (q_len == 1 and N > 0 and self.use_cuda_graphs and self.supports_dynamic_n

@@ -84,11 +84,15 @@ class VirtualKV:
     first arena row, valid rows).  `materialise()` makes the copy after all, for consumers that need the contiguous rows
     (long-suffix / ALiBi attention kernels, callers indexing the reference-shaped views)."""
 
-    __slots__ = ("arena", "tiles", "n_tiles", "rows", "_materialise", "done")
+    __slots__ = ("arena", "tiles", "n_tiles", "rows", "_materialise", "done", "slot_rows")
 
-    def __init__(self, arena: torch.Tensor, tiles: torch.Tensor, n_tiles: int, rows: int, materialise):
+    def __init__(self, arena: torch.Tensor, tiles: torch.Tensor, n_tiles: int, rows: int, materialise,
+                 slot_rows: Optional[torch.Tensor] = None):
         self.arena, self.tiles, self.n_tiles, self.rows = arena, tiles, n_tiles, rows
         self._materialise, self.done = materialise, False
+        # int64 [n_tiles * 128] on the device: the buffer row each tile slot WOULD occupy after a copy (0 for slots past a
+        # tile's valid rows) -- what a model with per-key position ids (MPT's ALiBi) needs to put its ids in tile order
+        self.slot_rows = slot_rows
 
     def materialise(self) -> None:
         if not self.done:
@@ -97,7 +101,8 @@ class VirtualKV:
 
     def key(self):
         """What a captured CUDA graph bakes in (tensor maps over the arena, tile-list address, tile and row counts)."""
-        return (self.arena.data_ptr(), int(self.arena.shape[3]), self.tiles.data_ptr(), self.n_tiles, self.rows)
+        return (self.arena.data_ptr(), int(self.arena.shape[3]), self.tiles.data_ptr(), self.n_tiles, self.rows,
+                self.slot_rows.data_ptr() if self.slot_rows is not None else 0)
 
     def planes(self, layer: int):
         return (self.arena[layer, 0], self.arena[layer, 1], self.tiles, self.n_tiles, self.rows)

@@ -109,6 +109,13 @@ class MptForCausalLM(B200CausalLM):
         return model
 
     supports_dynamic_n = True  # decode graph: the key ids live in a max_ctx-long static buffer, N is read on the device
+    virtual_kv_full_ids = True  # virtual splice with ALiBi: the key ids are gathered into tile order (VirtualKV.slot_rows)
+
+    def virtual_kv_max_q(self) -> int:  # the short-suffix kernel reads segments in place: D=128, one query head per KV head
+        return 32 if self.head_dim == 128 else 0
+
+    def _virtual_ok(self, virt, q_len: int) -> bool:
+        return virt.slot_rows is not None and 0 < q_len <= self.virtual_kv_max_q()
 
     def _layers(self, ids: torch.Tensor, pos: torch.Tensor, kv, extra=(), n_dev=None) -> torch.Tensor:
         q_len = ids.shape[0]
@@ -119,6 +126,9 @@ class MptForCausalLM(B200CausalLM):
         # host value nor a kernel parameter changes from step to step; with n_dev `pos` is the max_ctx-long static buffer
         # (zeros behind the live ids, which never exceed the maximum)
         key_pos = (pos - pos.max()).to(torch.int32)
+        virt = kv.virtual  # cached rows still in the schema arena: attention walks them in TILE order, so do the ids --
+        if virt is not None:  # [128 slots per virtual tile][rows appended behind the cached ones]
+            key_pos = torch.cat([key_pos[virt.slot_rows], key_pos[virt.rows:]])
         x = F.embedding(ids, self.wte)
         ln = torch.empty_like(x)
         q_out = torch.empty(H, q_len, D, dtype=torch.float16, device=self.device)
@@ -146,8 +156,8 @@ class MptForCausalLM(B200CausalLM):
                                 nd, H, H, D)                                                # no rotary: transpose + append (:148-151)
             nat.attention(q_out, kv.k[l], kv.v[l], ctx, N if n_dev is None else kv.max_ctx - q_len, q_len, H, H, D, self.scale,
                           self.rounding, workspace=ws, alibi_slopes=self.slopes, key_pos=key_pos, alibi_max_pos=0,
-                          impl=self.attn_impl if n_dev is None else nat.PC_ATTN_TCGEN05, decode=(q_len == 1),
-                          n_cached_dev=n_dev)                                               # :156-185
+                          impl=self.attn_impl if (n_dev is None and virt is None) else nat.PC_ATTN_TCGEN05, decode=(q_len == 1),
+                          n_cached_dev=n_dev, virtual=virt.planes(l) if virt is not None else None)   # :156-185
             if lin:
                 nat.linear_partials(ctx, self.wo[l], pbuf_o, lws, w_tiled=self._wt(("o", l), self.wo[l], nat.PC_LIN_PARTIALS))
                 nat.add_layernorm(x, pbuf_o, None, self.norm2[l], None, ln, self.eps)       # x += attn (:251); norm_2

@@ -229,3 +229,84 @@ def test_stale_cache_raises_and_reused_past_forks(native):
     assert not torch.equal(o2.past_key_values[0][0][..., -1, :], k1[..., -1, :])
     o1b = lm(input_ids=ids_t, position_ids=pos_t, past_key_values=past, use_cache=True)  # forked again: same answer
     assert _rel(o1b.logits, o1.logits) <= 1e-3
+
+
+@pytest.mark.parametrize("lens,order,q,tail_old", [([256, 128, 384], [2, 0], 7, 0), ([100, 45, 300, 17], [3, 1, 0], 1, 5),
+                                                   ([128] * 6, [4, 1, 5, 0], 32, 0)])
+def test_virtual_splice_with_alibi_key_ids_in_tile_order(native, lens, order, q, tail_old):
+    """MPT: ALiBi bias at the KEY's position id (mpt.py:97-110,172-175).  With a tile list the id table is laid out in tile
+    order ([128 slots per virtual tile][appended rows]); result == the copied path with the ids in buffer order."""
+    H = Hkv = 8
+    D = 128
+    Q, K, V, AK, AV, tiles, nt, nv, N = _arena_case(H, Hkv, lens, order, q, seed=11 + q, tail_old=tail_old, std=1.0)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    pos = torch.randperm(4 * (N + q), generator=g)[:N + q].to(torch.int32)  # gapped, unordered ids of all keys (buffer order)
+    key_pos = (pos - pos.max()).to(DEV)
+    slopes = (2.0 ** (-torch.arange(1, H + 1, dtype=torch.float32))).to(DEV)
+    # slot -> buffer row, as PromptCache._upload_tiles builds it (test tiles follow the request's order, one run per segment)
+    slot_rows, row = [], 0
+    for i in order:
+        for t in range(0, lens[i], 128):
+            n = min(128, lens[i] - t)
+            slot_rows += list(range(row + t, row + t + n)) + [0] * (128 - n)
+        row += lens[i]
+    slot_rows = torch.tensor(slot_rows, dtype=torch.int64, device=DEV)
+    key_pos_tiles = torch.cat([key_pos[slot_rows], key_pos[nv:]]).contiguous()
+    ws = torch.zeros(native.attn_workspace_bytes(H, q, D), dtype=torch.uint8, device=DEV)
+
+    def run(kp, virtual, Kb, Vb):
+        out = torch.full((q, H * D), float("nan"), dtype=torch.half, device=DEV)
+        native.attention(Q, Kb, Vb, out, N, q, H, Hkv, D, native.softmax_scale(D), native.PC_ROUND_LLAMA, workspace=ws,
+                         alibi_slopes=slopes, key_pos=kp, alibi_max_pos=0, decode=(q == 1), impl=native.PC_ATTN_TCGEN05, virtual=virtual)
+        torch.cuda.synchronize()
+        return out
+
+    copied = run(key_pos.contiguous(), None, K, V)
+    Kh, Vh = _hide_cached_rows(K, V, nv)
+    virt = run(key_pos_tiles, (AK, AV, tiles, nt, nv), Kh, Vh)
+    assert torch.isfinite(virt.float()).all()
+    assert _rel(virt, copied) <= 1e-3  # tile boundaries differ where segments are ragged: fp32 summation order only
+    if all(n % 128 == 0 for n in lens):
+        assert torch.equal(virt, copied)
+
+
+def test_mpt_engine_virtual_splice_equals_copied_splice(native):
+    """MPT through the engine with full position ids: the virtual splice (no copy; ids gathered into tile order through
+    VirtualKV.slot_rows) against the copied splice -- same logits, same greedy continuation (incl. the graph-replayed decode),
+    also after the usage counters have reordered the buffer layout (buffer order != arena order)."""
+    from promptcache_b200 import CacheEngine, GenerationEngine, GenerationParameters, Prompt
+    from promptcache_b200.model import Mpt
+    from promptcache_b200.model.mpt import MptConfigLite, MptForCausalLM
+    from tests.helpers import WordTokenizer
+    torch.manual_seed(3)
+    model = MptForCausalLM(MptConfigLite(d_model=256, n_heads=2, n_layers=2, vocab_size=256), device=DEV)
+    lm = Mpt("tiny-mpt", model=model, tokenizer=WordTokenizer(256))
+    assert model.virtual_kv_max_q() == 32 and model.virtual_kv_full_ids
+    eng = CacheEngine(1024, lm)
+    words = lambda p, n: " ".join(f"{p}{i}" for i in range(n))
+    eng.add_schema(f'<schema name="s"><module name="a">{words("a", 150)}</module><module name="b">{words("b", 70)}</module>'
+                   f'<union><module name="c1">{words("c", 200)}</module><module name="c2">{words("d", 33)}</module></union>'
+                   f'<module name="e">{words("e", 90)}</module></schema>')
+    params = GenerationParameters(temperature=0.0, max_new_tokens=8, stop_token_ids=[], stop_str=[])
+    gen = GenerationEngine(lm)
+
+    def serve(xml, virtual):
+        eng.virtual_splice = virtual
+        before = native.launch_count()
+        ids, pos, _, cache = eng.process(Prompt(xml), return_full_position_ids=True)
+        assert (cache.virtual is not None) == virtual
+        out = lm(input_ids=torch.tensor([ids], device=DEV), position_ids=torch.tensor([pos], device=DEV), past_key_values=cache,
+                 use_cache=True)
+        logits = out.logits.clone()
+        ids, pos, _, cache = eng.process(Prompt(xml), return_full_position_ids=True)
+        text = [o.new_text for o in gen.generate(ids, pos, params, cache, stream_interval=1, use_full_position_ids=True)][-1]
+        return logits, text
+
+    x1 = '<prompt schema="s"><a/><c2/><e/>what now my friend</prompt>'
+    x2 = '<prompt schema="s"><b/><c1/><e/>and then</prompt>'
+    for xml in (x1, x2, x1, x2, x2):  # repeated: graph capture + replay; the counters of b / c1 / e overtake a's on the way
+        lv, tv = serve(xml, True)
+        lc, tc = serve(xml, False)
+        assert _rel(lv, lc) <= 2e-3
+        assert tv == tc and len(tv.split()) == 8
+    assert any(k[0] == "decode" for k in model._graphs)
