@@ -339,7 +339,11 @@ def family_block(model_key, cfg_name, dev, steps, warmup):
            "e2e_ttft_ms": e2e_ms, "e2e_tok_s": tokens / (e2e_ms * 1e-3), "decode_ms_per_token": decode_ms,
            "splice_ms": statistics.mean(a.elapsed_time(b) for a, b in w.splice_ev),
            "roofline_step": {"bound": "hbm", "algorithmic_bytes": wb, "achieved": wb / (dev_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                             "frac": wb / (dev_ms * 1e-3) / 1e9 / peak, "note": "weights only; the linears of this family are cuBLAS"}}
+                             "frac": wb / (dev_ms * 1e-3) / 1e9 / peak,
+                             "note": "weights only; " + ("cuBLAS linears (the weight-streaming kernel ties with them at Falcon's shapes), "
+                                                         "long-suffix attention kernel with the 71 heads folded into M"
+                                                         if model_key.startswith("falcon") else
+                                                         "weight-streaming linears, virtual splice with ALiBi key ids in tile order")}}
     del w, lm
     torch.cuda.empty_cache()
     return res
