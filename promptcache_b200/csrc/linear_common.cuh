@@ -62,6 +62,9 @@ struct LinParams {
   int w_one_box;         // the weight tile is 128 consecutive rows: one TMA box instead of two
   const unsigned char* w_tiled;  // TILED: weights re-laid out as [tile][k-block] 16 KiB shared-memory images
   int grid;              // CTAs this linear is partitioned over (== gridDim.x of a single-linear launch)
+  int cl_helper_units;   // > 0: clusters of cl_size CTAs = cl_size - 1 tile owners + 1 helper that streams the last
+  int cl_size;           // cl_helper_units units of each owner's K range and hands the fp32 partials over through
+                         // distributed shared memory (cl_size 3 or 4)
   // optional: unit boundaries of the stream-K region per partition index, [grid + 1] entries (bounds[0] = 0, bounds[grid] =
   // units_total) instead of the uniform split -- a partition weighted by how fast each SM streams (see sm_weights)
   const long long* bounds;
@@ -420,7 +423,8 @@ struct LinLaunch {
   int grid, npad, epilogue;
   bool tiled;
 };
-int prepare_linear(const pc_linear_params* p, LinLaunch* out);
+// allow_cluster: the single-launch kernel may pick the owner + helper cluster partition (lp.cl_helper_units > 0)
+int prepare_linear(const pc_linear_params* p, LinLaunch* out, bool allow_cluster = false);
 int tiled_k_blocks(int k);
 
 }  // namespace lin

@@ -26,14 +26,42 @@
 // * epilogues: plain fp16 store; half(silu(gate)) * up (llama2.py:241) with gate and up rows of the same
 //   features in one tile; RoPE at explicit position ids + in-place KV append with the reference's three fp16
 //   roundings (llama2.py:195-210,357-364) when a tile is one head (D = 128).
+#include <type_traits>
+
 #include "linear_common.cuh"
 
 namespace pc {
 namespace lin {
 namespace {
-template <int NPAD, int EPI, bool TILED>
+// Work list of a CTA in the owner + helper cluster partition (CL): clusters of S (3 or 4) consecutive CTAs serve S - 1
+// consecutive row tiles; ranks 0..S-2 own one tile each and stream units [0, KB - KH) of it, rank S-1 streams the remaining
+// KH units of every owner's tile.  All CTAs of the cluster stream (nearly) the same number of bytes and nothing crosses HBM
+// twice: the helper's fp32 partials travel through distributed shared memory (two cluster barriers at the very end).
+struct ClIter {
+  int tile0, rank, S, KB, KH, j;
+  __device__ ClIter(int c, int S_, int KB_, int KH_) : tile0((c / S_) * (S_ - 1)), rank(c % S_), S(S_), KB(KB_), KH(KH_), j(0) {}
+  __device__ bool next(Seg& s) {
+    if (rank < S - 1) {
+      if (j > 0) return false;
+      s.tile = tile0 + rank;
+      s.kb0 = 0;
+      s.n = KB - KH;
+    } else {
+      if (j >= S - 1) return false;
+      s.tile = tile0 + j;
+      s.kb0 = KB - KH;
+      s.n = KH;
+    }
+    s.rel = -1;
+    ++j;
+    return true;
+  }
+};
+
+template <int NPAD, int EPI, bool TILED, bool CL = false>
 __global__ void __launch_bounds__(kThreads, LCfg<NPAD, TILED ? 2 : 1>::kMinBlocks)
 linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const LinParams p) {
+  static_assert(!CL || (TILED && EPI == PC_LIN_ROPE_APPEND), "the cluster partition serves the pre-tiled QKV projection");
   constexpr int KPS = TILED ? 2 : 1;
   using C = LCfg<NPAD, KPS>;
   pdl_launch_dependents();  // the next kernel may start its prologue (and its own weight prefetch) right away
@@ -63,6 +91,12 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
 #endif
   long long u0, u1;
   lin_cta_range(p, EPI, c, KB, u0, u1);
+  auto make_iter = [&]() {
+    if constexpr (CL) return ClIter(c, p.cl_size, KB, p.cl_helper_units);
+    else return WorkIter(u0, u1, KB, p.whole_per_cta, G, c);
+  };
+  // CL: the accumulator rows the epilogue threads carry across the two cluster barriers (owner: its tile; helper: three partials)
+  float cl_v[CL ? 3 : 1][NPAD];
   if (tid == 0) LIN_TRACE(0);
   if (tid == 0 && p.trace != nullptr) {  // slot 7: the SM this CTA runs on
     unsigned smid;
@@ -96,7 +130,7 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
       // One TMA instruction costs this thread ~110 ns whatever its size, so the weight tile travels as ONE 128-row box
       // when its rows are consecutive, and the X tiles are issued by a thread of their own (warp 6).  The weights are
       // static: the ring is filled with them without waiting for the previous kernel (whose output is X).
-      WorkIter it(u0, u1, KB, p.whole_per_cta, G, c);
+      std::conditional_t<CL, ClIter, WorkIter> it = make_iter();
       Seg sg;
       int i = 0;
       while (it.next(sg)) {
@@ -140,7 +174,7 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
     // ===================== TMA producer: the X tiles (output of the previous kernel) =====================
     if (lane == 0) {
       pdl_wait();
-      WorkIter it(u0, u1, KB, p.whole_per_cta, G, c);
+      std::conditional_t<CL, ClIter, WorkIter> it = make_iter();
       Seg sg;
       int i = 0;
       while (it.next(sg)) {
@@ -160,7 +194,7 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(BM, NPAD, 0, 0);  // both operands K-major
       int i = 0, seg = 0;
-      WorkIter it(u0, u1, KB, p.whole_per_cta, G, c);
+      std::conditional_t<CL, ClIter, WorkIter> it = make_iter();
       Seg sg;
       while (it.next(sg)) {
         const int buf = seg & 1;
@@ -200,24 +234,75 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
     int row0 = p.row0;
     if (EPI == PC_LIN_ROPE_APPEND && p.row0_dev != nullptr) row0 = max(0, min(__ldg(p.row0_dev), p.max_ctx - p.q_len));
     int seg = 0;
-    WorkIter it(u0, u1, KB, p.whole_per_cta, G, c);
-    const int t_first = it.it.t_first;
-    Seg sg;
-    while (it.next(sg)) {
-      const int buf = seg & 1;
-      mbar_wait(&acc_full[buf], static_cast<uint32_t>((seg >> 1) & 1));
-      tc_fence_after();
-      if (et == 0) LIN_TRACE(4);
-      float v[NPAD];
-      tmem_ld_acc<NPAD>(tmem_base + lane_base + buf * NPAD, v);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&acc_empty[buf]);
-      lin_epilogue<NPAD, EPI>(p, sg, v, c, KB, t_first, exch, flag, f, et, row0);
-      if (et == 0 && sg.n != KB) LIN_TRACE(5);  // end of a partial segment's epilogue (incl. the cross-CTA reduction if last)
-      ++seg;
+    if constexpr (CL) {
+      // read this CTA's accumulators (owner: one, helper: three); the exchange and the epilogue follow the role branches
+      const int n_seg = (c % p.cl_size) < p.cl_size - 1 ? 1 : p.cl_size - 1;
+#pragma unroll
+      for (int sgi = 0; sgi < 3; ++sgi) {  // compile-time indices keep cl_v in registers
+        if (sgi < n_seg) {
+          const int buf = sgi & 1;
+          mbar_wait(&acc_full[buf], static_cast<uint32_t>((sgi >> 1) & 1));
+          tc_fence_after();
+          tmem_ld_acc<NPAD>(tmem_base + lane_base + buf * NPAD, cl_v[sgi]);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(&acc_empty[buf]);
+        }
+      }
+      seg = n_seg;
+    } else {
+      WorkIter it(u0, u1, KB, p.whole_per_cta, G, c);
+      const int t_first = it.it.t_first;
+      Seg sg;
+      while (it.next(sg)) {
+        const int buf = seg & 1;
+        mbar_wait(&acc_full[buf], static_cast<uint32_t>((seg >> 1) & 1));
+        tc_fence_after();
+        if (et == 0) LIN_TRACE(4);
+        float v[NPAD];
+        tmem_ld_acc<NPAD>(tmem_base + lane_base + buf * NPAD, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&acc_empty[buf]);
+        lin_epilogue<NPAD, EPI>(p, sg, v, c, KB, t_first, exch, flag, f, et, row0);
+        if (et == 0 && sg.n != KB) LIN_TRACE(5);  // end of a partial segment's epilogue (incl. the cross-CTA reduction if last)
+        ++seg;
+      }
     }
     if (et == 0) LIN_TRACE(6);
+  }
+
+  if constexpr (CL) {
+    // ---- helper -> owners through distributed shared memory: fp32 [token][row] into the start of each owner's (drained) ring ----
+    const bool epi_warp = warp >= 2 && warp < 6;
+    const int S = p.cl_size, rank = c % S;
+    const int f = (warp & 3) * 32 + lane;
+    float* recv = reinterpret_cast<float*>(smem);  // NPAD * 128 floats
+    cluster_sync_all();  // A: every CTA of the cluster has read its accumulators -> the owners' rings are free
+    if (epi_warp && rank == S - 1) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        if (j < S - 1) {
+          const uint32_t dst = cluster_map_shared(smem_u32(recv + f), static_cast<uint32_t>(j));
+#pragma unroll
+          for (int t = 0; t < NPAD; ++t) st_cluster_f32(dst + t * BM * 4, cl_v[j][t]);
+        }
+      }
+    }
+    cluster_sync_all();  // B: the partials have landed
+    if (epi_warp && rank < S - 1) {
+      const int et = tid - 64;
+      int row0 = p.row0;
+      if (p.row0_dev != nullptr) row0 = max(0, min(__ldg(p.row0_dev), p.max_ctx - p.q_len));
+#pragma unroll
+      for (int t = 0; t < NPAD; ++t) cl_v[0][t] += recv[t * BM + f];
+      Seg whole;
+      whole.tile = (c / S) * (S - 1) + rank;
+      whole.kb0 = 0;
+      whole.n = KB;  // complete sum: the plain RoPE + append epilogue
+      whole.rel = -1;
+      lin_epilogue<NPAD, EPI>(p, whole, cl_v[0], c, KB, 0, exch, flag, f, et, row0);
+    }
   }
 
   tc_fence_before();
@@ -226,6 +311,38 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
     tc_fence_after();
     tmem_free<C::kTmemCols>(tmem_base);
   }
+}
+
+// owner + helper clusters for the pre-tiled QKV projection (see ClIter)
+template <int NPAD>
+cudaError_t configure_cl() {
+  return cudaFuncSetAttribute(linear_small_kernel<NPAD, PC_LIN_ROPE_APPEND, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              LCfg<NPAD, 2>::kSmem);
+}
+template <int NPAD>
+bool cl_clusters_fit(int cl_size, int n_clusters) {
+  static int fit[5] = {-1, -1, -1, -1, -1};
+  if (fit[cl_size] < 0) {
+    if (configure_cl<NPAD>() != cudaSuccess) return false;
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[2];
+    fill_launch_config(cfg, attr, dim3(cl_size * 32), dim3(kThreads), LCfg<NPAD, 2>::kSmem, nullptr, cl_size);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, linear_small_kernel<NPAD, PC_LIN_ROPE_APPEND, true, true>, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      n = 0;
+    }
+    fit[cl_size] = n;
+  }
+  return fit[cl_size] >= n_clusters;
+}
+template <int NPAD>
+int launch_lin_cl(const CUtensorMap& mw, const CUtensorMap& mx, const LinParams& lp, int grid, cudaStream_t st) {
+  PC_CHECK_CUDA(configure_cl<NPAD>());
+  PC_CHECK_CUDA(launch_pdl_cluster(linear_small_kernel<NPAD, PC_LIN_ROPE_APPEND, true, true>, lp.cl_size, dim3(grid), dim3(kThreads),
+                                   LCfg<NPAD, 2>::kSmem, st, mw, mx, lp));
+  count_launch();
+  return PC_OK;
 }
 
 template <int NPAD, int EPI, bool TILED>
@@ -408,7 +525,7 @@ PC_API size_t pc_linear_workspace_bytes(void) {
   return pc::lin::kLinCounterBytes + static_cast<size_t>(pc::sm_count()) * 2 * 32 * pc::lin::BM * sizeof(float) + pc::lin::kChainBarBytes;
 }
 
-int pc::lin::prepare_linear(const pc_linear_params* p, LinLaunch* out) {
+int pc::lin::prepare_linear(const pc_linear_params* p, LinLaunch* out, bool allow_cluster) {
   using namespace pc;
   using namespace pc::lin;
   if (!p) return set_error(PC_ERR_INVALID, "pc_linear_small: null params");
@@ -551,6 +668,34 @@ int pc::lin::prepare_linear(const pc_linear_params* p, LinLaunch* out) {
   if (int rc = make_tensor_map_3d(&mw, p->w, p->k, p->n_rows, 1, static_cast<long long>(p->n_rows) * p->k, lp.w_one_box ? 128 : 64))
     return rc;
   const int npad = p->q_len <= 16 ? 16 : 32;
+  // QKV projection on whole head tiles (96 for Llama-2-7B) leaves a third of the SMs idle, and sharing tiles stream-K fashion
+  // costs a global reduction in front of the RoPE epilogue.  Clusters of 3 owners + 1 helper use 4/3 as many SMs with the
+  // exchange in distributed shared memory (ClIter).
+  lp.cl_helper_units = 0;
+  lp.cl_size = 0;
+#ifdef PC_LIN_NO_CL
+  allow_cluster = false;
+#endif
+  if (allow_cluster && tiled && npad == 16 && p->epilogue == PC_LIN_ROPE_APPEND && lp.whole_per_cta == 0 && grid == n_tiles &&
+      p->n_rows % BM == 0 && units_per_tile >= 8) {
+    int cl_force = 0;
+    if (const char* e = dbg_env("PC_LIN_CL_SIZE")) cl_force = atoi(e);
+    // 3 owners + helper (4/3 as many SMs).  2 owners + helper (48 clusters of 3 = 144 SMs) was measured SLOWER than no clusters
+    // at all (C2 step 3.36 vs 3.31 ms; clusters of 4: 3.25-3.27): kept selectable in debug builds only.
+    for (int S = 4; S >= 3; --S) {
+      if (cl_force == 0 ? S != 4 : cl_force != S) continue;
+      if (n_tiles % (S - 1) != 0) continue;
+      const int n_clusters = n_tiles / (S - 1);
+      if (n_clusters * S > sm_count() || !cl_clusters_fit<16>(S, n_clusters)) continue;
+      // the helper streams KH units of each of its S - 1 tiles, an owner KB - KH: balance (S - 1) * KH against KB - KH
+      int KH = units_per_tile / S;
+      lp.cl_helper_units = KH;
+      lp.cl_size = S;
+      grid = n_clusters * S;
+      lp.grid = grid;
+      break;
+    }
+  }
   // rows >= q_len of the X box read as zeros
   if (int rc = make_tensor_map_3d(&mx, p->x, p->k, p->q_len, 1, static_cast<long long>(p->q_len) * p->x_stride, npad)) return rc;
   out->grid = grid;
@@ -566,8 +711,9 @@ PC_API int pc_linear_small(const pc_linear_params* p, void* stream) {
   if (!p) return set_error(PC_ERR_INVALID, "pc_linear_small: null params");
   if (p->q_len == 0) return PC_OK;
   LinLaunch L;
-  if (int rc = prepare_linear(p, &L)) return rc;
+  if (int rc = prepare_linear(p, &L, true)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (L.lp.cl_helper_units > 0) return launch_lin_cl<16>(L.map_w, L.map_x, L.lp, L.grid, st);
   if (L.tiled)
     return L.npad == 16 ? launch_lin_n<16, true>(L.epilogue, L.map_w, L.map_x, L.lp, L.grid, st)
                         : launch_lin_n<32, true>(L.epilogue, L.map_w, L.map_x, L.lp, L.grid, st);
