@@ -15,7 +15,8 @@
 //   thread (waits: X is the previous kernel's output), an MMA-issuing thread with two TMEM accumulators, four
 //   epilogue warps; 6 (pre-tiled) or 10-11 (tensor-map) ring stages, i.e. ~190 KiB of weights in flight per SM;
 // * work partition (chosen on the host per shape, all expressed as a list of (tile, k-range) segments per CTA):
-//     - whole tiles per CTA when the tile count divides a grid of >= 5/8 of the SMs (QKV: 96 head tiles);
+//     - whole tiles per CTA when the tile count divides a grid of >= 5/8 of the SMs; the QKV projection (96 head tiles) runs
+//       as clusters of 3 tile owners + 1 helper CTA whose fp32 partials travel through distributed shared memory (ClIter);
 //     - more tiles than SMs (gate/up, lm_head): whole tiles dealt out per CTA + the remainder shared stream-K
 //       fashion and visited FIRST, so that its reduction overlaps the streaming of the whole tiles;
 //     - PC_LIN_PARTIALS (o_proj, down_proj): regular split-K, NO reduction here -- the consumer
