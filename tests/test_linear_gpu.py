@@ -108,7 +108,7 @@ def test_linear_silu_mul(native, q, k, inter, tiled):
     (32, 8, 2, 512, 5, True, 128),         # GQA, NPAD 32
     (9, 4, 4, 256, 0, False, 128),         # MPT: no rotation, plain append
     (12, 32, 32, 4096, 100, False, 128),   # MPT-7B: 96 head tiles -> owner + helper clusters (pre-tiled), no rotation
-    (3, 16, 16, 512, 9, True, 128),        # 48 tiles -> 16 clusters of 4
+    (5, 36, 36, 512, 9, True, 128),        # 108 head tiles -> 36 clusters of 4 = 144 CTAs
     (16, 71, 1, 4544, 256, True, 64),      # Falcon-7B: head_dim 64 (two heads per tile, last tile half padding), 71 k-blocks
     (1, 71, 1, 4544, 1999, True, 64),      # Falcon decode
     (21, 6, 2, 320, 7, True, 64),          # D=64 GQA, 5 k-blocks, NPAD 32
