@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PC_ABI_VERSION 5
+#define PC_ABI_VERSION 6
 
 enum {
   PC_OK = 0,
@@ -182,6 +182,11 @@ typedef struct pc_attn_params {
   int32_t kv_n_tiles;
   int32_t kv_rows;
   int32_t kv_reserved;
+  /* ---- optional hint (short-suffix kernel): `prefetch_bytes` bytes at `prefetch` -- the pre-tiled weights of the projection
+   * that follows (o_proj) -- are asked into L2 by the CTAs once their last K/V loads are out.  That kernel cannot start before
+   * this one's CTAs leave their SMs (shared memory), so its weight stream would otherwise idle through the merge phase. */
+  const void* prefetch;
+  size_t prefetch_bytes;
 } pc_attn_params;
 
 size_t pc_attn_workspace_bytes(int n_heads, int q_len, int head_dim);

@@ -64,7 +64,8 @@ class pc_attn_params(C.Structure):
                 ("alibi_max_pos", C.c_int32), ("impl", C.c_int32), ("n_cached_dev", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
                 ("kv_arena_k", C.c_void_p), ("kv_arena_v", C.c_void_p), ("kv_tiles", C.c_void_p),
-                ("kv_arena_rows", C.c_int32), ("kv_n_tiles", C.c_int32), ("kv_rows", C.c_int32), ("kv_reserved", C.c_int32)]
+                ("kv_arena_rows", C.c_int32), ("kv_n_tiles", C.c_int32), ("kv_rows", C.c_int32), ("kv_reserved", C.c_int32),
+                ("prefetch", C.c_void_p), ("prefetch_bytes", C.c_size_t)]
 
 
 class pc_linear_params(C.Structure):
@@ -304,7 +305,8 @@ def attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, out
               q_len: int, n_heads: int, n_kv_heads: int, head_dim: int, scale: float, rounding: int,
               workspace: Optional[torch.Tensor] = None, alibi_slopes: Optional[torch.Tensor] = None,
               key_pos: Optional[torch.Tensor] = None, alibi_max_pos: int = 0, impl: int = PC_ATTN_AUTO,
-              decode: bool = False, n_cached_dev: Optional[torch.Tensor] = None, virtual: Optional[tuple] = None) -> None:
+              decode: bool = False, n_cached_dev: Optional[torch.Tensor] = None, virtual: Optional[tuple] = None,
+              prefetch: Optional[torch.Tensor] = None) -> None:
     """q: [H,q,D] fp16; caches [Hkv,max_ctx,D] (row-contiguous views allowed); out: [q,H*D] fp16.
     `virtual` = (arena_k [Hkv,R,D], arena_v [Hkv,R,D], tiles int32 [T,2] on the device, T, rows): the first `rows` cached
     keys are read in place from the segment arena through the tile list instead of from k_cache/v_cache (virtual splice)."""
@@ -343,6 +345,9 @@ def attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, out
             raise NativeError("attention: the tile list must be a contiguous int32 [T,2] CUDA tensor")
         p.kv_arena_k, p.kv_arena_v, p.kv_tiles = ak.data_ptr(), av.data_ptr(), tiles.data_ptr()
         p.kv_arena_rows, p.kv_n_tiles, p.kv_rows = int(ak.shape[1]), int(n_tiles), int(rows)
+    if prefetch is not None:  # hint: the next projection's pre-tiled weights go to L2 while this kernel merges its splits
+        _require_cuda(prefetch)
+        p.prefetch, p.prefetch_bytes = prefetch.data_ptr(), prefetch.numel() * prefetch.element_size()
     fn = lib.pc_decode_attn if decode else lib.pc_prefill_attn
     _check(fn(C.byref(p), _stream_flush()), "pc_decode_attn" if decode else "pc_prefill_attn")
 

@@ -63,6 +63,9 @@ struct SmallParams {
   // virtual splice: the first v_rows keys are not in k/v but in n_vtiles tiles {arena row, valid rows} of the segment arena
   const int2* vtiles;         // device; nullptr = everything is read from k/v
   int n_vtiles, v_rows;
+  // hint: bytes of the NEXT projection's pre-tiled weights, asked into L2 once this CTA's last K/V loads are out
+  const unsigned char* pf;
+  unsigned long long pf_bytes;
 };
 
 __device__ __forceinline__ unsigned long long gtime() {
@@ -275,6 +278,18 @@ attn_small_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       for (int j = pre; j < T; ++j) {
         if (j >= kStages) mbar_wait(&kv_empty[j % kStages], static_cast<uint32_t>(((j / kStages) - 1) & 1));
         load_kv(j);
+      }
+    }
+    if (lane == 0 && p.pf != nullptr) {
+      // This CTA's K/V stream is out.  The projection that follows cannot start before the CTAs of this kernel leave their
+      // SMs (shared memory), so HBM would idle through the last tiles' softmax and the split merge: ask L2 for this CTA's
+      // share of that projection's weight stream now (33.5 MB for Llama-2-7B's o_proj: it fits L2 many times over).
+      constexpr unsigned long long kChunk = 32768;
+      const unsigned long long chunks = (p.pf_bytes + kChunk - 1) / kChunk;
+      for (unsigned long long ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+        const unsigned long long off = ch * kChunk;
+        const unsigned long long n = min(kChunk, p.pf_bytes - off);
+        bulk_prefetch_l2(p.pf + off, static_cast<uint32_t>(n & ~15ull));
       }
     }
   } else if (warp == kSoftmaxWarps + 1) {
@@ -686,6 +701,9 @@ int launch_small_n(const pc_attn_params& p, cudaStream_t st) {
   sp.scale = p.scale;
   sp.trace = nullptr;
   sp.global_merge = (p.impl & PC_ATTN_GLOBAL_MERGE) != 0;
+  sp.pf = (p.prefetch != nullptr && p.prefetch_bytes >= 16 && reinterpret_cast<uintptr_t>(p.prefetch) % 16 == 0)
+              ? static_cast<const unsigned char*>(p.prefetch) : nullptr;
+  sp.pf_bytes = p.prefetch_bytes;
   sp.vtiles = virt ? reinterpret_cast<const int2*>(p.kv_tiles) : nullptr;
   sp.n_vtiles = n_vtiles;
   sp.v_rows = v_rows;

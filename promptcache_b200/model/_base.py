@@ -49,6 +49,10 @@ class B200CausalLM(nn.Module):
         # of the 5 grid barriers + 2 in-kernel norms of a layer is a chain of L2 round trips under a saturated memory system,
         # ~33 us of consumer stalls per layer against the ring's 4.3 us of run-ahead
         self.linear_chain = os.environ.get("PC_LINEAR_CHAIN", "0") != "0"
+        # experiment, off: the short-suffix attention kernel asks L2 for the output projection's weight stream once its own K/V
+        # loads are out (that projection's CTAs cannot start before the attention CTAs leave their SMs).  Measured same-box:
+        # C2 step 3.250 -> 3.268 ms, decode 3.18 -> 3.17 ms/token -- like every other L2 prefetch tried here, no gain
+        self.attn_prefetch_o = os.environ.get("PC_ATTN_PREFETCH", "0") != "0"
         # CUDA graphs of the whole single-sequence forward, keyed by (q_len, n_cached, KV buffer): the per-layer
         # launch sequence is fixed once those are, so a repeated request shape is replayed with one launch
         self.ablate = frozenset()  # measurement only: kernel families left out of the step (see LlamaForCausalLM._layers_ablated)
@@ -126,7 +130,8 @@ class B200CausalLM(nn.Module):
         """Every switch that changes the launch sequence of `_layers`; part of each graph key so that toggling one
         after a capture can never replay a stale sequence."""
         return (self.linear_impl, tuple(sorted(self.linear_native_ops)), self.linear_max_q, self.linear_partials,
-                self.linear_tiled, self.linear_prefetch, self.linear_chain, self.attn_impl, tuple(sorted(self.ablate)))
+                self.linear_tiled, self.linear_prefetch, self.linear_chain, self.attn_prefetch_o, self.attn_impl,
+                tuple(sorted(self.ablate)))
 
     def _note_seen(self, key) -> None:
         if len(self._graph_seen) >= 256:  # bounded: forked / short-lived buffers would otherwise grow it forever

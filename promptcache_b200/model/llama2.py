@@ -283,7 +283,9 @@ class LlamaForCausalLM(B200CausalLM):
                 nat.attention(q_rot, kv.k[l], kv.v[l], attn_out, N if n_dev is None else kv.max_ctx - q_len, q_len, H, Hkv,
                               D, self.scale, self.rounding, workspace=ws, decode=(q_len == 1), n_cached_dev=n_dev,
                               impl=self.attn_impl if (n_dev is None and virt is None) else nat.PC_ATTN_TCGEN05,
-                              virtual=virt.planes(l) if virt is not None else None)
+                              virtual=virt.planes(l) if virt is not None else None,
+                              prefetch=self._wt(("o", l), self.wo[l], nat.PC_LIN_PARTIALS if pbuf_o is not None else nat.PC_LIN_PLAIN)
+                              if (lin_o and self.attn_prefetch_o) else None)
                 if lin_o and pbuf_o is not None:
                     nat.linear_partials(attn_out, self.wo[l], pbuf_o, lws, w_tiled=self._wt(("o", l), self.wo[l], nat.PC_LIN_PARTIALS),
                                         nxt=self._hint("gu", l, False) if lin_gu else None)

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol(native):
     assert declared == set(native.EXPORTS), declared ^ set(native.EXPORTS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.pc_version() == 5
+    assert lib.pc_version() == 6
     assert lib.pc_launch_count() >= 0
 
 
@@ -29,7 +29,7 @@ def test_struct_layout_matches_header(native):
     # sizes the C compiler gives the same structs (natural alignment on x86-64)
     assert ctypes.sizeof(native.pc_segment) == 16
     assert ctypes.sizeof(native.pc_copy2d) == 48
-    assert ctypes.sizeof(native.pc_attn_params) == 152
+    assert ctypes.sizeof(native.pc_attn_params) == 168
     assert ctypes.sizeof(native.pc_linear_params) == 176 and ctypes.sizeof(native.pc_chain_op) == 256
     import subprocess, tempfile, textwrap
     src = textwrap.dedent('''
@@ -42,7 +42,7 @@ def test_struct_layout_matches_header(native):
         open(os.path.join(d, "t.c"), "w").write(src)
         subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")], check=True)
         out = subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.split()
-    assert [int(x) for x in out] == [16, 48, 152, 176, 256]
+    assert [int(x) for x in out] == [16, 48, 168, 176, 256]
 
 
 def test_argument_validation_needs_no_gpu(native):
