@@ -317,8 +317,12 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
 // owner + helper clusters for the pre-tiled QKV projection (see ClIter)
 template <int NPAD>
 cudaError_t configure_cl() {
-  return cudaFuncSetAttribute(linear_small_kernel<NPAD, PC_LIN_ROPE_APPEND, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              LCfg<NPAD, 2>::kSmem);
+  static bool configured = false;
+  if (configured) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(linear_small_kernel<NPAD, PC_LIN_ROPE_APPEND, true, true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, LCfg<NPAD, 2>::kSmem);
+  configured = e == cudaSuccess;
+  return e;
 }
 template <int NPAD>
 bool cl_clusters_fit(int cl_size, int n_clusters) {
