@@ -1,8 +1,9 @@
 #!/bin/bash
-# A/B of the long-suffix attention kernel's key-tile width (PC_PP_BN = 128 default | 64)
-P="32,32,128,1024,8192 32,32,128,256,2048 32,32,128,64,2048 32,32,128,1024,2048 32,32,128,2048,0 71,1,64,256,2048 71,1,64,21,256 40,40,128,512,4096"
-echo "== BN=128"; python -m pytest tests/test_kernels_gpu.py tests/test_models_gpu.py tests/test_properties_gpu.py tests/test_reference_gpu.py -m gpu -q -x -k "not c2_llama7b" 2>&1 | tail -4
-python tools/attn_point.py $P 2>&1 | grep "^{"
-echo "== BN=64"; PC_NVCC_EXTRA=-DPC_PP_BN=64 python tools/attn_point.py $P 2>&1 | grep "^{"
-echo "== BN=128 NO_SOFTMAX"; PC_NVCC_EXTRA=-DPC_EXP_NO_SOFTMAX python tools/attn_point.py 32,32,128,1024,8192 32,32,128,2048,0 71,1,64,256,2048 2>&1 | grep "^{"
-echo "== BN=128 NO_MUFU"; PC_NVCC_EXTRA=-DPC_EXP_NO_MUFU python tools/attn_point.py 32,32,128,1024,8192 32,32,128,2048,0 71,1,64,256,2048 2>&1 | grep "^{"
+# key-tile width of the long-suffix kernel: 64 (default) vs 128 (-DPC_PP_BN=128), Falcon MQA (D=64) and Llama (D=128) points
+SH="71,1,64,256,2048 71,1,64,21,256 71,1,64,1,2048 71,1,64,16,2048 32,32,128,1024,8192 32,32,128,256,2048"
+run() { timeout 300 python tools/attn_point.py $SH 2>/dev/null | grep "^{" | python -c "
+import sys, json
+print('  '.join('H%d/q%d/N%d %.2f' % (d['H'], d['q'], d['N'], d['us']) for d in map(json.loads, sys.stdin)))"; }
+echo "BN=64"; run
+export PC_NVCC_EXTRA="-DPC_PP_BN=128"
+echo "BN=128"; run
