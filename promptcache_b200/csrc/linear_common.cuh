@@ -354,20 +354,31 @@ __device__ __forceinline__ void lin_epilogue(const LinParams& p, const Seg& sg, 
         if (t < p.q_len) p.out[t * p.out_stride + col] = __float2half_rn(v[t]);
     }
   } else if constexpr (EPI == PC_LIN_SILU_MUL) {
-    // rows [0,64) of the tile are gate features, rows [64,128) the up features of the same columns
+    // rows [0,64) of the tile are gate features, rows [64,128) the up features of the same columns.  The two threads of a
+    // feature split the tokens: the gate thread takes tokens [0, NPAD/2) and needs the up values of those, the up thread takes
+    // [NPAD/2, NPAD) and needs the gate values (all 128 threads share the expf / division work)
+    constexpr int TH = NPAD / 2;
+    const int ff = f & 63;
     if (f >= 64) {
 #pragma unroll
-      for (int t = 0; t < NPAD; ++t) exch[t * 64 + (f - 64)] = __float2half_rn(v[t]);
+      for (int t = 0; t < TH; ++t) exch[t * 64 + ff] = __float2half_rn(v[t]);            // up, first half of the tokens
+    } else {
+#pragma unroll
+      for (int t = TH; t < NPAD; ++t) exch[t * 64 + ff] = __float2half_rn(v[t]);         // gate, second half
     }
     named_bar_sync(1, kEpiThreads);
-    const int col = tile * 64 + f;
-    if (f < 64 && col < p.n_out) {
+    const int col = tile * 64 + ff;
+    if (col < p.n_out) {
+      const int t_lo = f < 64 ? 0 : TH;
 #pragma unroll
-      for (int t = 0; t < NPAD; ++t) {
+      for (int tt = 0; tt < TH; ++tt) {
+        const int t = t_lo + tt;
         if (t < p.q_len) {
-          const float g = __half2float(__float2half_rn(v[t]));  // gate_proj output is fp16
+          const __half other = exch[t * 64 + ff];
+          const float g = __half2float(f < 64 ? __float2half_rn(v[tt]) : other);        // gate_proj output is fp16
+          const __half u = f < 64 ? other : __float2half_rn(v[TH + tt]);
           const float s = g / (1.f + expf(-g));
-          p.out[t * p.out_stride + col] = __hmul_rn(__float2half_rn(s), exch[t * 64 + f]);
+          p.out[t * p.out_stride + col] = __hmul_rn(__float2half_rn(s), u);
         }
       }
     }
