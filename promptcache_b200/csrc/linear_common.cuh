@@ -265,9 +265,25 @@ __device__ __forceinline__ void lin_cta_range(const LinParams& p, int epi, int c
 // Epilogue of ONE accumulator segment `sg` of linear `p`, run by the 128 epilogue threads (f = row of the tile = TMEM lane,
 // et = thread index in the group, c = this CTA's index in the linear's partition); v = the fp32 accumulator row.
 //   exch: NPAD * BM halfs of shared memory, flag: 3 ints of shared memory; named barrier 1 is used.
+// cos / sin of every token's position id at column d of the RoPE table (clamped ids, as pc_rope_append): independent of the
+// accumulators, so a caller may issue these gathers while the MMAs are still running and hand the values to lin_epilogue
+template <int NPAD>
+__device__ __forceinline__ void rope_gather(const LinParams& p, int d, __half (&cs)[NPAD], __half (&sn)[NPAD]) {
+  const int HD = p.head_dim;
+#pragma unroll
+  for (int t = 0; t < NPAD; ++t) {
+    long long pos = t < p.q_len ? __ldg(p.pos + t) : 0;
+    if (pos < 0) pos = 0;
+    if (pos >= p.table_rows) pos = p.table_rows - 1;
+    cs[t] = __ldg(p.cos + pos * HD + d);
+    sn[t] = __ldg(p.sin + pos * HD + d);
+  }
+}
+
 template <int NPAD, int EPI>
 __device__ __forceinline__ void lin_epilogue(const LinParams& p, const Seg& sg, float (&v)[NPAD], int c, int KB, int t_first,
-                                             __half* exch, int* flag, int f, int et, int row0) {
+                                             __half* exch, int* flag, int f, int et, int row0, const __half* cs_pre = nullptr,
+                                             const __half* sn_pre = nullptr) {
   const int tile = sg.tile;
   const long long U = p.units_total;
   const int Gs = static_cast<int>(min(static_cast<long long>(p.grid), U));
@@ -399,13 +415,14 @@ __device__ __forceinline__ void lin_epilogue(const LinParams& p, const Seg& sg, 
       if (rotate) {
         // all table gathers first (independent loads in flight together), then the arithmetic
         __half cs[NPAD], sn[NPAD];
+        if (cs_pre != nullptr) {
 #pragma unroll
-        for (int t = 0; t < NPAD; ++t) {
-          long long pos = t < p.q_len ? __ldg(p.pos + t) : 0;
-          if (pos < 0) pos = 0;
-          if (pos >= p.table_rows) pos = p.table_rows - 1;
-          cs[t] = __ldg(p.cos + pos * HD + d);
-          sn[t] = __ldg(p.sin + pos * HD + d);
+          for (int t = 0; t < NPAD; ++t) {
+            cs[t] = cs_pre[t];
+            sn[t] = sn_pre[t];
+          }
+        } else {
+          rope_gather<NPAD>(p, d, cs, sn);
         }
         const int half_d = HD >> 1;
 #pragma unroll

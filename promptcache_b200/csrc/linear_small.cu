@@ -98,6 +98,7 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
   };
   // CL: the accumulator rows the epilogue threads carry across the two cluster barriers (owner: its tile; helper: three partials)
   float cl_v[CL ? 3 : 1][NPAD];
+  __half cl_cs[CL ? NPAD : 1], cl_sn[CL ? NPAD : 1];  // owners: the RoPE table values of their rows, gathered under the MMAs
   if (tid == 0) LIN_TRACE(0);
   if (tid == 0 && p.trace != nullptr) {  // slot 7: the SM this CTA runs on
     unsigned smid;
@@ -238,6 +239,10 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
     if constexpr (CL) {
       // read this CTA's accumulators (owner: one, helper: three); the exchange and the epilogue follow the role branches
       const int n_seg = (c % p.cl_size) < p.cl_size - 1 ? 1 : p.cl_size - 1;
+      if (n_seg == 1 && p.cos != nullptr) {  // owner of a rotated (query / key) head: its table gathers do not wait for the sums
+        const int own_tile = (c / p.cl_size) * (p.cl_size - 1) + c % p.cl_size;
+        if ((own_tile * BM + f) / p.head_dim < p.n_heads + p.n_kv_heads) rope_gather<NPAD>(p, f & (p.head_dim - 1), cl_cs, cl_sn);
+      }
 #pragma unroll
       for (int sgi = 0; sgi < 3; ++sgi) {  // compile-time indices keep cl_v in registers
         if (sgi < n_seg) {
@@ -302,7 +307,7 @@ linear_small_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
       whole.kb0 = 0;
       whole.n = KB;  // complete sum: the plain RoPE + append epilogue
       whole.rel = -1;
-      lin_epilogue<NPAD, EPI>(p, whole, cl_v[0], c, KB, 0, exch, flag, f, et, row0);
+      lin_epilogue<NPAD, EPI>(p, whole, cl_v[0], c, KB, 0, exch, flag, f, et, row0, p.cos != nullptr ? cl_cs : nullptr, cl_sn);
     }
   }
 
