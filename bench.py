@@ -644,7 +644,10 @@ def main():
         while not sampler.lines and time.time() < deadline:
             time.sleep(0.02)
     sync_all()
-    w.device_step()  # one more untimed step after that wait, so that the timed region starts on a busy GPU
+    # more untimed steps after that wait (the GPU may have idled for up to 2 s: one 3 ms step does not bring clocks and
+    # power state back): the timed region starts on a GPU that has been busy for ~0.15 s
+    for _ in range(max(args.warmup, 48)):
+        w.device_step()
     sync_all()
     sampler.mark()
     launches0 = nat.launch_count()
