@@ -545,7 +545,8 @@ def config_dict(args, case):
                         f"{case.q_len}-token uncached suffix, one request per GPU per step",
             "n_cached": case.n_cached, "q_len": case.q_len, "segments": case.n_segments,
             "l2": "inputs larger than L2 (1 GiB of segments + 13.5 GB of weights stream per step)",
-            "parallelism": f"batch partition x{args.gpus} (replicated weights and segment store)"}
+            "parallelism": f"batch partition x{args.gpus} (replicated weights and segment store)",
+            "untimed_steps_before_timing": f"{args.warmup} (--warmup) + {max(args.warmup, 48)} after the clock sampler came up"}
 
 
 def main():
