@@ -23,10 +23,11 @@
 //       (pc_add_rmsnorm_partials) adds the fp32 partials in split order and rounds once;
 //     - otherwise stream-K: equal contiguous ranges of the (tile, k-block) space; a range that covers only part of
 //       a tile's K parks its fp32 partial in a per-CTA slot and the LAST CTA to arrive at the tile (arrival counter,
-//       self-cleaning) adds the slots in a fixed order -- deterministic, no second launch;
+//       self-cleaning, ONE acq_rel RMW per arrival: gpu-scope fences do not complete while the SM's TMA stream keeps its
+//       memory pipe full) adds the slots in a fixed order -- deterministic, no second launch;
 // * epilogues: plain fp16 store; half(silu(gate)) * up (llama2.py:241) with gate and up rows of the same
 //   features in one tile; RoPE at explicit position ids + in-place KV append with the reference's three fp16
-//   roundings (llama2.py:195-210,357-364) when a tile is one head (D = 128).
+//   roundings (llama2.py:195-210,357-364), a tile holding one head (D = 128) or two (D = 64, Falcon).
 #include <type_traits>
 
 #include "linear_common.cuh"
